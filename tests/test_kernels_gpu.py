@@ -1,0 +1,181 @@
+"""Parity of the sm_100a kernels (called through the C ABI) against the oracle and the
+committed golden vectors.  Integer / byte work: every comparison is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import synth
+from scanner_b200 import cabi, kernels
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _cases(npz):
+    return sorted(k[:-5] for k in npz.files if k.endswith("_meta"))
+
+
+# ----------------------------------------------------------------------------- histogram
+def test_hist_golden_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hist_cv2.npz"))
+    for k in _cases(g):
+        meta = g[k + "_meta"]
+        if meta[3] == 2:
+            img = np.full((meta[1], meta[2], 3), meta[0], np.uint8)
+        else:
+            img = synth.frame(int(meta[0]), int(meta[1]), int(meta[2]), int(meta[3]))
+        got = kernels.histogram(dev(img[None]))[0].cpu().numpy()
+        assert (got == g[k + "_hist"]).all(), k
+
+
+@pytest.mark.parametrize("h,w,n", [(480, 640, 5), (1080, 1920, 3), (17, 31, 4), (1, 1, 2), (2, 3, 70),
+                                   (240, 1, 3), (333, 77, 2)])
+def test_hist_vs_oracle_batches(h, w, n):
+    frames = np.stack([synth.rand_frame(10 + i, h, w) for i in range(n)])
+    got = kernels.histogram(dev(frames)).cpu().numpy()
+    for i in range(n):
+        assert (got[i] == oracle.hist16(frames[i])).all(), i
+    assert (got.sum(axis=(1, 2)) == 3 * h * w).all()
+
+
+def test_hist_pointer_list_and_misaligned_frames():
+    # frames carved at odd byte offsets out of one buffer -> generic (unaligned) path
+    h, w = 37, 53
+    raw = np.random.default_rng(3).integers(0, 256, 5 + 3 * (h * w * 3 + 7), dtype=np.uint8)
+    buf = dev(raw)
+    offs = [5 + i * (h * w * 3 + 7) for i in range(3)]
+    views = [buf[o:o + h * w * 3].view(h, w, 3) for o in offs]
+    got = kernels.histogram(views).cpu().numpy()
+    for i, o in enumerate(offs):
+        assert (got[i] == oracle.hist16(raw[o:o + h * w * 3].reshape(h, w, 3))).all()
+
+
+def test_hist_empty_batch_and_overwrite():
+    l = cabi.lib()
+    assert l.scn_hist16_u8c3_strided(None, 0, 0, 4, 4, None, None) == 0
+    # `out` is fully overwritten even if it held garbage
+    frames = dev(synth.rand_frame(1, 8, 8)[None])
+    out = torch.full((1, 3, 16), 12345, dtype=torch.int32, device="cuda")
+    rc = l.scn_hist16_u8c3_strided(frames.data_ptr(), 8 * 8 * 3, 1, 8, 8, out.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert rc == 0 and out.sum().item() == 3 * 64
+
+
+def test_hist_full_size_property():
+    """1080p x 64 (BASELINE size): sum of bins == 3*W*H per frame and linear in concatenation."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    frames = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device="cuda", generator=g)
+    hist = kernels.histogram(frames)
+    assert (hist.sum(dim=(1, 2)) == 3 * 1080 * 1920).all()
+    ref = torch.stack([torch.bincount((frames[:, :, :, c] >> 4).flatten().int() +
+                                      16 * torch.arange(64, device="cuda").repeat_interleave(1080 * 1920).int(),
+                                      minlength=64 * 16).view(64, 16) for c in range(3)], 1)
+    assert (hist == ref.int()).all()
+
+
+# ----------------------------------------------------------------------------- resize
+def test_resize_golden_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "resize_cv2.npz"))
+    for k in _cases(g):
+        seed, h, w, dh, dw, kind = [int(x) for x in g[k + "_meta"]]
+        img = synth.frame(seed, h, w, kind)
+        got = kernels.resize(dev(img[None]), dw, dh)[0].cpu().numpy()
+        assert (got == g[k + "_out"]).all(), (k, h, w, dh, dw)
+
+
+@pytest.mark.parametrize("h,w,dh,dw,n", [(1080, 1920, 224, 224, 4), (480, 640, 224, 224, 3), (50, 70, 25, 35, 2),
+                                         (33, 47, 99, 120, 2), (5, 1, 3, 4, 1)])
+def test_resize_vs_oracle_batches(h, w, dh, dw, n):
+    frames = np.stack([synth.rand_frame(20 + i, h, w) for i in range(n)])
+    got = kernels.resize(dev(frames), dw, dh).cpu().numpy()
+    for i in range(n):
+        assert (got[i] == oracle.resize(frames[i], dw, dh)).all()
+
+
+def test_resize_missing_plan_is_an_error():
+    f = dev(synth.rand_frame(1, 8, 8)[None])
+    out = torch.empty((1, 3, 3, 3), dtype=torch.uint8, device="cuda")
+    rc = cabi.lib().scn_resize_bilinear_u8c3_strided(f.data_ptr(), 192, 1, 8, 8, out.data_ptr(), 27, 3, 3, None, None)
+    assert rc == -3
+
+
+# ----------------------------------------------------------------------------- blur
+def test_blur_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "blur_np.npz"))
+    for k in _cases(g):
+        seed, h, w, ks = [int(x) for x in g[k + "_meta"]]
+        img = synth.rand_frame(seed, h, w)
+        got = kernels.blur(dev(img[None]), ks)[0].cpu().numpy()
+        assert (got == g[k + "_out"]).all(), (k, h, w, ks)
+
+
+@pytest.mark.parametrize("h,w,k,n", [(480, 640, 3, 2), (2160, 3840, 3, 1), (100, 70, 7, 3), (65, 129, 31, 1),
+                                     (10, 10, 12, 1)])
+def test_blur_vs_oracle(h, w, k, n):
+    frames = np.stack([synth.rand_frame(30 + i, h, w) for i in range(n)])
+    got = kernels.blur(dev(frames), k).cpu().numpy()
+    for i in range(n):
+        assert (got[i] == oracle.blur(frames[i], k)).all()
+
+
+# ----------------------------------------------------------------------------- nv12
+def _surfaces(seed, n, h, w, pitch):
+    out = np.zeros((n, h * 3 // 2, pitch), np.uint8)
+    for i in range(n):
+        l, c = synth.nv12_surface(seed + i, h, w, pitch)
+        out[i, :h], out[i, h:] = l, c
+    return out
+
+
+def test_nv12_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nv12_np.npz"))
+    for k in _cases(g):
+        seed, h, w, pitch = [int(x) for x in g[k + "_meta"]]
+        l, c = synth.nv12_surface(seed, h, w, pitch)
+        surf = np.concatenate([l, c])[None]
+        got = kernels.nv12_to_rgb(dev(surf), w, h)[0].cpu().numpy()
+        assert (got == g[k + "_out"]).all(), (k, h, w, pitch)
+
+
+@pytest.mark.parametrize("h,w,pitch,n", [(1080, 1920, 2048, 2), (480, 640, 640, 3), (30, 50, 64, 2), (2, 2, 4, 1),
+                                         (16, 18, 18, 2)])
+def test_nv12_vs_oracle(h, w, pitch, n):
+    surf = _surfaces(40, n, h, w, pitch)
+    got = kernels.nv12_to_rgb(dev(surf), w, h).cpu().numpy()
+    for i in range(n):
+        assert (got[i] == oracle.nv12_to_rgb(surf[i, :h], surf[i, h:], w)).all()
+
+
+# ----------------------------------------------------------------------------- fused C2 DAG
+@pytest.mark.parametrize("h,w,pitch,dh,dw,n", [(1080, 1920, 2048, 224, 224, 3), (480, 640, 640, 224, 224, 2),
+                                               (48, 64, 64, 24, 32, 2), (30, 50, 64, 45, 70, 2)])
+def test_fused_nv12_hist_resize_vs_oracle(h, w, pitch, dh, dw, n):
+    surf = _surfaces(50, n, h, w, pitch)
+    hist, res = kernels.nv12_hist_resize(dev(surf), w, h, dw, dh)
+    hist, res = hist.cpu().numpy(), res.cpu().numpy()
+    for i in range(n):
+        oh, orr = oracle.nv12_hist_resize(surf[i, :h], surf[i, h:], dw, dh, w)
+        assert (hist[i] == oh).all()
+        assert (res[i] == orr).all()
+
+
+def test_fused_equals_three_pass_composition():
+    h, w, pitch, n = 1080, 1920, 1920, 8
+    g = torch.Generator(device="cuda").manual_seed(9)
+    surf = torch.randint(0, 256, (n, h * 3 // 2, pitch), dtype=torch.uint8, device="cuda", generator=g)
+    hist, res = kernels.nv12_hist_resize(surf, w, h, 224, 224)
+    rgb = kernels.nv12_to_rgb(surf, w, h)
+    assert (hist == kernels.histogram(rgb)).all()
+    assert (res == kernels.resize(rgb, 224, 224)).all()
+
+
+def test_launch_counter_counts():
+    before = cabi.lib().scn_launch_count()
+    kernels.histogram(dev(synth.rand_frame(1, 8, 8)[None]))
+    assert cabi.lib().scn_launch_count() > before

@@ -1,0 +1,102 @@
+"""The oracle (oracle/scn_oracle.c) against the committed golden vectors.
+
+hist_cv2 / resize_cv2 come from OpenCV itself (cv2.calcHist / cv2.resize called the way
+tests/test_ops.cpp:38-43,156 of the reference calls them); blur_np / nv12_np come from the
+independent numpy restatement in oracle/make_golden.py.  CPU only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import synth
+
+
+def _cases(npz):
+    keys = sorted(k[:-5] for k in npz.files if k.endswith("_meta"))
+    return keys
+
+
+def test_hist_matches_cv2_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hist_cv2.npz"))
+    for k in _cases(g):
+        meta = g[k + "_meta"]
+        if meta[3] == 2:
+            img = np.full((meta[1], meta[2], 3), meta[0], np.uint8)
+        else:
+            img = synth.frame(int(meta[0]), int(meta[1]), int(meta[2]), int(meta[3]))
+        got = oracle.hist16(img)
+        assert got.dtype == np.int32 and got.shape == (3, 16)
+        assert (got == g[k + "_hist"]).all(), k
+        assert got.sum() == 3 * meta[1] * meta[2]
+
+
+def test_resize_matches_cv2_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "resize_cv2.npz"))
+    for k in _cases(g):
+        seed, h, w, dh, dw, kind = [int(x) for x in g[k + "_meta"]]
+        img = synth.frame(seed, h, w, kind)
+        got = oracle.resize(img, dw, dh)
+        assert (got == g[k + "_out"]).all(), (k, h, w, dh, dw)
+
+
+def test_blur_matches_numpy_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "blur_np.npz"))
+    for k in _cases(g):
+        seed, h, w, ks = [int(x) for x in g[k + "_meta"]]
+        img = synth.rand_frame(seed, h, w)
+        assert (oracle.blur(img, ks) == g[k + "_out"]).all(), (k, h, w, ks)
+
+
+def test_nv12_matches_numpy_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "nv12_np.npz"))
+    for k in _cases(g):
+        seed, h, w, pitch = [int(x) for x in g[k + "_meta"]]
+        luma, chroma = synth.nv12_surface(seed, h, w, pitch)
+        assert (oracle.nv12_to_rgb(luma, chroma, w) == g[k + "_out"]).all(), (k, h, w, pitch)
+
+
+def test_nv12_exhaustive_yuv_triples():
+    """All 2^24 (Y,Cb,Cr) triples on even rows equal the float formula evaluated in numpy."""
+    # even rows only use the co-sited chroma sample: build a surface where each 2x2 block has
+    # one (Cb,Cr) and two distinct Y on the even row.
+    cb, cr = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    for y0 in (0, 1, 16, 127, 128, 235, 254, 255):
+        w = 2 * 256
+        luma = np.full((2 * 256, w), y0, np.uint8)
+        chroma = np.zeros((256, w), np.uint8)
+        chroma[:, 0::2] = cb
+        chroma[:, 1::2] = cr
+        rgb = oracle.nv12_to_rgb(luma, chroma)[0::2, 0::2]
+        lf = np.float32(y0 * 4) * np.float32(1.1644)
+        fcb = (cb.astype(np.int32) * 4 - 512).astype(np.float64)
+        fcr = (cr.astype(np.int32) * 4 - 512).astype(np.float64)
+        r = (fcr * np.float64(np.float32(1.596)) + np.float64(lf)).astype(np.float32)
+        r = (np.clip(r, 0, 1023).astype(np.uint32) >> 2).astype(np.uint8)
+        assert (rgb[..., 0] == r).all()
+
+
+def test_resize_target_rules():
+    # tests/test_ops.cpp:126-147
+    assert oracle.resize_target(1920, 1080, 224, 224) == (224, 224)
+    assert oracle.resize_target(1920, 1080, 0, 540, preserve_aspect=True) == (960, 540)
+    assert oracle.resize_target(1920, 1080, 640, 0, preserve_aspect=True) == (640, 360)
+    assert oracle.resize_target(640, 480, 1000, 1000, min=True) == (640, 480)
+    assert oracle.resize_target(640, 480, 320, 1000, min=True) == (320, 1000)
+
+
+def test_index_column():
+    b = oracle.index_column(5, 4)
+    assert (np.frombuffer(b.tobytes(), "<i8") == np.arange(5, 9)).all()
+
+
+def test_blur_interior_only_and_border_zero():
+    img = synth.rand_frame(1, 12, 14)
+    out = oracle.blur(img, 3)
+    ys, xs = oracle.blur_interior(12, 14, 3)
+    mask = np.ones((12, 14), bool)
+    mask[ys, xs] = False
+    assert (out[mask] == 0).all()
+    # k=1 is the identity on the whole frame (fl=fr=0)
+    assert (oracle.blur(img, 1) == img).all()
