@@ -1,0 +1,232 @@
+// scanner/api/kernel.h -- the Kernel side of Scanner's plugin boundary (reference
+// scanner/api/kernel.h:28-475, kernel.cpp:23-145), re-declared so that op sources written for the
+// reference compile against scanner-b200:
+//   Element / Elements / BatchedElements / StenciledBatchedElements, insert_element/frame,
+//   add_element_ref / delete_element, KernelConfig, BaseKernel and the four calling conventions
+//   (Kernel, BatchedKernel, StenciledKernel, StenciledBatchedKernel), VideoKernel::check_frame,
+//   REGISTER_KERNEL(...).device().num_devices().batch().input_device().output_device().
+// Calling contract: one evaluate thread owns a kernel instance; inputs are borrowed;
+// outputs are allocated by the kernel on its declared output device, exactly one per input row.
+// B200 addition: GPU kernels enqueue on device_stream(device) and need not synchronise.
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "scanner/api/frame.h"
+#include "scanner/util/common.h"
+#include "scanner/util/memory.h"
+#include "scanner/util/profiler.h"
+
+namespace scanner {
+
+struct Element {
+  Element() = default;
+  Element(u8* buffer_, size_t size_) : buffer(buffer_), size(size_), is_frame(false) {}
+  Element(Frame* frame) : buffer((u8*)frame), size(sizeof(Frame)), is_frame(true) {}
+
+  Frame* as_frame() { return reinterpret_cast<Frame*>(buffer); }
+  const Frame* as_const_frame() const { return reinterpret_cast<Frame*>(buffer); }
+  FrameInfo* as_frame_info() { return reinterpret_cast<FrameInfo*>(buffer); }
+  const FrameInfo* as_const_frame_info() const { return reinterpret_cast<FrameInfo*>(buffer); }
+  bool is_null() const { return buffer == nullptr; }
+
+  u8* buffer = nullptr;
+  size_t size = 0;
+  bool is_frame = false;
+  i64 index = 0;  // row id of the element in the op's input domain
+};
+
+using Elements = std::vector<Element>;
+using BatchedElements = std::vector<Elements>;
+using StenciledElements = std::vector<Elements>;
+using StenciledBatchedElements = std::vector<std::vector<Elements>>;  // column -> batch -> stencil
+
+inline size_t num_rows(const Elements& column) { return column.size(); }
+
+inline void insert_element(Elements& column, u8* buffer, size_t size) {
+  column.push_back(Element{buffer, size});
+}
+inline void insert_frame(Elements& column, Frame* frame) { column.push_back(Element{frame}); }
+inline void insert_element(Element& element, u8* buffer, size_t size) {
+  element = Element{buffer, size};
+}
+inline void insert_frame(Element& element, Frame* frame) { element = Element{frame}; }
+
+// A second handle on the same payload: bumps the block refcount; frame elements get their own
+// Frame header (headers are not refcounted).
+inline Element add_element_ref(DeviceHandle device, Element& element) {
+  if (element.is_null()) return Element();
+  Element ele;
+  if (element.is_frame) {
+    Frame* frame = element.as_frame();
+    add_buffer_ref(device, frame->data);
+    ele = Element{new Frame(frame->as_frame_info(), frame->data)};
+  } else {
+    add_buffer_ref(device, element.buffer);
+    ele = element;
+  }
+  ele.index = element.index;
+  return ele;
+}
+
+inline void delete_element(DeviceHandle device, Element& element) {
+  if (element.is_null()) return;
+  if (element.is_frame) {
+    Frame* frame = element.as_frame();
+    delete_buffer(device, frame->data);
+    delete frame;
+  } else {
+    delete_buffer(device, element.buffer);
+  }
+}
+
+struct KernelConfig {
+  std::vector<DeviceHandle> devices;  // non-empty; devices[0] is where the kernel runs
+  std::vector<std::string> input_columns;
+  std::vector<proto::ColumnType> input_column_types;
+  std::vector<std::string> output_columns;
+  std::vector<proto::ColumnType> output_column_types;
+  std::vector<u8> args;  // serialized <Op>Args (proto3 wire bytes), may be empty
+  i32 node_id = 0;
+
+  static KernelConfig dummy() {
+    KernelConfig config;
+    config.devices.push_back(CPU_DEVICE);
+    return config;
+  }
+};
+
+class BaseKernel {
+ public:
+  static const i32 UnlimitedDevices = 0;
+  BaseKernel(const KernelConfig&) {}
+  virtual ~BaseKernel() {}
+
+  virtual void validate(proto::Result* result) { result->set_success(true); }
+  virtual void fetch_resources(proto::Result* result) { result->set_success(true); }
+  virtual void setup_with_resources(proto::Result* result) { result->set_success(true); }
+  virtual void new_stream(const std::vector<u8>& /*args*/) {}
+  virtual void reset() {}
+
+  // engine entry point; the typed subclasses below adapt it to their execute() shape
+  virtual void execute_kernel(const StenciledBatchedElements& input_columns,
+                              BatchedElements& output_columns) = 0;
+  virtual void set_profiler(Profiler* profiler) { profiler_ = profiler; }
+
+  Profiler* profiler_ = nullptr;
+};
+
+class StenciledBatchedKernel : public BaseKernel {
+ public:
+  StenciledBatchedKernel(const KernelConfig& config) : BaseKernel(config) {}
+  void execute_kernel(const StenciledBatchedElements& input_columns,
+                      BatchedElements& output_columns) override;
+
+ protected:
+  virtual void execute(const StenciledBatchedElements& input_columns,
+                       BatchedElements& output_columns) = 0;
+};
+
+class BatchedKernel : public BaseKernel {
+ public:
+  BatchedKernel(const KernelConfig& config) : BaseKernel(config) {}
+  void execute_kernel(const StenciledBatchedElements& input_columns,
+                      BatchedElements& output_columns) override;
+
+ protected:
+  virtual void execute(const BatchedElements& input_columns,
+                       BatchedElements& output_columns) = 0;
+};
+
+class StenciledKernel : public BaseKernel {
+ public:
+  StenciledKernel(const KernelConfig& config) : BaseKernel(config) {}
+  void execute_kernel(const StenciledBatchedElements& input_columns,
+                      BatchedElements& output_columns) override;
+
+ protected:
+  virtual void execute(const StenciledElements& input_columns, Elements& output_columns) = 0;
+};
+
+class Kernel : public BaseKernel {
+ public:
+  Kernel(const KernelConfig& config) : BaseKernel(config) {}
+  void execute_kernel(const StenciledBatchedElements& input_columns,
+                      BatchedElements& output_columns) override;
+
+ protected:
+  virtual void execute(const Elements& input_columns, Elements& output_columns) = 0;
+};
+
+// Mix-in for kernels that consume frame columns: check_frame() fires new_frame_info() when the
+// shape/type differs from the cached one (reference kernel.cpp:97-109).
+class VideoKernel {
+ protected:
+  void check_frame(const DeviceHandle& device, const Element& element);
+  void check_frame_info(const DeviceHandle& device, const Element& element);
+  virtual void new_frame_info() {}
+  virtual ~VideoKernel() {}
+
+  FrameInfo frame_info_{};
+};
+
+namespace internal {
+
+class KernelBuilder;
+using KernelConstructor = std::function<BaseKernel*(const KernelConfig& config)>;
+
+class KernelRegistration {
+ public:
+  KernelRegistration(const KernelBuilder& builder);
+};
+
+class KernelBuilder {
+ public:
+  friend class KernelRegistration;
+  KernelBuilder(const std::string& name, KernelConstructor constructor)
+    : name_(name), constructor_(constructor) {}
+
+  KernelBuilder& device(DeviceType device_type) {
+    device_type_ = device_type;
+    return *this;
+  }
+  KernelBuilder& num_devices(i32 devices) {
+    num_devices_ = devices;
+    return *this;
+  }
+  KernelBuilder& input_device(const std::string& input_name, DeviceType device_type) {
+    input_devices_[input_name] = device_type;
+    return *this;
+  }
+  KernelBuilder& output_device(const std::string& output_name, DeviceType device_type) {
+    output_devices_[output_name] = device_type;
+    return *this;
+  }
+  KernelBuilder& batch(i32 preferred_batch_size = 1) {
+    can_batch_ = true;
+    preferred_batch_size_ = preferred_batch_size;
+    return *this;
+  }
+
+ private:
+  std::string name_;
+  KernelConstructor constructor_;
+  DeviceType device_type_ = DeviceType::CPU;
+  i32 num_devices_ = 1;
+  std::map<std::string, DeviceType> input_devices_;
+  std::map<std::string, DeviceType> output_devices_;
+  bool can_batch_ = false;
+  i32 preferred_batch_size_ = 1;
+};
+}  // namespace internal
+
+#define REGISTER_KERNEL(name__, kernel__) REGISTER_KERNEL_HELPER(__COUNTER__, name__, kernel__)
+#define REGISTER_KERNEL_HELPER(uid__, name__, kernel__) REGISTER_KERNEL_UID(uid__, name__, kernel__)
+#define REGISTER_KERNEL_UID(uid__, name__, kernel__)                                          \
+  static ::scanner::internal::KernelRegistration kernel_registration_##uid__                  \
+      __attribute__((unused)) = ::scanner::internal::KernelBuilder(                           \
+          #name__, [](const ::scanner::KernelConfig& config) { return new kernel__(config); })
+
+}  // namespace scanner

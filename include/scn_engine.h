@@ -1,0 +1,131 @@
+/*
+ * scn_engine.h -- C ABI of the scanner-b200 host pipeline (libscn_engine.so).
+ *
+ * What a foreign binding (the scannerpy-shaped Python layer in scanner_b200/, or a cgo/JNI stub)
+ * drives: register op plugins, describe an op graph, bind per-job streams and run the
+ * load -> decode -> evaluate -> save pipeline of the reference's worker
+ * (scanner/engine/worker.cpp:868-2148 process_job; load_worker.cpp, evaluate_worker.cpp,
+ * save_worker.cpp) on the GPUs of one box.  Plain pointers and sizes only.
+ *
+ * All functions return 0 / a non-negative id on success and a negative value on error;
+ * scn_last_error() gives the message of the last failure on the calling thread.
+ * Device type codes: 0 = CPU, 1 = GPU (scanner/metadata.proto DeviceType).
+ */
+#ifndef SCN_ENGINE_H_
+#define SCN_ENGINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SCN_ENGINE_API __attribute__((visibility("default")))
+#else
+#define SCN_ENGINE_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scn_engine scn_engine;
+typedef struct scn_graph scn_graph;
+typedef struct scn_job scn_job;
+
+SCN_ENGINE_API const char* scn_last_error(void);
+
+/* ---- op plugins (reference Client.load_op -> dlopen, worker.cpp:732-744) ------------------ */
+SCN_ENGINE_API int scn_load_op_library(const char* so_path);
+SCN_ENGINE_API int scn_op_registered(const char* op_name);                    /* 1 / 0 */
+SCN_ENGINE_API int scn_kernel_registered(const char* op_name, int device_type); /* 1 / 0 */
+/* Writes "name:n_inputs:n_outputs:can_stencil:bounded:unbounded:warmup\n" per registered op. */
+SCN_ENGINE_API int scn_list_ops(char* host_buf, size_t cap);
+
+/* ---- engine ------------------------------------------------------------------------------- */
+/* gpu_ids/n_gpus: GPUs this process drives (n_gpus = 0: CPU only).
+ * instances_per_gpu: pipeline instances (thread + CUDA stream + NVDEC session) per GPU
+ *   (reference pipeline_instances_per_node, worker.cpp:1297-1337); 0 = auto.
+ * cpu_instances: instances without a GPU (CPU kernels only); used when n_gpus = 0; 0 = 1. */
+SCN_ENGINE_API scn_engine* scn_engine_create(const int* gpu_ids, int n_gpus, int instances_per_gpu,
+                                             int cpu_instances);
+SCN_ENGINE_API void scn_engine_destroy(scn_engine* e);
+
+/* ---- input streams (the "tables" a job reads) ---------------------------------------------- */
+/* Ingest an H.264 Annex-B elementary stream: builds the sample/keyframe index
+ * (reference h264_byte_stream_index_creator.cpp).  The bytes are copied.  Returns a stream id. */
+SCN_ENGINE_API int64_t scn_stream_add_h264(scn_engine* e, const uint8_t* bytes, size_t size);
+/* n dense HWC frames of `type` (FrameType: 0 U8, 1 F32, 2 F64, 3 U16), copied; the reference's
+ * RAW (uncompressed) video column. */
+SCN_ENGINE_API int64_t scn_stream_add_raw_frames(scn_engine* e, const uint8_t* frames, int64_t n, int height,
+                                                 int width, int channels, int type);
+/* n byte-string rows: data is the concatenation, sizes[i] their lengths (size 0 = null row). */
+SCN_ENGINE_API int64_t scn_stream_add_bytes(scn_engine* e, const uint8_t* data, const uint64_t* sizes,
+                                            int64_t n);
+SCN_ENGINE_API int64_t scn_stream_rows(scn_engine* e, int64_t stream);
+/* info[0..5] = is_video, width, height, channels, keyframes, encoded_bytes */
+SCN_ENGINE_API int scn_stream_info(scn_engine* e, int64_t stream, int64_t info[6]);
+SCN_ENGINE_API int scn_stream_remove(scn_engine* e, int64_t stream);
+
+/* ---- op graph ------------------------------------------------------------------------------ */
+SCN_ENGINE_API scn_graph* scn_graph_create(void);
+SCN_ENGINE_API void scn_graph_destroy(scn_graph* g);
+/* Every add_* returns the new op's index (inputs must refer to earlier indices). */
+SCN_ENGINE_API int scn_graph_add_source(scn_graph* g, int is_video);
+SCN_ENGINE_API int scn_graph_add_op(scn_graph* g, const char* op_name, int device_type, const int* input_ops,
+                                    const char* const* input_columns, int n_inputs, const uint8_t* args,
+                                    size_t args_size, int batch /* -1 = kernel default */,
+                                    const int* stencil, int n_stencil /* 0 = op default */,
+                                    int warmup /* -1 = op default */);
+SCN_ENGINE_API int scn_graph_add_sample(scn_graph* g, int input_op, const char* input_column);
+SCN_ENGINE_API int scn_graph_add_space(scn_graph* g, int input_op, const char* input_column);
+SCN_ENGINE_API int scn_graph_add_sink(scn_graph* g, int input_op, const char* input_column,
+                                      const char* stored_name);
+/* Output column names of op `index`, '\n'-separated. */
+SCN_ENGINE_API int scn_graph_op_outputs(scn_graph* g, int index, char* host_buf, size_t cap);
+
+/* ---- jobs (one per output stream; reference proto::Job) ------------------------------------ */
+SCN_ENGINE_API scn_job* scn_job_create(void);
+SCN_ENGINE_API void scn_job_destroy(scn_job* j);
+SCN_ENGINE_API int scn_job_bind_source(scn_job* j, int source_op, int64_t stream);
+/* sampler function: All | Strided | StridedRanges | Gather | SpaceNull | SpaceRepeat; args are the
+ * proto3 bytes of the matching message of scanner/sampler_args.proto. */
+SCN_ENGINE_API int scn_job_set_sampler(scn_job* j, int op, const char* function, const uint8_t* args,
+                                       size_t args_size);
+SCN_ENGINE_API int scn_job_set_stream_args(scn_job* j, int op, const uint8_t* args, size_t args_size);
+
+/* ---- run ----------------------------------------------------------------------------------- */
+/* work_packet_size / io_packet_size: rows per evaluate packet / per task (reference
+ * BulkJobParameters, rpc.proto:238-274; io must be a multiple of work).  out_dir: if non-NULL the
+ * sink columns are also written in the reference's column file layout
+ * (<out_dir>/tables/<job>/<col>_<task>.bin + _metadata.bin, column_sink.cpp:159-195).
+ * Tasks of all jobs are sharded over the engine's pipeline instances (one shared work queue). */
+SCN_ENGINE_API int scn_engine_run(scn_engine* e, scn_graph* g, scn_job* const* jobs, int n_jobs,
+                                  int work_packet_size, int io_packet_size, const char* out_dir);
+
+/* ---- results ------------------------------------------------------------------------------- */
+SCN_ENGINE_API int64_t scn_job_output_rows(scn_job* j, int sink_op);
+/* Row `row` of sink `sink_op`: *data/*size point into engine-owned host memory valid until the job
+ * is destroyed; shape[0..3] = {h, w, c, frame_type} for frame rows, {0,0,0,-1} for byte rows.
+ * A null row has size 0. */
+SCN_ENGINE_API int scn_job_output_row(scn_job* j, int sink_op, int64_t row, const uint8_t** data,
+                                      uint64_t* size, int shape[4]);
+/* Copies rows [row0, row0+n) of equal-sized elements into dst (n * row_bytes). */
+SCN_ENGINE_API int scn_job_output_copy(scn_job* j, int sink_op, int64_t row0, int64_t n, uint8_t* dst,
+                                       size_t row_bytes);
+
+/* JSON: profiler interval totals / counters of the last run (frames_decoded, frames_used, ...). */
+SCN_ENGINE_API int scn_engine_stats_json(scn_engine* e, char* host_buf, size_t cap);
+
+/* ---- synthetic H.264 (tests / bench input generation; no encoder exists offline) ----------- */
+/* Encodes `frames` I420 pictures (planes at yuv + f*(w*h*3/2): Y, U, V) as an Annex-B stream of
+ * I_PCM macroblocks, IDR every `gop` frames; non_key_mode 0 = P slices of I_PCM macroblocks,
+ * 1 = P_Skip (repeat previous).  Returns the stream size, or the required size if cap is too
+ * small (nothing written then). */
+SCN_ENGINE_API int64_t scn_h264_synth(const uint8_t* yuv, int width, int height, int64_t frames, int gop,
+                                      int non_key_mode, uint8_t* out, size_t cap);
+/* NVDEC probe: info[0..5] = available, h264_supported, engines, max_w, max_h, min_w. */
+SCN_ENGINE_API int scn_nvdec_caps(int gpu_id, int info[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCN_ENGINE_H_ */

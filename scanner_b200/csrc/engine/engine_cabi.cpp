@@ -1,0 +1,331 @@
+// engine_cabi.cpp -- extern "C" surface of include/scn_engine.h over the C++ pipeline.
+#include <cstring>
+#include <sstream>
+
+#include "nvdec.h"
+#include "pipeline.h"
+#include "scn_engine.h"
+
+using namespace scanner;
+using namespace scanner::internal;
+
+struct scn_engine {
+  std::unique_ptr<Engine> impl;
+};
+struct scn_graph {
+  Graph g;
+  bool analyzed = false;
+};
+struct scn_job {
+  Job j;
+};
+
+namespace {
+thread_local std::string t_error;
+int fail(const std::string& msg, int code = -1) {
+  t_error = msg;
+  return code;
+}
+int from_result(const Result& r) { return r.success() ? 0 : fail(r.msg()); }
+int copy_out(const std::string& s, char* buf, size_t cap) {
+  if (!buf || cap < s.size() + 1) return fail("buffer too small", -2);
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+}  // namespace
+
+extern "C" {
+
+const char* scn_last_error(void) { return t_error.c_str(); }
+
+int scn_load_op_library(const char* so_path) {
+  if (!so_path) return fail("null path");
+  return from_result(load_op_library(so_path));
+}
+int scn_op_registered(const char* name) { return name && get_op_registry()->has_op(name) ? 1 : 0; }
+int scn_kernel_registered(const char* name, int device_type) {
+  return name && get_kernel_registry()->has_kernel(name, device_type == 1 ? proto::GPU : proto::CPU) ? 1 : 0;
+}
+int scn_list_ops(char* buf, size_t cap) {
+  std::ostringstream ss;
+  for (const std::string& n : get_op_registry()->names()) {
+    const OpInfo* i = get_op_registry()->get_op_info(n);
+    ss << n << ":" << i->input_columns.size() << ":" << i->output_columns.size() << ":" << i->can_stencil << ":"
+       << i->has_bounded_state << ":" << i->has_unbounded_state << ":" << i->warmup << "\n";
+  }
+  return copy_out(ss.str(), buf, cap);
+}
+
+scn_engine* scn_engine_create(const int* gpu_ids, int n_gpus, int instances_per_gpu, int cpu_instances) {
+  std::vector<i32> ids;
+  for (int i = 0; i < n_gpus; ++i) ids.push_back(gpu_ids[i]);
+  scn_engine* e = new scn_engine();
+  e->impl.reset(new Engine(ids, instances_per_gpu, cpu_instances));
+  return e;
+}
+void scn_engine_destroy(scn_engine* e) { delete e; }
+
+int64_t scn_stream_add_h264(scn_engine* e, const uint8_t* bytes, size_t size) {
+  if (!e || !bytes || !size) return fail("bad arguments");
+  std::unique_ptr<InputStream> s(new InputStream());
+  s->kind = InputStream::H264;
+  s->encoded.assign(bytes, bytes + size);
+  Result r = index_bytestream(s->encoded.data(), s->encoded.size(), s->index);
+  if (!r.success()) return fail(r.msg());
+  return e->impl->add_stream(std::move(s));
+}
+
+int64_t scn_stream_add_raw_frames(scn_engine* e, const uint8_t* frames, int64_t n, int height, int width,
+                                  int channels, int type) {
+  if (!e || n < 0 || height <= 0 || width <= 0 || channels <= 0 || (n > 0 && !frames)) return fail("bad arguments");
+  std::unique_ptr<InputStream> s(new InputStream());
+  s->kind = InputStream::RawFrames;
+  s->info = FrameInfo(height, width, channels, FrameType((proto::FrameType)type));
+  const size_t fb = s->info.size();
+  s->data.assign(frames, frames + (size_t)n * fb);
+  for (int64_t i = 0; i < n; ++i) {
+    s->offsets.push_back((u64)i * fb);
+    s->sizes.push_back(fb);
+  }
+  return e->impl->add_stream(std::move(s));
+}
+
+int64_t scn_stream_add_bytes(scn_engine* e, const uint8_t* data, const uint64_t* sizes, int64_t n) {
+  if (!e || n < 0 || (n > 0 && !sizes)) return fail("bad arguments");
+  std::unique_ptr<InputStream> s(new InputStream());
+  s->kind = InputStream::Bytes;
+  u64 total = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    s->offsets.push_back(total);
+    s->sizes.push_back(sizes[i]);
+    total += sizes[i];
+  }
+  if (total) s->data.assign(data, data + total);
+  else s->data.assign(1, 0);  // keep a non-empty backing store so rows are addressable
+  return e->impl->add_stream(std::move(s));
+}
+
+int64_t scn_stream_rows(scn_engine* e, int64_t id) {
+  InputStream* s = e ? e->impl->stream(id) : nullptr;
+  return s ? s->rows() : fail("unknown stream");
+}
+
+int scn_stream_info(scn_engine* e, int64_t id, int64_t info[6]) {
+  InputStream* s = e ? e->impl->stream(id) : nullptr;
+  if (!s || !info) return fail("unknown stream");
+  memset(info, 0, 6 * sizeof(int64_t));
+  if (s->kind == InputStream::H264) {
+    info[0] = 1;
+    info[1] = s->index.width;
+    info[2] = s->index.height;
+    info[3] = 3;
+    info[4] = (int64_t)s->index.keyframe_indices.size();
+    info[5] = (int64_t)s->encoded.size();
+  } else if (s->kind == InputStream::RawFrames) {
+    info[0] = 1;
+    info[1] = s->info.width();
+    info[2] = s->info.height();
+    info[3] = s->info.channels();
+    info[5] = (int64_t)s->data.size();
+  } else {
+    info[5] = (int64_t)s->data.size();
+  }
+  return 0;
+}
+int scn_stream_remove(scn_engine* e, int64_t id) { return e && e->impl->remove_stream(id) ? 0 : fail("unknown stream"); }
+
+scn_graph* scn_graph_create(void) { return new scn_graph(); }
+void scn_graph_destroy(scn_graph* g) { delete g; }
+
+int scn_graph_add_source(scn_graph* g, int is_video) {
+  if (!g) return fail("null graph");
+  GraphOp op;
+  op.kind = OpKind::Source;
+  op.name = "Input";
+  op.column_type = is_video ? proto::Video : proto::Bytes;
+  op.output_columns = {is_video ? "frame" : "column"};
+  g->g.ops.push_back(op);
+  return (int)g->g.ops.size() - 1;
+}
+
+int scn_graph_add_op(scn_graph* g, const char* name, int device_type, const int* input_ops,
+                     const char* const* input_columns, int n_inputs, const uint8_t* args, size_t args_size,
+                     int batch, const int* stencil, int n_stencil, int warmup) {
+  if (!g || !name || n_inputs < 0) return fail("bad arguments");
+  const OpInfo* info = get_op_registry()->get_op_info(name);
+  if (!info) return fail(std::string("Op ") + name + " is not registered.");
+  GraphOp op;
+  op.kind = OpKind::Kernel;
+  op.name = name;
+  op.device_type = device_type == 1 ? proto::GPU : proto::CPU;
+  for (int i = 0; i < n_inputs; ++i) op.inputs.push_back({input_ops[i], input_columns[i] ? input_columns[i] : ""});
+  if (args && args_size) op.args.assign(args, args + args_size);
+  op.batch = batch;
+  for (int i = 0; i < n_stencil; ++i) op.stencil.push_back(stencil[i]);
+  op.warmup = warmup;
+  for (auto& c : info->output_columns) op.output_columns.push_back(c.name);
+  g->g.ops.push_back(op);
+  return (int)g->g.ops.size() - 1;
+}
+
+static int add_builtin(scn_graph* g, OpKind kind, const char* name, int input_op, const char* col, const char* stored) {
+  if (!g || !col) return fail("bad arguments");
+  if (input_op < 0 || input_op >= (int)g->g.ops.size()) return fail("input op out of range");
+  GraphOp op;
+  op.kind = kind;
+  op.name = name;
+  op.inputs.push_back({input_op, col});
+  if (kind != OpKind::Sink) op.output_columns = {col};
+  if (stored) op.sink_column_name = stored;
+  g->g.ops.push_back(op);
+  return (int)g->g.ops.size() - 1;
+}
+int scn_graph_add_sample(scn_graph* g, int input_op, const char* col) {
+  return add_builtin(g, OpKind::Sample, "Sample", input_op, col, nullptr);
+}
+int scn_graph_add_space(scn_graph* g, int input_op, const char* col) {
+  return add_builtin(g, OpKind::Space, "Space", input_op, col, nullptr);
+}
+int scn_graph_add_sink(scn_graph* g, int input_op, const char* col, const char* stored) {
+  return add_builtin(g, OpKind::Sink, "Output", input_op, col, stored ? stored : col);
+}
+int scn_graph_op_outputs(scn_graph* g, int index, char* buf, size_t cap) {
+  if (!g || index < 0 || index >= (int)g->g.ops.size()) return fail("op out of range");
+  std::string s;
+  for (auto& c : g->g.ops[index].output_columns) s += c + "\n";
+  return copy_out(s, buf, cap);
+}
+
+scn_job* scn_job_create(void) { return new scn_job(); }
+void scn_job_destroy(scn_job* j) { delete j; }
+int scn_job_bind_source(scn_job* j, int op, int64_t stream) {
+  if (!j) return fail("null job");
+  j->j.source_streams[op] = stream;
+  return 0;
+}
+int scn_job_set_sampler(scn_job* j, int op, const char* fn, const uint8_t* args, size_t n) {
+  if (!j || !fn) return fail("bad arguments");
+  std::unique_ptr<DomainSampler> s;
+  std::vector<u8> a(args ? args : (const uint8_t*)"", args ? args + n : (const uint8_t*)"");
+  Result r = make_domain_sampler(fn, a, s);
+  if (!r.success()) return fail(r.msg());
+  j->j.params.samplers[op] = {fn, a};
+  return 0;
+}
+int scn_job_set_stream_args(scn_job* j, int op, const uint8_t* args, size_t n) {
+  if (!j) return fail("null job");
+  j->j.params.stream_args[op] = std::vector<u8>(args ? args : (const uint8_t*)"", args ? args + n : (const uint8_t*)"");
+  return 0;
+}
+
+int scn_engine_run(scn_engine* e, scn_graph* g, scn_job* const* jobs, int n_jobs, int wps, int ios,
+                   const char* out_dir) {
+  if (!e || !g || n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail("bad arguments");
+  std::vector<Job*> js;
+  for (int i = 0; i < n_jobs; ++i) js.push_back(&jobs[i]->j);
+  return from_result(e->impl->run(g->g, js, wps, ios, out_dir ? out_dir : ""));
+}
+
+int64_t scn_job_output_rows(scn_job* j, int sink) {
+  if (!j) return fail("null job");
+  auto it = j->j.outputs.find(sink);
+  if (it == j->j.outputs.end()) return fail("op is not a sink of this job");
+  int64_t n = 0;
+  for (const TaskOutput& t : it->second) n += (int64_t)t.sizes.size();
+  return n;
+}
+
+static const TaskOutput* locate(scn_job* j, int sink, int64_t row, size_t& idx) {
+  auto it = j->j.outputs.find(sink);
+  if (it == j->j.outputs.end() || j->j.io_packet <= 0 || row < 0) return nullptr;
+  const size_t task = (size_t)(row / j->j.io_packet);
+  if (task >= it->second.size()) return nullptr;
+  idx = (size_t)(row % j->j.io_packet);
+  const TaskOutput& t = it->second[task];
+  return idx < t.sizes.size() ? &t : nullptr;
+}
+
+int scn_job_output_row(scn_job* j, int sink, int64_t row, const uint8_t** data, uint64_t* size, int shape[4]) {
+  if (!j) return fail("null job");
+  size_t idx;
+  const TaskOutput* t = locate(j, sink, row, idx);
+  if (!t) return fail("row out of range");
+  if (data) *data = t->data.data() + t->offsets[idx];
+  if (size) *size = t->sizes[idx];
+  if (shape)
+    for (int k = 0; k < 4; ++k) shape[k] = t->shapes[idx * 4 + k];
+  return 0;
+}
+
+int scn_job_output_copy(scn_job* j, int sink, int64_t row0, int64_t n, uint8_t* dst, size_t row_bytes) {
+  if (!j || !dst) return fail("bad arguments");
+  for (int64_t i = 0; i < n; ++i) {
+    size_t idx;
+    const TaskOutput* t = locate(j, sink, row0 + i, idx);
+    if (!t) return fail("row out of range");
+    if (t->sizes[idx] != row_bytes) return fail("row " + std::to_string(row0 + i) + " has " +
+                                                std::to_string(t->sizes[idx]) + " bytes, expected " +
+                                                std::to_string(row_bytes));
+    memcpy(dst + (size_t)i * row_bytes, t->data.data() + t->offsets[idx], row_bytes);
+  }
+  return 0;
+}
+
+int scn_engine_stats_json(scn_engine* e, char* buf, size_t cap) {
+  if (!e) return fail("null engine");
+  const RunStats& s = e->impl->stats();
+  std::ostringstream ss;
+  ss << "{\"wall_seconds\": " << s.wall_seconds << ", \"counters\": {";
+  bool first = true;
+  for (auto& kv : s.counters) {
+    ss << (first ? "" : ", ") << "\"" << kv.first << "\": " << kv.second;
+    first = false;
+  }
+  ss << "}, \"intervals_ms\": {";
+  first = true;
+  for (auto& kv : s.interval_ns) {
+    ss << (first ? "" : ", ") << "\"" << kv.first << "\": " << (double)kv.second * 1e-6;
+    first = false;
+  }
+  ss << "}, \"interval_counts\": {";
+  first = true;
+  for (auto& kv : s.interval_counts) {
+    ss << (first ? "" : ", ") << "\"" << kv.first << "\": " << kv.second;
+    first = false;
+  }
+  ss << "}}";
+  return copy_out(ss.str(), buf, cap);
+}
+
+int64_t scn_h264_synth(const uint8_t* yuv, int width, int height, int64_t frames, int gop, int non_key_mode,
+                       uint8_t* out, size_t cap) {
+  if (!yuv || width <= 0 || height <= 0 || (width & 1) || (height & 1) || frames <= 0) return fail("bad arguments");
+  const size_t ysz = (size_t)width * height, csz = ysz / 4, fsz = ysz + 2 * csz;
+  std::vector<u8> stream;
+  stream.reserve((size_t)frames * (fsz + fsz / 64 + 4096));
+  write_ipcm_stream(width, height, frames, gop, non_key_mode == 1 ? SynthNonKey::Skip : SynthNonKey::Pcm,
+                    [&](i64 f, u8* y, u8* u, u8* v) {
+                      const u8* src = yuv + (size_t)f * fsz;
+                      memcpy(y, src, ysz);
+                      memcpy(u, src + ysz, csz);
+                      memcpy(v, src + ysz + csz, csz);
+                    },
+                    stream);
+  if (out && cap >= stream.size()) memcpy(out, stream.data(), stream.size());
+  return (int64_t)stream.size();
+}
+
+int scn_nvdec_caps(int gpu_id, int info[6]) {
+  if (!info) return fail("null info");
+  const NvdecCaps& c = nvdec_caps(gpu_id);
+  info[0] = c.available;
+  info[1] = c.h264_supported;
+  info[2] = c.num_engines;
+  info[3] = c.max_width;
+  info[4] = c.max_height;
+  info[5] = c.min_width;
+  if (!c.available) t_error = c.error;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,534 @@
+// pipeline.cpp -- see pipeline.h.
+#include "pipeline.h"
+
+#include <cuda_runtime.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <thread>
+
+#include "engine_internal.h"
+#include "nvdec.h"
+#include "scn_kernels.h"
+
+namespace scanner {
+namespace internal {
+
+namespace {
+
+Result ok() {
+  Result r;
+  r.set_success(true);
+  return r;
+}
+
+void mkdirs(const std::string& path) {
+  std::string cur;
+  for (size_t i = 0; i <= path.size(); ++i) {
+    if (i == path.size() || path[i] == '/') {
+      if (!cur.empty()) mkdir(cur.c_str(), 0755);
+    }
+    if (i < path.size()) cur.push_back(path[i]);
+  }
+}
+
+// One keyframe interval of a task's rows (reference column_source.cpp:124-184
+// slice_into_video_intervals): frames [kf_start, kf_end) must be fed, `wanted` are the positions
+// (relative to kf_start) of the rows this task needs, out_base their index in the task's rows.
+struct VideoInterval {
+  i64 kf_start, kf_end;
+  std::vector<i64> wanted;
+  i64 out_base;
+};
+
+std::vector<VideoInterval> slice_into_intervals(const H264Index& idx, const std::vector<i64>& rows) {
+  std::vector<VideoInterval> out;
+  const std::vector<i64>& kf = idx.keyframe_indices;
+  for (size_t i = 0; i < rows.size(); ++i) {
+    const i64 r = rows[i];
+    // keyframe interval containing r
+    const size_t k = (size_t)(std::upper_bound(kf.begin(), kf.end(), r) - kf.begin()) - 1;
+    const i64 start = kf[k];
+    const i64 end = k + 1 < kf.size() ? kf[k + 1] : idx.frames();
+    if (out.empty() || out.back().kf_start != start) out.push_back({start, end, {}, (i64)i});
+    out.back().wanted.push_back(r - start);
+  }
+  return out;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct Engine::RunState {
+  Graph* graph = nullptr;
+  GraphAnalysis an;
+  std::vector<Job*> jobs;
+  i32 wps = 0, ios = 0;
+  std::string out_dir;
+  struct Task {
+    i32 job, task;
+    i64 row0, row1;
+  };
+  std::vector<Task> tasks;
+  std::atomic<size_t> next{0};
+  std::atomic<bool> failed{false};
+  std::mutex err_mu;
+  std::string error;
+  Profiler profiler;
+  std::atomic<i64> frames_decoded{0}, frames_used{0};
+
+  void fail(const std::string& msg) {
+    std::lock_guard<std::mutex> g(err_mu);
+    if (!failed.exchange(true)) error = msg;
+  }
+};
+
+struct Engine::Instance {
+  Engine* eng;
+  i32 gpu_id;
+  i32 node_id;
+  std::thread th;
+};
+
+Engine::Engine(std::vector<i32> gpu_ids, i32 instances_per_gpu, i32 cpu_instances)
+  : gpu_ids_(std::move(gpu_ids)), instances_per_gpu_(instances_per_gpu), cpu_instances_(cpu_instances) {
+  if (!gpu_ids_.empty() && !cuda_available()) {
+    LOG(ERROR) << "engine created with GPUs but CUDA is not available; GPU work will fail";
+  }
+  init_memory_allocators(MemoryPoolConfig(), gpu_ids_);
+}
+
+Engine::~Engine() {
+  std::lock_guard<std::mutex> g(streams_mu_);
+  for (auto& kv : streams_)
+    if (!kv.second->data.empty()) disown_block(CPU_DEVICE, kv.second->data.data());
+}
+
+i64 Engine::add_stream(std::unique_ptr<InputStream> s) {
+  if (!s->data.empty()) {
+    adopt_block(CPU_DEVICE, s->data.data(), s->data.size());
+    // page-lock the payload so GPU instances can DMA straight from it
+    if (cuda_available() && !gpu_ids_.empty()) {
+      if (cudaHostRegister(s->data.data(), s->data.size(), cudaHostRegisterPortable) != cudaSuccess) cudaGetLastError();
+    }
+  }
+  std::lock_guard<std::mutex> g(streams_mu_);
+  const i64 id = next_stream_id_++;
+  streams_[id] = std::move(s);
+  return id;
+}
+
+InputStream* Engine::stream(i64 id) {
+  std::lock_guard<std::mutex> g(streams_mu_);
+  auto it = streams_.find(id);
+  return it == streams_.end() ? nullptr : it->second.get();
+}
+
+bool Engine::remove_stream(i64 id) {
+  std::lock_guard<std::mutex> g(streams_mu_);
+  auto it = streams_.find(id);
+  if (it == streams_.end()) return false;
+  if (!it->second->data.empty()) {
+    disown_block(CPU_DEVICE, it->second->data.data());
+    if (cuda_available() && !gpu_ids_.empty()) {
+      if (cudaHostUnregister(it->second->data.data()) != cudaSuccess) cudaGetLastError();
+    }
+  }
+  streams_.erase(it);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// Per-source cursor over the rows one task needs.
+struct SourceCursor {
+  i32 op = 0;
+  InputStream* stream = nullptr;
+  std::vector<i64> rows;
+  // video state
+  std::vector<VideoInterval> intervals;
+  size_t cur_interval = 0;
+  bool interval_open = false;
+  std::unique_ptr<NvdecSession> session;
+  std::map<i64, u8*> blocks;  // packet index -> RGB24 frame block on the GPU
+  size_t frame_bytes = 0;
+  i64 wps = 1;
+  DeviceHandle gpu_dev;
+
+  // destination of decoded picture `out_index` (index into `rows`); packet blocks are allocated
+  // on first touch because a decoder may deliver pictures of the next packet early
+  u8* slot(i64 out_index) {
+    const i64 pk = out_index / wps;
+    auto it = blocks.find(pk);
+    if (it == blocks.end()) {
+      const size_t n = std::min(rows.size(), (size_t)(pk + 1) * (size_t)wps) - (size_t)pk * (size_t)wps;
+      it = blocks.emplace(pk, new_block_buffer_size(gpu_dev, frame_bytes, (i32)n)).first;
+    }
+    return it->second + (size_t)(out_index - pk * wps) * frame_bytes;
+  }
+};
+
+}  // namespace
+
+void Engine::instance_main(Instance* inst) {
+  RunState& rs = *run_;
+  const i32 gpu = inst->gpu_id;
+  cudaStream_t stream = nullptr;
+  if (gpu >= 0) {
+    if (cudaSetDevice(gpu) != cudaSuccess || cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+      rs.fail("cannot initialise GPU " + std::to_string(gpu));
+      return;
+    }
+    set_thread_stream(gpu, stream);
+  }
+  const DeviceHandle gpu_dev(DeviceType::GPU, gpu);
+  {
+    EvaluateWorker ew(*rs.graph, rs.an, gpu, inst->node_id, &rs.profiler);
+    Result r = ew.init();
+    if (!r.success()) {
+      rs.fail(r.msg());
+      return;
+    }
+    std::map<i32, std::unique_ptr<NvdecSession>> sessions;  // per video source op
+
+    while (!rs.failed.load()) {
+      const size_t ti = rs.next.fetch_add(1);
+      if (ti >= rs.tasks.size()) break;
+      const RunState::Task& t = rs.tasks[ti];
+      Job& job = *rs.jobs[t.job];
+      const timepoint_t task_start = now();
+
+      std::vector<i64> out_rows;
+      for (i64 row = t.row0; row < t.row1; ++row) out_rows.push_back(row);
+      std::vector<TaskStream> streams;
+      r = rs.graph->derive_task_streams(rs.an, job.params, job.rows_per_op, out_rows, streams);
+      if (r.success()) r = ew.new_task(job.params, job.rows_per_op, streams);
+      if (!r.success()) {
+        rs.fail(r.msg());
+        break;
+      }
+
+      // ---- load stage: cursors over every source's rows (reference LoadWorker::yield)
+      std::vector<SourceCursor> cursors;
+      size_t max_rows = 0;
+      for (size_t k = 0; k < rs.graph->ops.size() && r.success(); ++k) {
+        if (rs.graph->ops[k].kind != OpKind::Source) continue;
+        SourceCursor c;
+        c.op = (i32)k;
+        {
+          auto bit = job.source_streams.find((i32)k);
+          c.stream = bit == job.source_streams.end() ? nullptr : this->stream(bit->second);
+        }
+        c.wps = rs.wps;
+        c.gpu_dev = gpu_dev;
+        c.rows = streams[k].valid_output_rows;
+        if (!c.stream) {
+          RESULT_ERROR(&r, "job %d does not bind source op %zu to a stream", t.job, k);
+          break;
+        }
+        max_rows = std::max(max_rows, c.rows.size());
+        if (c.stream->kind == InputStream::H264) {
+          if (gpu < 0) {
+            RESULT_ERROR(&r, "H.264 sources need a GPU pipeline instance (NVDEC); there is no software decoder");
+            break;
+          }
+          auto& s = sessions[(i32)k];
+          if (!s) {
+            s.reset(new NvdecSession(gpu, stream));
+            Result ir = s->init();
+            if (!ir.success()) {
+              r = ir;
+              break;
+            }
+          }
+          c.intervals = slice_into_intervals(c.stream->index, c.rows);
+          c.frame_bytes = (size_t)c.stream->index.width * c.stream->index.height * 3;
+        }
+        cursors.push_back(std::move(c));
+      }
+      if (!r.success()) {
+        rs.fail(r.msg());
+        break;
+      }
+
+      const size_t n_packets = (max_rows + (size_t)rs.wps - 1) / (size_t)rs.wps;
+      std::map<i32, TaskOutput*> outs;
+      for (auto& kv : job.outputs) outs[kv.first] = &kv.second[t.task];
+
+      for (size_t p = 0; p < n_packets && r.success(); ++p) {
+        std::map<i32, ColumnBatch> src_cols;
+        for (SourceCursor& c : cursors) {
+          const size_t i0 = std::min(c.rows.size(), p * (size_t)rs.wps);
+          const size_t i1 = std::min(c.rows.size(), (p + 1) * (size_t)rs.wps);
+          ColumnBatch cb;
+          InputStream& st = *c.stream;
+          if (st.kind == InputStream::H264) {
+            // ---- decode stage (reference PreEvaluateWorker::yield + DecoderAutomata::get_frames)
+            const timepoint_t d0 = now();
+            cb.device = gpu_dev;
+            NvdecSession& sess = *sessions[c.op];
+            const FrameInfo finfo(st.index.height, st.index.width, 3, FrameType::U8);
+            size_t delivered_global = c.cur_interval < c.intervals.size()
+                                          ? (size_t)c.intervals[c.cur_interval].out_base +
+                                                (c.interval_open ? sess.delivered() : 0)
+                                          : c.rows.size();
+            while (delivered_global < i1 && r.success()) {
+              VideoInterval& iv = c.intervals[c.cur_interval];
+              if (!c.interval_open) {
+                std::vector<u64> offs(st.index.sample_offsets.begin() + iv.kf_start,
+                                      st.index.sample_offsets.begin() + iv.kf_end);
+                std::vector<u64> szs(st.index.sample_sizes.begin() + iv.kf_start,
+                                     st.index.sample_sizes.begin() + iv.kf_end);
+                const size_t w = (size_t)st.index.width, h = (size_t)st.index.height;
+                r = sess.begin_interval(
+                    st.encoded.data(), offs, szs, st.index.metadata_packets, iv.wanted, iv.out_base,
+                    [cur = &c, rsp = &rs, stream, w, h](i64 out_index, const Nv12Surface& s) {
+                      const u8* lp = s.luma;
+                      const u8* cp = s.chroma;
+                      u8* dst = cur->slot(out_index);
+                      const int rc = scn_nv12_to_rgb24(&lp, &cp, s.pitch, 1, (int)w, (int)h, &dst, w * 3, stream);
+                      if (rc != 0) rsp->fail("scn_nv12_to_rgb24 failed: " + std::to_string(rc));
+                    });
+                if (!r.success()) break;
+                c.interval_open = true;
+              }
+              const size_t want_in_iv = std::min(iv.wanted.size(), i1 - (size_t)iv.out_base);
+              r = sess.advance(want_in_iv);
+              if (!r.success()) break;
+              if (sess.delivered() >= iv.wanted.size()) {
+                r = sess.end_interval();
+                c.interval_open = false;
+                ++c.cur_interval;
+                delivered_global = c.cur_interval < c.intervals.size() ? (size_t)c.intervals[c.cur_interval].out_base
+                                                                       : c.rows.size();
+              } else {
+                delivered_global = (size_t)iv.out_base + sess.delivered();
+              }
+            }
+            if (!r.success()) break;
+            for (size_t i = i0; i < i1; ++i) {
+              cb.elements.push_back(Element(new Frame(finfo, c.slot((i64)i))));
+              cb.row_ids.push_back(c.rows[i]);
+            }
+            c.blocks.erase((i64)p);  // ownership of the packet's block now rides on its elements
+            rs.profiler.add_interval("get_frames", d0, now());
+          } else {
+            cb.device = CPU_DEVICE;
+            for (size_t i = i0; i < i1; ++i) {
+              const i64 row = c.rows[i];
+              if (row < 0 || row >= st.rows()) {
+                RESULT_ERROR(&r, "source row %ld out of range (%ld rows)", (long)row, (long)st.rows());
+                break;
+              }
+              u8* ptr = st.data.data() + st.offsets[row];
+              if (st.kind == InputStream::RawFrames) {
+                add_buffer_ref(CPU_DEVICE, ptr);
+                cb.elements.push_back(Element(new Frame(st.info, ptr)));
+              } else if (st.sizes[row] == 0) {
+                cb.elements.emplace_back();  // null row
+              } else {
+                add_buffer_ref(CPU_DEVICE, ptr);
+                cb.elements.push_back(Element(ptr, st.sizes[row]));
+              }
+              cb.row_ids.push_back(row);
+            }
+            rs.profiler.increment("io_read", (i64)(i1 - i0));
+          }
+          src_cols[c.op] = std::move(cb);
+        }
+        if (!r.success()) break;
+
+        // ---- evaluate stage
+        std::map<i32, ColumnBatch> sink_cols;
+        r = ew.feed(src_cols, sink_cols);
+        if (!r.success()) break;
+
+        // ---- post-evaluate + save: bring sink rows to the host and append them to the task
+        for (auto& kv : sink_cols) {
+          ColumnBatch& cb = kv.second;
+          Elements host = cb.device.is_gpu() ? copy_or_ref_elements(cb.device, CPU_DEVICE, cb.elements) : cb.elements;
+          TaskOutput& to = *outs[kv.first];
+          for (Element& e : host) {
+            const u8* src = nullptr;
+            size_t n = 0;
+            i32 shape[4] = {0, 0, 0, -1};
+            if (!e.is_null()) {
+              if (e.is_frame) {
+                const Frame* f = e.as_const_frame();
+                src = f->data;
+                n = f->size();
+                shape[0] = f->shape[0];
+                shape[1] = f->shape[1];
+                shape[2] = f->shape[2];
+                shape[3] = (i32)(proto::FrameType)f->type;
+              } else {
+                src = e.buffer;
+                n = e.size;
+              }
+            }
+            to.offsets.push_back(to.data.size());
+            to.sizes.push_back(n);
+            to.shapes.insert(to.shapes.end(), shape, shape + 4);
+            if (n) to.data.insert(to.data.end(), src, src + n);
+          }
+          if (cb.device.is_gpu()) {
+            delete_elements(CPU_DEVICE, host);
+            delete_elements(cb.device, cb.elements);
+          } else {
+            delete_elements(CPU_DEVICE, cb.elements);
+          }
+        }
+      }
+      // close decoder intervals left open by a task that did not need their tail
+      for (SourceCursor& c : cursors) {
+        if (c.interval_open) {
+          Result e = sessions[c.op]->end_interval();
+          if (r.success() && !e.success()) r = e;
+        }
+        for (auto& kv : c.blocks) delete_buffer(gpu_dev, kv.second);
+      }
+      if (r.success()) r = ew.end_task();
+      if (!r.success()) {
+        rs.fail(r.msg());
+        break;
+      }
+      for (auto& kv : outs) {
+        if ((i64)kv.second->sizes.size() != t.row1 - t.row0) {
+          rs.fail("sink " + std::to_string(kv.first) + " stored " + std::to_string(kv.second->sizes.size()) +
+                  " rows for a task of " + std::to_string(t.row1 - t.row0));
+          break;
+        }
+        kv.second->done = true;
+      }
+      if (rs.failed.load()) break;
+
+      // ---- column files (reference ColumnSink::write, column_sink.cpp:159-195)
+      if (!rs.out_dir.empty()) {
+        const std::string dir = rs.out_dir + "/tables/" + std::to_string(t.job);
+        mkdirs(dir);
+        auto write_col = [&](i32 col, const std::vector<u64>& sizes, const u8* data, size_t nbytes) {
+          const std::string base = dir + "/" + std::to_string(col) + "_" + std::to_string(t.task);
+          std::ofstream meta(base + "_metadata.bin", std::ios::binary);
+          const u64 n = sizes.size();
+          meta.write((const char*)&n, 8);
+          meta.write((const char*)sizes.data(), (std::streamsize)(8 * sizes.size()));
+          std::ofstream dat(base + ".bin", std::ios::binary);
+          dat.write((const char*)data, (std::streamsize)nbytes);
+          rs.profiler.increment("io_write", (i64)nbytes);
+        };
+        // column 0: the index column, row i = little-endian int64 i (reference ingest.cpp:337-345)
+        std::vector<u64> isz((size_t)(t.row1 - t.row0), 8);
+        std::vector<i64> idx;
+        for (i64 row = t.row0; row < t.row1; ++row) idx.push_back(row);
+        write_col(0, isz, (const u8*)idx.data(), idx.size() * 8);
+        i32 col = 1;
+        for (auto& kv : outs) write_col(col++, kv.second->sizes, kv.second->data.data(), kv.second->data.size());
+      }
+      rs.profiler.add_interval("task", task_start, now());
+    }
+    for (auto& kv : sessions) {
+      kv.second->drain();
+      rs.frames_decoded += kv.second->frames_decoded();
+      rs.frames_used += kv.second->frames_used();
+    }
+    if (gpu >= 0) cudaStreamSynchronize(stream);
+  }  // kernels and sessions destroyed here, while the stream is alive
+  if (gpu >= 0) {
+    set_thread_stream(gpu, nullptr);
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+  }
+}
+
+Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios, const std::string& out_dir) {
+  Result r;
+  if (wps <= 0 || ios <= 0 || ios % wps != 0) {
+    // reference master.cpp:1421
+    RESULT_ERROR(&r, "IO packet size (%d) must be a multiple of work packet size (%d).", ios, wps);
+    return r;
+  }
+  run_.reset(new RunState());
+  RunState& rs = *run_;
+  rs.graph = &graph;
+  rs.jobs = jobs;
+  rs.wps = wps;
+  rs.ios = ios;
+  rs.out_dir = out_dir;
+  r = graph.analyze(rs.an);
+  if (!r.success()) return r;
+
+  // per job: bind source sizes, domain sizes, partition output rows into tasks
+  // (reference master.cpp:1543-1606)
+  for (size_t j = 0; j < jobs.size(); ++j) {
+    Job& job = *jobs[j];
+    job.params.source_rows.clear();
+    for (auto& kv : job.source_streams) {
+      InputStream* s = stream(kv.second);
+      if (!s) {
+        RESULT_ERROR(&r, "job %zu binds source %d to unknown stream %ld", j, kv.first, (long)kv.second);
+        return r;
+      }
+      const GraphOp& op = graph.ops.at(kv.first);
+      if (op.kind != OpKind::Source) {
+        RESULT_ERROR(&r, "job %zu binds op %d which is not a Source", j, kv.first);
+        return r;
+      }
+      if ((op.column_type == proto::Video) != (s->kind != InputStream::Bytes)) {
+        RESULT_ERROR(&r, "job %zu: source %d column type does not match stream %ld", j, kv.first, (long)kv.second);
+        return r;
+      }
+      job.params.source_rows[kv.first] = s->rows();
+    }
+    r = graph.domain_sizes(job.params, job.rows_per_op);
+    if (!r.success()) return r;
+    job.total_rows = 0;
+    job.outputs.clear();
+    for (size_t k = 0; k < graph.ops.size(); ++k)
+      if (graph.ops[k].kind == OpKind::Sink) job.total_rows = job.rows_per_op[k];
+    job.io_packet = ios;
+    const i64 n_tasks = (job.total_rows + ios - 1) / ios;
+    for (size_t k = 0; k < graph.ops.size(); ++k)
+      if (graph.ops[k].kind == OpKind::Sink) job.outputs[(i32)k].resize((size_t)n_tasks);
+    for (i64 t = 0; t < n_tasks; ++t)
+      rs.tasks.push_back({(i32)j, (i32)t, t * ios, std::min<i64>(job.total_rows, (t + 1) * ios)});
+  }
+
+  // pipeline instances (reference worker.cpp:1297-1337)
+  std::vector<std::unique_ptr<Instance>> instances;
+  i32 node = 0;
+  if (!gpu_ids_.empty()) {
+    const i32 per = instances_per_gpu_ > 0 ? instances_per_gpu_ : 4;
+    for (i32 g : gpu_ids_)
+      for (i32 i = 0; i < per; ++i) instances.emplace_back(new Instance{this, g, node++, {}});
+  } else {
+    const i32 n = cpu_instances_ > 0 ? cpu_instances_ : 1;
+    for (i32 i = 0; i < n; ++i) instances.emplace_back(new Instance{this, -1, node++, {}});
+  }
+  // never more instances than tasks
+  while (instances.size() > std::max<size_t>(1, rs.tasks.size())) instances.pop_back();
+
+  const auto t0 = std::chrono::steady_clock::now();
+  for (auto& inst : instances) inst->th = std::thread([this, p = inst.get()] { instance_main(p); });
+  for (auto& inst : instances) inst->th.join();
+  stats_ = RunStats();
+  stats_.wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  stats_.counters = rs.profiler.counters();
+  stats_.counters["frames_decoded"] = rs.frames_decoded.load();
+  stats_.counters["frames_used"] = rs.frames_used.load();
+  stats_.counters["tasks"] = (i64)rs.tasks.size();
+  stats_.counters["instances"] = (i64)instances.size();
+  stats_.interval_ns = rs.profiler.interval_totals_ns();
+  stats_.interval_counts = rs.profiler.interval_counts();
+  if (rs.failed.load()) {
+    RESULT_ERROR(&r, "%s", rs.error.c_str());
+    return r;
+  }
+  return ok();
+}
+
+}  // namespace internal
+}  // namespace scanner

@@ -1,0 +1,95 @@
+// pipeline.h -- the worker: input streams, jobs, tasks and the pipeline instances that run
+// load -> decode -> evaluate -> post -> save for them.
+// Restates reference scanner/engine/worker.cpp:868-2148 (process_job: instances, task pull loop),
+// load_worker.cpp:80-189 + column_source.cpp:124-301 (rows -> keyframe intervals -> encoded bytes),
+// evaluate_worker.cpp:316-406 (PreEvaluateWorker::yield: one frame block per work packet),
+// :1373-1557 (PostEvaluateWorker: move sink columns to the host) and save_worker.cpp /
+// column_sink.cpp:71-265 (column files).  The master/worker gRPC control plane is replaced by one
+// in-process task queue shared by every pipeline instance of every GPU.
+#pragma once
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "evaluate.h"
+#include "graph.h"
+#include "h264.h"
+#include "scanner/api/frame.h"
+
+namespace scanner {
+namespace internal {
+
+struct InputStream {
+  enum Kind { H264, RawFrames, Bytes } kind = Bytes;
+  // H264
+  std::vector<u8> encoded;
+  H264Index index;
+  // RawFrames: n dense frames of `info`
+  FrameInfo info;
+  // RawFrames / Bytes payload + per-row extents
+  std::vector<u8> data;
+  std::vector<u64> offsets, sizes;
+  i64 rows() const { return kind == H264 ? index.frames() : (i64)sizes.size(); }
+};
+
+// Rows a sink stored for one task, host memory.
+struct TaskOutput {
+  bool done = false;
+  std::vector<u8> data;
+  std::vector<u64> offsets, sizes;
+  std::vector<i32> shapes;  // 4 per row: h, w, c, frame type (-1 for byte rows)
+};
+
+struct Job {
+  std::map<i32, i64> source_streams;  // source op -> stream id
+  JobParams params;
+  // filled by the run
+  std::vector<i64> rows_per_op;
+  i64 total_rows = 0;
+  i32 io_packet = 0;
+  std::map<i32, std::vector<TaskOutput>> outputs;  // sink op -> per task
+};
+
+struct RunStats {
+  std::map<std::string, i64> counters;
+  std::map<std::string, i64> interval_ns;
+  std::map<std::string, i64> interval_counts;
+  double wall_seconds = 0;
+};
+
+class Engine {
+ public:
+  Engine(std::vector<i32> gpu_ids, i32 instances_per_gpu, i32 cpu_instances);
+  ~Engine();
+
+  i64 add_stream(std::unique_ptr<InputStream> s);
+  InputStream* stream(i64 id);
+  bool remove_stream(i64 id);
+
+  Result run(Graph& graph, const std::vector<Job*>& jobs, i32 work_packet_size, i32 io_packet_size,
+             const std::string& out_dir);
+
+  const RunStats& stats() const { return stats_; }
+  const std::vector<i32>& gpu_ids() const { return gpu_ids_; }
+
+ private:
+  struct Instance;
+  void instance_main(Instance* inst);
+
+  std::vector<i32> gpu_ids_;
+  i32 instances_per_gpu_, cpu_instances_;
+  std::mutex streams_mu_;
+  std::map<i64, std::unique_ptr<InputStream>> streams_;
+  i64 next_stream_id_ = 1;
+  RunStats stats_;
+
+  // state of the run in flight
+  struct RunState;
+  std::unique_ptr<RunState> run_;
+};
+
+}  // namespace internal
+}  // namespace scanner

@@ -1,0 +1,183 @@
+// stdlib_ops.cu -- the per-frame ops of the hot path as a Scanner op plugin (libscn_stdlib.so).
+// Same op names, columns and argument messages as the reference's in-tree ops
+// (tests/test_ops.cpp:13-59 Histogram, :114-170 Resize, :239-310 Blur) -- but the kernels are
+// registered for DeviceType::GPU and run the sm_100a kernels of libscn_kernels.so on the
+// pipeline instance's stream.  Loaded with dlopen like any user op library (Client.load_op).
+#include <map>
+
+#include "scanner/api/kernel.h"
+#include "scanner/api/op.h"
+#include "scanner/util/cuda.h"
+#include "scanner/util/memory.h"
+#include "scn_kernels.h"
+#include "stdlib_args.pb.h"
+
+namespace scanner {
+namespace {
+
+#define SCN_CHECK(call__)                                                              \
+  do {                                                                                 \
+    const int rc__ = (call__);                                                         \
+    if (rc__ != 0) LOG(FATAL) << #call__ << " failed with code " << rc__;              \
+  } while (0)
+
+// batches may mix frame sizes (different videos): process runs of equal geometry
+template <typename F>
+void for_each_run(const Elements& col, F&& fn) {
+  size_t i = 0;
+  while (i < col.size()) {
+    const Frame* f0 = col[i].as_const_frame();
+    size_t j = i + 1;
+    while (j < col.size() && col[j].as_const_frame()->as_frame_info() == f0->as_frame_info()) ++j;
+    fn(i, j, f0);
+    i = j;
+  }
+}
+
+void require_rgb8(const Frame* f, const char* op) {
+  if (f->channels() != 3 || (proto::FrameType)f->type != proto::U8)
+    LOG(FATAL) << op << " expects HxWx3 uint8 frames, got " << f->height() << "x" << f->width() << "x"
+               << f->channels() << " type " << (int)(proto::FrameType)f->type;
+}
+
+// ---------------------------------------------------------------------------------------------
+class HistogramKernelGPU : public BatchedKernel {
+ public:
+  HistogramKernelGPU(const KernelConfig& config) : BatchedKernel(config), device_(config.devices[0]) {}
+
+  void execute(const BatchedElements& input_columns, BatchedElements& output_columns) override {
+    const Elements& frames = input_columns[0];
+    const i32 n = (i32)num_rows(frames);
+    if (n == 0) return;
+    CU_CHECK(cudaSetDevice(device_.id));
+    constexpr size_t kHistBytes = 3 * 16 * sizeof(i32);
+    u8* block = new_block_buffer_size(device_, kHistBytes, n);  // one block for the batch
+    for_each_run(frames, [&](size_t i0, size_t i1, const Frame* f0) {
+      require_rgb8(f0, "Histogram");
+      std::vector<const u8*> ptrs;
+      for (size_t i = i0; i < i1; ++i) ptrs.push_back(frames[i].as_const_frame()->data);
+      SCN_CHECK(scn_hist16_u8c3(ptrs.data(), (int)ptrs.size(), f0->width(), f0->height(),
+                                (int32_t*)(block + i0 * kHistBytes), device_stream(device_)));
+    });
+    for (i32 i = 0; i < n; ++i) insert_element(output_columns[0], block + (size_t)i * kHistBytes, kHistBytes);
+  }
+
+ private:
+  DeviceHandle device_;
+};
+
+REGISTER_OP(Histogram).frame_input("frame").output("histogram", ColumnType::Bytes, "Histogram");
+
+REGISTER_KERNEL(Histogram, HistogramKernelGPU).device(DeviceType::GPU).batch(64).num_devices(1);
+
+// ---------------------------------------------------------------------------------------------
+class ResizeKernelGPU : public BatchedKernel {
+ public:
+  ResizeKernelGPU(const KernelConfig& config) : BatchedKernel(config), device_(config.devices[0]) {}
+  ~ResizeKernelGPU() {
+    for (auto& kv : plans_) delete_buffer(device_, kv.second);
+  }
+
+  void new_stream(const std::vector<u8>& args) override { args_.ParseFromArray(args.data(), (int)args.size()); }
+
+  void execute(const BatchedElements& input_columns, BatchedElements& output_columns) override {
+    const Elements& frames = input_columns[0];
+    if (frames.empty()) return;
+    CU_CHECK(cudaSetDevice(device_.id));
+    for_each_run(frames, [&](size_t i0, size_t i1, const Frame* f0) {
+      require_rgb8(f0, "Resize");
+      int tw = 0, th = 0;
+      scn_resize_target(f0->width(), f0->height(), args_.width(), args_.height(), args_.min(),
+                        args_.preserve_aspect(), &tw, &th);
+      if (tw <= 0 || th <= 0) LOG(FATAL) << "Resize: invalid target size " << tw << "x" << th;
+      const i32 n = (i32)(i1 - i0);
+      FrameInfo info(th, tw, 3, FrameType::U8);
+      std::vector<Frame*> outs = new_frames(device_, info, n);
+      std::vector<const u8*> src;
+      std::vector<u8*> dst;
+      for (i32 i = 0; i < n; ++i) {
+        src.push_back(frames[i0 + i].as_const_frame()->data);
+        dst.push_back(outs[i]->data);
+      }
+      SCN_CHECK(scn_resize_bilinear_u8c3(src.data(), n, f0->width(), f0->height(), dst.data(), tw, th,
+                                         plan_for(f0->width(), f0->height(), tw, th), device_stream(device_)));
+      for (i32 i = 0; i < n; ++i) insert_frame(output_columns[0], outs[i]);
+    });
+  }
+
+ private:
+  // coefficient tables are built on the host once per geometry and kept on the device
+  const void* plan_for(int sw, int sh, int dw, int dh) {
+    const std::array<int, 4> key = {sw, sh, dw, dh};
+    auto it = plans_.find(key);
+    if (it != plans_.end()) return it->second;
+    const size_t bytes = scn_resize_plan_bytes(dw, dh);
+    std::vector<u8> host(bytes);
+    SCN_CHECK(scn_resize_plan_fill(sw, sh, dw, dh, host.data()));
+    u8* dev = new_buffer(device_, bytes);
+    memcpy_buffer(dev, device_, host.data(), CPU_DEVICE, bytes);
+    plans_[key] = dev;
+    return dev;
+  }
+
+  DeviceHandle device_;
+  ResizeArgs args_;
+  std::map<std::array<int, 4>, u8*> plans_;
+};
+
+REGISTER_OP(Resize).frame_input("frame").frame_output("frame").stream_protobuf_name("ResizeArgs");
+
+REGISTER_KERNEL(Resize, ResizeKernelGPU).device(DeviceType::GPU).batch(64).num_devices(1);
+
+// ---------------------------------------------------------------------------------------------
+class BlurKernelGPU : public BatchedKernel {
+ public:
+  BlurKernelGPU(const KernelConfig& config) : BatchedKernel(config), device_(config.devices[0]) {
+    BlurArgs args;
+    const bool parsed = args.ParseFromArray(config.args.data(), (int)config.args.size());
+    if (!parsed || config.args.empty()) {
+      RESULT_ERROR(&valid_, "Could not parse BlurArgs");
+      return;
+    }
+    kernel_size_ = args.kernel_size();
+    if (kernel_size_ < 1 || kernel_size_ > 31) {
+      RESULT_ERROR(&valid_, "Blur kernel_size %d is outside [1, 31]", kernel_size_);
+      return;
+    }
+    valid_.set_success(true);
+  }
+
+  void validate(Result* result) override { result->CopyFrom(valid_); }
+
+  void execute(const BatchedElements& input_columns, BatchedElements& output_columns) override {
+    const Elements& frames = input_columns[0];
+    if (frames.empty()) return;
+    CU_CHECK(cudaSetDevice(device_.id));
+    for_each_run(frames, [&](size_t i0, size_t i1, const Frame* f0) {
+      require_rgb8(f0, "Blur");
+      const i32 n = (i32)(i1 - i0);
+      std::vector<Frame*> outs = new_frames(device_, f0->as_frame_info(), n);
+      std::vector<const u8*> src;
+      std::vector<u8*> dst;
+      for (i32 i = 0; i < n; ++i) {
+        src.push_back(frames[i0 + i].as_const_frame()->data);
+        dst.push_back(outs[i]->data);
+      }
+      SCN_CHECK(scn_box_blur_u8c3(src.data(), n, f0->width(), f0->height(), kernel_size_, dst.data(),
+                                  device_stream(device_)));
+      for (i32 i = 0; i < n; ++i) insert_frame(output_columns[0], outs[i]);
+    });
+  }
+
+ private:
+  DeviceHandle device_;
+  i32 kernel_size_ = 0;
+  Result valid_;
+};
+
+REGISTER_OP(Blur).frame_input("frame").frame_output("frame").protobuf_name("BlurArgs");
+
+REGISTER_KERNEL(Blur, BlurKernelGPU).device(DeviceType::GPU).batch(16).num_devices(1);
+
+}  // namespace
+}  // namespace scanner

@@ -1,0 +1,269 @@
+"""ctypes binding of include/scn_engine.h (libscn_engine.so) -- the C++ host pipeline."""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import cabi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ENGINE_PATH = os.path.join(_HERE, "lib", "libscn_engine.so")
+STDLIB_PATH = os.path.join(_HERE, "lib", "libscn_stdlib.so")
+
+_c = ctypes
+_VP, _I, _I64, _SZ, _CP = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t, _c.c_char_p
+_IP = _c.POINTER(_c.c_int)
+
+SIGNATURES = {
+    "scn_last_error": (_CP, []),
+    "scn_load_op_library": (_I, [_CP]),
+    "scn_op_registered": (_I, [_CP]),
+    "scn_kernel_registered": (_I, [_CP, _I]),
+    "scn_list_ops": (_I, [_CP, _SZ]),
+    "scn_engine_create": (_VP, [_IP, _I, _I, _I]),
+    "scn_engine_destroy": (None, [_VP]),
+    "scn_stream_add_h264": (_I64, [_VP, _VP, _SZ]),
+    "scn_stream_add_raw_frames": (_I64, [_VP, _VP, _I64, _I, _I, _I, _I]),
+    "scn_stream_add_bytes": (_I64, [_VP, _VP, _VP, _I64]),
+    "scn_stream_rows": (_I64, [_VP, _I64]),
+    "scn_stream_info": (_I, [_VP, _I64, _c.POINTER(_I64)]),
+    "scn_stream_remove": (_I, [_VP, _I64]),
+    "scn_graph_create": (_VP, []),
+    "scn_graph_destroy": (None, [_VP]),
+    "scn_graph_add_source": (_I, [_VP, _I]),
+    "scn_graph_add_op": (_I, [_VP, _CP, _I, _IP, _c.POINTER(_CP), _I, _VP, _SZ, _I, _IP, _I, _I]),
+    "scn_graph_add_sample": (_I, [_VP, _I, _CP]),
+    "scn_graph_add_space": (_I, [_VP, _I, _CP]),
+    "scn_graph_add_sink": (_I, [_VP, _I, _CP, _CP]),
+    "scn_graph_op_outputs": (_I, [_VP, _I, _CP, _SZ]),
+    "scn_job_create": (_VP, []),
+    "scn_job_destroy": (None, [_VP]),
+    "scn_job_bind_source": (_I, [_VP, _I, _I64]),
+    "scn_job_set_sampler": (_I, [_VP, _I, _CP, _VP, _SZ]),
+    "scn_job_set_stream_args": (_I, [_VP, _I, _VP, _SZ]),
+    "scn_engine_run": (_I, [_VP, _VP, _c.POINTER(_VP), _I, _I, _I, _CP]),
+    "scn_job_output_rows": (_I64, [_VP, _I]),
+    "scn_job_output_row": (_I, [_VP, _I, _I64, _c.POINTER(_VP), _c.POINTER(_c.c_uint64), _IP]),
+    "scn_job_output_copy": (_I, [_VP, _I, _I64, _I64, _VP, _SZ]),
+    "scn_engine_stats_json": (_I, [_VP, _CP, _SZ]),
+    "scn_h264_synth": (_I64, [_VP, _I, _I, _I64, _I, _I, _VP, _SZ]),
+    "scn_nvdec_caps": (_I, [_I, _IP]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ENGINE_PATH):
+            raise EngineError(f"{ENGINE_PATH} not found: run __graft_entry__.build()")
+        cabi.lib()  # the engine links libscn_kernels.so
+        l = ctypes.CDLL(ENGINE_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc is None or rc < 0:
+        raise EngineError(f"{what}: {lib().scn_last_error().decode()}")
+    return rc
+
+
+def load_op_library(path):
+    check(lib().scn_load_op_library(os.path.abspath(path).encode()), f"load_op({path})")
+
+
+_stdlib_loaded = False
+
+
+def load_stdlib():
+    global _stdlib_loaded
+    if not _stdlib_loaded:
+        load_op_library(STDLIB_PATH)
+        _stdlib_loaded = True
+
+
+def list_ops():
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().scn_list_ops(buf, len(buf)), "scn_list_ops")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        n, ni, no, st, b, ub, w = line.split(":")
+        out[n] = dict(inputs=int(ni), outputs=int(no), can_stencil=bool(int(st)), bounded=bool(int(b)),
+                      unbounded=bool(int(ub)), warmup=int(w))
+    return out
+
+
+def nvdec_caps(gpu=0):
+    info = (ctypes.c_int * 6)()
+    lib().scn_nvdec_caps(gpu, info)
+    keys = ["available", "h264", "engines", "max_w", "max_h", "min_w"]
+    d = dict(zip(keys, list(info)))
+    if not d["available"]:
+        d["error"] = lib().scn_last_error().decode()
+    return d
+
+
+def h264_synth(yuv_frames, width, height, gop=30, non_key="pcm"):
+    """yuv_frames: uint8 array (n, h*3/2, w) I420 (Y rows, then U rows packed w/2, V rows) or flat
+    (n, w*h*3/2).  Returns the Annex-B stream as bytes."""
+    arr = np.ascontiguousarray(yuv_frames, dtype=np.uint8).reshape(len(yuv_frames), -1)
+    n = arr.shape[0]
+    assert arr.shape[1] == width * height * 3 // 2
+    mode = {"pcm": 0, "skip": 1}[non_key]
+    need = lib().scn_h264_synth(arr.ctypes.data, width, height, n, gop, mode, None, 0)
+    check(need, "scn_h264_synth")
+    out = np.empty(need, np.uint8)
+    got = lib().scn_h264_synth(arr.ctypes.data, width, height, n, gop, mode, out.ctypes.data, out.size)
+    assert got == need
+    return out.tobytes()
+
+
+class Engine:
+    def __init__(self, gpus=(), instances_per_gpu=0, cpu_instances=1):
+        gpus = list(gpus)
+        arr = (ctypes.c_int * max(1, len(gpus)))(*gpus)
+        self._h = lib().scn_engine_create(arr, len(gpus), instances_per_gpu, cpu_instances)
+        self.gpus = gpus
+
+    def close(self):
+        if self._h:
+            lib().scn_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_h264(self, data):
+        buf = np.frombuffer(data, np.uint8)
+        return check(lib().scn_stream_add_h264(self._h, buf.ctypes.data, buf.size), "add_h264")
+
+    def add_raw_frames(self, frames):
+        frames = np.ascontiguousarray(frames)
+        tcode = {np.dtype(np.uint8): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2, np.dtype(np.uint16): 3}[
+            frames.dtype]
+        n, h, w, c = frames.shape
+        return check(lib().scn_stream_add_raw_frames(self._h, frames.ctypes.data, n, h, w, c, tcode), "add_raw_frames")
+
+    def add_bytes(self, rows):
+        sizes = np.array([len(r) for r in rows], np.uint64)
+        data = np.frombuffer(b"".join(bytes(r) for r in rows) or b"\0", np.uint8)
+        return check(lib().scn_stream_add_bytes(self._h, data.ctypes.data, sizes.ctypes.data, len(rows)), "add_bytes")
+
+    def stream_rows(self, sid):
+        return check(lib().scn_stream_rows(self._h, sid), "stream_rows")
+
+    def stream_info(self, sid):
+        info = (ctypes.c_int64 * 6)()
+        check(lib().scn_stream_info(self._h, sid, info), "stream_info")
+        return dict(zip(["is_video", "width", "height", "channels", "keyframes", "bytes"], list(info)))
+
+    def remove_stream(self, sid):
+        check(lib().scn_stream_remove(self._h, sid), "remove_stream")
+
+    def run(self, graph, jobs, work_packet_size, io_packet_size, out_dir=None):
+        arr = (ctypes.c_void_p * len(jobs))(*[j._h for j in jobs])
+        rc = lib().scn_engine_run(self._h, graph._h, arr, len(jobs), work_packet_size, io_packet_size,
+                                  out_dir.encode() if out_dir else None)
+        check(rc, "scn_engine_run")
+
+    def stats(self):
+        buf = ctypes.create_string_buffer(1 << 18)
+        check(lib().scn_engine_stats_json(self._h, buf, len(buf)), "stats")
+        return json.loads(buf.value.decode())
+
+
+class Graph:
+    def __init__(self):
+        self._h = lib().scn_graph_create()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().scn_graph_destroy(self._h)
+            self._h = None
+
+    def add_source(self, is_video=True):
+        return check(lib().scn_graph_add_source(self._h, int(is_video)), "add_source")
+
+    def add_op(self, name, inputs, device=0, args=b"", batch=-1, stencil=(), warmup=-1):
+        n = len(inputs)
+        ops = (ctypes.c_int * max(1, n))(*[i[0] for i in inputs])
+        cols = (ctypes.c_char_p * max(1, n))(*[i[1].encode() for i in inputs])
+        st = (ctypes.c_int * max(1, len(stencil)))(*stencil)
+        abuf = ctypes.create_string_buffer(args, len(args)) if args else None
+        return check(lib().scn_graph_add_op(self._h, name.encode(), int(device), ops, cols, n,
+                                            ctypes.cast(abuf, ctypes.c_void_p) if abuf else None, len(args), batch,
+                                            st, len(stencil), warmup), f"add_op({name})")
+
+    def add_sample(self, inp):
+        return check(lib().scn_graph_add_sample(self._h, inp[0], inp[1].encode()), "add_sample")
+
+    def add_space(self, inp):
+        return check(lib().scn_graph_add_space(self._h, inp[0], inp[1].encode()), "add_space")
+
+    def add_sink(self, inp, name=None):
+        return check(lib().scn_graph_add_sink(self._h, inp[0], inp[1].encode(), (name or inp[1]).encode()), "add_sink")
+
+    def op_outputs(self, idx):
+        buf = ctypes.create_string_buffer(4096)
+        check(lib().scn_graph_op_outputs(self._h, idx, buf, len(buf)), "op_outputs")
+        return [c for c in buf.value.decode().split("\n") if c]
+
+
+class Job:
+    def __init__(self):
+        self._h = lib().scn_job_create()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().scn_job_destroy(self._h)
+            self._h = None
+
+    def bind_source(self, op, stream_id):
+        check(lib().scn_job_bind_source(self._h, op, stream_id), "bind_source")
+
+    def set_sampler(self, op, function, args=b""):
+        buf = ctypes.create_string_buffer(args, len(args)) if args else None
+        check(lib().scn_job_set_sampler(self._h, op, function.encode(), ctypes.cast(buf, ctypes.c_void_p) if buf else None,
+                                        len(args)), f"set_sampler({function})")
+
+    def set_stream_args(self, op, args):
+        buf = ctypes.create_string_buffer(args, len(args)) if args else None
+        check(lib().scn_job_set_stream_args(self._h, op, ctypes.cast(buf, ctypes.c_void_p) if buf else None, len(args)),
+              "set_stream_args")
+
+    def output_rows(self, sink):
+        return check(lib().scn_job_output_rows(self._h, sink), "output_rows")
+
+    def output_row(self, sink, row):
+        """-> bytes for a byte row, ndarray for a frame row, None for a null row."""
+        data, size, shape = ctypes.c_void_p(), ctypes.c_uint64(), (ctypes.c_int * 4)()
+        check(lib().scn_job_output_row(self._h, sink, row, ctypes.byref(data), ctypes.byref(size), shape),
+              "output_row")
+        if size.value == 0:
+            return None
+        raw = ctypes.string_at(data.value, size.value)
+        if shape[3] >= 0:
+            dt = {0: np.uint8, 1: np.float32, 2: np.float64, 3: np.uint16}[shape[3]]
+            return np.frombuffer(raw, dt).reshape(shape[0], shape[1], shape[2])
+        return raw
+
+    def output_array(self, sink, row_bytes, dtype=np.uint8):
+        """All rows of equal size as one (n, row_bytes/itemsize) array."""
+        n = self.output_rows(sink)
+        out = np.empty((n, row_bytes), np.uint8)
+        check(lib().scn_job_output_copy(self._h, sink, 0, n, out.ctypes.data, row_bytes), "output_copy")
+        return out.view(dtype)

@@ -1,0 +1,210 @@
+"""The pipeline on a real B200: NVDEC decode of synthetic (lossless I_PCM) H.264 into device frames,
+the stdlib GPU ops behind REGISTER_KERNEL, results brought back through the save stage.
+Every comparison is bit-exact: I_PCM decodes to the source planes, so the expected RGB is the
+oracle's NV12->RGB of the planes the stream was made from."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import synth
+from scanner_b200 import engine as E
+from scanner_b200 import protolite
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STD_ARGS = protolite.parse_proto(open(os.path.join(ROOT, "scanner_b200", "csrc", "ops", "stdlib_args.proto")).read())
+
+
+@pytest.fixture(scope="module", autouse=True)
+def stdlib():
+    E.load_stdlib()
+
+
+@pytest.fixture()
+def eng():
+    e = E.Engine(gpus=[0], instances_per_gpu=3)
+    yield e
+    e.close()
+
+
+def make_clip(seed, n, h, w, gop, non_key="pcm"):
+    """-> (stream bytes, expected RGB frames (n,h,w,3)) ; planes are uniform random bytes."""
+    rng = np.random.default_rng(seed)
+    y = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    u = rng.integers(0, 256, (n, h // 2, w // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (n, h // 2, w // 2), dtype=np.uint8)
+    yuv = np.concatenate([y.reshape(n, -1), u.reshape(n, -1), v.reshape(n, -1)], axis=1)
+    data = E.h264_synth(yuv, w, h, gop=gop, non_key=non_key)
+    rgb = []
+    for i in range(n):
+        src = i if non_key == "pcm" else (i // gop) * gop  # P_Skip repeats the last key picture
+        chroma = np.empty((h // 2, w), np.uint8)
+        chroma[:, 0::2], chroma[:, 1::2] = u[src], v[src]
+        rgb.append(oracle.nv12_to_rgb(y[src], chroma))
+    return data, np.stack(rgb)
+
+
+def test_nvdec_is_present():
+    caps = E.nvdec_caps(0)
+    assert caps["available"] and caps["h264"] and caps["engines"] >= 1, caps
+
+
+@pytest.mark.parametrize("h,w,n,gop,mode", [(96, 128, 11, 4, "pcm"), (480, 640, 9, 5, "pcm"), (1080, 1920, 7, 3, "pcm"),
+                                            (112, 200, 8, 8, "pcm"), (96, 128, 10, 5, "skip")])
+def test_decode_all_frames_bit_exact(eng, h, w, n, gop, mode):
+    data, want = make_clip(11, n, h, w, gop, mode)
+    sid = eng.add_h264(data)
+    info = eng.stream_info(sid)
+    assert (info["width"], info["height"]) == (w, h) and eng.stream_rows(sid) == n
+    g = E.Graph()
+    src = g.add_source(True)
+    sink = g.add_sink((src, "frame"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    for (wps, ios) in [(4, 8), (1, 1), (16, 16)]:
+        eng.run(g, [j], wps, ios)
+        assert j.output_rows(sink) == n
+        for i in range(n):
+            got = j.output_row(sink, i)
+            assert got.shape == (h, w, 3)
+            assert (got == want[i]).all(), (i, wps, ios)
+    st = eng.stats()["counters"]
+    assert st["frames_used"] == n
+
+
+def test_gather_decodes_only_needed_gops(eng):
+    n, gop = 40, 8
+    data, want = make_clip(12, n, 96, 128, gop)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    s = g.add_sample((src, "frame"))
+    sink = g.add_sink((s, "frame"))
+    rows = [3, 4, 17, 39]
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_sampler(s, "Gather", protolite.encode(protolite.SAMPLER_ARGS["GatherSamplerArgs"], {"rows": rows}))
+    eng.run(g, [j], 2, 4)
+    for k, r in enumerate(rows):
+        assert (j.output_row(sink, k) == want[r]).all()
+    c = eng.stats()["counters"]
+    assert c["frames_used"] == 4
+    # rows 3,4 need frames 0..4 of GOP 0; 17 needs 16..17; 39 needs 32..39: 5 + 2 + 8 decoded
+    assert c["frames_decoded"] == 15
+
+
+def test_stride_30_only_keyframes(eng):
+    """configs[4] shape: Stride(gop) touches exactly the IDR of every GOP."""
+    n, gop = 60, 6
+    data, want = make_clip(13, n, 96, 128, gop)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    s = g.add_sample((src, "frame"))
+    h = g.add_op("Histogram", [(s, "frame")], device=1)
+    sink = g.add_sink((h, "histogram"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_sampler(s, "Strided", protolite.encode(protolite.SAMPLER_ARGS["StridedSamplerArgs"], {"stride": gop}))
+    eng.run(g, [j], 5, 10)
+    hist = j.output_array(sink, 192, np.int32).reshape(-1, 3, 16)
+    assert len(hist) == n // gop
+    for k in range(n // gop):
+        assert (hist[k] == oracle.hist16(want[k * gop])).all()
+    c = eng.stats()["counters"]
+    assert c["frames_used"] == c["frames_decoded"] == n // gop
+
+
+def test_c2_dag_histogram_and_resize_on_decoded_frames(eng):
+    """BASELINE configs[1] DAG through the engine: decode -> {Histogram, Resize(224)}."""
+    n = 10
+    data, want = make_clip(14, n, 1080, 1920, 5)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("Histogram", [(src, "frame")], device=1)
+    rz = g.add_op("Resize", [(src, "frame")], device=1)
+    s_h = g.add_sink((hs, "histogram"))
+    s_r = g.add_sink((rz, "frame"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_stream_args(rz, protolite.encode(STD_ARGS["ResizeArgs"], {"width": 224, "height": 224}))
+    eng.run(g, [j], 4, 8)
+    hist = j.output_array(s_h, 192, np.int32).reshape(n, 3, 16)
+    for i in range(n):
+        assert (hist[i] == oracle.hist16(want[i])).all()
+        assert (j.output_row(s_r, i) == oracle.resize(want[i], 224, 224)).all()
+
+
+def test_c3_dag_blur_then_histogram(eng):
+    n = 6
+    data, want = make_clip(15, n, 480, 640, 3)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    bl = g.add_op("Blur", [(src, "frame")], device=1,
+                  args=protolite.encode(STD_ARGS["BlurArgs"], {"kernel_size": 3, "sigma": 0.5}))
+    hs = g.add_op("Histogram", [(bl, "frame")], device=1)
+    sink = g.add_sink((hs, "histogram"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    eng.run(g, [j], 3, 3)
+    hist = j.output_array(sink, 192, np.int32).reshape(n, 3, 16)
+    for i in range(n):
+        assert (hist[i] == oracle.hist16(oracle.blur(want[i], 3))).all()
+
+
+def test_blur_without_args_fails_validation(eng):
+    g = E.Graph()
+    src = g.add_source(True)
+    g.add_sink((g.add_op("Blur", [(src, "frame")], device=1), "frame"))
+    j = E.Job()
+    j.bind_source(src, eng.add_raw_frames(np.zeros((2, 8, 8, 3), np.uint8)))
+    with pytest.raises(E.EngineError, match="Could not parse BlurArgs"):
+        eng.run(g, [j], 1, 1)
+
+
+def test_raw_frames_host_to_device_marshalling(eng):
+    """The reference's only GPU input path (host frames copied to the device per packet,
+    runtime.cpp:141-189): RAW frame column -> GPU Histogram / Resize(preserve_aspect)."""
+    n = 13
+    frames = np.stack([synth.rand_frame(80 + i, 360, 640) for i in range(n)])
+    sid = eng.add_raw_frames(frames)
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("Histogram", [(src, "frame")], device=1, batch=5)
+    rz = g.add_op("Resize", [(src, "frame")], device=1)
+    s_h, s_r = g.add_sink((hs, "histogram")), g.add_sink((rz, "frame"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_stream_args(rz, protolite.encode(STD_ARGS["ResizeArgs"], {"width": 0, "height": 90, "preserve_aspect": True}))
+    eng.run(g, [j], 4, 8)
+    hist = j.output_array(s_h, 192, np.int32).reshape(n, 3, 16)
+    for i in range(n):
+        assert (hist[i] == oracle.hist16(frames[i])).all()
+        got = j.output_row(s_r, i)
+        assert got.shape == (90, 160, 3) and (got == oracle.resize(frames[i], 160, 90)).all()
+
+
+def test_many_clips_sharded_over_instances(eng):
+    clips = [make_clip(100 + k, 12 + k, 96, 128, 4) for k in range(6)]
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("Histogram", [(src, "frame")], device=1)
+    sink = g.add_sink((hs, "histogram"))
+    jobs = []
+    for data, _ in clips:
+        j = E.Job()
+        j.bind_source(src, eng.add_h264(data))
+        jobs.append(j)
+    eng.run(g, jobs, 4, 8)
+    for (data, want), j in zip(clips, jobs):
+        hist = j.output_array(sink, 192, np.int32).reshape(-1, 3, 16)
+        assert len(hist) == len(want)
+        for i in range(len(want)):
+            assert (hist[i] == oracle.hist16(want[i])).all()
+    assert eng.stats()["counters"]["instances"] == 3
