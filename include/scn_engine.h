@@ -117,8 +117,9 @@ SCN_ENGINE_API int scn_engine_stats_json(scn_engine* e, char* host_buf, size_t c
 
 /* ---- synthetic H.264 (tests / bench input generation; no encoder exists offline) ----------- */
 /* Encodes `frames` I420 pictures (planes at yuv + f*(w*h*3/2): Y, U, V) as an Annex-B stream of
- * I_PCM macroblocks, IDR every `gop` frames; non_key_mode 0 = P slices of I_PCM macroblocks,
- * 1 = P_Skip (repeat previous).  Returns the stream size, or the required size if cap is too
+ * I_PCM macroblocks, IDR every `gop` frames; non_key_mode 0 = P slices of I_PCM macroblocks
+ * (yuv holds `frames` pictures), 1 = P_Skip pictures that repeat the last key picture (yuv holds
+ * only the ceil(frames/gop) key pictures, consecutively).  Returns the stream size, or the required size if cap is too
  * small (nothing written then). */
 SCN_ENGINE_API int64_t scn_h264_synth(const uint8_t* yuv, int width, int height, int64_t frames, int gop,
                                       int non_key_mode, uint8_t* out, size_t cap);

@@ -305,7 +305,8 @@ int64_t scn_h264_synth(const uint8_t* yuv, int width, int height, int64_t frames
   stream.reserve((size_t)frames * (fsz + fsz / 64 + 4096));
   write_ipcm_stream(width, height, frames, gop, non_key_mode == 1 ? SynthNonKey::Skip : SynthNonKey::Pcm,
                     [&](i64 f, u8* y, u8* u, u8* v) {
-                      const u8* src = yuv + (size_t)f * fsz;
+                      // skip mode: only key pictures carry content, yuv holds one per GOP
+                      const u8* src = yuv + (size_t)(non_key_mode == 1 ? f / (gop < 1 ? 1 : gop) : f) * fsz;
                       memcpy(y, src, ysz);
                       memcpy(u, src + ysz, csz);
                       memcpy(v, src + ysz + csz, csz);

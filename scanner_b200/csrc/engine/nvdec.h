@@ -44,6 +44,10 @@ struct Nv12Surface {
   i32 width, height;  // display size
 };
 
+// cumulative host nanoseconds inside driver calls since process start:
+// parse (whole cuvidParseVideoData), decode_picture, map, consumer, release wait, create decoder
+void nvdec_host_ns(long long out[6]);
+
 class NvdecSession {
  public:
   // consumer(frame_index_in_request_order, surface): enqueue work reading the surface on

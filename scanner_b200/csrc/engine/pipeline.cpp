@@ -93,6 +93,15 @@ struct Engine::Instance {
   std::thread th;
 };
 
+// What survives between runs for pipeline-instance slot `node_id`: its CUDA stream and its NVDEC
+// sessions (creating a decoder costs ~0.25 s; the reference re-creates parser and decoder on
+// every configure(), nvidia_video_decoder.cpp:100-112).
+struct Engine::Slot {
+  i32 gpu_id = -1;
+  cudaStream_t stream = nullptr;
+  std::map<i32, std::unique_ptr<NvdecSession>> sessions;  // per video source op index
+};
+
 Engine::Engine(std::vector<i32> gpu_ids, i32 instances_per_gpu, i32 cpu_instances)
   : gpu_ids_(std::move(gpu_ids)), instances_per_gpu_(instances_per_gpu), cpu_instances_(cpu_instances) {
   if (!gpu_ids_.empty() && !cuda_available()) {
@@ -102,9 +111,21 @@ Engine::Engine(std::vector<i32> gpu_ids, i32 instances_per_gpu, i32 cpu_instance
 }
 
 Engine::~Engine() {
+  for (auto& sl : slots_) {
+    if (sl->gpu_id >= 0 && cuda_available()) {
+      cudaSetDevice(sl->gpu_id);
+      sl->sessions.clear();
+      if (sl->stream) cudaStreamDestroy(sl->stream);
+    }
+  }
+  slots_.clear();
   std::lock_guard<std::mutex> g(streams_mu_);
   for (auto& kv : streams_)
-    if (!kv.second->data.empty()) disown_block(CPU_DEVICE, kv.second->data.data());
+    if (!kv.second->data.empty()) {
+      disown_block(CPU_DEVICE, kv.second->data.data());
+      // the payload was page-locked in add_stream: release the registration before the memory
+      if (kv.second->registered && cudaHostUnregister(kv.second->data.data()) != cudaSuccess) cudaGetLastError();
+    }
 }
 
 i64 Engine::add_stream(std::unique_ptr<InputStream> s) {
@@ -112,7 +133,10 @@ i64 Engine::add_stream(std::unique_ptr<InputStream> s) {
     adopt_block(CPU_DEVICE, s->data.data(), s->data.size());
     // page-lock the payload so GPU instances can DMA straight from it
     if (cuda_available() && !gpu_ids_.empty()) {
-      if (cudaHostRegister(s->data.data(), s->data.size(), cudaHostRegisterPortable) != cudaSuccess) cudaGetLastError();
+      if (cudaHostRegister(s->data.data(), s->data.size(), cudaHostRegisterPortable) == cudaSuccess)
+        s->registered = true;
+      else
+        cudaGetLastError();
     }
   }
   std::lock_guard<std::mutex> g(streams_mu_);
@@ -133,9 +157,7 @@ bool Engine::remove_stream(i64 id) {
   if (it == streams_.end()) return false;
   if (!it->second->data.empty()) {
     disown_block(CPU_DEVICE, it->second->data.data());
-    if (cuda_available() && !gpu_ids_.empty()) {
-      if (cudaHostUnregister(it->second->data.data()) != cudaSuccess) cudaGetLastError();
-    }
+    if (it->second->registered && cudaHostUnregister(it->second->data.data()) != cudaSuccess) cudaGetLastError();
   }
   streams_.erase(it);
   return true;
@@ -177,14 +199,25 @@ struct SourceCursor {
 void Engine::instance_main(Instance* inst) {
   RunState& rs = *run_;
   const i32 gpu = inst->gpu_id;
-  cudaStream_t stream = nullptr;
+  Slot& slot = *slots_[(size_t)inst->node_id];
   if (gpu >= 0) {
-    if (cudaSetDevice(gpu) != cudaSuccess || cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(gpu) != cudaSuccess) {
       rs.fail("cannot initialise GPU " + std::to_string(gpu));
       return;
     }
-    set_thread_stream(gpu, stream);
+    if (slot.gpu_id != gpu || !slot.stream) {
+      slot.sessions.clear();
+      if (slot.stream) cudaStreamDestroy(slot.stream);
+      slot.stream = nullptr;
+      if (cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        rs.fail("cannot create a stream on GPU " + std::to_string(gpu));
+        return;
+      }
+      slot.gpu_id = gpu;
+    }
+    set_thread_stream(gpu, slot.stream);
   }
+  cudaStream_t stream = slot.stream;
   const DeviceHandle gpu_dev(DeviceType::GPU, gpu);
   {
     EvaluateWorker ew(*rs.graph, rs.an, gpu, inst->node_id, &rs.profiler);
@@ -193,7 +226,12 @@ void Engine::instance_main(Instance* inst) {
       rs.fail(r.msg());
       return;
     }
-    std::map<i32, std::unique_ptr<NvdecSession>> sessions;  // per video source op
+    std::map<i32, std::unique_ptr<NvdecSession>>& sessions = slot.sessions;
+    i64 decoded0 = 0, used0 = 0;
+    for (auto& kv : sessions) {
+      decoded0 += kv.second->frames_decoded();
+      used0 += kv.second->frames_used();
+    }
 
     while (!rs.failed.load()) {
       const size_t ti = rs.next.fetch_add(1);
@@ -435,12 +473,13 @@ void Engine::instance_main(Instance* inst) {
       rs.frames_decoded += kv.second->frames_decoded();
       rs.frames_used += kv.second->frames_used();
     }
+    rs.frames_decoded -= decoded0;
+    rs.frames_used -= used0;
     if (gpu >= 0) cudaStreamSynchronize(stream);
-  }  // kernels and sessions destroyed here, while the stream is alive
+  }  // kernels destroyed here, while the stream is alive
   if (gpu >= 0) {
-    set_thread_stream(gpu, nullptr);
     cudaStreamSynchronize(stream);
-    cudaStreamDestroy(stream);
+    set_thread_stream(gpu, nullptr);
   }
 }
 
@@ -508,6 +547,7 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
     const i32 n = cpu_instances_ > 0 ? cpu_instances_ : 1;
     for (i32 i = 0; i < n; ++i) instances.emplace_back(new Instance{this, -1, node++, {}});
   }
+  while (slots_.size() < instances.size()) slots_.emplace_back(new Slot());
   // never more instances than tasks
   while (instances.size() > std::max<size_t>(1, rs.tasks.size())) instances.pop_back();
 
@@ -519,6 +559,13 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   stats_.counters = rs.profiler.counters();
   stats_.counters["frames_decoded"] = rs.frames_decoded.load();
   stats_.counters["frames_used"] = rs.frames_used.load();
+  {
+    long long ns[6];
+    nvdec_host_ns(ns);
+    static const char* names[6] = {"nvdec_parse_us", "nvdec_decode_call_us", "nvdec_map_us", "nvdec_consume_us",
+                                   "nvdec_release_wait_us", "nvdec_create_us"};
+    for (int i = 0; i < 6; ++i) stats_.counters[names[i]] = ns[i] / 1000;
+  }
   stats_.counters["tasks"] = (i64)rs.tasks.size();
   stats_.counters["instances"] = (i64)instances.size();
   stats_.interval_ns = rs.profiler.interval_totals_ns();

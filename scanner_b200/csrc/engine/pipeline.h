@@ -32,6 +32,7 @@ struct InputStream {
   // RawFrames / Bytes payload + per-row extents
   std::vector<u8> data;
   std::vector<u64> offsets, sizes;
+  bool registered = false;  // payload is cudaHostRegister'ed
   i64 rows() const { return kind == H264 ? index.frames() : (i64)sizes.size(); }
 };
 
@@ -77,7 +78,9 @@ class Engine {
 
  private:
   struct Instance;
+  struct Slot;
   void instance_main(Instance* inst);
+  std::vector<std::unique_ptr<Slot>> slots_;  // persistent per-instance state (stream, decoders)
 
   std::vector<i32> gpu_ids_;
   i32 instances_per_gpu_, cpu_instances_;

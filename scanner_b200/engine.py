@@ -114,13 +114,19 @@ def nvdec_caps(gpu=0):
     return d
 
 
-def h264_synth(yuv_frames, width, height, gop=30, non_key="pcm"):
-    """yuv_frames: uint8 array (n, h*3/2, w) I420 (Y rows, then U rows packed w/2, V rows) or flat
-    (n, w*h*3/2).  Returns the Annex-B stream as bytes."""
+def h264_synth(yuv_frames, width, height, gop=30, non_key="pcm", frames=None):
+    """yuv_frames: uint8 I420 pictures, flat (k, w*h*3/2) (Y plane, then U, then V).
+    non_key="pcm": k = number of frames, every picture is coded (P slices of I_PCM macroblocks
+    between IDRs).  non_key="skip": k = number of GOPs, `frames` total pictures are emitted, the
+    non-key ones as P_Skip repeats.  Returns the Annex-B stream as bytes."""
     arr = np.ascontiguousarray(yuv_frames, dtype=np.uint8).reshape(len(yuv_frames), -1)
-    n = arr.shape[0]
     assert arr.shape[1] == width * height * 3 // 2
     mode = {"pcm": 0, "skip": 1}[non_key]
+    if mode == 1:
+        n = frames if frames is not None else arr.shape[0] * gop
+        assert arr.shape[0] >= (n + gop - 1) // gop
+    else:
+        n = arr.shape[0]
     need = lib().scn_h264_synth(arr.ctypes.data, width, height, n, gop, mode, None, 0)
     check(need, "scn_h264_synth")
     out = np.empty(need, np.uint8)

@@ -38,7 +38,10 @@ def make_clip(seed, n, h, w, gop, non_key="pcm"):
     u = rng.integers(0, 256, (n, h // 2, w // 2), dtype=np.uint8)
     v = rng.integers(0, 256, (n, h // 2, w // 2), dtype=np.uint8)
     yuv = np.concatenate([y.reshape(n, -1), u.reshape(n, -1), v.reshape(n, -1)], axis=1)
-    data = E.h264_synth(yuv, w, h, gop=gop, non_key=non_key)
+    if non_key == "skip":
+        data = E.h264_synth(yuv[::gop], w, h, gop=gop, non_key="skip", frames=n)
+    else:
+        data = E.h264_synth(yuv, w, h, gop=gop)
     rgb = []
     for i in range(n):
         src = i if non_key == "pcm" else (i // gop) * gop  # P_Skip repeats the last key picture
