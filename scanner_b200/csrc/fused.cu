@@ -4,6 +4,7 @@
 // read them back).  Here the surface (1.5 WH bytes) is the only large read: the histogram is
 // taken from RGB values converted in registers, and the resize converts just the 4 taps of each
 // destination pixel.  Results are bit-identical to the three-pass composition.
+#include "nv12_csa.cuh"
 #include "nv12_math.cuh"
 #include "scn_common.cuh"
 
@@ -156,12 +157,17 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
       d.p[i] = do_resize ? host_dst_ptrs[i0 + i] : nullptr;
       if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i]) & 3) vec_ok = 0;
     }
+    const bool use_csa = nvcsa::eligible(l.p, c.p, cnt, pitch, width, height);
+    if (use_csa) {
+      int rc = nvcsa::launch(l.p, c.p, cnt, pitch, width, height, hist_out + (size_t)i0 * 48, st);
+      if (rc) return rc;
+    }
     const int gx = (quads + HT - 1) / HT;
     int gy = (sm_count() * 8 + gx * cnt - 1) / (gx * cnt);
     if (gy < 1) gy = 1;
     if (gy > height) gy = height;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
-    {
+    if (!use_csa) {
       LaunchScope ls("nv12_hist_kernel", st);
       nv12_hist_kernel<<<grid, HT, 0, st>>>(l, c, pitch, width, height, quads, vec_ok,
                                           hist_out + (size_t)i0 * 48);

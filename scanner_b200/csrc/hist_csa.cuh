@@ -244,7 +244,7 @@ struct Params {
 
 // One warp owns a contiguous range of the global warp-block index space and walks it frame by
 // frame; at most kMaxBlocks blocks between flushes.
-__global__ void __launch_bounds__(kThreads, 1)
+static __global__ void __launch_bounds__(kThreads, 1)
 hist16_csa_kernel(const Params prm, int32_t* __restrict__ out) {
   __shared__ int sh[kWarps][48];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -275,12 +275,12 @@ hist16_csa_kernel(const Params prm, int32_t* __restrict__ out) {
 #pragma unroll
     for (int r = 0; r < 12; ++r) cur[r] = ld_stream_u4(src + r * 512);
     for (uint32_t blk = 0; blk < nb; ++blk) {
+      // unconditional prefetch (the last iteration re-reads its own block): loads inside a
+      // conditional region make ptxas wait for them at the reconvergence point
       uint4 nxt[12];
-      const uint8_t* nsrc = src + (size_t)(blk + 1) * kWarpBlock;
-      if (blk + 1 < nb) {
+      const uint8_t* nsrc = src + (size_t)(blk + 1 < nb ? blk + 1 : blk) * kWarpBlock;
 #pragma unroll
-        for (int r = 0; r < 12; ++r) nxt[r] = ld_stream_u4(nsrc + r * 512);
-      }
+      for (int r = 0; r < 12; ++r) nxt[r] = ld_stream_u4(nsrc + r * 512);
       uint32_t cA[3], cB[3];
       eat_round<0>(A, B, cA, cB, cur[0]);
       eat_round<1>(A, B, cA, cB, cur[1]);
@@ -299,10 +299,8 @@ hist16_csa_kernel(const Params prm, int32_t* __restrict__ out) {
         fold_block(A[s], cA[s], (int)blk);
         fold_block(B[s], cB[s], (int)blk);
       }
-      if (blk + 1 < nb) {
 #pragma unroll
-        for (int r = 0; r < 12; ++r) cur[r] = nxt[r];
-      }
+      for (int r = 0; r < 12; ++r) cur[r] = nxt[r];
     }
     flush_span(A, B, (int)nb, lane, h);
 

@@ -1,0 +1,395 @@
+// nv12_csa.cuh -- histogram of the RGB image of an NV12 decoder surface without materialising it
+// (the Histogram half of BASELINE configs[1], fused with the reference's NV12->RGB arithmetic,
+// scanner/util/image.cu:67-200 + tests/test_ops.cpp:19-49).
+//
+// A thread converts a "unit" = 16 pixels x 2 rows (one chroma row pair) per step from four 128-bit
+// loads (2 luma, 2 chroma).  The colour math runs on the FMA pipe in a 2^-11 scaled domain, which
+// is exact (power-of-two scaling commutes with IEEE rounding) and makes the lower clamp free:
+//     byte -> float      PRMT builds the bits of 2^23 + byte, one FFMA/FADD removes the bias
+//     ly  = Y * (4*1.1644*2^-11)                      (== fl(Y'*1.1644) * 2^-11)
+//     r   = fma.sat(cr, 4*1.596*2^-11, ly)            (.sat == max(.,0); min(.,1) never binds)
+//     g   = fma.sat(cr, 4*-.813*2^-11, fma(cb, 4*-.3918*2^-11, ly));  b likewise
+//     bin = floor(min(v,1023)/64) = floor(32 * min(x, 1023*2^-11))   via fma.rm(x, 32, 2^23)
+// Eight bins of one channel are packed into one 32-bit word (nibbles) with IMADs, decoded to
+// one-hot bytes with PRMT as an 8-entry LUT and counted with the bit-sliced carry-save adders of
+// hist_csa.cuh (6 accumulators: R,G,B x bins 0-7 / 8-14; bin 15 recovered from the total).
+// ~11 integer-pipe + ~12 FMA-pipe operations per pixel.  Bit-exact with the three-pass path.
+#pragma once
+#include "hist_csa.cuh"
+#include "nv12_math.cuh"
+#include "scn_common.cuh"
+
+namespace scn {
+namespace nvcsa {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kPlanes = 10;
+constexpr int kHi = kPlanes - 3;   // planes 3..9
+constexpr int kMaxSteps = 127;     // 127 * 8 words per accumulator <= 1023
+
+using csa::csa3;
+
+struct Acc {
+  uint32_t p0, p1, p2;
+  uint32_t t0, t1, t2;
+  uint32_t hi[kHi];
+  uint32_t pend3, pend4;
+};
+
+__device__ __forceinline__ void acc_clear(Acc& a) {
+  a.p0 = a.p1 = a.p2 = a.t0 = a.t1 = a.t2 = 0;
+#pragma unroll
+  for (int i = 0; i < kHi; ++i) a.hi[i] = 0;
+  a.pend3 = a.pend4 = 0;
+}
+
+template <int K>  // K-th (0..7) word of a step; K == 7 yields the weight-8 carry
+__device__ __forceinline__ void push8(Acc& a, uint32_t x, uint32_t& c8) {
+  if constexpr ((K & 1) == 0) {
+    a.t0 = x;
+  } else {
+    uint32_t tw;
+    csa3(tw, a.p0, a.p0, a.t0, x);
+    if constexpr (((K >> 1) & 1) == 0) {
+      a.t1 = tw;
+    } else {
+      uint32_t fo;
+      csa3(fo, a.p1, a.p1, a.t1, tw);
+      if constexpr (((K >> 2) & 1) == 0) {
+        a.t2 = fo;
+      } else {
+        csa3(c8, a.p2, a.p2, a.t2, fo);
+      }
+    }
+  }
+}
+
+template <int FROM>
+__device__ __forceinline__ void ripple(Acc& a, uint32_t c) {
+#pragma unroll
+  for (int q = FROM; q < kHi; ++q) {
+    const uint32_t t = a.hi[q] & c;
+    a.hi[q] ^= c;
+    c = t;
+  }
+}
+
+__device__ __forceinline__ void fold_step(Acc& a, uint32_t c8, int step) {
+  if (step & 1) {
+    uint32_t c16;
+    csa3(c16, a.hi[0], a.hi[0], a.pend3, c8);
+    if (step & 2) {
+      uint32_t c32;
+      csa3(c32, a.hi[1], a.hi[1], a.pend4, c16);
+      ripple<2>(a, c32);
+    } else {
+      a.pend4 = c16;
+    }
+  } else {
+    a.pend3 = c8;
+  }
+}
+
+__device__ __forceinline__ void finish_span(Acc& a, int nsteps) {
+  if (nsteps & 2) ripple<1>(a, a.pend4);
+  if (nsteps & 1) ripple<0>(a, a.pend3);
+}
+
+// 2^-11 scaled constants (exact power-of-two rescalings of image.cu's matrix, times 4 for the
+// 8->10 bit widening of the inputs)
+constexpr float kS = 1.0f / 2048.0f;
+constexpr float kCY = 4.0f * 1.1644f * kS;
+constexpr float kKR = 4.0f * 1.596f * kS;
+constexpr float kKG1 = 4.0f * -0.3918f * kS;
+constexpr float kKG2 = 4.0f * -0.813f * kS;
+constexpr float kKB = 4.0f * 2.0172f * kS;
+constexpr float kMagic = 8388608.0f;        // 2^23
+constexpr float kTop = 1023.0f * kS;        // upper clamp
+
+__device__ __forceinline__ float byte_magic(uint32_t word, uint32_t sel) {
+  // bits of (2^23 + byte): byte -> mantissa LSBs, 0x4B exponent byte on top
+  return __uint_as_float(prmt(word, 0x4B000000u, sel));
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t bin_bits(float x) {  // 0x4B000000 + floor(32*x)
+  float r;
+  asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(x), "f"(32.0f), "f"(kMagic));
+  return __float_as_uint(r);
+}
+
+struct Z3 {
+  uint32_t r, g, b;
+};
+
+// one pixel: append its three bins to the packed words.  `sixteen` is 16 passed at run time so
+// the packing stays an IMAD on the FMA pipe instead of an integer-pipe LEA.
+__device__ __forceinline__ void pixel(Z3& z, float yf, float cbf, float crf, uint32_t sixteen) {
+  const float ly = __fmaf_rn(yf, kCY, -kMagic * kCY);
+  const float r = fminf(fma_sat(crf, kKR, ly), kTop);
+  const float g = fminf(fma_sat(crf, kKG2, __fmaf_rn(cbf, kKG1, ly)), kTop);
+  const float b = fminf(fma_sat(cbf, kKB, ly), kTop);
+  z.r = z.r * sixteen + bin_bits(r);
+  z.g = z.g * sixteen + bin_bits(g);
+  z.b = z.b * sixteen + bin_bits(b);
+}
+
+// after 8 appends the word holds the 8 nibbles plus 0x4B000000 * (1 + 16) of exponent residue
+constexpr uint32_t kResidueFix = 0u - 0xFB000000u;
+
+template <int K>
+__device__ __forceinline__ void count8(Acc& A, Acc& B, uint32_t z, uint32_t& cA, uint32_t& cB) {
+  z += kResidueFix;
+  const uint32_t zx = z ^ 0x88888888u;
+  push8<K>(A, prmt(csa::kLutLo, csa::kLutHiA, z), cA);
+  push8<K + 1>(A, prmt(csa::kLutLo, csa::kLutHiA, z >> 16), cA);
+  push8<K>(B, prmt(csa::kLutLo, csa::kLutHiB, zx), cB);
+  push8<K + 1>(B, prmt(csa::kLutLo, csa::kLutHiB, zx >> 16), cB);
+}
+
+// 8 pixels of one row: luma words y0,y1 (4 px each), chroma words c0,c1 (2 pairs each)
+template <int K>
+__device__ __forceinline__ void eight(Acc (&A)[3], Acc (&B)[3], uint32_t (&cA)[3], uint32_t (&cB)[3], uint32_t y0,
+                                      uint32_t y1, uint32_t c0, uint32_t c1, uint32_t sixteen) {
+  Z3 z{0u, 0u, 0u};
+  const float bias = -(kMagic + 128.0f);
+  {
+    const float cb0 = byte_magic(c0, 0x7440u) + bias, cr0 = byte_magic(c0, 0x7441u) + bias;
+    const float cb1 = byte_magic(c0, 0x7442u) + bias, cr1 = byte_magic(c0, 0x7443u) + bias;
+    pixel(z, byte_magic(y0, 0x7440u), cb0, cr0, sixteen);
+    pixel(z, byte_magic(y0, 0x7441u), cb0, cr0, sixteen);
+    pixel(z, byte_magic(y0, 0x7442u), cb1, cr1, sixteen);
+    pixel(z, byte_magic(y0, 0x7443u), cb1, cr1, sixteen);
+  }
+  {
+    const float cb0 = byte_magic(c1, 0x7440u) + bias, cr0 = byte_magic(c1, 0x7441u) + bias;
+    const float cb1 = byte_magic(c1, 0x7442u) + bias, cr1 = byte_magic(c1, 0x7443u) + bias;
+    pixel(z, byte_magic(y1, 0x7440u), cb0, cr0, sixteen);
+    pixel(z, byte_magic(y1, 0x7441u), cb0, cr0, sixteen);
+    pixel(z, byte_magic(y1, 0x7442u), cb1, cr1, sixteen);
+    pixel(z, byte_magic(y1, 0x7443u), cb1, cr1, sixteen);
+  }
+  count8<K>(A[0], B[0], z.r, cA[0], cB[0]);
+  count8<K>(A[1], B[1], z.g, cA[1], cB[1]);
+  count8<K>(A[2], B[2], z.b, cA[2], cB[2]);
+}
+
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >> 1
+  return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1);
+}
+
+__device__ uint4 g_zero_page[1];  // what inactive lanes load (zero-initialised module memory)
+
+struct Params {
+  PtrBatch luma, chroma;
+  size_t pitch;
+  int width, height;
+  uint32_t units_per_row;     // width / 16
+  uint32_t units_per_frame;   // units_per_row * height / 2
+  uint32_t steps_per_frame;   // ceil(units_per_frame / 32)
+  uint64_t total_steps;
+  uint32_t sixteen;           // == 16 (see pixel())
+};
+
+__device__ __forceinline__ void warp_sum(uint32_t (&pl)[kPlanes + 5]) {
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int p = 0; p < kPlanes + 5; ++p) {
+      if (p < kPlanes + d) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, pl[p], 1 << d);
+        const uint32_t u = pl[p] ^ o;
+        const uint32_t nc = (pl[p] & o) | (u & carry);
+        pl[p] = u ^ carry;
+        carry = nc;
+      } else if (p == kPlanes + d) {
+        pl[p] = carry;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t lane_count(const Acc& a, int lane) {
+  uint32_t pl[kPlanes + 5];
+  pl[0] = a.p0;
+  pl[1] = a.p1;
+  pl[2] = a.p2;
+#pragma unroll
+  for (int q = 0; q < kHi; ++q) pl[3 + q] = a.hi[q];
+#pragma unroll
+  for (int q = kPlanes; q < kPlanes + 5; ++q) pl[q] = 0;
+  warp_sum(pl);
+  uint32_t v = 0;
+#pragma unroll
+  for (int p = 0; p < kPlanes + 5; ++p) v |= ((pl[p] >> lane) & 1u) << p;
+  // the four byte slots of a word carry the same channel: fold them onto lanes 0..7
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+static __global__ void __launch_bounds__(kThreads, 1)
+nv12_hist_csa_kernel(const Params prm, int32_t* __restrict__ out) {
+  __shared__ int sh[kWarps][48];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* h = sh[warp];
+  const uint64_t gwarp = (uint64_t)blockIdx.x * kWarps + warp;
+  const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+  uint64_t g0 = prm.total_steps * gwarp / nwarps;
+  const uint64_t g1 = prm.total_steps * (gwarp + 1) / nwarps;
+  const uint32_t sixteen = prm.sixteen;
+  const int last_crow = (prm.height >> 1) - 1;
+
+  while (g0 < g1) {
+    const uint32_t frame = (uint32_t)(g0 / prm.steps_per_frame);
+    const uint32_t s0 = (uint32_t)(g0 - (uint64_t)frame * prm.steps_per_frame);
+    uint32_t ns = prm.steps_per_frame - s0;
+    if ((uint64_t)ns > g1 - g0) ns = (uint32_t)(g1 - g0);
+    if (ns > (uint32_t)kMaxSteps) ns = kMaxSteps;
+    const uint8_t* __restrict__ luma = prm.luma.p[frame];
+    const uint8_t* __restrict__ chroma = prm.chroma.p[frame];
+
+    for (int i = lane; i < 48; i += 32) h[i] = 0;
+    __syncwarp();
+    Acc A[3], B[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      acc_clear(A[c]);
+      acc_clear(B[c]);
+    }
+    uint32_t padded_units = 0;
+
+    // Loads are unconditional and never sit in a divergent region: ptxas makes the first
+    // instruction after a reconvergence point wait for every load issued inside it, which
+    // turned the prefetch of the next step into a blocking load (r01 ncu: 30 % of all stall
+    // samples on that one instruction).  Inactive lanes (only in a frame's last step) read a
+    // zero page instead, and the step index is clamped instead of predicated.
+    auto load_unit = [&](uint32_t step, uint4& ya, uint4& yb, uint4& c0, uint4& c1) -> bool {
+      const uint32_t unit = (s0 + step) * 32u + (uint32_t)lane;
+      const bool active = unit < prm.units_per_frame;
+      const uint32_t yp = unit / prm.units_per_row;
+      const uint32_t xs = unit - yp * prm.units_per_row;
+      const uint8_t* lp = luma + (size_t)(2 * yp) * prm.pitch + (size_t)xs * 16;
+      const uint8_t* cp = chroma + (size_t)yp * prm.pitch + (size_t)xs * 16;
+      const size_t cnext = ((int)yp < last_crow) ? prm.pitch : 0;
+      const uint8_t* zero = reinterpret_cast<const uint8_t*>(g_zero_page);
+      const uint8_t* p0 = active ? lp : zero;
+      const uint8_t* p1 = active ? lp + prm.pitch : zero;
+      const uint8_t* p2 = active ? cp : zero;
+      const uint8_t* p3 = active ? cp + cnext : zero;
+      ya = ld_stream_u4(p0);
+      yb = ld_stream_u4(p1);
+      c0 = ld_stream_u4(p2);
+      c1 = ld_stream_u4(p3);
+      return active;
+    };
+
+    uint4 ya, yb, c0, c1;
+    bool act = load_unit(0, ya, yb, c0, c1);
+    for (uint32_t step = 0; step < ns; ++step) {
+      uint4 nya, nyb, nc0, nc1;
+      const uint32_t nstep = step + 1 < ns ? step + 1 : step;  // last iteration re-reads its own unit
+      const bool nact = load_unit(nstep, nya, nyb, nc0, nc1);
+      padded_units += act ? 0u : 1u;
+      // odd luma row: rounded average of the two neighbouring chroma rows (image.cu:133-151)
+      const uint4 ca = make_uint4(avg4(c0.x, c1.x), avg4(c0.y, c1.y), avg4(c0.z, c1.z), avg4(c0.w, c1.w));
+      uint32_t cA[3], cB[3];
+      eight<0>(A, B, cA, cB, ya.x, ya.y, c0.x, c0.y, sixteen);
+      eight<2>(A, B, cA, cB, ya.z, ya.w, c0.z, c0.w, sixteen);
+      eight<4>(A, B, cA, cB, yb.x, yb.y, ca.x, ca.y, sixteen);
+      eight<6>(A, B, cA, cB, yb.z, yb.w, ca.z, ca.w, sixteen);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        fold_step(A[c], cA[c], (int)step);
+        fold_step(B[c], cB[c], (int)step);
+      }
+      ya = nya;
+      yb = nyb;
+      c0 = nc0;
+      c1 = nc1;
+      act = nact;
+    }
+
+    // ---- flush the span
+    const uint32_t values = ns * 32u * 32u;  // pixels (per channel) this warp fed, padding included
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      finish_span(A[c], (int)ns);
+      finish_span(B[c], (int)ns);
+      uint32_t ca = lane_count(A[c], lane);  // lanes 0..7: bins 0..7 (+ n15 each)
+      uint32_t cb = lane_count(B[c], lane);  // lanes 0..6: bins 8..14
+      uint32_t sum = (lane < 8) ? ca + cb : 0u;
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const uint32_t n15 = (sum - values) / 7u;
+      if (lane < 8) {
+        ca -= n15;
+        if (lane == 7) cb = n15;
+        if (ca) atomicAdd(&h[c * 16 + lane], (int)ca);
+        if (cb) atomicAdd(&h[c * 16 + 8 + lane], (int)cb);
+      }
+    }
+    // padding units were fed as all-zero bytes: remove what 32 such pixels each contributed
+    const uint32_t pad_total = __reduce_add_sync(0xffffffffu, padded_units);
+    __syncwarp();
+    if (pad_total && lane == 0) {
+      const Rgb8 z = yuv_to_rgb(0, 0, 0);
+      atomicSub(&h[0 * 16 + (z.r >> 4)], (int)(pad_total * 32u));
+      atomicSub(&h[1 * 16 + (z.g >> 4)], (int)(pad_total * 32u));
+      atomicSub(&h[2 * 16 + (z.b >> 4)], (int)(pad_total * 32u));
+    }
+    __syncwarp();
+    for (int i = lane; i < 48; i += 32)
+      if (h[i]) atomicAdd(&out[(size_t)frame * 48 + i], h[i]);
+    __syncwarp();
+    g0 += ns;
+  }
+}
+
+inline bool eligible(const uint8_t* const* lp, const uint8_t* const* cp, int n, size_t pitch, int width, int height) {
+  if ((width & 15) || (pitch & 15) || (height & 1)) return false;
+  if ((size_t)width * height < 64 * 1024) return false;
+  for (int i = 0; i < n; ++i)
+    if ((reinterpret_cast<uintptr_t>(lp[i]) | reinterpret_cast<uintptr_t>(cp[i])) & 15) return false;
+  return true;
+}
+
+// `out` must already be zeroed.
+inline int launch(const uint8_t* const* lp, const uint8_t* const* cp, int n, size_t pitch, int width, int height,
+                  int32_t* out, cudaStream_t st) {
+  for (int i0 = 0; i0 < n; i0 += SCN_MAX_PTRS) {
+    const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
+    Params p;
+    for (int i = 0; i < cnt; ++i) {
+      p.luma.p[i] = lp[i0 + i];
+      p.chroma.p[i] = cp[i0 + i];
+    }
+    p.pitch = pitch;
+    p.width = width;
+    p.height = height;
+    p.units_per_row = (uint32_t)(width / 16);
+    p.units_per_frame = p.units_per_row * (uint32_t)(height / 2);
+    p.steps_per_frame = (p.units_per_frame + 31) / 32;
+    p.total_steps = (uint64_t)cnt * p.steps_per_frame;
+    p.sixteen = 16;
+    uint64_t ctas = (p.total_steps + kWarps * 8 - 1) / (kWarps * 8);
+    if (ctas > (uint64_t)sm_count()) ctas = sm_count();
+    if (ctas < 1) ctas = 1;
+    {
+      LaunchScope ls("nv12_hist_csa_kernel", st);
+      nv12_hist_csa_kernel<<<(unsigned)ctas, kThreads, 0, st>>>(p, out + (size_t)i0 * 48);
+    }
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace nvcsa
+}  // namespace scn

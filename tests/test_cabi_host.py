@@ -91,3 +91,20 @@ def test_no_silent_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(cabi.ScnError):
         kernels.histogram(torch.zeros((1, 4, 4, 3), dtype=torch.uint8))
+
+
+def test_engine_library_exports_every_declared_symbol():
+    import re as _re
+    from scanner_b200 import engine as E
+    src = open(os.path.join(ROOT, "include", "scn_engine.h")).read()
+    names = sorted(set(_re.findall(r"SCN_ENGINE_API\s+[\w\s\*]+?\b(scn_\w+)\s*\(", src)))
+    assert len(names) >= 30
+    l = ctypes.CDLL(E.ENGINE_PATH)
+    for n in names:
+        assert hasattr(l, n), f"libscn_engine.so does not export {n}"
+    assert sorted(E.SIGNATURES) == names
+    # the stdlib plugin loads and registers the three GPU ops without touching a GPU
+    E.load_stdlib()
+    ops = E.list_ops()
+    for op in ("Histogram", "Resize", "Blur"):
+        assert op in ops and E.lib().scn_kernel_registered(op.encode(), 1) == 1
