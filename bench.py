@@ -312,7 +312,7 @@ def main():
         roof = None
         if kname:
             per_launch_s = prof[kname]["ms"] * 1e-3 / prof[kname]["launches"]
-            alg = (B_ALG_HIST_NV12 if kname == "nv12_hist_kernel" else B_ALG_FUSED) * B
+            alg = (B_ALG_HIST_NV12 if kname.startswith("nv12_hist") else B_ALG_FUSED) * B
             ach = alg / per_launch_s / 1e9
             roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "peak_kind": peak_kind + " (burst copy, MEASURED_PEAKS.json)",
