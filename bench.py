@@ -171,7 +171,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, sample),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -334,7 +334,7 @@ def main():
                 "whole_step_roofline_frac": value / world * B_ALG_FUSED / 1e9 / peak}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -10,5 +10,8 @@ There is no CPU fallback: importing works anywhere, but every op raises if the C
 missing or no device is present.
 """
 from . import cabi  # noqa: F401
+from .client import (CacheMode, Client, DeviceType, NamedStream, NamedVideoStream, PerfParams,  # noqa: F401
+                     ScannerException)
 
-__all__ = ["cabi"]
+__all__ = ["cabi", "Client", "DeviceType", "PerfParams", "NamedStream", "NamedVideoStream", "CacheMode",
+           "ScannerException"]

@@ -1,0 +1,342 @@
+"""scannerpy-shaped graph surface over the in-process engine.
+
+Keeps the names and call shapes of the reference's Python API for the hot path so pipelines read
+the same (python/scannerpy/client.py:1282-1590 `Client.run`, op.py:121-314 `sc.ops.<Name>(...)`,
+streams.py `sc.streams.Stride/Range/Gather/...`, storage.py:250-372 `NamedVideoStream`,
+`NamedStream`, common.py:78-234 `PerfParams`).  The transport underneath is not gRPC: the graph is
+handed to libscn_engine.so through its C ABI.  Not reproduced: the database / table catalogue,
+Slice/Unslice, Python kernels, multi-node master.
+
+    sc = Client(gpus=[0])
+    video = NamedVideoStream(sc, 'clip', path='clip.h264')         # Annex-B elementary stream
+    frames = sc.io.Input([video])
+    hists = sc.ops.Histogram(frame=sc.streams.Stride(frames, [2]), device=DeviceType.GPU)
+    out = NamedStream(sc, 'clip_hist')
+    sc.run(sc.io.Output(hists, [out]), PerfParams.manual(32, 64))
+    for h in out.load(): ...            # 3 arrays of 16 int32, like scannerpy.types.Histogram
+"""
+import enum
+import os
+
+import numpy as np
+
+from . import engine as E
+from . import protolite
+
+
+class DeviceType(enum.IntEnum):
+    CPU = 0
+    GPU = 1
+
+
+class CacheMode(enum.Enum):
+    Error = 1
+    Ignore = 2
+    Overwrite = 3
+
+
+class ScannerException(Exception):
+    pass
+
+
+class PerfParams:
+    def __init__(self, work_packet_size, io_packet_size, pipeline_instances_per_node=None, **_ignored):
+        self.work_packet_size = work_packet_size
+        self.io_packet_size = io_packet_size
+        self.pipeline_instances_per_node = pipeline_instances_per_node
+
+    @classmethod
+    def manual(cls, work_packet_size, io_packet_size, **kwargs):
+        return cls(work_packet_size, io_packet_size, **kwargs)
+
+    @classmethod
+    def estimate(cls, max_memory_util=0.7, total_memory=None, work_io_ratio=0.2, **kwargs):
+        # the reference sizes packets from host RAM (common.py:149-234); on a 180 GB GPU a packet of
+        # 64 1080p frames (398 MB) per instance is comfortably small: fixed, GOP-friendly defaults
+        return cls(32, 64 if work_io_ratio <= 0.5 else 32, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+class OpColumn:
+    def __init__(self, op, column, is_frame):
+        self._op, self._col, self._is_frame = op, column, is_frame
+
+
+class _Node:
+    def __init__(self, kind, name=None, inputs=(), device=DeviceType.CPU, args=b"", batch=-1, stencil=(),
+                 warmup=-1, per_stream=None, streams=None, sampler=None):
+        self.kind, self.name, self.inputs = kind, name, list(inputs)
+        self.device, self.args, self.batch, self.stencil, self.warmup = device, args, batch, list(stencil), warmup
+        self.per_stream = per_stream      # list (one per job) of serialized stream args / sampler args
+        self.streams = streams            # Input: list of stored streams; Output: list of NamedStream
+        self.sampler = sampler            # Sample/Space: sampler function name
+
+
+class OpGenerator:
+    """sc.ops.<Name>(col=..., device=..., batch=..., stencil=..., bounded_state=..., **args)"""
+
+    def __init__(self, sc):
+        self._sc = sc
+
+    def __getattr__(self, name):
+        ops = E.list_ops()
+        if name not in ops:
+            raise ScannerException(f"Op {name} is not registered (load_op first?)")
+
+        def make(device=DeviceType.CPU, batch=-1, stencil=(), bounded_state=None, **kwargs):
+            cols = [(k, v) for k, v in kwargs.items() if isinstance(v, OpColumn)]
+            rest = {k: v for k, v in kwargs.items() if not isinstance(v, OpColumn)}
+            protos = self._sc._op_protos.get(name, {})
+            init_fields, stream_fields = protos.get("init"), protos.get("stream")
+            init_vals, stream_vals = {}, {}
+            for k, v in rest.items():
+                # list-valued kwargs matching the stream message are per-stream args (op.py:278-314)
+                if stream_fields and any(f[0] == k for f in stream_fields) and isinstance(v, (list, tuple)):
+                    stream_vals[k] = list(v)
+                elif init_fields and any(f[0] == k for f in init_fields):
+                    init_vals[k] = v
+                else:
+                    raise ScannerException(f"Op {name} does not take argument {k!r}")
+            args = protolite.encode(init_fields, init_vals) if init_fields and init_vals else b""
+            per_stream = None
+            if stream_vals:
+                n = len(next(iter(stream_vals.values())))
+                per_stream = [protolite.encode(stream_fields, {k: v[i] for k, v in stream_vals.items()})
+                              for i in range(n)]
+            node = _Node("op", name, [c for _, c in cols], DeviceType(device), args, batch, stencil,
+                         -1 if bounded_state is None else bounded_state, per_stream)
+            node.input_names = [k for k, _ in cols]
+            outs = self._sc._op_outputs(name)
+            res = [OpColumn(node, c, t) for c, t in outs]
+            return res[0] if len(res) == 1 else tuple(res)
+
+        return make
+
+
+class StreamsGenerator:
+    """Row sampling ops; arguments are one entry per input stream (reference streams.py)."""
+
+    def __init__(self, sc):
+        self._sc = sc
+
+    def _sample(self, col, fn, msg, per_stream_dicts, kind="sample"):
+        enc = [protolite.encode(protolite.SAMPLER_ARGS[msg], d) if msg else b"" for d in per_stream_dicts]
+        node = _Node(kind, fn, [col], per_stream=enc, sampler=fn)
+        return OpColumn(node, col._col, col._is_frame)
+
+    def All(self, input):
+        return self._sample(input, "All", None, [{}])
+
+    def Stride(self, input, strides):
+        return self._sample(input, "Strided", "StridedSamplerArgs", [{"stride": s} for s in strides])
+
+    def Range(self, input, ranges):
+        return self.StridedRanges(input, [[r] for r in ranges], [1] * len(ranges))
+
+    def Ranges(self, input, intervals):
+        return self.StridedRanges(input, intervals, [1] * len(intervals))
+
+    def StridedRange(self, input, ranges):
+        return self.StridedRanges(input, [[(s, e)] for s, e, _ in ranges], [st for _, _, st in ranges])
+
+    def StridedRanges(self, input, intervals, strides):
+        strides = strides if isinstance(strides, (list, tuple)) else [strides] * len(intervals)
+        return self._sample(input, "StridedRanges", "StridedRangeSamplerArgs",
+                            [{"stride": st, "starts": [a for a, _ in iv], "ends": [b for _, b in iv]}
+                             for iv, st in zip(intervals, strides)])
+
+    def Gather(self, input, indices):
+        return self._sample(input, "Gather", "GatherSamplerArgs", [{"rows": list(r)} for r in indices])
+
+    def RepeatNull(self, input, spacings):
+        return self._sample(input, "SpaceNull", "SpaceNullSamplerArgs", [{"spacing": s} for s in spacings], "space")
+
+    def Repeat(self, input, spacings):
+        return self._sample(input, "SpaceRepeat", "SpaceRepeatSamplerArgs", [{"spacing": s} for s in spacings],
+                            "space")
+
+
+class IOGenerator:
+    def __init__(self, sc):
+        self._sc = sc
+
+    def Input(self, streams):
+        is_video = isinstance(streams[0], NamedVideoStream) or getattr(streams[0], "_is_frame", False)
+        node = _Node("input", "Input", streams=list(streams))
+        return OpColumn(node, "frame" if is_video else "column", is_video)
+
+    def Output(self, op, streams):
+        return _Node("output", "Output", [op], streams=list(streams))
+
+
+# ------------------------------------------------------------------------------------------------
+class NamedVideoStream:
+    """A stored video.  path: an H.264 Annex-B file; data: the bytes; frames: (n,h,w,3) uint8 RAW frames."""
+
+    def __init__(self, sc, name, path=None, data=None, frames=None):
+        self._sc, self._name = sc, name
+        if name in sc._streams and path is None and data is None and frames is None:
+            self._sid = sc._streams[name]
+        else:
+            if frames is not None:
+                self._sid = sc._engine.add_raw_frames(frames)
+            else:
+                if data is None:
+                    with open(path, "rb") as f:
+                        data = f.read()
+                self._sid = sc._engine.add_h264(data)
+            sc._streams[name] = self._sid
+
+    def name(self):
+        return self._name
+
+    def len(self):
+        return self._sc._engine.stream_rows(self._sid)
+
+    def info(self):
+        return self._sc._engine.stream_info(self._sid)
+
+
+class NamedStream:
+    """An output column (or a byte-row input when created with rows=[...])."""
+
+    def __init__(self, sc, name, rows=None):
+        self._sc, self._name, self._job, self._sink, self._type = sc, name, None, None, None
+        self._sid = None
+        if rows is not None:
+            self._sid = sc._engine.add_bytes(rows)
+            sc._streams[name] = self._sid
+
+    def name(self):
+        return self._name
+
+    def len(self):
+        if self._job is None:
+            return self._sc._engine.stream_rows(self._sid)
+        return self._job.output_rows(self._sink)
+
+    def load(self, ty=None, rows=None):
+        """Generator over rows, deserialised like scannerpy.types (types.py:91-132): frame columns
+        as ndarrays, `Histogram` as a list of three int32 arrays, anything else as bytes."""
+        if self._job is None:
+            raise ScannerException(f"stream {self._name} has not been written by a job")
+        ty = ty or self._type
+        idx = range(self.len()) if rows is None else rows
+        for i in idx:
+            r = self._job.output_row(self._sink, i)
+            if r is None or isinstance(r, np.ndarray):
+                yield r
+            elif ty == "Histogram":
+                a = np.frombuffer(r, np.int32)
+                yield [a[0:16], a[16:32], a[32:48]]
+            else:
+                yield r
+
+    def delete(self, sc=None):
+        self._job = None
+
+
+# ------------------------------------------------------------------------------------------------
+class Client:
+    """In-process stand-in for scannerpy.Client: same graph-building surface, runs on local GPUs."""
+
+    def __init__(self, gpus=None, instances_per_gpu=0, cpu_instances=1, load_stdlib=True, **_ignored):
+        import torch
+        if gpus is None:
+            gpus = list(range(torch.cuda.device_count())) if torch.cuda.is_available() else []
+        self._engine = E.Engine(gpus, instances_per_gpu, cpu_instances)
+        self._streams = {}
+        self._op_protos = {}
+        self.ops, self.streams, self.io = OpGenerator(self), StreamsGenerator(self), IOGenerator(self)
+        if load_stdlib:
+            E.load_stdlib()
+            std = protolite.parse_proto(open(os.path.join(os.path.dirname(E.ENGINE_PATH), "..", "csrc", "ops",
+                                                          "stdlib_args.proto")).read())
+            self._op_protos["Blur"] = {"init": std["BlurArgs"]}
+            self._op_protos["Resize"] = {"stream": std["ResizeArgs"]}
+
+    def load_op(self, so_path, proto_path=None, protos=None):
+        """Load an op library (reference Client.load_op, client.py:514-537).  `protos` maps op name to
+        {"init": MessageName, "stream": MessageName} inside `proto_path`."""
+        E.load_op_library(so_path)
+        if proto_path:
+            msgs = protolite.parse_proto(open(proto_path).read())
+            for op, d in (protos or {}).items():
+                self._op_protos[op] = {k: msgs[v] for k, v in d.items()}
+
+    def _op_outputs(self, name):
+        g = E.Graph()
+        n_in = E.list_ops()[name]["inputs"]
+        src = g.add_source(True)
+        # a scratch graph only to ask the registry for the op's output columns
+        idx = E.lib().scn_graph_add_op(g._h, name.encode(), 0, (E._c.c_int * max(1, n_in))(*([src] * n_in)),
+                                       (E._c.c_char_p * max(1, n_in))(*([b"frame"] * n_in)), n_in, None, 0, -1,
+                                       (E._c.c_int * 1)(), 0, -1)
+        E.check(idx, f"op {name}")
+        cols = g.op_outputs(idx)
+        types = self._op_output_types.get(name) if hasattr(self, "_op_output_types") else None
+        return [(c, (types or {}).get(c, c in ("frame", "flow"))) for c in cols]
+
+    def run(self, outputs, perf_params, cache_mode=CacheMode.Error, show_progress=False, out_dir=None, **_ignored):
+        outputs = outputs if isinstance(outputs, (list, tuple)) else [outputs]
+        order, seen = [], set()
+
+        def visit(node):
+            if id(node) in seen:
+                return
+            seen.add(id(node))
+            for c in node.inputs:
+                visit(c._op)
+            order.append(node)
+
+        for o in outputs:
+            visit(o)
+        g = E.Graph()
+        index, n_jobs = {}, None
+        for node in order:
+            if node.kind == "input":
+                index[id(node)] = g.add_source(isinstance(node.streams[0], NamedVideoStream))
+                n_jobs = len(node.streams) if n_jobs is None else n_jobs
+                if len(node.streams) != n_jobs:
+                    raise ScannerException("all Inputs must list the same number of streams")
+            elif node.kind == "op":
+                ins = [(index[id(c._op)], c._col) for c in node.inputs]
+                index[id(node)] = g.add_op(node.name, ins, int(node.device), node.args, node.batch, node.stencil,
+                                           node.warmup)
+            elif node.kind in ("sample", "space"):
+                c = node.inputs[0]
+                fn = g.add_sample if node.kind == "sample" else g.add_space
+                index[id(node)] = fn((index[id(c._op)], c._col))
+            elif node.kind == "output":
+                c = node.inputs[0]
+                index[id(node)] = g.add_sink((index[id(c._op)], c._col), node.streams[0].name())
+        jobs = []
+        for j in range(n_jobs):
+            job = E.Job()
+            for node in order:
+                if node.kind == "input":
+                    job.bind_source(index[id(node)], node.streams[j]._sid)
+                elif node.kind in ("sample", "space"):
+                    args = node.per_stream[j if len(node.per_stream) > 1 else 0]
+                    job.set_sampler(index[id(node)], node.sampler, args)
+                elif node.kind == "op" and node.per_stream:
+                    job.set_stream_args(index[id(node)], node.per_stream[j if len(node.per_stream) > 1 else 0])
+            jobs.append(job)
+        try:
+            self._engine.run(g, jobs, perf_params.work_packet_size, perf_params.io_packet_size, out_dir)
+        except E.EngineError as e:
+            raise ScannerException(str(e)) from e
+        for node in order:
+            if node.kind == "output":
+                src_col = node.inputs[0]
+                for j, s in enumerate(node.streams):
+                    s._job, s._sink = jobs[j], index[id(node)]
+                    s._type = "Histogram" if src_col._col == "histogram" else None
+        self._last_graph = g
+        return len(jobs)
+
+    def stats(self):
+        return self._engine.stats()
+
+    def stop(self):
+        self._engine.close()

@@ -1,0 +1,86 @@
+"""The scannerpy-shaped surface (scanner_b200.client) on the CPU with the test op library:
+the same call shapes as the reference's tests/py_test.py and examples/tutorials/00_basic.py."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import synth
+import scanner_b200 as sp
+from scanner_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sc():
+    oracle.build()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
+    c = sp.Client(gpus=[], cpu_instances=2)
+    so = os.path.join(ROOT, "build", "tests", "libtest_plugin_ops.so")
+    if "TestWindow" not in E.list_ops():
+        c.load_op(so)
+    from scanner_b200 import protolite
+    msgs = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
+    c._op_protos["TestAffine"] = {"init": msgs["TestScaleArgs"], "stream": msgs["TestOffsetArgs"]}
+    c._op_protos["TestResizeOracle"] = {"stream": msgs["TestSizeArgs"]}
+    yield c
+    c.stop()
+
+
+def test_basic_tutorial_shape(sc):
+    """examples/tutorials/00_basic.py:27-80 -- two videos, Histogram, len(hist)==3, 16 bins."""
+    clips = [np.stack([synth.smooth_frame(10 * k + i, 48, 64) for i in range(9 + k)]) for k in range(2)]
+    v1 = sp.NamedVideoStream(sc, "example1", frames=clips[0])
+    v2 = sp.NamedVideoStream(sc, "example2", frames=clips[1])
+    frames = sc.io.Input([v1, v2])
+    hists = sc.ops.TestHistogramOracle(frame=frames)
+    o1, o2 = sp.NamedStream(sc, "example1_hist"), sp.NamedStream(sc, "example2_hist")
+    sc.run(sc.io.Output(hists, [o1, o2]), sp.PerfParams.estimate())
+    for clip, out, v in zip(clips, (o1, o2), (v1, v2)):
+        num_rows = 0
+        for i, hist in enumerate(out.load()):
+            assert len(hist) == 3 and hist[0].shape[0] == 16
+            assert (np.stack(hist) == oracle.hist16(clip[i])).all()
+            num_rows += 1
+        assert num_rows == v.len() == out.len()
+
+
+def test_streams_and_per_stream_args(sc):
+    rows = [struct.pack("<q", i) for i in range(40)]
+    a, b = sp.NamedStream(sc, "ints_a", rows=rows), sp.NamedStream(sc, "ints_b", rows=rows[:20])
+    col = sc.io.Input([a, b])
+    sampled = sc.streams.Stride(col, [4, 5])
+    aff = sc.ops.TestAffine(col=sampled, scale=2, offset=[100, 200])
+    oa, ob = sp.NamedStream(sc, "oa"), sp.NamedStream(sc, "ob")
+    sc.run(sc.io.Output(aff, [oa, ob]), sp.PerfParams.manual(2, 4))
+    assert [struct.unpack("<q", r)[0] for r in oa.load()] == [2 * i + 100 for i in range(0, 40, 4)]
+    assert [struct.unpack("<q", r)[0] for r in ob.load()] == [2 * i + 200 for i in range(0, 20, 5)]
+
+
+def test_gather_range_and_bounded_state(sc):
+    """reference py_test.py:407-423."""
+    rows = [struct.pack("<q", i) for i in range(40)]
+    a = sp.NamedStream(sc, "ints_c", rows=rows)
+    col = sc.io.Input([a])
+    inc = sc.ops.TestIncrementBounded(ignore=col, bounded_state=3)
+    g = sc.streams.Gather(inc, indices=[[0, 10, 25, 26, 27]])
+    out = sp.NamedStream(sc, "test_bounded_state")
+    sc.run(sc.io.Output(g, [out]), sp.PerfParams.estimate())
+    assert [struct.unpack("=q", buf)[0] for buf in out.load()] == [0, 3, 3, 4, 5]
+    r = sc.streams.Range(col, [(0, 30)])
+    out2 = sp.NamedStream(sc, "range")
+    sc.run(sc.io.Output(r, [out2]), sp.PerfParams.estimate())
+    assert out2.len() == 30
+
+
+def test_errors_are_scanner_exceptions(sc):
+    with pytest.raises(sp.ScannerException):
+        sc.ops.NoSuchOp
+    rows = [struct.pack("<q", i) for i in range(4)]
+    a = sp.NamedStream(sc, "ints_d", rows=rows)
+    with pytest.raises(sp.ScannerException, match="does not take argument"):
+        sc.ops.TestAffine(col=sc.io.Input([a]), bogus=1)

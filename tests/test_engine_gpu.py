@@ -211,3 +211,26 @@ def test_many_clips_sharded_over_instances(eng):
         for i in range(len(want)):
             assert (hist[i] == oracle.hist16(want[i])).all()
     assert eng.stats()["counters"]["instances"] == 3
+
+
+def test_client_surface_on_gpu_like_tutorial_00():
+    """The scannerpy-shaped API end to end on the GPU: H.264 in, Stride, GPU Histogram + Resize."""
+    import scanner_b200 as sp
+    data, want = make_clip(21, 24, 96, 128, 6)
+    sc = sp.Client(gpus=[0], instances_per_gpu=2)
+    video = sp.NamedVideoStream(sc, "clip", data=data)
+    assert video.len() == 24
+    frames = sc.io.Input([video])
+    strided = sc.streams.Stride(frames, [3])
+    hists = sc.ops.Histogram(frame=strided, device=sp.DeviceType.GPU)
+    small = sc.ops.Resize(frame=strided, device=sp.DeviceType.GPU, width=[64], height=[48])
+    o_h, o_r = sp.NamedStream(sc, "clip_hist"), sp.NamedStream(sc, "clip_small")
+    sc.run([sc.io.Output(hists, [o_h]), sc.io.Output(small, [o_r])], sp.PerfParams.manual(4, 8))
+    got = list(o_h.load())
+    assert len(got) == 8
+    for k, hist in enumerate(got):
+        assert len(hist) == 3 and hist[0].shape[0] == 16
+        assert (np.stack(hist) == oracle.hist16(want[3 * k])).all()
+    for k, fr in enumerate(o_r.load()):
+        assert (fr == oracle.resize(want[3 * k], 64, 48)).all()
+    sc.stop()
