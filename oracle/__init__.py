@@ -114,3 +114,30 @@ def index_column(start, n):
     out = np.zeros(n * 8, np.uint8)
     lib().orc_index_column(ctypes.c_int64(start), ctypes.c_int64(n), _p(out))
     return out
+
+
+def bgr2gray(frame):
+    """cv::cvtColor(COLOR_BGR2GRAY) as the reference applies it to its RGB frames
+    (tests/test_ops.cpp:91-92): 15-bit fixed point, first channel weighted 0.114."""
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    h, w, c = frame.shape
+    assert c == 3
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_bgr2gray_u8c3(_p(frame), w, h, _p(out))
+    return out
+
+
+def farneback(gray0, gray1, num_levels=3, pyr_scale=0.5, win_size=15, num_iters=3, poly_n=5, poly_sigma=1.2):
+    """cv::FarnebackOpticalFlow(3, 0.5, false, 15, 3, 5, 1.2, 0)->calc (tests/test_ops.cpp:68-69,94)."""
+    gray0 = np.ascontiguousarray(gray0, dtype=np.uint8)
+    gray1 = np.ascontiguousarray(gray1, dtype=np.uint8)
+    h, w = gray0.shape
+    out = np.zeros((h, w, 2), np.float32)
+    lib().orc_farneback_u8(_p(gray0), _p(gray1), w, h, int(num_levels), ctypes.c_double(pyr_scale), int(win_size),
+                           int(num_iters), int(poly_n), ctypes.c_double(poly_sigma), _p(out))
+    return out
+
+
+def optical_flow(frame0, frame1):
+    """The reference's OpticalFlow op on one stencil window {0,1} of RGB frames -> (H,W,2) float32."""
+    return farneback(bgr2gray(frame0), bgr2gray(frame1))

@@ -21,7 +21,7 @@ import cv2
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from oracle.synth import rand_frame, smooth_frame, nv12_surface  # noqa: E402
+from oracle.synth import rand_frame, smooth_frame, nv12_surface, flow_pair  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 
@@ -128,6 +128,16 @@ def main():
         cases[f"c{i}_meta"] = np.array([seed, h, w, pitch], np.int64)
         cases[f"c{i}_out"] = np_nv12_to_rgb(luma, chroma, w)
     np.savez_compressed(os.path.join(OUT, "nv12_np.npz"), **cases)
+    # ---- optical flow: cv2 gray conversion + cv2 Farneback with the reference's parameters
+    cases = {}
+    for i, (h, w, kind) in enumerate([(96, 128, "shift"), (64, 80, "shift"), (120, 160, "noise"), (37, 53, "shift")]):
+        seed = 500 + i
+        a, b = flow_pair(seed, h, w, kind)
+        cases[f"c{i}_meta"] = np.array([seed, h, w, 0 if kind == "shift" else 1], np.int64)
+        g0, g1 = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY), cv2.cvtColor(b, cv2.COLOR_BGR2GRAY)
+        cases[f"c{i}_gray0"] = g0
+        cases[f"c{i}_flow"] = cv2.FarnebackOpticalFlow_create(3, 0.5, False, 15, 3, 5, 1.2, 0).calc(g0, g1, None)
+    np.savez_compressed(os.path.join(OUT, "flow_cv2.npz"), **cases)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -28,3 +28,27 @@ def nv12_surface(seed, h, w, pitch=None):
     luma = rng.integers(0, 256, (h, pitch), dtype=np.uint8)
     chroma = rng.integers(0, 256, (h // 2, pitch), dtype=np.uint8)
     return luma, chroma
+
+
+def flow_pair(seed, h, w, kind="shift"):
+    """Two RGB frames with a known relation: "shift" = smooth texture translated by a sub-pixel
+    amount (well-conditioned flow), "noise" = unrelated noise (ill-conditioned: tests robustness).
+    No cv2 here: the texture is a sum of sinusoids, the shift is analytic."""
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rand_frame(seed, h, w), rand_frame(seed + 1, h, w)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    dx, dy = 1.5, -0.75
+
+    def tex(x, y):
+        out = np.zeros((h, w, 3))
+        for c in range(3):
+            acc = np.zeros((h, w))
+            r2 = np.random.default_rng(seed * 10 + c)
+            for _ in range(6):
+                fx, fy, ph = r2.uniform(0.02, 0.25), r2.uniform(0.02, 0.25), r2.uniform(0, 6.28)
+                acc += np.sin(fx * x + fy * y + ph)
+            out[..., c] = 127.5 + 20 * acc
+        return np.clip(out, 0, 255).astype(np.uint8)
+
+    return tex(xx, yy), tex(xx - dx, yy - dy)
