@@ -130,6 +130,23 @@ SCN_API int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
                          uint8_t* const* host_dst_ptrs, int dst_w, int dst_h, const void* plan,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * OpticalFlow  (replaces OpticalFlowKernelCPU::execute, tests/test_ops.cpp:79-98:
+ *   cvtColor(COLOR_BGR2GRAY) on each RGB frame of the {0,1} stencil window, then
+ *   cv::FarnebackOpticalFlow(numLevels, pyrScale, fastPyramids=false, winSize, numIters, polyN,
+ *   polySigma, flags=0)->calc; the reference constructs it with (3, 0.5, 15, 3, 5, 1.2), :68-69)
+ * For each of n frame pairs writes a dense flow field float32[H][W][2] (dx, dy) to
+ * host_flow_ptrs[i].  Floating point: matches cv2.calcOpticalFlowFarneback within a tolerance
+ * (max |d| <= 2e-3 px on well-conditioned input; see tests/test_flow_gpu.py), not bit-exact.
+ * `workspace` is caller-owned device scratch of scn_farneback_workspace_bytes(w, h) bytes,
+ * reusable across calls on the same stream.
+ */
+SCN_API size_t scn_farneback_workspace_bytes(int width, int height);
+SCN_API int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const uint8_t* const* host_next_ptrs,
+                               int n, int width, int height, float* const* host_flow_ptrs, int num_levels,
+                               double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,459 @@
+// flow.cu -- dense optical flow of the reference's OpticalFlow op on the GPU (sm_100a).
+// Replaces OpticalFlowKernelCPU::execute (reference tests/test_ops.cpp:63-111):
+//   gray = cvtColor(frame, COLOR_BGR2GRAY)                           (15-bit fixed point)
+//   flow = cv::FarnebackOpticalFlow(3, 0.5, false, 15, 3, 5, 1.2, 0)->calc(gray0, gray1)
+// The Farneback arithmetic is OpenCV's (modules/video/src/optflowgf.cpp): per pyramid level
+//   I_i   = resize(GaussianBlur(gray_i as f32, smooth_sz, sigma), level size)   (fastPyramids=false)
+//   R_i   = polynomial expansion (separable (2n+1)-tap Gaussian-weighted basis, 5 coefficients)
+//   M     = UpdateMatrices(R0, R1 warped by the current flow)        (5 floats per pixel)
+//   flow  = solve 2x2 from the winSize x winSize box average of M,   numIters times
+// Floating point: sums are taken in a different order than OpenCV's SIMD code, so parity is within
+// a tolerance (tests/test_flow_gpu.py), not bit-exact.  The box sums and the 2x2 solve run in
+// double like OpenCV's (the determinant cancels catastrophically in float).
+// All kernels are plain per-pixel / separable memory-bound passes (no tensor cores).
+#include <math.h>
+#include <string.h>
+
+#include "scn_common.cuh"
+
+namespace scn {
+namespace {
+
+constexpr int kMaxTaps = 32;   // Gaussian half-width limit (ksize <= 63)
+constexpr int kMaxPolyN = 7;
+
+struct GaussK {
+  int radius;
+  float k[2 * kMaxTaps + 1];
+};
+struct PolyK {
+  int n;
+  float g[kMaxPolyN + 1], xg[kMaxPolyN + 1], xxg[kMaxPolyN + 1];
+  float ig11, ig03, ig33, ig55;
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// RGB24 -> gray (as float) with OpenCV's BGR2GRAY weights applied to channel order as stored
+__global__ void gray_kernel(const uint8_t* __restrict__ src, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* p = src + (size_t)i * 3;
+  dst[i] = (float)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+}
+
+__global__ void gauss_h_kernel(const float* __restrict__ src, int w, int h, GaussK gk, float* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float* row = src + (size_t)y * w;
+  float s = 0.f;
+  for (int i = -gk.radius; i <= gk.radius; ++i) s += gk.k[i + gk.radius] * row[reflect101(x + i, w)];
+  dst[(size_t)y * w + x] = s;
+}
+
+__global__ void gauss_v_kernel(const float* __restrict__ src, int w, int h, GaussK gk, float* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  float s = 0.f;
+  for (int i = -gk.radius; i <= gk.radius; ++i) s += gk.k[i + gk.radius] * src[(size_t)reflect101(y + i, h) * w + x];
+  dst[(size_t)y * w + x] = s;
+}
+
+// cv::resize INTER_LINEAR on float images with CN channels; `mul` scales the result (flow upsample)
+template <int CN>
+__global__ void resize_f32_kernel(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst, int dw,
+                                  int dh, double sx, double sy, float mul) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= dw) return;
+  float fy = (float)__dsub_rn(__dmul_rn((double)y + 0.5, sy), 0.5);
+  int iy = (int)floorf(fy);
+  fy -= (float)iy;
+  if (iy < 0) { fy = 0.f; iy = 0; }
+  if (iy >= sh - 1) { fy = 0.f; iy = sh - 1; }
+  const int iy1 = min(iy + 1, sh - 1);
+  float fx = (float)__dsub_rn(__dmul_rn((double)x + 0.5, sx), 0.5);
+  int ix = (int)floorf(fx);
+  fx -= (float)ix;
+  if (ix < 0) { fx = 0.f; ix = 0; }
+  if (ix >= sw - 1) { fx = 0.f; ix = sw - 1; }
+  const int ix1 = min(ix + 1, sw - 1);
+#pragma unroll
+  for (int c = 0; c < CN; ++c) {
+    const float a = src[((size_t)iy * sw + ix) * CN + c], b = src[((size_t)iy * sw + ix1) * CN + c];
+    const float d = src[((size_t)iy1 * sw + ix) * CN + c], e = src[((size_t)iy1 * sw + ix1) * CN + c];
+    const float top = __fadd_rn(__fmul_rn(a, 1.f - fx), __fmul_rn(b, fx));
+    const float bot = __fadd_rn(__fmul_rn(d, 1.f - fx), __fmul_rn(e, fx));
+    dst[((size_t)y * dw + x) * CN + c] = __fadd_rn(__fmul_rn(top, 1.f - fy), __fmul_rn(bot, fy)) * mul;
+  }
+}
+
+// polynomial expansion, vertical pass: (t0,t1,t2) per pixel, rows clamped at the border
+__global__ void poly_v_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* __restrict__ dst3) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  float t0 = src[(size_t)y * w + x] * pk.g[0], t1 = 0.f, t2 = 0.f;
+  for (int k = 1; k <= pk.n; ++k) {
+    const float sp = src[(size_t)clampi(y + k, 0, h - 1) * w + x], sm = src[(size_t)clampi(y - k, 0, h - 1) * w + x];
+    t0 += pk.g[k] * (sp + sm);
+    t1 += pk.xg[k] * (sp - sm);
+    t2 += pk.xxg[k] * (sp + sm);
+  }
+  float* d = dst3 + ((size_t)y * w + x) * 3;
+  d[0] = t0;
+  d[1] = t1;
+  d[2] = t2;
+}
+
+// horizontal pass: columns clamped (OpenCV replicates the edge triple into its row padding)
+__global__ void poly_h_kernel(const float* __restrict__ src3, int w, int h, PolyK pk, float* __restrict__ dst5) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float* row = src3 + (size_t)y * w * 3;
+  const float* c0 = row + (size_t)x * 3;
+  float b1 = c0[0] * pk.g[0], b2 = 0.f, b3 = c0[1] * pk.g[0], b4 = 0.f, b5 = c0[2] * pk.g[0], b6 = 0.f;
+  for (int k = 1; k <= pk.n; ++k) {
+    const float* p = row + (size_t)clampi(x + k, 0, w - 1) * 3;
+    const float* m = row + (size_t)clampi(x - k, 0, w - 1) * 3;
+    const float tg = p[0] + m[0];
+    b1 += tg * pk.g[k];
+    b2 += (p[0] - m[0]) * pk.xg[k];
+    b4 += tg * pk.xxg[k];
+    b3 += (p[1] + m[1]) * pk.g[k];
+    b6 += (p[1] - m[1]) * pk.xg[k];
+    b5 += (p[2] + m[2]) * pk.g[k];
+  }
+  float* d = dst5 + ((size_t)y * w + x) * 5;
+  d[1] = b2 * pk.ig11;
+  d[0] = b3 * pk.ig11;
+  d[3] = b1 * pk.ig03 + b4 * pk.ig33;
+  d[2] = b1 * pk.ig03 + b5 * pk.ig33;
+  d[4] = b6 * pk.ig55;
+}
+
+__global__ void update_matrices_kernel(const float* __restrict__ R0, const float* __restrict__ R1,
+                                       const float* __restrict__ flow, int w, int h, float* __restrict__ M) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
+  const int BORDER = 5;
+  const float* r0 = R0 + ((size_t)y * w + x) * 5;
+  const float dx = flow[((size_t)y * w + x) * 2], dy = flow[((size_t)y * w + x) * 2 + 1];
+  float fx = (float)x + dx, fy = (float)y + dy;
+  const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+  fx -= (float)x1;
+  fy -= (float)y1;
+  float r2, r3, r4, r5, r6;
+  if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+    const float* p = R1 + ((size_t)y1 * w + x1) * 5;
+    const float* q = p + (size_t)w * 5;
+    r2 = a00 * p[0] + a01 * p[5] + a10 * q[0] + a11 * q[5];
+    r3 = a00 * p[1] + a01 * p[6] + a10 * q[1] + a11 * q[6];
+    r4 = a00 * p[2] + a01 * p[7] + a10 * q[2] + a11 * q[7];
+    r5 = a00 * p[3] + a01 * p[8] + a10 * q[3] + a11 * q[8];
+    r6 = a00 * p[4] + a01 * p[9] + a10 * q[4] + a11 * q[9];
+    r4 = (r0[2] + r4) * 0.5f;
+    r5 = (r0[3] + r5) * 0.5f;
+    r6 = (r0[4] + r6) * 0.25f;
+  } else {
+    r2 = r3 = 0.f;
+    r4 = r0[2];
+    r5 = r0[3];
+    r6 = r0[4] * 0.5f;
+  }
+  r2 = (r0[0] - r2) * 0.5f;
+  r3 = (r0[1] - r3) * 0.5f;
+  r2 += r4 * dy + r6 * dx;
+  r3 += r6 * dy + r5 * dx;
+  if ((unsigned)(x - BORDER) >= (unsigned)(w - BORDER * 2) || (unsigned)(y - BORDER) >= (unsigned)(h - BORDER * 2)) {
+    const float scale = (x < BORDER ? border[x] : 1.f) * (x >= w - BORDER ? border[w - x - 1] : 1.f) *
+                        (y < BORDER ? border[y] : 1.f) * (y >= h - BORDER ? border[h - y - 1] : 1.f);
+    r2 *= scale;
+    r3 *= scale;
+    r4 *= scale;
+    r5 *= scale;
+    r6 *= scale;
+  }
+  float* m = M + ((size_t)y * w + x) * 5;
+  m[0] = r4 * r4 + r6 * r6;
+  m[1] = (r4 + r5) * r6;
+  m[2] = r5 * r5 + r6 * r6;
+  m[3] = r4 * r2 + r6 * r3;
+  m[4] = r6 * r2 + r5 * r3;
+}
+
+// box filter, vertical pass in double (rows clamped); one thread per (x, channel)
+__global__ void box_v_kernel(const float* __restrict__ M, int w, int h, int m, double* __restrict__ V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (i >= w * 5) return;
+  double s = 0.0;
+  for (int k = -m; k <= m; ++k) s += (double)M[(size_t)clampi(y + k, 0, h - 1) * w * 5 + i];
+  V[(size_t)y * w * 5 + i] = s;
+}
+
+// horizontal pass (columns clamped) + the 2x2 solve of FarnebackUpdateFlow_Blur
+__global__ void box_h_solve_kernel(const double* __restrict__ V, int w, int h, int m, double scale,
+                                   float* __restrict__ flow) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const double* row = V + (size_t)y * w * 5;
+  double hs[5] = {0, 0, 0, 0, 0};
+  for (int k = -m; k <= m; ++k) {
+    const double* p = row + (size_t)clampi(x + k, 0, w - 1) * 5;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) hs[c] += p[c];
+  }
+  const double g11 = hs[0] * scale, g12 = hs[1] * scale, g22 = hs[2] * scale, h1 = hs[3] * scale, h2 = hs[4] * scale;
+  const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+  flow[((size_t)y * w + x) * 2] = (float)((g11 * h2 - g12 * h1) * idet);
+  flow[((size_t)y * w + x) * 2 + 1] = (float)((g22 * h1 - g12 * h2) * idet);
+}
+
+// ---- host-side constants --------------------------------------------------------------------
+void make_gauss(int ksize, double sigma, GaussK& gk) {
+  static const float small_tab[4][7] = {{1.f},
+                                        {0.25f, 0.5f, 0.25f},
+                                        {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f},
+                                        {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f}};
+  gk.radius = ksize / 2;
+  if (sigma <= 0 && (ksize & 1) && ksize <= 7) {
+    for (int i = 0; i < ksize; ++i) gk.k[i] = small_tab[ksize >> 1][i];
+    return;
+  }
+  if (sigma <= 0) sigma = ((ksize - 1) * 0.5 - 1) * 0.3 + 0.8;
+  const double scale2x = -0.5 / (sigma * sigma);
+  double tmp[2 * kMaxTaps + 1], sum = 0;
+  for (int i = 0; i < ksize; ++i) {
+    const double x = i - (ksize - 1) * 0.5;
+    tmp[i] = exp(scale2x * x * x);
+    sum += tmp[i];
+  }
+  for (int i = 0; i < ksize; ++i) gk.k[i] = (float)(tmp[i] / sum);
+}
+
+void make_poly(int n, double sigma, PolyK& pk) {
+  float g[2 * kMaxPolyN + 1];
+  double s = 0;
+  for (int x = -n; x <= n; ++x) {
+    g[x + n] = (float)exp(-x * x / (2 * sigma * sigma));
+    s += g[x + n];
+  }
+  s = 1. / s;
+  for (int x = -n; x <= n; ++x) g[x + n] = (float)(g[x + n] * s);
+  pk.n = n;
+  for (int x = 0; x <= n; ++x) {
+    pk.g[x] = g[x + n];
+    pk.xg[x] = (float)(x * g[x + n]);
+    pk.xxg[x] = (float)(x * x * g[x + n]);
+  }
+  double G[6][6];
+  memset(G, 0, sizeof(G));
+  for (int y = -n; y <= n; ++y)
+    for (int x = -n; x <= n; ++x) {
+      G[0][0] += g[y + n] * g[x + n];
+      G[1][1] += g[y + n] * g[x + n] * x * x;
+      G[3][3] += g[y + n] * g[x + n] * x * x * x * x;
+      G[5][5] += g[y + n] * g[x + n] * x * x * y * y;
+    }
+  G[2][2] = G[0][3] = G[0][4] = G[3][0] = G[4][0] = G[1][1];
+  G[4][4] = G[3][3];
+  G[3][4] = G[4][3] = G[5][5];
+  double A[6][12];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 12; ++j) A[i][j] = j < 6 ? G[i][j] : (j - 6 == i ? 1.0 : 0.0);
+  for (int c = 0; c < 6; ++c) {
+    int p = c;
+    for (int r = c + 1; r < 6; ++r)
+      if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+    if (p != c)
+      for (int j = 0; j < 12; ++j) {
+        const double t = A[c][j];
+        A[c][j] = A[p][j];
+        A[p][j] = t;
+      }
+    const double d = A[c][c];
+    for (int j = 0; j < 12; ++j) A[c][j] /= d;
+    for (int r = 0; r < 6; ++r)
+      if (r != c) {
+        const double f = A[r][c];
+        for (int j = 0; j < 12; ++j) A[r][j] -= f * A[c][j];
+      }
+  }
+  pk.ig11 = (float)A[1][7];
+  pk.ig03 = (float)A[0][9];
+  pk.ig33 = (float)A[3][9];
+  pk.ig55 = (float)A[5][11];
+}
+
+struct Level {
+  int w, h, smooth;
+  double sigma;
+};
+
+int plan_levels(int width, int height, int num_levels, double pyr_scale, Level* lv /* [num_levels+1] */) {
+  int levels = num_levels, k;
+  double scale = 1;
+  for (k = 0; k < levels; ++k) {
+    scale *= pyr_scale;
+    if (width * scale < 32 || height * scale < 32) break;
+  }
+  levels = k;
+  for (k = 0; k <= levels; ++k) {
+    scale = 1;
+    for (int i = 0; i < k; ++i) scale *= pyr_scale;
+    lv[k].sigma = (1. / scale - 1) * 0.5;
+    int sm = (int)lrint(lv[k].sigma * 5) | 1;
+    lv[k].smooth = sm < 3 ? 3 : sm;
+    lv[k].w = (int)lrint(width * scale);
+    lv[k].h = (int)lrint(height * scale);
+  }
+  return levels;
+}
+
+// workspace layout (floats unless noted), all sized for the full-resolution level
+struct Workspace {
+  float *gray[2], *tmp, *blur, *I, *poly3, *R[2], *M, *flow_a, *flow_b;
+  double* V;
+};
+
+size_t carve(void* base, int w, int h, Workspace* ws) {
+  const size_t px = (size_t)w * h;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((uint8_t*)base + off) : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  Workspace tmpws;
+  Workspace& o = ws ? *ws : tmpws;
+  o.gray[0] = (float*)take(px * 4);
+  o.gray[1] = (float*)take(px * 4);
+  o.tmp = (float*)take(px * 4);
+  o.blur = (float*)take(px * 4);
+  o.I = (float*)take(px * 4);
+  o.poly3 = (float*)take(px * 12);
+  o.R[0] = (float*)take(px * 20);
+  o.R[1] = (float*)take(px * 20);
+  o.M = (float*)take(px * 20);
+  o.flow_a = (float*)take(px * 8);
+  o.flow_b = (float*)take(px * 8);
+  o.V = (double*)take(px * 40);
+  return off;
+}
+
+}  // namespace
+}  // namespace scn
+
+extern "C" size_t scn_farneback_workspace_bytes(int width, int height) {
+  if (width <= 0 || height <= 0) return 0;
+  return scn::carve(nullptr, width, height, nullptr);
+}
+
+extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const uint8_t* const* host_next_ptrs, int n,
+                                  int width, int height, float* const* host_flow_ptrs, int num_levels,
+                                  double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace scn;
+  if (n < 0 || width <= 0 || height <= 0 || num_levels < 0 || num_levels > 15 || pyr_scale <= 0 || pyr_scale >= 1 ||
+      win_size < 1 || num_iters < 1 || poly_n < 1 || poly_n > kMaxPolyN || poly_sigma <= 0)
+    return SCN_E_BADARG;
+  if (n == 0) return 0;
+  if (!host_prev_ptrs || !host_next_ptrs || !host_flow_ptrs || !workspace) return SCN_E_BADARG;
+  if (workspace_bytes < scn_farneback_workspace_bytes(width, height)) return SCN_E_BADARG;
+  if (height > 65535) return SCN_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws;
+  carve(workspace, width, height, &ws);
+  Level lv[16];
+  const int levels = plan_levels(width, height, num_levels, pyr_scale, lv);
+  for (int k = 0; k <= levels; ++k)
+    if (lv[k].smooth / 2 > kMaxTaps) return SCN_E_UNSUPPORTED;
+  PolyK pk;
+  make_poly(poly_n, poly_sigma, pk);
+  const int T = 128;
+  auto grid2 = [&](int w, int h) { return dim3((unsigned)((w + T - 1) / T), (unsigned)h); };
+
+  for (int pair = 0; pair < n; ++pair) {
+    const int npx = width * height;
+    {
+      LaunchScope ls("flow_gray_kernel", st);
+      gray_kernel<<<(npx + 255) / 256, 256, 0, st>>>(host_prev_ptrs[pair], npx, ws.gray[0]);
+    }
+    {
+      LaunchScope ls("flow_gray_kernel", st);
+      gray_kernel<<<(npx + 255) / 256, 256, 0, st>>>(host_next_ptrs[pair], npx, ws.gray[1]);
+    }
+    float* prev_flow = nullptr;
+    int pw = 0, ph = 0;
+    for (int k = levels; k >= 0; --k) {
+      const int w = lv[k].w, h = lv[k].h;
+      // the coarser levels ping-pong between two scratch flows; level 0 writes the caller's frame
+      float* flow = k == 0 ? host_flow_ptrs[pair] : (prev_flow == ws.flow_a ? ws.flow_b : ws.flow_a);
+      if (!prev_flow) {
+        cudaError_t e = cudaMemsetAsync(flow, 0, (size_t)w * h * 8, st);
+        if (e != cudaSuccess) return (int)e;
+      } else {
+        LaunchScope ls("flow_resize_kernel", st);
+        resize_f32_kernel<2><<<grid2(w, h), T, 0, st>>>(prev_flow, pw, ph, flow, w, h, (double)pw / w,
+                                                        (double)ph / h, (float)(1. / pyr_scale));
+      }
+      GaussK gk;
+      make_gauss(lv[k].smooth, lv[k].sigma, gk);
+      for (int i = 0; i < 2; ++i) {
+        {
+          LaunchScope ls("flow_gauss_h_kernel", st);
+          gauss_h_kernel<<<grid2(width, height), T, 0, st>>>(ws.gray[i], width, height, gk, ws.tmp);
+        }
+        {
+          LaunchScope ls("flow_gauss_v_kernel", st);
+          gauss_v_kernel<<<grid2(width, height), T, 0, st>>>(ws.tmp, width, height, gk, ws.blur);
+        }
+        const float* I = ws.blur;
+        if (w != width || h != height) {
+          LaunchScope ls("flow_resize_kernel", st);
+          resize_f32_kernel<1><<<grid2(w, h), T, 0, st>>>(ws.blur, width, height, ws.I, w, h, (double)width / w,
+                                                          (double)height / h, 1.f);
+          I = ws.I;
+        }
+        {
+          LaunchScope ls("flow_poly_v_kernel", st);
+          poly_v_kernel<<<grid2(w, h), T, 0, st>>>(I, w, h, pk, ws.poly3);
+        }
+        {
+          LaunchScope ls("flow_poly_h_kernel", st);
+          poly_h_kernel<<<grid2(w, h), T, 0, st>>>(ws.poly3, w, h, pk, ws.R[i]);
+        }
+      }
+      {
+        LaunchScope ls("flow_update_matrices_kernel", st);
+        update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(ws.R[0], ws.R[1], flow, w, h, ws.M);
+      }
+      const int m = win_size / 2;
+      for (int it = 0; it < num_iters; ++it) {
+        {
+          LaunchScope ls("flow_box_v_kernel", st);
+          box_v_kernel<<<grid2(w * 5, h), T, 0, st>>>(ws.M, w, h, m, ws.V);
+        }
+        {
+          LaunchScope ls("flow_box_h_solve_kernel", st);
+          box_h_solve_kernel<<<grid2(w, h), T, 0, st>>>(ws.V, w, h, m, 1.0 / ((double)win_size * win_size), flow);
+        }
+        if (it < num_iters - 1) {
+          LaunchScope ls("flow_update_matrices_kernel", st);
+          update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(ws.R[0], ws.R[1], flow, w, h, ws.M);
+        }
+      }
+      prev_flow = flow;
+      pw = w;
+      ph = h;
+    }
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return 0;
+}

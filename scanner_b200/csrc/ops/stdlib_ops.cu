@@ -179,5 +179,49 @@ REGISTER_OP(Blur).frame_input("frame").frame_output("frame").protobuf_name("Blur
 
 REGISTER_KERNEL(Blur, BlurKernelGPU).device(DeviceType::GPU).batch(16).num_devices(1);
 
+// ---------------------------------------------------------------------------------------------
+// OpticalFlow: stencil {0,1}, Farneback with the reference's constructor arguments
+// (tests/test_ops.cpp:68-69), output Frame(H, W, 2, F32) on the GPU (:85-87).
+class OpticalFlowKernelGPU : public StenciledKernel, public VideoKernel {
+ public:
+  OpticalFlowKernelGPU(const KernelConfig& config) : StenciledKernel(config), device_(config.devices[0]) {}
+  ~OpticalFlowKernelGPU() {
+    if (workspace_) delete_buffer(device_, workspace_);
+  }
+
+  void new_frame_info() override {
+    if (workspace_) delete_buffer(device_, workspace_);
+    workspace_bytes_ = scn_farneback_workspace_bytes(frame_info_.width(), frame_info_.height());
+    workspace_ = new_buffer(device_, workspace_bytes_);
+  }
+
+  void execute(const StenciledElements& input_columns, Elements& output_columns) override {
+    const Elements& window = input_columns[0];
+    CU_CHECK(cudaSetDevice(device_.id));
+    check_frame(device_, window[0]);
+    const Frame* f0 = window[0].as_const_frame();
+    const Frame* f1 = window[1].as_const_frame();
+    require_rgb8(f0, "OpticalFlow");
+    if (!(f0->as_frame_info() == f1->as_frame_info())) LOG(FATAL) << "OpticalFlow: frames of one window differ in size";
+    FrameInfo out_info(f0->height(), f0->width(), 2, FrameType::F32);
+    Frame* out = new_frame(device_, out_info);
+    const u8* prev = f0->data;
+    const u8* next = f1->data;
+    float* flow = reinterpret_cast<float*>(out->data);
+    SCN_CHECK(scn_farneback_u8c3(&prev, &next, 1, f0->width(), f0->height(), &flow, 3, 0.5, 15, 3, 5, 1.2, workspace_,
+                                 workspace_bytes_, device_stream(device_)));
+    insert_frame(output_columns[0], out);
+  }
+
+ private:
+  DeviceHandle device_;
+  u8* workspace_ = nullptr;
+  size_t workspace_bytes_ = 0;
+};
+
+REGISTER_OP(OpticalFlow).frame_input("frame").frame_output("flow").stencil({0, 1});
+
+REGISTER_KERNEL(OpticalFlow, OpticalFlowKernelGPU).device(DeviceType::GPU).num_devices(1);
+
 }  // namespace
 }  // namespace scanner

@@ -138,3 +138,23 @@ def nv12_hist_resize(surfaces, width, height, dst_w, dst_h, plan=None, want_resi
                                          pptr, _stream())
     cabi.check(rc, "scn_nv12_hist_resize")
     return hist, res
+
+
+def optical_flow(prev_frames, next_frames, num_levels=3, pyr_scale=0.5, win_size=15, num_iters=3, poly_n=5,
+                 poly_sigma=1.2, workspace=None):
+    """Farneback flow of n frame pairs: (N,H,W,3) uint8 x2 -> (N,H,W,2) float32 (reference OpticalFlow op)."""
+    _need_cuda(prev_frames, next_frames)
+    prev_frames, next_frames = prev_frames.contiguous(), next_frames.contiguous()
+    n, h, w, _ = prev_frames.shape
+    out = torch.empty((n, h, w, 2), dtype=torch.float32, device=prev_frames.device)
+    need = cabi.lib().scn_farneback_workspace_bytes(w, h)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=prev_frames.device)
+    fb = h * w * 3
+    pp, k1 = cabi.ptr_array([prev_frames.data_ptr() + i * fb for i in range(n)])
+    np_, k2 = cabi.ptr_array([next_frames.data_ptr() + i * fb for i in range(n)])
+    op, k3 = cabi.ptr_array([out.data_ptr() + i * h * w * 8 for i in range(n)])
+    rc = cabi.lib().scn_farneback_u8c3(pp, np_, n, w, h, op, num_levels, pyr_scale, win_size, num_iters, poly_n,
+                                       poly_sigma, workspace.data_ptr(), workspace.numel(), _stream())
+    cabi.check(rc, "scn_farneback_u8c3")
+    return out

@@ -1,0 +1,78 @@
+"""OpticalFlow (Farneback) on the GPU against the oracle (itself pinned to cv2 within 1e-4 px).
+Floating point: the CUDA kernels sum in a different order and keep the polynomial expansion in
+float32.  Stated tolerance: max |d| <= 2e-3 px and mean |d| <= 1e-4 px on well-conditioned
+(smooth, textured) input; on pure noise (ill-conditioned 2x2 systems) mean |d| <= 1e-3 px."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import synth
+from scanner_b200 import engine as E
+from scanner_b200 import kernels
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("h,w", [(96, 128), (64, 80), (120, 160), (37, 53), (270, 480)])
+def test_flow_vs_oracle_smooth_motion(h, w):
+    a, b = synth.flow_pair(600 + h, h, w, "shift")
+    got = kernels.optical_flow(dev(a[None]), dev(b[None]))[0].cpu().numpy()
+    want = oracle.optical_flow(a, b)
+    d = np.abs(got - want)
+    assert d.max() <= 2e-3 and d.mean() <= 1e-4, (d.max(), d.mean())
+
+
+def test_flow_vs_cv2_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "flow_cv2.npz"))
+    for k in sorted(x[:-5] for x in g.files if x.endswith("_meta")):
+        seed, h, w, kind = [int(x) for x in g[k + "_meta"]]
+        a, b = synth.flow_pair(seed, h, w, "shift" if kind == 0 else "noise")
+        got = kernels.optical_flow(dev(a[None]), dev(b[None]))[0].cpu().numpy()
+        d = np.abs(got - g[k + "_flow"])
+        if kind == 0:
+            assert d.max() <= 2e-3 and d.mean() <= 1e-4, (k, d.max(), d.mean())
+        else:
+            assert d.mean() <= 1e-3 and np.quantile(d, 0.999) <= 5e-2, (k, d.max(), d.mean())
+
+
+def test_flow_batch_and_identity():
+    frames = np.stack([synth.flow_pair(700, 96, 128, "shift")[i] for i in (0, 1, 0)])
+    out = kernels.optical_flow(dev(frames[:2]), dev(frames[1:])).cpu().numpy()
+    assert np.abs(out[0] - oracle.optical_flow(frames[0], frames[1])).max() <= 2e-3
+    assert np.abs(out[1] - oracle.optical_flow(frames[1], frames[2])).max() <= 2e-3
+    # identical frames: NOT zero flow -- the last row/column take OpenCV's out-of-range branch of
+    # UpdateMatrices (r2 = r3 = 0) and the coarse levels spread that inwards; same as the oracle
+    same = kernels.optical_flow(dev(frames[:1]), dev(frames[:1]))[0].cpu().numpy()
+    assert np.abs(same - oracle.optical_flow(frames[0], frames[0])).max() <= 2e-3
+
+
+def test_optical_flow_op_stencil_through_the_engine():
+    """reference py_test.py:459-520 runs OpticalFlow with stencil [0,1] and checks row counts;
+    here every row is also compared with the oracle (last row: window clamps to the last frame)."""
+    E.load_stdlib()
+    n, h, w = 7, 64, 96
+    base = synth.flow_pair(800, h, w + n, "shift")[0]
+    frames = np.stack([np.ascontiguousarray(base[:, i:i + w]) for i in range(n)])  # pans 1 px / frame
+    eng = E.Engine(gpus=[0], instances_per_gpu=2)
+    g = E.Graph()
+    src = g.add_source(True)
+    fl = g.add_op("OpticalFlow", [(src, "frame")], device=1)
+    sink = g.add_sink((fl, "flow"))
+    j = E.Job()
+    j.bind_source(src, eng.add_raw_frames(frames))
+    for (wps, ios) in [(1, 1), (4, 4)]:
+        eng.run(g, [j], wps, ios)
+        assert j.output_rows(sink) == n
+        for i in range(n):
+            got = j.output_row(sink, i)
+            assert got.shape == (h, w, 2) and got.dtype == np.float32
+            want = oracle.optical_flow(frames[i], frames[min(i + 1, n - 1)])
+            assert np.abs(got - want).max() <= 2e-3, (i, wps)
+    eng.close()
