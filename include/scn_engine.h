@@ -65,6 +65,13 @@ SCN_ENGINE_API int64_t scn_stream_rows(scn_engine* e, int64_t stream);
 SCN_ENGINE_API int scn_stream_info(scn_engine* e, int64_t stream, int64_t info[6]);
 SCN_ENGINE_API int scn_stream_remove(scn_engine* e, int64_t stream);
 
+/* The decode stage on its own: `n` ascending frame indices of an H.264 stream -> dense RGB24 frames
+ * (n * w * h * 3 bytes) in caller-owned DEVICE memory on gpu_id; returns when the frames are
+ * complete.  Used by multi-GPU stencil jobs that exchange boundary frames between ranks
+ * (scanner_b200/halo.py) and by tests. */
+SCN_ENGINE_API int scn_engine_decode_to_device(scn_engine* e, int64_t stream, const int64_t* rows, int64_t n,
+                                               int gpu_id, uint8_t* dst_device);
+
 /* ---- op graph ------------------------------------------------------------------------------ */
 SCN_ENGINE_API scn_graph* scn_graph_create(void);
 SCN_ENGINE_API void scn_graph_destroy(scn_graph* g);

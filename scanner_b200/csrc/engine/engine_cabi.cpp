@@ -134,6 +134,13 @@ int scn_stream_info(scn_engine* e, int64_t id, int64_t info[6]) {
 }
 int scn_stream_remove(scn_engine* e, int64_t id) { return e && e->impl->remove_stream(id) ? 0 : fail("unknown stream"); }
 
+int scn_engine_decode_to_device(scn_engine* e, int64_t stream, const int64_t* rows, int64_t n, int gpu_id,
+                                uint8_t* dst) {
+  if (!e || n < 0 || (n > 0 && !rows)) return fail("bad arguments");
+  std::vector<i64> r(rows, rows + n);
+  return from_result(e->impl->decode_rows_to_device(stream, r, gpu_id, dst));
+}
+
 scn_graph* scn_graph_create(void) { return new scn_graph(); }
 void scn_graph_destroy(scn_graph* g) { delete g; }
 

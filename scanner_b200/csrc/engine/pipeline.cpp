@@ -483,6 +483,56 @@ void Engine::instance_main(Instance* inst) {
   }
 }
 
+Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows, i32 gpu_id, u8* dst) {
+  Result r;
+  InputStream* st = stream(stream_id);
+  if (!st || st->kind != InputStream::H264) {
+    RESULT_ERROR(&r, "stream %ld is not an H.264 stream", (long)stream_id);
+    return r;
+  }
+  for (size_t i = 0; i < rows.size(); ++i)
+    if (rows[i] < 0 || rows[i] >= st->rows() || (i && rows[i] <= rows[i - 1])) {
+      RESULT_ERROR(&r, "rows must be ascending and inside [0, %ld)", (long)st->rows());
+      return r;
+    }
+  if (rows.empty()) return ok();
+  if (!cuda_available() || gpu_id < 0 || !dst) {
+    RESULT_ERROR(&r, "decode needs a GPU (NVDEC); there is no software decoder");
+    return r;
+  }
+  ScopedDevice sd(gpu_id);
+  cudaStream_t cs = nullptr;
+  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
+    RESULT_ERROR(&r, "cannot create a stream on GPU %d", gpu_id);
+    return r;
+  }
+  {
+    NvdecSession sess(gpu_id, cs);
+    r = sess.init();
+    const size_t w = (size_t)st->index.width, h = (size_t)st->index.height, fb = w * h * 3;
+    std::string kerr;
+    for (const VideoInterval& iv : slice_into_intervals(st->index, rows)) {
+      if (!r.success()) break;
+      std::vector<u64> offs(st->index.sample_offsets.begin() + iv.kf_start, st->index.sample_offsets.begin() + iv.kf_end);
+      std::vector<u64> szs(st->index.sample_sizes.begin() + iv.kf_start, st->index.sample_sizes.begin() + iv.kf_end);
+      r = sess.begin_interval(st->encoded.data(), offs, szs, st->index.metadata_packets, iv.wanted, iv.out_base,
+                              [&, w, h, fb](i64 out_index, const Nv12Surface& s) {
+                                const u8* lp = s.luma;
+                                const u8* cp = s.chroma;
+                                u8* d = dst + (size_t)out_index * fb;
+                                const int rc = scn_nv12_to_rgb24(&lp, &cp, s.pitch, 1, (int)w, (int)h, &d, w * 3, cs);
+                                if (rc != 0) kerr = "scn_nv12_to_rgb24 failed: " + std::to_string(rc);
+                              });
+      if (r.success()) r = sess.end_interval();
+    }
+    sess.drain();
+    cudaStreamSynchronize(cs);
+    if (r.success() && !kerr.empty()) RESULT_ERROR(&r, "%s", kerr.c_str());
+  }
+  cudaStreamDestroy(cs);
+  return r;
+}
+
 Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios, const std::string& out_dir) {
   Result r;
   if (wps <= 0 || ios <= 0 || ios % wps != 0) {

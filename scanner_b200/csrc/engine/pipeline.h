@@ -73,6 +73,10 @@ class Engine {
   Result run(Graph& graph, const std::vector<Job*>& jobs, i32 work_packet_size, i32 io_packet_size,
              const std::string& out_dir);
 
+  // Decode stage on its own: rows (ascending frame indices) of an H.264 stream -> dense RGB24
+  // frames in caller-owned device memory on `gpu_id` (n * w * h * 3 bytes); returns when done.
+  Result decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows, i32 gpu_id, u8* dst);
+
   const RunStats& stats() const { return stats_; }
   const std::vector<i32>& gpu_ids() const { return gpu_ids_; }
 

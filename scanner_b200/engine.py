@@ -29,6 +29,7 @@ SIGNATURES = {
     "scn_stream_rows": (_I64, [_VP, _I64]),
     "scn_stream_info": (_I, [_VP, _I64, _c.POINTER(_I64)]),
     "scn_stream_remove": (_I, [_VP, _I64]),
+    "scn_engine_decode_to_device": (_I, [_VP, _I64, _c.POINTER(_I64), _I64, _I, _VP]),
     "scn_graph_create": (_VP, []),
     "scn_graph_destroy": (None, [_VP]),
     "scn_graph_add_source": (_I, [_VP, _I]),
@@ -176,6 +177,17 @@ class Engine:
         info = (ctypes.c_int64 * 6)()
         check(lib().scn_stream_info(self._h, sid, info), "stream_info")
         return dict(zip(["is_video", "width", "height", "channels", "keyframes", "bytes"], list(info)))
+
+    def decode_to_device(self, sid, rows, gpu=0):
+        """Decode `rows` (ascending) of an H.264 stream into a (n,h,w,3) uint8 CUDA tensor."""
+        import torch
+        info = self.stream_info(sid)
+        rows = list(rows)
+        out = torch.empty((len(rows), info["height"], info["width"], 3), dtype=torch.uint8, device=f"cuda:{gpu}")
+        arr = (ctypes.c_int64 * max(1, len(rows)))(*rows)
+        torch.cuda.synchronize(gpu)
+        check(lib().scn_engine_decode_to_device(self._h, sid, arr, len(rows), gpu, out.data_ptr()), "decode_to_device")
+        return out
 
     def remove_stream(self, sid):
         check(lib().scn_stream_remove(self._h, sid), "remove_stream")

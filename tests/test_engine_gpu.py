@@ -234,3 +234,32 @@ def test_client_surface_on_gpu_like_tutorial_00():
     for k, fr in enumerate(o_r.load()):
         assert (fr == oracle.resize(want[3 * k], 64, 48)).all()
     sc.stop()
+
+
+def test_decode_to_device_matches_engine_path(eng):
+    import torch
+    data, want = make_clip(31, 20, 96, 128, 6)
+    sid = eng.add_h264(data)
+    rows = [0, 1, 5, 6, 7, 13, 19]
+    got = eng.decode_to_device(sid, rows, 0)
+    assert got.shape == (len(rows), 96, 128, 3) and got.is_cuda
+    for k, r in enumerate(rows):
+        assert (got[k].cpu().numpy() == want[r]).all()
+    with pytest.raises(E.EngineError, match="ascending"):
+        eng.decode_to_device(sid, [3, 2], 0)
+
+
+def test_single_rank_sharded_flow_equals_direct():
+    """halo.sharded_optical_flow with world size 1 == decode + optical_flow with the edge repeated."""
+    import torch
+    from scanner_b200 import halo, kernels
+    data, want = make_clip(32, 6, 96, 128, 3)
+    e = E.Engine(gpus=[0])
+    sid = e.add_h264(data)
+    a, flows = halo.sharded_optical_flow(e, sid, 0)
+    assert a == 0 and flows.shape == (6, 96, 128, 2)
+    for i in range(6):
+        ref = oracle.optical_flow(want[i], want[min(i + 1, 5)])
+        d = np.abs(flows[i].cpu().numpy() - ref)
+        assert np.quantile(d, 0.999) <= 5e-2 and d.mean() <= 1e-3   # uniform-noise frames: ill-conditioned
+    e.close()

@@ -72,3 +72,55 @@ def test_two_gloo_ranks_shard_clips(tmp_path):
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
     assert "MULTIRANK_OK" in out.stdout, out.stdout[-3000:]
+
+
+HALO_WORKER = r'''
+import os, sys
+import numpy as np, torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["SCN_ROOT"])
+from scanner_b200 import halo
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 23
+seq = torch.arange(n * 6, dtype=torch.float32).reshape(n, 2, 3)       # the whole "clip"
+a, b = halo.interval_of(n, rank, world)
+mine = seq[a:b].clone()
+for stencil in ([0, 1], [-1, 0, 1], [-2, 0], [0]):
+    wins = halo.stencil_windows(mine, stencil)
+    for k, s in enumerate(sorted(stencil)):
+        idx = torch.clamp(torch.arange(a, b) + s, 0, n - 1)
+        assert torch.equal(wins[k], seq[idx]), (rank, stencil, s)
+# a stencil op computed shard-wise equals the single-process result
+cur, nxt = halo.stencil_windows(mine, [0, 1])
+diff = (nxt - cur).abs().sum(dim=(1, 2))
+full = (seq[torch.clamp(torch.arange(n) + 1, max=n - 1)] - seq).abs().sum(dim=(1, 2))
+assert torch.equal(diff, full[a:b])
+dist.barrier()
+if rank == 0:
+    print("HALO_OK", world)
+dist.destroy_process_group()
+'''
+
+
+def test_interval_of_partitions():
+    from scanner_b200 import halo
+    for n in (1, 7, 23, 64):
+        for world in (1, 2, 3, 4, 8):
+            parts = [halo.interval_of(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(tmp_path, world):
+    script = tmp_path / "halo_worker.py"
+    script.write_text(HALO_WORKER)
+    env = dict(os.environ, SCN_ROOT=ROOT, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29620 + world), str(script)]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert f"HALO_OK {world}" in out.stdout, out.stdout[-3000:]
