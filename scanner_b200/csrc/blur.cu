@@ -2,63 +2,142 @@
 // Replaces BlurKernel::execute (reference tests/test_ops.cpp:265-294): for interior pixels
 // out = (sum of the (fl+fr+1)^2 window) / (fl+fr+1)^2 with fl = ceil(k/2)-1, fr = k/2; the
 // reference never writes the border of its freshly allocated frame -- here it is written as 0.
+// Integer, bit-exact on the interior.
 //
-// Tiled: a CTA produces a TW x TH pixel tile; it stages the (TW+k-1) x (TH+k-1) source window in
-// shared memory with coalesced row reads, runs a separable running sum (horizontal pass into
-// shared u16 sums, vertical pass from those), so each source byte is read from HBM/L2 once per
-// tile instead of k^2 times.
+//   box3_kernel   kernel_size 3 (BASELINE configs[2]).  A thread owns one 32-bit column of the byte
+//                 image (4 bytes = 1 1/3 pixels) and walks down a strip of rows.  The three taps of
+//                 the horizontal pass are byte-shifted views of three neighbouring words (funnel
+//                 shifts), summed as packed u16x2 lanes; the vertical pass is a 3-row sliding sum
+//                 held in registers; /9 is an exact multiply-shift; four results are stored as one
+//                 32-bit word.  No shared memory: neighbouring threads' loads overlap in L1.
+//   box_generic_kernel   any kernel_size <= 31: shared-memory tile, separable direct sums.
 #include "scn_common.cuh"
 
 namespace scn {
 namespace {
 
+// ---------------------------------------------------------------------------------------------
+constexpr int B3_THREADS = 256;
+constexpr int B3_ROWS = 64;  // output rows per CTA strip
+
+// packed u16x2 horizontal sums of the 4 bytes of a word column: even = bytes 0,2 ; odd = bytes 1,3
+struct H3 {
+  uint32_t even, odd;
+};
+
+__device__ __forceinline__ H3 hsum3(uint32_t wm, uint32_t w0, uint32_t wp) {
+  // byte views: A = bytes [x-3 .. x], B = [x .. x+3], C = [x+3 .. x+6]
+  const uint32_t A = __funnelshift_r(wm, w0, 8);
+  const uint32_t C = __funnelshift_r(w0, wp, 24);
+  H3 h;
+  h.even = (A & 0x00FF00FFu) + (w0 & 0x00FF00FFu) + (C & 0x00FF00FFu);
+  h.odd = prmt(A, 0u, 0x4341u) + prmt(w0, 0u, 0x4341u) + prmt(C, 0u, 0x4341u);
+  return h;
+}
+
+// floor(v / 9) for v <= 2295 (3*3*255): (v * 7282) >> 16, exact (checked exhaustively in the tests)
+__device__ __forceinline__ uint32_t div9_pack(uint32_t even, uint32_t odd) {
+  const uint32_t e0 = ((even & 0xFFFFu) * 7282u) >> 16, e1 = __umulhi(even & 0xFFFF0000u, 7282u);
+  const uint32_t o0 = ((odd & 0xFFFFu) * 7282u) >> 16, o1 = __umulhi(odd & 0xFFFF0000u, 7282u);
+  return e0 | (o0 << 8) | (e1 << 16) | (o1 << 24);
+}
+
+// words_per_row = width*3/4 (requires width % 4 == 0 and 4-byte aligned frames)
+__global__ void __launch_bounds__(B3_THREADS)
+box3_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int words_per_row) {
+  const int wx = blockIdx.x * B3_THREADS + threadIdx.x;
+  if (wx >= words_per_row) return;
+  const uint32_t* __restrict__ s = reinterpret_cast<const uint32_t*>(src.p[blockIdx.z]);
+  uint32_t* __restrict__ d = reinterpret_cast<uint32_t*>(dst.p[blockIdx.z]);
+  const int y0 = blockIdx.y * B3_ROWS;
+  const int y1 = min(height, y0 + B3_ROWS);
+
+  // bytes of this word that are interior in x: pixel = byte / 3 must be in [1, width-2]
+  uint32_t xmask = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int px = (wx * 4 + b) / 3;
+    if (px >= 1 && px <= width - 2) xmask |= 0xFFu << (8 * b);
+  }
+  const bool has_m = wx > 0, has_p = wx + 1 < words_per_row;
+
+  auto load_h = [&](int y) -> H3 {
+    H3 h{0u, 0u};
+    if (y >= 0 && y < height) {
+      const uint32_t* row = s + (size_t)y * words_per_row + wx;
+      const uint32_t w0 = __ldg(row);
+      const uint32_t wm = has_m ? __ldg(row - 1) : 0u;
+      const uint32_t wp = has_p ? __ldg(row + 1) : 0u;
+      h = hsum3(wm, w0, wp);
+    }
+    return h;
+  };
+
+  H3 a = load_h(y0 - 1), b = load_h(y0);
+  for (int y = y0; y < y1; ++y) {
+    const H3 c = load_h(y + 1);
+    uint32_t out = 0;
+    if (y >= 1 && y <= height - 2) out = div9_pack(a.even + b.even + c.even, a.odd + b.odd + c.odd) & xmask;
+    d[(size_t)y * words_per_row + wx] = out;
+    a = b;
+    b = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int TW = 64;   // tile width in pixels
 constexpr int TH = 32;   // tile height in pixels
 constexpr int KMAX = 31;
-constexpr int BT = 256;
+constexpr int BT = 256;  // 8 warps: warp <-> row, lane <-> byte
 
 __global__ void __launch_bounds__(BT)
-box_blur_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int fl, int fr) {
+box_generic_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int fl, int fr) {
   extern __shared__ uint8_t smem_raw[];
   const int k = fl + fr + 1;
-  const int in_w = TW + k - 1;   // pixels
-  const int in_h = TH + k - 1;
-  const int in_wb = in_w * 3;    // bytes per staged row
-  uint8_t* tile = smem_raw;                                          // in_h x in_wb
-  uint16_t* hsum = reinterpret_cast<uint16_t*>(smem_raw + ((in_h * in_wb + 15) & ~15));  // in_h x TW*3
-
+  const int in_w = TW + k - 1, in_h = TH + k - 1;
+  const int in_wb = in_w * 3, out_wb = TW * 3;
+  uint8_t* tile = smem_raw;                                                              // in_h x in_wb
+  uint16_t* hsum = reinterpret_cast<uint16_t*>(smem_raw + ((in_h * in_wb + 15) & ~15));  // in_h x out_wb
   const uint8_t* __restrict__ s = src.p[blockIdx.z];
   uint8_t* __restrict__ d = dst.p[blockIdx.z];
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_bytes = width * 3;
 
-  // stage source window rows [y0-fl, y0+TH+fr) x cols [x0-fl, x0+TW+fr), zero outside the frame
-  for (int i = threadIdx.x; i < in_h * in_wb; i += BT) {
-    const int r = i / in_wb, cbyte = i - r * in_wb;
+  for (int r = warp; r < in_h; r += BT / 32) {
     const int sy = y0 - fl + r;
-    const int sxb = (x0 - fl) * 3 + cbyte;
-    uint8_t v = 0;
-    if (sy >= 0 && sy < height && sxb >= 0 && sxb < width * 3) v = __ldg(s + (size_t)sy * width * 3 + sxb);
-    tile[i] = v;
+    const bool row_ok = sy >= 0 && sy < height;
+    const uint8_t* srow = s + (size_t)(row_ok ? sy : 0) * row_bytes;
+    const int xb0 = (x0 - fl) * 3;
+    for (int c = lane; c < in_wb; c += 32) {
+      const int sxb = xb0 + c;
+      tile[r * in_wb + c] = (row_ok && sxb >= 0 && sxb < row_bytes) ? __ldg(srow + sxb) : (uint8_t)0;
+    }
   }
   __syncthreads();
-  // horizontal window sums: hsum[r][x*3+c] = sum_{j<k} tile[r][(x+j)*3+c]
-  for (int i = threadIdx.x; i < in_h * TW * 3; i += BT) {
-    const int r = i / (TW * 3), xb = i - r * (TW * 3);
-    const uint8_t* t = tile + r * in_wb + xb;
-    uint32_t acc = 0;
-    for (int j = 0; j < k; ++j) acc += t[j * 3];
-    hsum[i] = (uint16_t)acc;   // <= 31*255 = 7905
+  for (int r = warp; r < in_h; r += BT / 32) {
+    const uint8_t* trow = tile + r * in_wb;
+    for (int c = lane; c < out_wb; c += 32) {
+      uint32_t acc = 0;
+      for (int j = 0; j < k; ++j) acc += trow[c + j * 3];
+      hsum[r * out_wb + c] = (uint16_t)acc;  // <= 31 * 255
+    }
   }
   __syncthreads();
   const uint32_t div = (uint32_t)(k * k);
-  for (int i = threadIdx.x; i < TH * TW * 3; i += BT) {
-    const int r = i / (TW * 3), xb = i - r * (TW * 3);
-    const int x = x0 + xb / 3, y = y0 + r;
-    if (x >= width || y >= height) continue;
-    uint32_t acc = 0;
-    for (int j = 0; j < k; ++j) acc += hsum[(r + j) * (TW * 3) + xb];
-    const bool interior = (y >= fl) && (y < height - fr) && (x >= fl) && (x < width - fr);
-    d[((size_t)y * width) * 3 + (size_t)x0 * 3 + xb] = interior ? (uint8_t)(acc / div) : (uint8_t)0;
+  for (int r = warp; r < TH; r += BT / 32) {
+    const int y = y0 + r;
+    if (y >= height) break;
+    const bool row_in = y >= fl && y < height - fr;
+    for (int c = lane; c < out_wb; c += 32) {
+      const int xb = x0 * 3 + c;
+      if (xb >= row_bytes) break;
+      uint32_t acc = 0;
+      for (int j = 0; j < k; ++j) acc += hsum[(r + j) * out_wb + c];
+      const int x = xb / 3;
+      const bool interior = row_in && x >= fl && x < width - fr;
+      d[(size_t)y * row_bytes + xb] = interior ? (uint8_t)(acc / div) : (uint8_t)0;
+    }
   }
 }
 
@@ -74,8 +153,8 @@ int launch_blur(const uint8_t* const* sp, int n, int width, int height, int ksiz
   const size_t smem = (((size_t)in_h * in_w * 3 + 15) & ~(size_t)15) + (size_t)in_h * TW * 3 * 2;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(box_blur_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(box_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         100 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -84,14 +163,22 @@ int launch_blur(const uint8_t* const* sp, int n, int width, int height, int ksiz
     const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
     PtrBatch s;
     MutPtrBatch d;
+    bool aligned = (width % 4) == 0 && width >= 4 && height >= 3;
     for (int i = 0; i < cnt; ++i) {
       s.p[i] = sp[i0 + i];
       d.p[i] = dp[i0 + i];
+      if (((uintptr_t)s.p[i] | (uintptr_t)d.p[i]) & 3) aligned = false;
     }
-    dim3 grid((unsigned)((width + TW - 1) / TW), (unsigned)((height + TH - 1) / TH), (unsigned)cnt);
-    {
-      LaunchScope ls("box_blur_kernel", st);
-      box_blur_kernel<<<grid, BT, smem, st>>>(s, d, width, height, fl, fr);
+    if (ksize == 3 && aligned) {
+      const int wpr = width * 3 / 4;
+      dim3 grid((unsigned)((wpr + B3_THREADS - 1) / B3_THREADS), (unsigned)((height + B3_ROWS - 1) / B3_ROWS),
+                (unsigned)cnt);
+      LaunchScope ls("box3_kernel", st);
+      box3_kernel<<<grid, B3_THREADS, 0, st>>>(s, d, width, height, wpr);
+    } else {
+      dim3 grid((unsigned)((width + TW - 1) / TW), (unsigned)((height + TH - 1) / TH), (unsigned)cnt);
+      LaunchScope ls("box_generic_kernel", st);
+      box_generic_kernel<<<grid, BT, smem, st>>>(s, d, width, height, fl, fr);
     }
     int rc = launch_status();
     if (rc) return rc;

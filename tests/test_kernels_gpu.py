@@ -116,12 +116,18 @@ def test_blur_golden(golden_dir):
 
 
 @pytest.mark.parametrize("h,w,k,n", [(480, 640, 3, 2), (2160, 3840, 3, 1), (100, 70, 7, 3), (65, 129, 31, 1),
-                                     (10, 10, 12, 1)])
+                                     (10, 10, 12, 1), (33, 50, 3, 2), (3, 4, 3, 1), (70, 1028, 3, 2), (64, 64, 2, 1)])
 def test_blur_vs_oracle(h, w, k, n):
     frames = np.stack([synth.rand_frame(30 + i, h, w) for i in range(n)])
     got = kernels.blur(dev(frames), k).cpu().numpy()
     for i in range(n):
         assert (got[i] == oracle.blur(frames[i], k)).all()
+
+
+def test_div9_multiply_shift_is_exact():
+    """box3_kernel divides by 9 with (v * 7282) >> 16: exact for every reachable sum (<= 9*255)."""
+    v = np.arange(0, 9 * 255 + 1, dtype=np.uint64)
+    assert ((v * 7282) >> 16 == v // 9).all()
 
 
 # ----------------------------------------------------------------------------- nv12
