@@ -616,6 +616,14 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
                                    "nvdec_release_wait_us", "nvdec_create_us"};
     for (int i = 0; i < 6; ++i) stats_.counters[names[i]] = ns[i] / 1000;
   }
+  // live allocator bytes after the run: everything a run allocates is released when it ends
+  // (input streams are adopted, not allocated), so anything left here is a leak
+  stats_.counters["cpu_bytes_live"] = (i64)current_memory_allocated(CPU_DEVICE);
+  stats_.counters["cpu_bytes_peak"] = (i64)max_memory_allocated(CPU_DEVICE);
+  for (i32 g : gpu_ids_) {
+    stats_.counters["gpu" + std::to_string(g) + "_bytes_live"] = (i64)current_memory_allocated(DeviceHandle(DeviceType::GPU, g));
+    stats_.counters["gpu" + std::to_string(g) + "_bytes_peak"] = (i64)max_memory_allocated(DeviceHandle(DeviceType::GPU, g));
+  }
   stats_.counters["tasks"] = (i64)rs.tasks.size();
   stats_.counters["instances"] = (i64)instances.size();
   stats_.interval_ns = rs.profiler.interval_totals_ns();

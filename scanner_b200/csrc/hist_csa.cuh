@@ -1,21 +1,24 @@
 // hist_csa.cuh -- bit-sliced streaming histogram for large u8 HWC 3-channel frames (sm_100a).
 //
-// Why: a 16-bin histogram at HBM speed needs ~23-30 bytes/clk/SM; shared-memory atomics manage
-// ~1 and per-byte register counters ~8 (integer pipe: 64 lanes/clk/SM).  Here counting is done
-// 32 counters at a time in bit-sliced (vertical) form:
-//   1. PRMT as an 8-entry byte LUT turns the high nibbles of a 32-bit word (4 pixels' bytes) into
-//      one-hot bytes: word A has bit b of byte k set iff byte k's bin is b (b < 8), word B the
-//      same for bins 8..14.  Bin 15 is encoded as 0xFF in A (PRMT's sign-replicate mode) and
-//      recovered at the end from the known total:  n15 = (sum(A)+sum(B) - N) / 7.
-//      6 PRMT + 2 SHF + 1 LOP3 per 4 bytes.
-//   2. The one-hot words are summed with a Harley-Seal carry-save-adder tree (2 LOP3 per CSA,
-//      15 CSAs per 16 words) into bit planes: plane p holds bit p of 32 independent counters.
-//   3. Per warp span: bit-sliced butterfly add across the 32 lanes (SHFL + 2 LOP3 per plane and
-//      round), lane l extracts counter l, bin-15 correction, 48 atomics into the frame's bins.
-// Three accumulator sets track the byte->channel phase (a 32-bit word starts at byte offset
-// = 0,1,2 mod 3); the static set index is rotated per lane at flush time.
-// Main loop cost: ~3.3 integer ops per byte.  Bit-exact.
+// Why: a 16-bin histogram at HBM speed needs ~25 bytes/clk/SM; shared-memory atomics manage ~1 and
+// per-byte register counters ~8 (integer pipe: 64 lanes/clk/SM).  Here (csa_core.cuh) PRMT turns
+// high nibbles into one-hot bytes and carry-save adders count them 32 counters per LOP3.
+//
+// v3 layout: a warp streams blocks of 12 x 512 B (lane l owns 16 B of every 512 B round).  Words
+// three rounds apart start at the same byte offset mod 3, i.e. have the same byte->channel phase,
+// so they are PAIRED: the high nibbles of x go to the even nibbles and those of y stay in the odd
+// nibbles of one selector word  z = ((x >> 4) & 0x0F0F0F0F) | (y & 0xF0F0F0F0)  (SHF + LOP3), and
+// every PRMT lookup then decodes four useful bins instead of two (v1 decoded each word alone and
+// needed a third PRMT to compact): 9 integer ops per 8 bytes.
+// The low selector half of a pair of phase p covers channels (p, p, p+1, p+1) in its four byte
+// slots, the high half (p+2, p+2, p, p) -- which is exactly the low-half layout of phase p+2.  So
+// the high-half words of phase set s are added into the accumulator of set (s+2)%3 and six
+// accumulators suffice (3 layouts x bins 0-7 / 8-14), each fed 16 words per block through a
+// 4-level carry-save tree.  Two register buffers hold alternate blocks and prefetch each other
+// (loop unrolled by two: no register moves, no conditional loads).
+// Main loop ~2.3 integer ops per byte.  Bit-exact.
 #pragma once
+#include "csa_core.cuh"
 #include "scn_common.cuh"
 
 namespace scn {
@@ -23,203 +26,106 @@ namespace csa {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kPlanes = 10;           // per-lane counters hold up to 1023
-constexpr int kHigh = kPlanes - 4;    // planes 4..9
-constexpr int kWarpBlock = 6144;      // bytes per warp per block: 12 rounds x 32 lanes x 16 B
-constexpr int kMaxBlocks = 63;        // 63 * 16 words per set <= 1023
+constexpr int kHi = 6;                 // planes 4..9 -> counters up to 1023
+constexpr int kPlanes = 4 + kHi;
+constexpr int kWarpBlock = 6144;       // bytes per warp per block: 12 rounds x 32 lanes x 16 B
+constexpr int kMaxBlocks = 63;         // 63 * 16 words per accumulator <= 1023
 
-__device__ __forceinline__ void csa3(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t u = a ^ b;
-  h = (a & b) | (u & c);
-  l = u ^ c;
-}
+using Acc = Acc16<kHi>;
 
-struct Acc {
-  uint32_t p0, p1, p2, p3;     // planes 0..3 (ones, twos, fours, eights)
-  uint32_t t0, t1, t2, t3;     // pending inputs of the tree inside a 16-word block
-  uint32_t hi[kHigh];          // planes 4..9
-  uint32_t pend4, pend5;       // pending weight-16 / weight-32 carries between blocks
-};
-
-__device__ __forceinline__ void acc_clear(Acc& a) {
-  a.p0 = a.p1 = a.p2 = a.p3 = 0;
-  a.t0 = a.t1 = a.t2 = a.t3 = 0;
-#pragma unroll
-  for (int i = 0; i < kHigh; ++i) a.hi[i] = 0;
-  a.pend4 = a.pend5 = 0;
-}
-
-// K-th (0..15) word of a block for this accumulator; returns the weight-16 carry when K == 15.
-template <int K>
-__device__ __forceinline__ void push(Acc& a, uint32_t x, uint32_t& c16) {
-  if constexpr ((K & 1) == 0) {
-    a.t0 = x;
-  } else {
-    uint32_t tw;
-    csa3(tw, a.p0, a.p0, a.t0, x);
-    if constexpr (((K >> 1) & 1) == 0) {
-      a.t1 = tw;
-    } else {
-      uint32_t fo;
-      csa3(fo, a.p1, a.p1, a.t1, tw);
-      if constexpr (((K >> 2) & 1) == 0) {
-        a.t2 = fo;
-      } else {
-        uint32_t ei;
-        csa3(ei, a.p2, a.p2, a.t2, fo);
-        if constexpr (((K >> 3) & 1) == 0) {
-          a.t3 = ei;
-        } else {
-          csa3(c16, a.p3, a.p3, a.t3, ei);
-        }
-      }
-    }
-  }
-}
-
-// add a 1-bit-per-counter word of weight 2^(4+from) into the high planes (ripple half-adders)
-template <int FROM>
-__device__ __forceinline__ void ripple(Acc& a, uint32_t c) {
-#pragma unroll
-  for (int q = FROM; q < kHigh; ++q) {
-    const uint32_t t = a.hi[q] & c;
-    a.hi[q] ^= c;
-    c = t;
-  }
-}
-
-// after block number `blk` (0-based) of a span: fold the weight-16 carry into the high planes
-__device__ __forceinline__ void fold_block(Acc& a, uint32_t c16, int blk) {
-  if (blk & 1) {
-    uint32_t c32;
-    csa3(c32, a.hi[0], a.hi[0], a.pend4, c16);
-    if (blk & 2) {
-      uint32_t c64;
-      csa3(c64, a.hi[1], a.hi[1], a.pend5, c32);
-      ripple<2>(a, c64);
-    } else {
-      a.pend5 = c32;
-    }
-  } else {
-    a.pend4 = c16;
-  }
-}
-
-// span of `nblk` blocks is over: fold the carries still pending
-__device__ __forceinline__ void finish_span(Acc& a, int nblk) {
-  if (nblk & 2) ripple<1>(a, a.pend5);   // weight 32 -> plane 5
-  if (nblk & 1) ripple<0>(a, a.pend4);   // weight 16 -> plane 4
-}
-
-constexpr uint32_t kLutLo = 0x08040201u;   // one-hot bytes for index 0..3
-constexpr uint32_t kLutHiA = 0x80402010u;  // index 4..7 (A: bin 7 -> 0x80; bin 15 reads it in sign mode -> 0xFF)
-constexpr uint32_t kLutHiB = 0x00402010u;  // B: index 7 (bin 15) -> 0
-
-// static phase set of word j of round r inside a warp block, and its position within the set
-__host__ __device__ constexpr int set_of(int idx) { return (2 * (idx / 4) + (idx % 4)) % 3; }
-__host__ __device__ constexpr int rank_of(int idx) {
+// pair sequence index q = half*12 + r*4 + j (half block, round within the half, word of the uint4).
+// Its phase set; the low selector half is counted by accumulator set(q), the high half by
+// (set(q)+2)%3.  rank_* = how many words that accumulator has already received in the block.
+__host__ __device__ constexpr int pair_set(int q) { return (2 * ((q % 12) / 4) + (q % 4)) % 3; }
+__host__ __device__ constexpr int pushes_before(int q, int acc) {
   int c = 0;
-  for (int i = 0; i < idx; ++i)
-    if (set_of(i) == set_of(idx)) ++c;
+  for (int i = 0; i < q; ++i) {
+    if (pair_set(i) == acc) ++c;
+    if ((pair_set(i) + 2) % 3 == acc) ++c;
+  }
   return c;
 }
 
-template <int IDX>
-__device__ __forceinline__ void eat(Acc (&A)[3], Acc (&B)[3], uint32_t (&cA)[3], uint32_t (&cB)[3], uint32_t w) {
-  constexpr int S = set_of(IDX);
-  constexpr int K = rank_of(IDX);
-  const uint32_t a01 = prmt(kLutLo, kLutHiA, w);
-  const uint32_t a23 = prmt(kLutLo, kLutHiA, w >> 16);
-  const uint32_t a = prmt(a01, a23, 0x7531u);
-  const uint32_t wx = w ^ 0x80808080u;
-  const uint32_t b01 = prmt(kLutLo, kLutHiB, wx);
-  const uint32_t b23 = prmt(kLutLo, kLutHiB, wx >> 16);
-  const uint32_t b = prmt(b01, b23, 0x7531u);
-  push<K>(A[S], a, cA[S]);
-  push<K>(B[S], b, cB[S]);
+struct Sets {
+  Acc a[3], b[3];  // [channel layout]: bins 0-7(+15) / bins 8-14
+};
+struct Carries {
+  uint32_t a[3], b[3];
+};
+
+template <int Q>
+__device__ __forceinline__ void eat_pair(Sets& S, Carries& C, uint32_t x, uint32_t y) {
+  constexpr int lo = pair_set(Q), hi = (pair_set(Q) + 2) % 3;
+  constexpr int klo = pushes_before(Q, lo), khi = pushes_before(Q, hi);
+  const uint32_t z = ((x >> 4) & 0x0F0F0F0Fu) | (y & 0xF0F0F0F0u);
+  uint32_t a_lo, a_hi, b_lo, b_hi;
+  decode8(z, a_lo, a_hi, b_lo, b_hi);
+  push16<klo>(S.a[lo], a_lo, C.a[lo]);
+  push16<klo>(S.b[lo], b_lo, C.b[lo]);
+  push16<khi>(S.a[hi], a_hi, C.a[hi]);
+  push16<khi>(S.b[hi], b_hi, C.b[hi]);
 }
 
-template <int R>
-__device__ __forceinline__ void eat_round(Acc (&A)[3], Acc (&B)[3], uint32_t (&cA)[3], uint32_t (&cB)[3],
-                                          const uint4 v) {
-  eat<R * 4 + 0>(A, B, cA, cB, v.x);
-  eat<R * 4 + 1>(A, B, cA, cB, v.y);
-  eat<R * 4 + 2>(A, B, cA, cB, v.z);
-  eat<R * 4 + 3>(A, B, cA, cB, v.w);
+template <int HALF>
+__device__ __forceinline__ void eat_half(Sets& S, Carries& C, const uint4* v /* 6 rounds */) {
+  eat_pair<HALF * 12 + 0>(S, C, v[0].x, v[3].x);
+  eat_pair<HALF * 12 + 1>(S, C, v[0].y, v[3].y);
+  eat_pair<HALF * 12 + 2>(S, C, v[0].z, v[3].z);
+  eat_pair<HALF * 12 + 3>(S, C, v[0].w, v[3].w);
+  eat_pair<HALF * 12 + 4>(S, C, v[1].x, v[4].x);
+  eat_pair<HALF * 12 + 5>(S, C, v[1].y, v[4].y);
+  eat_pair<HALF * 12 + 6>(S, C, v[1].z, v[4].z);
+  eat_pair<HALF * 12 + 7>(S, C, v[1].w, v[4].w);
+  eat_pair<HALF * 12 + 8>(S, C, v[2].x, v[5].x);
+  eat_pair<HALF * 12 + 9>(S, C, v[2].y, v[5].y);
+  eat_pair<HALF * 12 + 10>(S, C, v[2].z, v[5].z);
+  eat_pair<HALF * 12 + 11>(S, C, v[2].w, v[5].w);
+}
+
+__device__ __forceinline__ void eat_block(Sets& S, const uint4 (&v)[12], int blk) {
+  Carries C;
+  eat_half<0>(S, C, v);
+  eat_half<1>(S, C, v + 6);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    fold_step(S.a[c], C.a[c], blk);
+    fold_step(S.b[c], C.b[c], blk);
+  }
 }
 
 __device__ __forceinline__ uint32_t sel3(int rot, uint32_t x0, uint32_t x1, uint32_t x2) {
   return rot == 0 ? x0 : (rot == 1 ? x1 : x2);
 }
 
-// cross-lane sum of a bit-sliced counter set: after the call every lane holds the warp total in
-// pl[0 .. kPlanes+4]
-__device__ __forceinline__ void warp_sum(uint32_t (&pl)[kPlanes + 5]) {
+// Flush one span: add this warp's counts of `nblk` blocks into hist48.
+// On lane l (rot = l % 3) accumulator c holds the layout of true phase (c + rot) % 3: byte slot k
+// of its words belongs to channel (phase + k/2) % 3.
+__device__ __forceinline__ void flush_span(Sets& S, int nblk, int lane, int* hist48) {
+  const int rot = lane % 3;
 #pragma unroll
-  for (int d = 0; d < 5; ++d) {
-    uint32_t carry = 0;
-#pragma unroll
-    for (int p = 0; p < kPlanes + 5; ++p) {
-      if (p < kPlanes + d) {
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, pl[p], 1 << d);
-        const uint32_t u = pl[p] ^ o;
-        const uint32_t nc = (pl[p] & o) | (u & carry);
-        pl[p] = u ^ carry;
-        carry = nc;
-      } else if (p == kPlanes + d) {
-        pl[p] = carry;
-      }
-    }
+  for (int c = 0; c < 3; ++c) {
+    finish_span(S.a[c], nblk);
+    finish_span(S.b[c], nblk);
   }
-}
-
-__device__ __forceinline__ uint32_t extract_lane(const uint32_t (&pl)[kPlanes + 5], int lane) {
-  uint32_t v = 0;
-#pragma unroll
-  for (int p = 0; p < kPlanes + 5; ++p) v |= ((pl[p] >> lane) & 1u) << p;
-  return v;
-}
-
-__device__ __forceinline__ void planes_of(const Acc& a, uint32_t (&pl)[kPlanes + 5]) {
-  pl[0] = a.p0;
-  pl[1] = a.p1;
-  pl[2] = a.p2;
-  pl[3] = a.p3;
-#pragma unroll
-  for (int q = 0; q < kHigh; ++q) pl[4 + q] = a.hi[q];
-#pragma unroll
-  for (int q = kPlanes; q < kPlanes + 5; ++q) pl[q] = 0;
-}
-
-// Flush one span: add this warp's counts of `nblk` blocks into hist48 (shared or global ints).
-__device__ __forceinline__ void flush_span(Acc (&A)[3], Acc (&B)[3], int nblk, int lane, int* hist48) {
-  const int rot = lane % 3;  // static set s holds true phase (s + rot) % 3 on this lane
-#pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    finish_span(A[s], nblk);
-    finish_span(B[s], nblk);
-  }
-  const uint32_t words_per_slot = (uint32_t)nblk * 16u * 32u;  // per phase set, whole warp
+  const uint32_t words_per_slot = (uint32_t)nblk * 16u * 32u;  // per accumulator, whole warp
 #pragma unroll
   for (int phase = 0; phase < 3; ++phase) {
-    // set holding true phase `phase` on this lane: (phase - rot) mod 3
-    uint32_t pa[kPlanes + 5], pb[kPlanes + 5], x0[kPlanes + 5], x1[kPlanes + 5], x2[kPlanes + 5];
     const int pick = (phase + 3 - rot) % 3;
-    planes_of(A[0], x0);
-    planes_of(A[1], x1);
-    planes_of(A[2], x2);
+    uint32_t pa[kPlanes + 5], pb[kPlanes + 5], x0[kPlanes + 5], x1[kPlanes + 5], x2[kPlanes + 5];
+    planes_of(S.a[0], x0);
+    planes_of(S.a[1], x1);
+    planes_of(S.a[2], x2);
 #pragma unroll
     for (int p = 0; p < kPlanes + 5; ++p) pa[p] = sel3(pick, x0[p], x1[p], x2[p]);
-    planes_of(B[0], x0);
-    planes_of(B[1], x1);
-    planes_of(B[2], x2);
+    planes_of(S.b[0], x0);
+    planes_of(S.b[1], x1);
+    planes_of(S.b[2], x2);
 #pragma unroll
     for (int p = 0; p < kPlanes + 5; ++p) pb[p] = sel3(pick, x0[p], x1[p], x2[p]);
-    warp_sum(pa);
-    warp_sum(pb);
-    uint32_t ca = extract_lane(pa, lane);  // A counter of (byte slot lane/8, bit lane%8), + n15
-    uint32_t cb = extract_lane(pb, lane);  // B counter: bins 8..14 (bit 7 stays 0)
-    // n15 of this byte slot: (sum A + sum B - N) / 7 over the 8 lanes of the slot
+    warp_sum<kPlanes>(pa);
+    warp_sum<kPlanes>(pb);
+    uint32_t ca = extract_lane<kPlanes>(pa, lane);  // A counter of (slot lane/8, bit lane%8), + n15 of the slot
+    uint32_t cb = extract_lane<kPlanes>(pb, lane);  // B counter: bins 8..14 (bit 7 stays 0)
     uint32_t sum = ca + cb;
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
@@ -228,7 +134,7 @@ __device__ __forceinline__ void flush_span(Acc (&A)[3], Acc (&B)[3], int nblk, i
     ca -= n15;
     const int bit = lane & 7, slot = lane >> 3;
     if (bit == 7) cb = n15;
-    const int ch = (phase + slot) % 3;
+    const int ch = (phase + (slot >> 1)) % 3;
     if (ca) atomicAdd(&hist48[ch * 16 + bit], (int)ca);
     if (cb) atomicAdd(&hist48[ch * 16 + 8 + bit], (int)cb);
   }
@@ -236,7 +142,7 @@ __device__ __forceinline__ void flush_span(Acc (&A)[3], Acc (&B)[3], int nblk, i
 
 struct Params {
   PtrBatch frames;
-  int n;                    // frames in this launch
+  int n;                      // frames in this launch
   uint32_t blocks_per_frame;  // whole warp blocks per frame
   uint32_t tail_bytes;        // bytes after the last whole block of a frame
   uint64_t total_blocks;      // n * blocks_per_frame
@@ -265,44 +171,36 @@ hist16_csa_kernel(const Params prm, int32_t* __restrict__ out) {
     for (int i = lane; i < 48; i += 32) h[i] = 0;
     __syncwarp();
 
-    Acc A[3], B[3];
+    Sets S;
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      acc_clear(A[s]);
-      acc_clear(B[s]);
+    for (int c = 0; c < 3; ++c) {
+      acc_clear(S.a[c]);
+      acc_clear(S.b[c]);
     }
-    uint4 cur[12];
+    // two register buffers hold alternate blocks; every load is unconditional (indices clamp to
+    // the last block) so no load sits in a divergent region
+    auto load_block = [&](uint4 (&v)[12], uint32_t blk) {
+      const uint8_t* p = src + (size_t)(blk < nb ? blk : nb - 1) * kWarpBlock;
 #pragma unroll
-    for (int r = 0; r < 12; ++r) cur[r] = ld_stream_u4(src + r * 512);
-    for (uint32_t blk = 0; blk < nb; ++blk) {
-      // unconditional prefetch (the last iteration re-reads its own block): loads inside a
-      // conditional region make ptxas wait for them at the reconvergence point
-      uint4 nxt[12];
-      const uint8_t* nsrc = src + (size_t)(blk + 1 < nb ? blk + 1 : blk) * kWarpBlock;
+      for (int r = 0; r < 12; ++r) v[r] = ld_stream_u4(p + r * 512);
+    };
+    uint4 va[12], vb[12];
+    uint32_t blk = 0;
+    load_block(va, 0);
+    if (nb & 1) {  // odd count: peel one block so the unrolled loop below always runs pairs
+      load_block(vb, 1);
+      eat_block(S, va, 0);
 #pragma unroll
-      for (int r = 0; r < 12; ++r) nxt[r] = ld_stream_u4(nsrc + r * 512);
-      uint32_t cA[3], cB[3];
-      eat_round<0>(A, B, cA, cB, cur[0]);
-      eat_round<1>(A, B, cA, cB, cur[1]);
-      eat_round<2>(A, B, cA, cB, cur[2]);
-      eat_round<3>(A, B, cA, cB, cur[3]);
-      eat_round<4>(A, B, cA, cB, cur[4]);
-      eat_round<5>(A, B, cA, cB, cur[5]);
-      eat_round<6>(A, B, cA, cB, cur[6]);
-      eat_round<7>(A, B, cA, cB, cur[7]);
-      eat_round<8>(A, B, cA, cB, cur[8]);
-      eat_round<9>(A, B, cA, cB, cur[9]);
-      eat_round<10>(A, B, cA, cB, cur[10]);
-      eat_round<11>(A, B, cA, cB, cur[11]);
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        fold_block(A[s], cA[s], (int)blk);
-        fold_block(B[s], cB[s], (int)blk);
-      }
-#pragma unroll
-      for (int r = 0; r < 12; ++r) cur[r] = nxt[r];
+      for (int r = 0; r < 12; ++r) va[r] = vb[r];
+      blk = 1;
     }
-    flush_span(A, B, (int)nb, lane, h);
+    for (; blk < nb; blk += 2) {
+      load_block(vb, blk + 1);
+      eat_block(S, va, (int)blk);
+      load_block(va, blk + 2);
+      eat_block(S, vb, (int)blk + 1);
+    }
+    flush_span(S, (int)nb, lane, h);
 
     // the warp that finishes a frame's last block also counts the frame's tail bytes
     if (b0 + nb == prm.blocks_per_frame && prm.tail_bytes) {

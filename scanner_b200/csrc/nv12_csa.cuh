@@ -15,7 +15,7 @@
 // hist_csa.cuh (6 accumulators: R,G,B x bins 0-7 / 8-14; bin 15 recovered from the total).
 // ~11 integer-pipe + ~12 FMA-pipe operations per pixel.  Bit-exact with the three-pass path.
 #pragma once
-#include "hist_csa.cuh"
+#include "csa_core.cuh"
 #include "nv12_math.cuh"
 #include "scn_common.cuh"
 
@@ -28,73 +28,11 @@ constexpr int kPlanes = 10;
 constexpr int kHi = kPlanes - 3;   // planes 3..9
 constexpr int kMaxSteps = 127;     // 127 * 8 words per accumulator <= 1023
 
-using csa::csa3;
-
-struct Acc {
-  uint32_t p0, p1, p2;
-  uint32_t t0, t1, t2;
-  uint32_t hi[kHi];
-  uint32_t pend3, pend4;
-};
-
-__device__ __forceinline__ void acc_clear(Acc& a) {
-  a.p0 = a.p1 = a.p2 = a.t0 = a.t1 = a.t2 = 0;
-#pragma unroll
-  for (int i = 0; i < kHi; ++i) a.hi[i] = 0;
-  a.pend3 = a.pend4 = 0;
-}
-
-template <int K>  // K-th (0..7) word of a step; K == 7 yields the weight-8 carry
-__device__ __forceinline__ void push8(Acc& a, uint32_t x, uint32_t& c8) {
-  if constexpr ((K & 1) == 0) {
-    a.t0 = x;
-  } else {
-    uint32_t tw;
-    csa3(tw, a.p0, a.p0, a.t0, x);
-    if constexpr (((K >> 1) & 1) == 0) {
-      a.t1 = tw;
-    } else {
-      uint32_t fo;
-      csa3(fo, a.p1, a.p1, a.t1, tw);
-      if constexpr (((K >> 2) & 1) == 0) {
-        a.t2 = fo;
-      } else {
-        csa3(c8, a.p2, a.p2, a.t2, fo);
-      }
-    }
-  }
-}
-
-template <int FROM>
-__device__ __forceinline__ void ripple(Acc& a, uint32_t c) {
-#pragma unroll
-  for (int q = FROM; q < kHi; ++q) {
-    const uint32_t t = a.hi[q] & c;
-    a.hi[q] ^= c;
-    c = t;
-  }
-}
-
-__device__ __forceinline__ void fold_step(Acc& a, uint32_t c8, int step) {
-  if (step & 1) {
-    uint32_t c16;
-    csa3(c16, a.hi[0], a.hi[0], a.pend3, c8);
-    if (step & 2) {
-      uint32_t c32;
-      csa3(c32, a.hi[1], a.hi[1], a.pend4, c16);
-      ripple<2>(a, c32);
-    } else {
-      a.pend4 = c16;
-    }
-  } else {
-    a.pend3 = c8;
-  }
-}
-
-__device__ __forceinline__ void finish_span(Acc& a, int nsteps) {
-  if (nsteps & 2) ripple<1>(a, a.pend4);
-  if (nsteps & 1) ripple<0>(a, a.pend3);
-}
+using Acc = csa::Acc8<kHi>;
+using csa::acc_clear;
+using csa::finish_span;
+using csa::fold_step;
+using csa::push8;
 
 // 2^-11 scaled constants (exact power-of-two rescalings of image.cu's matrix, times 4 for the
 // 8->10 bit widening of the inputs)
@@ -143,12 +81,12 @@ constexpr uint32_t kResidueFix = 0u - 0xFB000000u;
 
 template <int K>
 __device__ __forceinline__ void count8(Acc& A, Acc& B, uint32_t z, uint32_t& cA, uint32_t& cB) {
-  z += kResidueFix;
-  const uint32_t zx = z ^ 0x88888888u;
-  push8<K>(A, prmt(csa::kLutLo, csa::kLutHiA, z), cA);
-  push8<K + 1>(A, prmt(csa::kLutLo, csa::kLutHiA, z >> 16), cA);
-  push8<K>(B, prmt(csa::kLutLo, csa::kLutHiB, zx), cB);
-  push8<K + 1>(B, prmt(csa::kLutLo, csa::kLutHiB, zx >> 16), cB);
+  uint32_t a_lo, a_hi, b_lo, b_hi;
+  csa::decode8(z + kResidueFix, a_lo, a_hi, b_lo, b_hi);
+  push8<K>(A, a_lo, cA);
+  push8<K + 1>(A, a_hi, cA);
+  push8<K>(B, b_lo, cB);
+  push8<K + 1>(B, b_hi, cB);
 }
 
 // 8 pixels of one row: luma words y0,y1 (4 px each), chroma words c0,c1 (2 pairs each)
@@ -195,38 +133,11 @@ struct Params {
   uint32_t sixteen;           // == 16 (see pixel())
 };
 
-__device__ __forceinline__ void warp_sum(uint32_t (&pl)[kPlanes + 5]) {
-#pragma unroll
-  for (int d = 0; d < 5; ++d) {
-    uint32_t carry = 0;
-#pragma unroll
-    for (int p = 0; p < kPlanes + 5; ++p) {
-      if (p < kPlanes + d) {
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, pl[p], 1 << d);
-        const uint32_t u = pl[p] ^ o;
-        const uint32_t nc = (pl[p] & o) | (u & carry);
-        pl[p] = u ^ carry;
-        carry = nc;
-      } else if (p == kPlanes + d) {
-        pl[p] = carry;
-      }
-    }
-  }
-}
-
 __device__ __forceinline__ uint32_t lane_count(const Acc& a, int lane) {
   uint32_t pl[kPlanes + 5];
-  pl[0] = a.p0;
-  pl[1] = a.p1;
-  pl[2] = a.p2;
-#pragma unroll
-  for (int q = 0; q < kHi; ++q) pl[3 + q] = a.hi[q];
-#pragma unroll
-  for (int q = kPlanes; q < kPlanes + 5; ++q) pl[q] = 0;
-  warp_sum(pl);
-  uint32_t v = 0;
-#pragma unroll
-  for (int p = 0; p < kPlanes + 5; ++p) v |= ((pl[p] >> lane) & 1u) << p;
+  csa::planes_of(a, pl);
+  csa::warp_sum<kPlanes>(pl);
+  uint32_t v = csa::extract_lane<kPlanes>(pl, lane);
   // the four byte slots of a word carry the same channel: fold them onto lanes 0..7
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 16);

@@ -218,6 +218,24 @@ def test_many_jobs_share_the_task_queue(eng):
     assert eng.stats()["counters"]["tasks"] == sum((10 + k + 5) // 6 for k in range(7))
 
 
+def test_no_buffers_leak_across_runs(eng):
+    """Every element the pipeline allocates is released by the end of the run (refcounted blocks,
+    stencil caches, dropped warmup rows, unused output columns, sampled-away rows)."""
+    def build(g, src):
+        two = g.add_op("TestTwoOut", [(src, "column")])
+        win = g.add_op("TestWindow", [(two, "twice")])
+        inc = g.add_op("TestIncrementBounded", [(src, "column")], warmup=2)
+        s = g.add_sample((inc, "integer"))
+        s2 = g.add_sample((win, "window"))
+        return (g.add_sink((s2, "window")), g.add_sink((s, "integer"))), {"s": s, "s2": s2}
+    enc = protolite.encode(protolite.SAMPLER_ARGS["StridedSamplerArgs"], {"stride": 3})
+    for _ in range(3):
+        run_simple(eng, 30, build, wps=4, ios=12, samplers={"s": ("Strided", enc), "s2": ("Strided", enc)})
+        c = eng.stats()["counters"]
+        assert c["cpu_bytes_live"] == 0, c
+        assert c["cpu_bytes_peak"] > 0
+
+
 def test_errors(eng):
     with pytest.raises(E.EngineError, match="not registered"):
         E.Graph().add_op("NoSuchOp", [(0, "column")])

@@ -193,6 +193,26 @@ def test_raw_frames_host_to_device_marshalling(eng):
         assert got.shape == (90, 160, 3) and (got == oracle.resize(frames[i], 160, 90)).all()
 
 
+def test_no_device_memory_leaks(eng):
+    data, want = make_clip(16, 14, 96, 128, 4)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    bl = g.add_op("Blur", [(src, "frame")], device=1, args=protolite.encode(STD_ARGS["BlurArgs"], {"kernel_size": 3}))
+    hs = g.add_op("Histogram", [(bl, "frame")], device=1)
+    rz = g.add_op("Resize", [(src, "frame")], device=1)
+    g.add_sink((hs, "histogram"))
+    g.add_sink((rz, "frame"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_stream_args(rz, protolite.encode(STD_ARGS["ResizeArgs"], {"width": 32, "height": 24}))
+    for _ in range(2):
+        eng.run(g, [j], 3, 6)
+        c = eng.stats()["counters"]
+        assert c["gpu0_bytes_live"] == 0 and c["cpu_bytes_live"] == 0, c
+        assert c["gpu0_bytes_peak"] >= 3 * 96 * 128 * 3
+
+
 def test_many_clips_sharded_over_instances(eng):
     clips = [make_clip(100 + k, 12 + k, 96, 128, 4) for k in range(6)]
     g = E.Graph()
