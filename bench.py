@@ -88,6 +88,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def usable_cores():
+    """Host cores this process may actually use: scheduler affinity capped by the cgroup CPU quota
+    (the GPU boxes report 128 logical CPUs but run the container under cpu.max = 16 cores)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def make_surfaces_np(n, seed):
     import numpy as np
     rng = np.random.default_rng(seed)
@@ -129,7 +142,7 @@ def cpu_reference_fps(clip_bytes, n_clips, steps, warmup):
     """frames/s of the CPU path on all host cores; clips are written to /dev/shm once."""
     import multiprocessing as mp
     import tempfile
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     tmpdir = tempfile.mkdtemp(prefix="scn_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     paths = []
     for i in range(n_clips):
@@ -158,9 +171,9 @@ def run_reference(args, rank, world):
     """CPU arm (rank 0 only): FFmpeg decode + OpenCV Histogram/Resize, one clip per core."""
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     frames_per_clip = 60
-    n_clips = max(cores, 8)
+    n_clips = max(2 * cores, 8)
     clips = [make_clip_bytes(500 + i, frames_per_clip) for i in range(min(n_clips, 4))]
     fps, s_per_step, cores, sample = cpu_reference_fps(clips, n_clips, args.steps, max(1, min(args.warmup, 1)))
     desc = (f"{n_clips} clips x {frames_per_clip} frames per step ({sample} frames), cv2.VideoCapture (FFmpeg) decode + "
@@ -194,7 +207,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--e2e-clips", type=int, default=28)
     ap.add_argument("--e2e-frames", type=int, default=120)
-    ap.add_argument("--instances", type=int, default=14, help="pipeline instances per GPU for the e2e leg")
+    ap.add_argument("--instances", type=int, default=0,
+                    help="pipeline instances per GPU for the e2e leg (0 = 14 capped by 2 x usable host cores / ranks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -267,6 +281,10 @@ def main():
     E.load_stdlib()
     std = protolite.parse_proto(open(os.path.join(ROOT, "scanner_b200", "csrc", "ops", "stdlib_args.proto")).read())
     e2e_clips, e2e_frames = args.e2e_clips, args.e2e_frames
+    if args.instances <= 0:
+        # every instance is a host thread that spends most of its time blocked in the NVDEC driver;
+        # 14 per GPU saturate the 7 engines, but the ranks of one box share the host's CPU quota
+        args.instances = max(2, min(14, 2 * usable_cores() // world))
     eng = E.Engine(gpus=[local_rank], instances_per_gpu=args.instances)
     uniq = [make_clip_bytes(2000 + 16 * rank + i, e2e_frames) for i in range(min(e2e_clips, 4))]
     sids = [eng.add_h264(uniq[i % len(uniq)]) for i in range(e2e_clips)]
@@ -342,8 +360,8 @@ def main():
 
 def cpu_baseline(args):
     """The reference's CPU path (FFmpeg decode + OpenCV ops) on a bounded sample, all host cores."""
-    cores = os.cpu_count() or 1
-    n_clips = max(cores, 8)
+    cores = usable_cores()
+    n_clips = max(2 * cores, 8)
     clips = [make_clip_bytes(700 + i, 60) for i in range(min(n_clips, 4))]
     fps, s_per_step, cores, sample = cpu_reference_fps(clips, n_clips, 1, 1)
     return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
