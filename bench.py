@@ -184,7 +184,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, sample),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -198,7 +198,28 @@ def workload_config(args, batch):
 
 
 # ------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL (and anything else native) prints banners such
+    as "NCCL version ..." straight to fd 1, so fd 1 is pointed at stderr for the whole run and the
+    result line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -352,7 +373,7 @@ def main():
                 "whole_step_roofline_frac": value / world * B_ALG_FUSED / 1e9 / peak}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
