@@ -14,6 +14,16 @@ size_t size_of_frame_type(FrameType type);
 
 const i32 FRAME_DIMS = 3;
 
+// scanner-b200 extension (not in the reference): how the bytes of a frame element are laid out.
+//   HWC   dense height x width x channels, what every reference op expects (and the default)
+//   NV12  a decoder surface kept in its native form: shape = (H*3/2, W, 1) U8 -- W x H luma rows
+//         followed by W x H/2 rows of interleaved Cb,Cr (the convention cv::COLOR_YUV2RGB_NV12
+//         takes).  The decode stage emits it ONLY for a video column whose every consumer kernel
+//         registered `.input_layout(col, FrameLayout::NV12)`; such kernels must produce what they
+//         would have produced from the RGB24 frame the reference's decoder delivers
+//         (scanner/util/image.cu:109-200).
+enum class FrameLayout : u8 { HWC = 0, NV12 = 1 };
+
 struct FrameInfo {
   FrameInfo() = default;
   FrameInfo(int shape0, int shape1, int shape2, FrameType type);
@@ -27,15 +37,27 @@ struct FrameInfo {
   int height() const { return shape[0]; }
   int channels() const { return shape[2]; }
 
+  // NV12 surface of a width x height picture (both even)
+  static FrameInfo nv12(int width, int height) {
+    FrameInfo f(height + height / 2, width, 1, FrameType::U8);
+    f.layout = FrameLayout::NV12;
+    return f;
+  }
+
   int shape[FRAME_DIMS] = {0, 0, 0};
   FrameType type = FrameType::U8;
+  FrameLayout layout = FrameLayout::HWC;
 };
 
 class Frame {
  public:
   Frame(FrameInfo info, u8* buffer);
 
-  FrameInfo as_frame_info() const { return FrameInfo(shape[0], shape[1], shape[2], type); }
+  FrameInfo as_frame_info() const {
+    FrameInfo f(shape[0], shape[1], shape[2], type);
+    f.layout = layout;
+    return f;
+  }
   size_t size() const { return as_frame_info().size(); }
   int width() const { return shape[1]; }
   int height() const { return shape[0]; }
@@ -44,6 +66,7 @@ class Frame {
   int shape[FRAME_DIMS];
   FrameType type;
   u8* data;
+  FrameLayout layout = FrameLayout::HWC;  // extension, see above
 };
 
 Frame* new_frame(DeviceHandle device, FrameInfo info);

@@ -204,6 +204,12 @@ class KernelBuilder {
     output_devices_[output_name] = device_type;
     return *this;
   }
+  // scanner-b200 extension: this kernel also accepts `input_name` as a decoder-native surface
+  // (see FrameLayout in frame.h); without it the column always arrives as dense RGB24.
+  KernelBuilder& input_layout(const std::string& input_name, FrameLayout layout) {
+    input_layouts_[input_name] = layout;
+    return *this;
+  }
   KernelBuilder& batch(i32 preferred_batch_size = 1) {
     can_batch_ = true;
     preferred_batch_size_ = preferred_batch_size;
@@ -217,6 +223,7 @@ class KernelBuilder {
   i32 num_devices_ = 1;
   std::map<std::string, DeviceType> input_devices_;
   std::map<std::string, DeviceType> output_devices_;
+  std::map<std::string, FrameLayout> input_layouts_;
   bool can_batch_ = false;
   i32 preferred_batch_size_ = 1;
 };

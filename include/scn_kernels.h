@@ -115,13 +115,22 @@ SCN_API int scn_nv12_to_rgb24(const uint8_t* const* host_luma_ptrs,
                       int height, uint8_t* const* host_rgb_ptrs, size_t rgb_pitch,
                       void* stream);
 
+/* Pitched decoder surface -> packed NV12 frame element: `width` x `height` luma rows followed by
+ * `width` x height/2 interleaved CbCr rows, no padding (the FrameLayout::NV12 element of
+ * include/scanner/api/frame.h; what the decode stage hands to kernels that registered for it
+ * instead of the RGB24 frame of nvidia_video_decoder.cpp:288-296).  Byte copy. */
+SCN_API int scn_nv12_pack(const uint8_t* const* host_luma_ptrs, const uint8_t* const* host_chroma_ptrs,
+                          size_t pitch, int n, int width, int height, uint8_t* const* host_dst_ptrs,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused decode-side DAG of BASELINE.json configs[1]:
  *      NV12 surface -> RGB24 -> { Histogram , Resize(dst_w, dst_h) }
  * without materialising the RGB24 frame (what the reference does in three passes:
  * image.cu NV12_to_RGB, then test_ops.cpp Histogram and Resize kernels over the RGB frame).
- * hist_out: int32[n][3][16] (fully overwritten); resized: n dense RGB24 dst_h x dst_w frames
- * at host_dst_ptrs[i] (may be NULL to skip the resize output).  Results are bit-identical to
+ * hist_out: int32[n][3][16] (fully overwritten; NULL skips the histogram); resized: n dense RGB24
+ * dst_h x dst_w frames at host_dst_ptrs[i] (NULL skips the resize) -- so the same entry point is
+ * also "Histogram on an NV12 frame" and "Resize on an NV12 frame".  Results are bit-identical to
  * running scn_nv12_to_rgb24 + scn_hist16_u8c3 + scn_resize_bilinear_u8c3.
  */
 SCN_API int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "scn_box_blur_u8c3": (_c.c_int, [_PP, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _PP, _VP]),
     "scn_box_blur_u8c3_strided": (_c.c_int, [_VP, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _VP, _VP]),
     "scn_nv12_to_rgb24": (_c.c_int, [_PP, _PP, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _PP, _c.c_size_t, _VP]),
+    "scn_nv12_pack": (_c.c_int, [_PP, _PP, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _PP, _VP]),
     "scn_farneback_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "scn_farneback_u8c3": (_c.c_int, [_PP, _PP, _c.c_int, _c.c_int, _c.c_int, _PP, _c.c_int, _c.c_double, _c.c_int,
                                       _c.c_int, _c.c_int, _c.c_double, _VP, _c.c_size_t, _VP]),

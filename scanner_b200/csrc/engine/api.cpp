@@ -25,13 +25,13 @@ FrameInfo::FrameInfo(const std::vector<int> shapes, FrameType t) : type(t) {
 }
 bool FrameInfo::operator==(const FrameInfo& o) const {
   return (proto::FrameType)type == (proto::FrameType)o.type && shape[0] == o.shape[0] &&
-         shape[1] == o.shape[1] && shape[2] == o.shape[2];
+         shape[1] == o.shape[1] && shape[2] == o.shape[2] && layout == o.layout;
 }
 size_t FrameInfo::size() const {
   return size_of_frame_type(type) * (size_t)shape[0] * (size_t)shape[1] * (size_t)shape[2];
 }
 
-Frame::Frame(FrameInfo info, u8* b) : type(info.type), data(b) {
+Frame::Frame(FrameInfo info, u8* b) : type(info.type), data(b), layout(info.layout) {
   memcpy(shape, info.shape, sizeof(shape));
 }
 

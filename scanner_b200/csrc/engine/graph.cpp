@@ -397,6 +397,35 @@ Result Graph::analyze(GraphAnalysis& an) {
   return r;
 }
 
+bool Graph::consumers_accept_layout(i32 source_op, FrameLayout layout) const {
+  std::vector<i32> work = {source_op};
+  std::set<i32> seen;
+  bool any = false;
+  while (!work.empty()) {
+    const i32 producer = work.back();
+    work.pop_back();
+    if (!seen.insert(producer).second) continue;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const GraphOp& op = ops[i];
+      for (size_t k = 0; k < op.inputs.size(); ++k) {
+        if (op.inputs[k].op_index != producer) continue;
+        if (op.kind == OpKind::Sample || op.kind == OpKind::Space) {
+          work.push_back((i32)i);
+          continue;
+        }
+        if (op.kind != OpKind::Kernel) return false;  // a sink stores the frames: keep them RGB24
+        const OpInfo* info = get_op_registry()->get_op_info(op.name);
+        const KernelFactory* kf = get_kernel_registry()->get_kernel(op.name, op.device_type);
+        if (!info || !kf || info->variadic_inputs || k >= info->input_columns.size()) return false;
+        auto it = kf->input_layouts.find(info->input_columns[k].name);
+        if (it == kf->input_layouts.end() || it->second != layout) return false;
+        any = true;
+      }
+    }
+  }
+  return any;
+}
+
 Result Graph::domain_sizes(const JobParams& job, std::vector<i64>& rows) const {
   Result r;
   rows.assign(ops.size(), 0);

@@ -97,6 +97,11 @@ class Graph {
   // (reference validate_jobs_and_ops :43-466, populate_analysis_info, liveness).
   Result analyze(GraphAnalysis& out);
 
+  // True when every kernel that (transitively through Sample/Space ops) reads the output of
+  // `source_op` registered `layout` for that input column -- the decode stage may then deliver
+  // decoder-native surfaces instead of RGB24 (scanner-b200 extension, frame.h FrameLayout).
+  bool consumers_accept_layout(i32 source_op, FrameLayout layout) const;
+
   // Rows each op produces for this job (domain sizes).
   Result domain_sizes(const JobParams& job, std::vector<i64>& rows_per_op) const;
 

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <sstream>
 #include <unordered_map>
 
 #include "engine_internal.h"
@@ -284,8 +285,24 @@ static void copy_async(u8* dst, DeviceHandle dd, const u8* src, DeviceHandle sd,
   internal::ScopedDevice scoped(g.id);
   cudaError_t e =
       cudaMemcpyAsync(dst, src, size, cudaMemcpyDefault, (cudaStream_t)device_stream(g));
-  if (e != cudaSuccess)
-    LOG(FATAL) << "memcpy " << sd << " -> " << dd << " failed: " << cudaGetErrorString(e);
+  if (e != cudaSuccess) {
+    // say what the driver thinks the two ranges are: the usual cause is a host range that is only
+    // partly page-locked, or a device pointer that is no longer live
+    auto describe = [](const void* p) {
+      cudaPointerAttributes a;
+      std::ostringstream os;
+      os << p;
+      if (cudaPointerGetAttributes(&a, p) == cudaSuccess)
+        os << " (type " << (int)a.type << ", device " << a.device << ")";
+      else
+        cudaGetLastError();
+      return os.str();
+    };
+    LOG(FATAL) << "memcpy " << sd << " -> " << dd << " of " << size << " B failed: " << cudaGetErrorString(e)
+               << "; src " << describe(src) << " .. " << describe(src + size - 1) << ", dst " << describe(dst)
+               << " .. " << describe(dst + size - 1) << ", stream " << device_stream(g) << " query="
+               << cudaGetErrorString(cudaStreamQuery((cudaStream_t)device_stream(g)));
+  }
 }
 
 void memcpy_buffer_async(u8* dst, DeviceHandle dd, const u8* src, DeviceHandle sd, size_t size) {
@@ -300,14 +317,26 @@ void memcpy_buffer(u8* dst, DeviceHandle dd, const u8* src, DeviceHandle sd, siz
     sync_device(sd);
 }
 
+// true when both pointers lie inside the same live allocation of `device`
+static bool same_block(DeviceHandle device, const u8* a, const u8* b) {
+  DeviceTable& t = table_for(device);
+  std::lock_guard<std::mutex> g(t.mu);
+  auto ia = find_block(t, a), ib = find_block(t, b);
+  return ia != t.blocks.end() && ia == ib;
+}
+
 void memcpy_vec(std::vector<u8*>& dest_buffers, DeviceHandle dd, const std::vector<u8*>& src,
                 DeviceHandle sd, const std::vector<size_t>& sizes) {
-  // coalesce runs that are contiguous on both sides into one DMA
+  // Coalesce runs that are contiguous on both sides into one DMA -- but only inside ONE
+  // allocation on each side: two cudaMallocAsync blocks can be neighbours in the address space,
+  // and the driver rejects a copy that spans them ("invalid argument", seen when single-frame
+  // outputs of an unbatched kernel happened to be adjacent).
   size_t i = 0;
   while (i < src.size()) {
     size_t j = i, run = sizes[i];
     while (j + 1 < src.size() && src[j] + sizes[j] == src[j + 1] &&
-           dest_buffers[j] + sizes[j] == dest_buffers[j + 1]) {
+           dest_buffers[j] + sizes[j] == dest_buffers[j + 1] && same_block(sd, src[i], src[j + 1]) &&
+           same_block(dd, dest_buffers[i], dest_buffers[j + 1])) {
       ++j;
       run += sizes[j];
     }

@@ -78,7 +78,7 @@ struct Engine::RunState {
   std::mutex err_mu;
   std::string error;
   Profiler profiler;
-  std::atomic<i64> frames_decoded{0}, frames_used{0};
+  std::atomic<i64> frames_decoded{0}, frames_used{0}, frames_native{0};
 
   void fail(const std::string& msg) {
     std::lock_guard<std::mutex> g(err_mu);
@@ -133,7 +133,8 @@ i64 Engine::add_stream(std::unique_ptr<InputStream> s) {
     adopt_block(CPU_DEVICE, s->data.data(), s->data.size());
     // page-lock the payload so GPU instances can DMA straight from it
     if (cuda_available() && !gpu_ids_.empty()) {
-      if (cudaHostRegister(s->data.data(), s->data.size(), cudaHostRegisterPortable) == cudaSuccess)
+      if (cudaHostRegister(s->data.data(), PageAllocator<u8>::padded(s->data.size()), cudaHostRegisterPortable) ==
+          cudaSuccess)
         s->registered = true;
       else
         cudaGetLastError();
@@ -176,8 +177,9 @@ struct SourceCursor {
   size_t cur_interval = 0;
   bool interval_open = false;
   std::unique_ptr<NvdecSession> session;
-  std::map<i64, u8*> blocks;  // packet index -> RGB24 frame block on the GPU
+  std::map<i64, u8*> blocks;  // packet index -> frame block on the GPU (RGB24, or NV12 surfaces)
   size_t frame_bytes = 0;
+  bool nv12 = false;          // deliver decoder-native surfaces (every consumer accepts them)
   i64 wps = 1;
   DeviceHandle gpu_dev;
 
@@ -284,7 +286,13 @@ void Engine::instance_main(Instance* inst) {
             }
           }
           c.intervals = slice_into_intervals(c.stream->index, c.rows);
-          c.frame_bytes = (size_t)c.stream->index.width * c.stream->index.height * 3;
+          // decoder-native delivery when every consumer kernel takes NV12 (frame.h FrameLayout);
+          // SCN_DECODE_RGB=1 forces the reference's RGB24 elements
+          const char* force_rgb = getenv("SCN_DECODE_RGB");
+          c.nv12 = !(force_rgb && force_rgb[0] == '1') &&
+                   rs.graph->consumers_accept_layout((i32)k, FrameLayout::NV12);
+          const size_t px = (size_t)c.stream->index.width * c.stream->index.height;
+          c.frame_bytes = c.nv12 ? px + px / 2 : px * 3;
         }
         cursors.push_back(std::move(c));
       }
@@ -309,7 +317,8 @@ void Engine::instance_main(Instance* inst) {
             const timepoint_t d0 = now();
             cb.device = gpu_dev;
             NvdecSession& sess = *sessions[c.op];
-            const FrameInfo finfo(st.index.height, st.index.width, 3, FrameType::U8);
+            const FrameInfo finfo = c.nv12 ? FrameInfo::nv12(st.index.width, st.index.height)
+                                           : FrameInfo(st.index.height, st.index.width, 3, FrameType::U8);
             size_t delivered_global = c.cur_interval < c.intervals.size()
                                           ? (size_t)c.intervals[c.cur_interval].out_base +
                                                 (c.interval_open ? sess.delivered() : 0)
@@ -328,6 +337,11 @@ void Engine::instance_main(Instance* inst) {
                       const u8* lp = s.luma;
                       const u8* cp = s.chroma;
                       u8* dst = cur->slot(out_index);
+                      if (cur->nv12) {
+                        const int rc = scn_nv12_pack(&lp, &cp, s.pitch, 1, (int)w, (int)h, &dst, stream);
+                        if (rc != 0) rsp->fail("scn_nv12_pack failed: " + std::to_string(rc));
+                        return;
+                      }
                       const int rc = scn_nv12_to_rgb24(&lp, &cp, s.pitch, 1, (int)w, (int)h, &dst, w * 3, stream);
                       if (rc != 0) rsp->fail("scn_nv12_to_rgb24 failed: " + std::to_string(rc));
                     });
@@ -352,6 +366,7 @@ void Engine::instance_main(Instance* inst) {
               cb.elements.push_back(Element(new Frame(finfo, c.slot((i64)i))));
               cb.row_ids.push_back(c.rows[i]);
             }
+            if (c.nv12) rs.frames_native += (i64)(i1 - i0);
             c.blocks.erase((i64)p);  // ownership of the packet's block now rides on its elements
             rs.profiler.add_interval("get_frames", d0, now());
           } else {
@@ -608,6 +623,7 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   stats_.wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   stats_.counters = rs.profiler.counters();
   stats_.counters["frames_decoded"] = rs.frames_decoded.load();
+  stats_.counters["frames_delivered_nv12"] = rs.frames_native.load();
   stats_.counters["frames_used"] = rs.frames_used.load();
   {
     long long ns[6];

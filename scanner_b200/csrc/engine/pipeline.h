@@ -12,6 +12,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <cstdlib>
+#include <new>
 #include <vector>
 
 #include "evaluate.h"
@@ -22,6 +24,30 @@
 namespace scanner {
 namespace internal {
 
+// Payload storage that owns whole pages: the engine page-locks it in place (cudaHostRegister
+// works on page granularity -- a buffer sharing its first/last page with other heap objects would
+// leave those half-registered, and a later cudaMemcpy touching them fails with "invalid argument").
+template <typename T>
+struct PageAllocator {
+  using value_type = T;
+  static constexpr size_t kPage = 4096;
+  PageAllocator() = default;
+  template <typename U>
+  PageAllocator(const PageAllocator<U>&) {}
+  static size_t padded(size_t bytes) { return (bytes + kPage - 1) / kPage * kPage; }
+  T* allocate(size_t n) {
+    void* p = nullptr;
+    if (posix_memalign(&p, kPage, padded(n ? n * sizeof(T) : 1)) != 0) throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, size_t) { free(p); }
+  template <typename U>
+  bool operator==(const PageAllocator<U>&) const { return true; }
+  template <typename U>
+  bool operator!=(const PageAllocator<U>&) const { return false; }
+};
+using PageBuffer = std::vector<u8, PageAllocator<u8>>;
+
 struct InputStream {
   enum Kind { H264, RawFrames, Bytes } kind = Bytes;
   // H264
@@ -30,7 +56,7 @@ struct InputStream {
   // RawFrames: n dense frames of `info`
   FrameInfo info;
   // RawFrames / Bytes payload + per-row extents
-  std::vector<u8> data;
+  PageBuffer data;
   std::vector<u64> offsets, sizes;
   bool registered = false;  // payload is cudaHostRegister'ed
   i64 rows() const { return kind == H264 ? index.frames() : (i64)sizes.size(); }

@@ -111,6 +111,7 @@ KernelRegistration::KernelRegistration(const KernelBuilder& b) {
   f.max_devices = b.num_devices_;
   for (auto& kv : b.input_devices_) f.input_devices[kv.first] = (proto::DeviceType)kv.second;
   for (auto& kv : b.output_devices_) f.output_devices[kv.first] = (proto::DeviceType)kv.second;
+  f.input_layouts = b.input_layouts_;
   f.can_batch = b.can_batch_;
   f.preferred_batch_size = b.preferred_batch_size_;
   f.constructor = b.constructor_;

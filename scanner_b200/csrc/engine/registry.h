@@ -41,6 +41,7 @@ struct KernelFactory {
   i32 max_devices = 1;
   std::map<std::string, proto::DeviceType> input_devices;
   std::map<std::string, proto::DeviceType> output_devices;
+  std::map<std::string, FrameLayout> input_layouts;  // columns also accepted in a non-HWC layout
   bool can_batch = false;
   i32 preferred_batch_size = 1;
   KernelConstructor constructor;

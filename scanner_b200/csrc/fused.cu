@@ -137,14 +137,18 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
   if (n < 0 || width <= 0 || height <= 0 || (width & 1) || (height & 1) || pitch < (size_t)width)
     return SCN_E_BADARG;
   if (n == 0) return 0;
-  if (!host_luma_ptrs || !host_chroma_ptrs || !hist_out) return SCN_E_BADARG;
+  if (!host_luma_ptrs || !host_chroma_ptrs) return SCN_E_BADARG;
+  const bool do_hist = hist_out != nullptr;
   const bool do_resize = host_dst_ptrs != nullptr;
+  if (!do_hist && !do_resize) return SCN_E_BADARG;
   const bool area2x = do_resize && (width == 2 * dst_w && height == 2 * dst_h);
   if (do_resize && (dst_w <= 0 || dst_h <= 0)) return SCN_E_BADARG;
   if (do_resize && !area2x && !plan) return SCN_E_PLAN;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(hist_out, 0, (size_t)n * 48 * sizeof(int32_t), st);
-  if (e != cudaSuccess) return (int)e;
+  if (do_hist) {
+    cudaError_t e = cudaMemsetAsync(hist_out, 0, (size_t)n * 48 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+  }
   const int quads = (width + 3) / 4;
   for (int i0 = 0; i0 < n; i0 += SCN_MAX_PTRS) {
     const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
@@ -157,7 +161,7 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
       d.p[i] = do_resize ? host_dst_ptrs[i0 + i] : nullptr;
       if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i]) & 3) vec_ok = 0;
     }
-    const bool use_csa = nvcsa::eligible(l.p, c.p, cnt, pitch, width, height);
+    const bool use_csa = do_hist && nvcsa::eligible(l.p, c.p, cnt, pitch, width, height);
     if (use_csa) {
       int rc = nvcsa::launch(l.p, c.p, cnt, pitch, width, height, hist_out + (size_t)i0 * 48, st);
       if (rc) return rc;
@@ -167,7 +171,7 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
     if (gy < 1) gy = 1;
     if (gy > height) gy = height;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
-    if (!use_csa) {
+    if (do_hist && !use_csa) {
       LaunchScope ls("nv12_hist_kernel", st);
       nv12_hist_kernel<<<grid, HT, 0, st>>>(l, c, pitch, width, height, quads, vec_ok,
                                           hist_out + (size_t)i0 * 48);

@@ -65,8 +65,70 @@ nv12_to_rgb_kernel(PtrBatch lumas, PtrBatch chromas, MutPtrBatch rgbs, size_t pi
   }
 }
 
+// Pitched decoder surface -> packed NV12 element (W x H luma rows, then W x H/2 CbCr rows).
+// Row r of the packed image comes from the luma plane for r < H, from the chroma plane after.
+// 16 bytes per thread when everything is 16-byte aligned, else bytes.
+__global__ void __launch_bounds__(256)
+nv12_pack_kernel(PtrBatch lumas, PtrBatch chromas, MutPtrBatch dsts, size_t pitch, int width, int height,
+                 int vec16) {
+  const uint8_t* __restrict__ luma = lumas.p[blockIdx.z];
+  const uint8_t* __restrict__ chroma = chromas.p[blockIdx.z];
+  uint8_t* __restrict__ dst = dsts.p[blockIdx.z];
+  const int rows = height + (height >> 1);
+  if (vec16) {
+    const int vpr = width >> 4;  // 16-byte vectors per row
+    const long total = (long)vpr * rows;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / vpr), v = (int)(i - (long)r * vpr);
+      const uint8_t* src = (r < height ? luma + (size_t)r * pitch : chroma + (size_t)(r - height) * pitch) + v * 16;
+      *reinterpret_cast<uint4*>(dst + (size_t)r * width + v * 16) = ld_stream_u4(src);
+    }
+  } else {
+    const long total = (long)width * rows;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+      const int r = (int)(i / width), x = (int)(i - (long)r * width);
+      dst[i] = r < height ? luma[(size_t)r * pitch + x] : chroma[(size_t)(r - height) * pitch + x];
+    }
+  }
+}
+
 }  // namespace
 }  // namespace scn
+
+extern "C" int scn_nv12_pack(const uint8_t* const* host_luma_ptrs, const uint8_t* const* host_chroma_ptrs,
+                             size_t pitch, int n, int width, int height, uint8_t* const* host_dst_ptrs,
+                             void* stream) {
+  using namespace scn;
+  if (n < 0 || width <= 0 || height <= 0 || (width & 1) || (height & 1) || pitch < (size_t)width)
+    return SCN_E_BADARG;
+  if (n == 0) return 0;
+  if (!host_luma_ptrs || !host_chroma_ptrs || !host_dst_ptrs) return SCN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i0 = 0; i0 < n; i0 += SCN_MAX_PTRS) {
+    const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
+    PtrBatch l, c;
+    MutPtrBatch d;
+    int vec16 = ((pitch & 15) == 0) && ((width & 15) == 0);
+    for (int i = 0; i < cnt; ++i) {
+      l.p[i] = host_luma_ptrs[i0 + i];
+      c.p[i] = host_chroma_ptrs[i0 + i];
+      d.p[i] = host_dst_ptrs[i0 + i];
+      if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i] | (uintptr_t)d.p[i]) & 15) vec16 = 0;
+    }
+    const long work = vec16 ? (long)(width >> 4) * (height + height / 2) : (long)width * (height + height / 2);
+    long gx = (work + 255) / 256;
+    const long cap = (long)sm_count() * 8 / cnt + 1;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, 1, (unsigned)cnt);
+    {
+      LaunchScope ls("nv12_pack_kernel", st);
+      nv12_pack_kernel<<<grid, 256, 0, st>>>(l, c, d, pitch, width, height, vec16);
+    }
+    int rc = launch_status();
+    if (rc) return rc;
+  }
+  return 0;
+}
 
 extern "C" int scn_nv12_to_rgb24(const uint8_t* const* host_luma_ptrs,
                                  const uint8_t* const* host_chroma_ptrs, size_t pitch, int n,

@@ -34,7 +34,18 @@ void for_each_run(const Elements& col, F&& fn) {
   }
 }
 
+bool is_nv12(const Frame* f) { return f->layout == FrameLayout::NV12; }
+
+// geometry of the picture a frame element holds (an NV12 element is (H*3/2, W, 1))
+int pic_width(const Frame* f) { return f->width(); }
+int pic_height(const Frame* f) { return is_nv12(f) ? f->height() / 3 * 2 : f->height(); }
+
 void require_rgb8(const Frame* f, const char* op) {
+  if (is_nv12(f)) {
+    if (f->channels() != 1 || (proto::FrameType)f->type != proto::U8 || f->height() % 3 != 0 || (f->width() & 1))
+      LOG(FATAL) << op << ": malformed NV12 frame element " << f->height() << "x" << f->width();
+    return;
+  }
   if (f->channels() != 3 || (proto::FrameType)f->type != proto::U8)
     LOG(FATAL) << op << " expects HxWx3 uint8 frames, got " << f->height() << "x" << f->width() << "x"
                << f->channels() << " type " << (int)(proto::FrameType)f->type;
@@ -56,6 +67,16 @@ class HistogramKernelGPU : public BatchedKernel {
       require_rgb8(f0, "Histogram");
       std::vector<const u8*> ptrs;
       for (size_t i = i0; i < i1; ++i) ptrs.push_back(frames[i].as_const_frame()->data);
+      if (is_nv12(f0)) {
+        // decoder-native surface: colour conversion happens in registers, RGB24 never exists
+        const int w = pic_width(f0), h = pic_height(f0);
+        std::vector<const u8*> chroma;
+        for (const u8* p : ptrs) chroma.push_back(p + (size_t)w * h);
+        SCN_CHECK(scn_nv12_hist_resize(ptrs.data(), chroma.data(), (size_t)w, (int)ptrs.size(), w, h,
+                                       (int32_t*)(block + i0 * kHistBytes), nullptr, 0, 0, nullptr,
+                                       device_stream(device_)));
+        return;
+      }
       SCN_CHECK(scn_hist16_u8c3(ptrs.data(), (int)ptrs.size(), f0->width(), f0->height(),
                                 (int32_t*)(block + i0 * kHistBytes), device_stream(device_)));
     });
@@ -68,7 +89,11 @@ class HistogramKernelGPU : public BatchedKernel {
 
 REGISTER_OP(Histogram).frame_input("frame").output("histogram", ColumnType::Bytes, "Histogram");
 
-REGISTER_KERNEL(Histogram, HistogramKernelGPU).device(DeviceType::GPU).batch(64).num_devices(1);
+REGISTER_KERNEL(Histogram, HistogramKernelGPU)
+    .device(DeviceType::GPU)
+    .batch(64)
+    .num_devices(1)
+    .input_layout("frame", FrameLayout::NV12);
 
 // ---------------------------------------------------------------------------------------------
 class ResizeKernelGPU : public BatchedKernel {
@@ -86,9 +111,9 @@ class ResizeKernelGPU : public BatchedKernel {
     CU_CHECK(cudaSetDevice(device_.id));
     for_each_run(frames, [&](size_t i0, size_t i1, const Frame* f0) {
       require_rgb8(f0, "Resize");
+      const int sw = pic_width(f0), sh = pic_height(f0);
       int tw = 0, th = 0;
-      scn_resize_target(f0->width(), f0->height(), args_.width(), args_.height(), args_.min(),
-                        args_.preserve_aspect(), &tw, &th);
+      scn_resize_target(sw, sh, args_.width(), args_.height(), args_.min(), args_.preserve_aspect(), &tw, &th);
       if (tw <= 0 || th <= 0) LOG(FATAL) << "Resize: invalid target size " << tw << "x" << th;
       const i32 n = (i32)(i1 - i0);
       FrameInfo info(th, tw, 3, FrameType::U8);
@@ -99,8 +124,15 @@ class ResizeKernelGPU : public BatchedKernel {
         src.push_back(frames[i0 + i].as_const_frame()->data);
         dst.push_back(outs[i]->data);
       }
-      SCN_CHECK(scn_resize_bilinear_u8c3(src.data(), n, f0->width(), f0->height(), dst.data(), tw, th,
-                                         plan_for(f0->width(), f0->height(), tw, th), device_stream(device_)));
+      if (is_nv12(f0)) {
+        std::vector<const u8*> chroma;
+        for (const u8* p : src) chroma.push_back(p + (size_t)sw * sh);
+        SCN_CHECK(scn_nv12_hist_resize(src.data(), chroma.data(), (size_t)sw, n, sw, sh, nullptr, dst.data(), tw, th,
+                                       plan_for(sw, sh, tw, th), device_stream(device_)));
+      } else {
+        SCN_CHECK(scn_resize_bilinear_u8c3(src.data(), n, sw, sh, dst.data(), tw, th, plan_for(sw, sh, tw, th),
+                                           device_stream(device_)));
+      }
       for (i32 i = 0; i < n; ++i) insert_frame(output_columns[0], outs[i]);
     });
   }
@@ -127,7 +159,11 @@ class ResizeKernelGPU : public BatchedKernel {
 
 REGISTER_OP(Resize).frame_input("frame").frame_output("frame").stream_protobuf_name("ResizeArgs");
 
-REGISTER_KERNEL(Resize, ResizeKernelGPU).device(DeviceType::GPU).batch(64).num_devices(1);
+REGISTER_KERNEL(Resize, ResizeKernelGPU)
+    .device(DeviceType::GPU)
+    .batch(64)
+    .num_devices(1)
+    .input_layout("frame", FrameLayout::NV12);
 
 // ---------------------------------------------------------------------------------------------
 class BlurKernelGPU : public BatchedKernel {

@@ -117,13 +117,27 @@ def nv12_to_rgb(surfaces, width, height):
     return out
 
 
-def nv12_hist_resize(surfaces, width, height, dst_w, dst_h, plan=None, want_resize=True):
+def nv12_pack(surfaces, width, height):
+    """Pitched NVDEC-layout surfaces (N, H*3/2, pitch) -> packed NV12 frame elements (N, H*3/2, width)."""
+    _need_cuda(surfaces)
+    surfaces = surfaces.contiguous()
+    n = surfaces.shape[0]
+    lum, chr_, pitch = _surface_ptrs(surfaces, height)
+    out = torch.empty((n, height * 3 // 2, width), dtype=torch.uint8, device=surfaces.device)
+    lp, k1 = cabi.ptr_array(lum)
+    cp, k2 = cabi.ptr_array(chr_)
+    op, k3 = cabi.ptr_array([out.data_ptr() + i * (height * 3 // 2) * width for i in range(n)])
+    cabi.check(cabi.lib().scn_nv12_pack(lp, cp, pitch, n, width, height, op, _stream()), "scn_nv12_pack")
+    return out
+
+
+def nv12_hist_resize(surfaces, width, height, dst_w, dst_h, plan=None, want_resize=True, want_hist=True):
     """Fused configs[1] DAG on NVDEC-layout surfaces -> (hist (N,3,16) i32, resized (N,dh,dw,3) u8)."""
     _need_cuda(surfaces)
     surfaces = surfaces.contiguous()
     n = surfaces.shape[0]
     lum, chr_, pitch = _surface_ptrs(surfaces, height)
-    hist = torch.empty((n, 3, 16), dtype=torch.int32, device=surfaces.device)
+    hist = torch.empty((n, 3, 16), dtype=torch.int32, device=surfaces.device) if want_hist else None
     lp, k1 = cabi.ptr_array(lum)
     cp, k2 = cabi.ptr_array(chr_)
     res = None
@@ -134,8 +148,8 @@ def nv12_hist_resize(surfaces, width, height, dst_w, dst_h, plan=None, want_resi
         res = torch.empty((n, dst_h, dst_w, 3), dtype=torch.uint8, device=surfaces.device)
         op, k3 = cabi.ptr_array([res.data_ptr() + i * dst_h * dst_w * 3 for i in range(n)])
         pptr = plan.ptr
-    rc = cabi.lib().scn_nv12_hist_resize(lp, cp, pitch, n, width, height, hist.data_ptr(), op, dst_w, dst_h,
-                                         pptr, _stream())
+    rc = cabi.lib().scn_nv12_hist_resize(lp, cp, pitch, n, width, height, hist.data_ptr() if want_hist else None,
+                                         op, dst_w, dst_h, pptr, _stream())
     cabi.check(rc, "scn_nv12_hist_resize")
     return hist, res
 

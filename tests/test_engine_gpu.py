@@ -122,8 +122,15 @@ def test_stride_30_only_keyframes(eng):
     assert c["frames_used"] == c["frames_decoded"] == n // gop
 
 
-def test_c2_dag_histogram_and_resize_on_decoded_frames(eng):
-    """BASELINE configs[1] DAG through the engine: decode -> {Histogram, Resize(224)}."""
+@pytest.mark.parametrize("force_rgb", [False, True])
+def test_c2_dag_histogram_and_resize_on_decoded_frames(eng, force_rgb, monkeypatch):
+    """BASELINE configs[1] DAG through the engine: decode -> {Histogram, Resize(224)}.  Both consumers
+    registered for NV12 surfaces, so the decode stage hands them the decoder's own format and RGB24 is
+    never written; SCN_DECODE_RGB=1 forces the reference's RGB24 elements.  Same bits either way."""
+    if force_rgb:
+        monkeypatch.setenv("SCN_DECODE_RGB", "1")
+    else:
+        monkeypatch.delenv("SCN_DECODE_RGB", raising=False)
     n = 10
     data, want = make_clip(14, n, 1080, 1920, 5)
     sid = eng.add_h264(data)
@@ -141,6 +148,51 @@ def test_c2_dag_histogram_and_resize_on_decoded_frames(eng):
     for i in range(n):
         assert (hist[i] == oracle.hist16(want[i])).all()
         assert (j.output_row(s_r, i) == oracle.resize(want[i], 224, 224)).all()
+    assert eng.stats()["counters"]["frames_delivered_nv12"] == (0 if force_rgb else n)
+
+
+def test_mixed_consumers_keep_rgb_elements(eng):
+    """One consumer (Blur) only takes dense RGB24 -> the column is delivered as RGB24 to everyone."""
+    n = 5
+    data, want = make_clip(31, n, 96, 128, 5)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("Histogram", [(src, "frame")], device=1)
+    bl = g.add_op("Blur", [(src, "frame")], device=1,
+                  args=protolite.encode(STD_ARGS["BlurArgs"], {"kernel_size": 3, "sigma": 0.5}))
+    s_h = g.add_sink((hs, "histogram"))
+    s_b = g.add_sink((bl, "frame"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    eng.run(g, [j], 5, 5)
+    hist = j.output_array(s_h, 192, np.int32).reshape(n, 3, 16)
+    for i in range(n):
+        assert (hist[i] == oracle.hist16(want[i])).all()
+        got = j.output_row(s_b, i).reshape(96, 128, 3)
+        assert (got[1:-1, 1:-1] == oracle.blur(want[i], 3)[1:-1, 1:-1]).all()
+    assert eng.stats()["counters"]["frames_delivered_nv12"] == 0
+
+
+def test_nv12_elements_through_sampler_and_small_unaligned_frames(eng):
+    """Stride sampler between source and Histogram keeps NV12 delivery; 200x112 (width % 16 != 0)
+    takes the generic NV12 histogram kernel."""
+    n, gop = 12, 3
+    data, want = make_clip(32, n, 112, 200, gop)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    smp = g.add_sample((src, "frame"))
+    hs = g.add_op("Histogram", [(smp, "frame")], device=1)
+    sink = g.add_sink((hs, "histogram"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_sampler(smp, "Strided", protolite.encode(protolite.SAMPLER_ARGS["StridedSamplerArgs"], {"stride": gop}))
+    eng.run(g, [j], 2, 4)
+    hist = j.output_array(sink, 192, np.int32).reshape(n // gop, 3, 16)
+    for k in range(n // gop):
+        assert (hist[k] == oracle.hist16(want[k * gop])).all()
+    assert eng.stats()["counters"]["frames_delivered_nv12"] == n // gop
 
 
 def test_c3_dag_blur_then_histogram(eng):

@@ -181,6 +181,21 @@ def test_fused_equals_three_pass_composition():
     assert (res == kernels.resize(rgb, 224, 224)).all()
 
 
+@pytest.mark.parametrize("h,w,pitch,n", [(1080, 1920, 2048, 3), (30, 50, 64, 2), (48, 64, 80, 2), (2, 2, 4, 1)])
+def test_nv12_pack_is_a_byte_copy_and_ops_accept_packed_elements(h, w, pitch, n):
+    """The FrameLayout::NV12 element: surface rows without the pitch; Histogram-only / Resize-only
+    entry points on it give what the fused call gives on the pitched surface."""
+    surf = _surfaces(60, n, h, w, pitch)
+    packed = kernels.nv12_pack(dev(surf), w, h)
+    assert (packed.cpu().numpy() == surf[:, :, :w]).all()
+    dh, dw = max(1, h // 3), max(1, w // 3)
+    hist, res = kernels.nv12_hist_resize(dev(surf), w, h, dw, dh)
+    h_only, none = kernels.nv12_hist_resize(packed, w, h, dw, dh, want_resize=False)
+    none2, r_only = kernels.nv12_hist_resize(packed, w, h, dw, dh, want_hist=False)
+    assert none is None and none2 is None
+    assert (h_only == hist).all() and (r_only == res).all()
+
+
 def test_launch_counter_counts():
     before = cabi.lib().scn_launch_count()
     kernels.histogram(dev(synth.rand_frame(1, 8, 8)[None]))
