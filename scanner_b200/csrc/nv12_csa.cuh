@@ -10,8 +10,8 @@
 //     r   = fma.sat(cr, 4*1.596*2^-11, ly)            (.sat == max(.,0); min(.,1) never binds)
 //     g   = fma.sat(cr, 4*-.813*2^-11, fma(cb, 4*-.3918*2^-11, ly));  b likewise
 //     bin = floor(min(v,1023)/64) = floor(32 * min(x, 1023*2^-11))   via fma.rm(x, 32, 2^23)
-// Eight bins of one channel are packed into one 32-bit word (nibbles) with IMADs, decoded to
-// one-hot bytes with PRMT as an 8-entry LUT and counted with the bit-sliced carry-save adders of
+// Four bins of one channel are packed into the low half of a 32-bit word (nibbles) with IMADs,
+// decoded to one-hot bytes with PRMT as an 8-entry LUT and counted with the bit-sliced carry-save adders of
 // hist_csa.cuh (6 accumulators: R,G,B x bins 0-7 / 8-14; bin 15 recovered from the total).
 // ~11 integer-pipe + ~12 FMA-pipe operations per pixel.  Bit-exact with the three-pass path.
 #pragma once
@@ -43,7 +43,6 @@ constexpr float kKG1 = 4.0f * -0.3918f * kS;
 constexpr float kKG2 = 4.0f * -0.813f * kS;
 constexpr float kKB = 4.0f * 2.0172f * kS;
 constexpr float kMagic = 8388608.0f;        // 2^23
-constexpr float kTop = 1023.0f * kS;        // upper clamp
 
 __device__ __forceinline__ float byte_magic(uint32_t word, uint32_t sel) {
   // bits of (2^23 + byte): byte -> mantissa LSBs, 0x4B exponent byte on top
@@ -54,66 +53,105 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c) {
   asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ uint32_t bin_bits(float x) {  // 0x4B000000 + floor(32*x)
-  float r;
-  asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(x), "f"(32.0f), "f"(kMagic));
-  return __float_as_uint(r);
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2: one issue slot, two FMAs) -------------
+using f2 = unsigned long long;  // two floats in an aligned register pair
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
+__device__ __forceinline__ void unpack2(f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2 fma2_rm(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 splat(float v) { return pack2(v, v); }
 
-struct Z3 {
-  uint32_t r, g, b;
+// Two pixels at a time (pixel j of luma word A with pixel j of luma word B), all on the FMA pipe:
+//   x  = fma.sat(c, k, ly)                    value in the 2^-11 domain, lower clamp from .sat
+//   y  = fma.rm(x, 32, 2^23)      [x2]        2^23 + m,  m = floor(v / 64) in 0..31
+//   q  = fma.sat(y, 1/16, 1/16 - 2^19)        (m + 1) / 16 clamped to 1: (min(m, 15) + 1) / 16, exact
+//   S  = fma(q, 16^(j+1), S)      [x2]        S starts at 2^23 - 0x1111, so after pixels j = 0..3 the
+//                                             float's low 16 bits ARE the four bin nibbles
+// -- the upper clamp costs no integer-pipe FMNMX, the packing no IMAD chain, and PRMT only reads
+// the low half of the selector, so the exponent bits of S need no masking.
+constexpr float kQScale = 0.0625f;
+constexpr float kQBias = 0.0625f - 524288.0f;     // 1/16 - 2^19, exactly representable
+constexpr float kSInit = kMagic - 4369.0f;        // 2^23 - 0x1111
+
+struct S3 {
+  f2 r, g, b;  // (word A, word B) accumulators per channel
 };
 
-// one pixel: append its three bins to the packed words.  `sixteen` is 16 passed at run time so
-// the packing stays an IMAD on the FMA pipe instead of an integer-pipe LEA.
-__device__ __forceinline__ void pixel(Z3& z, float yf, float cbf, float crf, uint32_t sixteen) {
-  const float ly = __fmaf_rn(yf, kCY, -kMagic * kCY);
-  const float r = fminf(fma_sat(crf, kKR, ly), kTop);
-  const float g = fminf(fma_sat(crf, kKG2, __fmaf_rn(cbf, kKG1, ly)), kTop);
-  const float b = fminf(fma_sat(cbf, kKB, ly), kTop);
-  z.r = z.r * sixteen + bin_bits(r);
-  z.g = z.g * sixteen + bin_bits(g);
-  z.b = z.b * sixteen + bin_bits(b);
+template <int J>  // J = pixel index inside the 4-pixel words
+__device__ __forceinline__ void pixel_pair(S3& s, float yA, float yB, float cbA, float crA, float cbB, float crB) {
+  constexpr float w = (float)(16 << (4 * J));  // 16^(J+1)
+  const f2 ly = fma2(pack2(yA, yB), splat(kCY), splat(-kMagic * kCY));
+  const f2 gi = fma2(pack2(cbA, cbB), splat(kKG1), ly);
+  float lyA, lyB, giA, giB;
+  unpack2(ly, lyA, lyB);
+  unpack2(gi, giA, giB);
+  const f2 r = pack2(fma_sat(crA, kKR, lyA), fma_sat(crB, kKR, lyB));
+  const f2 g = pack2(fma_sat(crA, kKG2, giA), fma_sat(crB, kKG2, giB));
+  const f2 b = pack2(fma_sat(cbA, kKB, lyA), fma_sat(cbB, kKB, lyB));
+  const f2 k32 = splat(32.0f), mg = splat(kMagic);
+  float ra, rb, ga, gb, ba, bb;
+  unpack2(fma2_rm(r, k32, mg), ra, rb);
+  unpack2(fma2_rm(g, k32, mg), ga, gb);
+  unpack2(fma2_rm(b, k32, mg), ba, bb);
+  const f2 qr = pack2(fma_sat(ra, kQScale, kQBias), fma_sat(rb, kQScale, kQBias));
+  const f2 qg = pack2(fma_sat(ga, kQScale, kQBias), fma_sat(gb, kQScale, kQBias));
+  const f2 qb = pack2(fma_sat(ba, kQScale, kQBias), fma_sat(bb, kQScale, kQBias));
+  s.r = fma2(qr, splat(w), s.r);
+  s.g = fma2(qg, splat(w), s.g);
+  s.b = fma2(qb, splat(w), s.b);
 }
 
-// after 8 appends the word holds the 8 nibbles plus 0x4B000000 * (1 + 16) of exponent residue
-constexpr uint32_t kResidueFix = 0u - 0xFB000000u;
-
 template <int K>
-__device__ __forceinline__ void count8(Acc& A, Acc& B, uint32_t z, uint32_t& cA, uint32_t& cB) {
-  uint32_t a_lo, a_hi, b_lo, b_hi;
-  csa::decode8(z + kResidueFix, a_lo, a_hi, b_lo, b_hi);
-  push8<K>(A, a_lo, cA);
-  push8<K + 1>(A, a_hi, cA);
-  push8<K>(B, b_lo, cB);
-  push8<K + 1>(B, b_hi, cB);
+__device__ __forceinline__ void count4(Acc& A, Acc& B, uint32_t z, uint32_t& cA, uint32_t& cB) {
+  push8<K>(A, prmt(csa::kLutLo, csa::kLutHiA, z), cA);
+  push8<K>(B, prmt(csa::kLutLo, csa::kLutHiB, z ^ 0x8888u), cB);
 }
 
-// 8 pixels of one row: luma words y0,y1 (4 px each), chroma words c0,c1 (2 pairs each)
+// 8 pixels: luma words yA, yB (4 px each) with their chroma words cA, cB (2 Cb,Cr pairs each);
+// feeds pushes K and K+1 of every accumulator
 template <int K>
-__device__ __forceinline__ void eight(Acc (&A)[3], Acc (&B)[3], uint32_t (&cA)[3], uint32_t (&cB)[3], uint32_t y0,
-                                      uint32_t y1, uint32_t c0, uint32_t c1, uint32_t sixteen) {
-  Z3 z{0u, 0u, 0u};
-  const float bias = -(kMagic + 128.0f);
-  {
-    const float cb0 = byte_magic(c0, 0x7440u) + bias, cr0 = byte_magic(c0, 0x7441u) + bias;
-    const float cb1 = byte_magic(c0, 0x7442u) + bias, cr1 = byte_magic(c0, 0x7443u) + bias;
-    pixel(z, byte_magic(y0, 0x7440u), cb0, cr0, sixteen);
-    pixel(z, byte_magic(y0, 0x7441u), cb0, cr0, sixteen);
-    pixel(z, byte_magic(y0, 0x7442u), cb1, cr1, sixteen);
-    pixel(z, byte_magic(y0, 0x7443u), cb1, cr1, sixteen);
-  }
-  {
-    const float cb0 = byte_magic(c1, 0x7440u) + bias, cr0 = byte_magic(c1, 0x7441u) + bias;
-    const float cb1 = byte_magic(c1, 0x7442u) + bias, cr1 = byte_magic(c1, 0x7443u) + bias;
-    pixel(z, byte_magic(y1, 0x7440u), cb0, cr0, sixteen);
-    pixel(z, byte_magic(y1, 0x7441u), cb0, cr0, sixteen);
-    pixel(z, byte_magic(y1, 0x7442u), cb1, cr1, sixteen);
-    pixel(z, byte_magic(y1, 0x7443u), cb1, cr1, sixteen);
-  }
-  count8<K>(A[0], B[0], z.r, cA[0], cB[0]);
-  count8<K>(A[1], B[1], z.g, cA[1], cB[1]);
-  count8<K>(A[2], B[2], z.b, cA[2], cB[2]);
+__device__ __forceinline__ void eight(Acc (&A)[3], Acc (&B)[3], uint32_t (&cyA)[3], uint32_t (&cyB)[3], uint32_t yA,
+                                      uint32_t yB, uint32_t cA, uint32_t cB) {
+  const f2 bias = splat(-(kMagic + 128.0f));
+  float cb0A, cb0B, cr0A, cr0B, cb1A, cb1B, cr1A, cr1B;
+  unpack2(add2(pack2(byte_magic(cA, 0x7440u), byte_magic(cB, 0x7440u)), bias), cb0A, cb0B);
+  unpack2(add2(pack2(byte_magic(cA, 0x7441u), byte_magic(cB, 0x7441u)), bias), cr0A, cr0B);
+  unpack2(add2(pack2(byte_magic(cA, 0x7442u), byte_magic(cB, 0x7442u)), bias), cb1A, cb1B);
+  unpack2(add2(pack2(byte_magic(cA, 0x7443u), byte_magic(cB, 0x7443u)), bias), cr1A, cr1B);
+  S3 s{splat(kSInit), splat(kSInit), splat(kSInit)};
+  pixel_pair<0>(s, byte_magic(yA, 0x7440u), byte_magic(yB, 0x7440u), cb0A, cr0A, cb0B, cr0B);
+  pixel_pair<1>(s, byte_magic(yA, 0x7441u), byte_magic(yB, 0x7441u), cb0A, cr0A, cb0B, cr0B);
+  pixel_pair<2>(s, byte_magic(yA, 0x7442u), byte_magic(yB, 0x7442u), cb1A, cr1A, cb1B, cr1B);
+  pixel_pair<3>(s, byte_magic(yA, 0x7443u), byte_magic(yB, 0x7443u), cb1A, cr1A, cb1B, cr1B);
+  float lo, hi;
+  unpack2(s.r, lo, hi);
+  count4<K>(A[0], B[0], __float_as_uint(lo), cyA[0], cyB[0]);
+  count4<K + 1>(A[0], B[0], __float_as_uint(hi), cyA[0], cyB[0]);
+  unpack2(s.g, lo, hi);
+  count4<K>(A[1], B[1], __float_as_uint(lo), cyA[1], cyB[1]);
+  count4<K + 1>(A[1], B[1], __float_as_uint(hi), cyA[1], cyB[1]);
+  unpack2(s.b, lo, hi);
+  count4<K>(A[2], B[2], __float_as_uint(lo), cyA[2], cyB[2]);
+  count4<K + 1>(A[2], B[2], __float_as_uint(hi), cyA[2], cyB[2]);
 }
 
 __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >> 1
@@ -130,7 +168,6 @@ struct Params {
   uint32_t units_per_frame;   // units_per_row * height / 2
   uint32_t steps_per_frame;   // ceil(units_per_frame / 32)
   uint64_t total_steps;
-  uint32_t sixteen;           // == 16 (see pixel())
 };
 
 __device__ __forceinline__ uint32_t lane_count(const Acc& a, int lane) {
@@ -153,7 +190,6 @@ nv12_hist_csa_kernel(const Params prm, int32_t* __restrict__ out) {
   const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
   uint64_t g0 = prm.total_steps * gwarp / nwarps;
   const uint64_t g1 = prm.total_steps * (gwarp + 1) / nwarps;
-  const uint32_t sixteen = prm.sixteen;
   const int last_crow = (prm.height >> 1) - 1;
 
   while (g0 < g1) {
@@ -210,10 +246,10 @@ nv12_hist_csa_kernel(const Params prm, int32_t* __restrict__ out) {
       // odd luma row: rounded average of the two neighbouring chroma rows (image.cu:133-151)
       const uint4 ca = make_uint4(avg4(c0.x, c1.x), avg4(c0.y, c1.y), avg4(c0.z, c1.z), avg4(c0.w, c1.w));
       uint32_t cA[3], cB[3];
-      eight<0>(A, B, cA, cB, ya.x, ya.y, c0.x, c0.y, sixteen);
-      eight<2>(A, B, cA, cB, ya.z, ya.w, c0.z, c0.w, sixteen);
-      eight<4>(A, B, cA, cB, yb.x, yb.y, ca.x, ca.y, sixteen);
-      eight<6>(A, B, cA, cB, yb.z, yb.w, ca.z, ca.w, sixteen);
+      eight<0>(A, B, cA, cB, ya.x, ya.y, c0.x, c0.y);
+      eight<2>(A, B, cA, cB, ya.z, ya.w, c0.z, c0.w);
+      eight<4>(A, B, cA, cB, yb.x, yb.y, ca.x, ca.y);
+      eight<6>(A, B, cA, cB, yb.z, yb.w, ca.z, ca.w);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         fold_step(A[c], cA[c], (int)step);
@@ -288,7 +324,6 @@ inline int launch(const uint8_t* const* lp, const uint8_t* const* cp, int n, siz
     p.units_per_frame = p.units_per_row * (uint32_t)(height / 2);
     p.steps_per_frame = (p.units_per_frame + 31) / 32;
     p.total_steps = (uint64_t)cnt * p.steps_per_frame;
-    p.sixteen = 16;
     uint64_t ctas = (p.total_steps + kWarps * 8 - 1) / (kWarps * 8);
     if (ctas > (uint64_t)sm_count()) ctas = sm_count();
     if (ctas < 1) ctas = 1;
