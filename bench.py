@@ -88,6 +88,11 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+# DRAM bytes per launch (read + write) from the committed ncu --set full captures of the bench's own
+# launch shape (64 surfaces 1920x1080, pitch 2048); see profiles/
+NCU_DRAM_BYTES = {"nv12_hist_csa_kernel": 201362944 + 3201792}
+
+
 def usable_cores():
     """Host cores this process may actually use: scheduler affinity capped by the cgroup CPU quota
     (the GPU boxes report 128 logical CPUs but run the container under cpu.max = 16 cores)."""
@@ -288,10 +293,14 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # --- roofline leg: same steps with per-kernel events (scn_prof_*), not used for `value`
+    # --- roofline leg: the same kernels on the same batches with per-kernel events (scn_prof_*), not
+    # used for `value`.  In the value leg the Resize kernel overlaps the Histogram kernel on a forked
+    # stream; here each kernel is launched on its own (Histogram-only call, then Resize-only call) so
+    # that a launch's duration is that kernel's and nothing else's.
     L.scn_prof_enable(1)
     for i in range(args.steps):
-        step(i)
+        kernels.nv12_hist_resize(batches[i & 1], W, H, DW, DH, plan, want_resize=False)
+        kernels.nv12_hist_resize(batches[i & 1], W, H, DW, DH, plan, want_hist=False)
     torch.cuda.synchronize()
     prof = cabi.prof_report()
     L.scn_prof_enable(0)
@@ -355,7 +364,12 @@ def main():
             ach = alg / per_launch_s / 1e9
             roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "peak_kind": peak_kind + " (burst copy, MEASURED_PEAKS.json)",
-                    "alg_bytes_per_launch": alg, "ms_per_launch": per_launch_s * 1e3, "traffic": None,
+                    "alg_bytes_per_launch": alg, "ms_per_launch": per_launch_s * 1e3,
+                    "traffic": NCU_DRAM_BYTES.get(kname) if B == 64 else None,
+                    "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this launch "
+                                      "shape (profiles/r01_nv12_hist_csa_v3.md)",
+                    "launch_mode": "kernels timed one at a time; in the value leg Resize overlaps Histogram "
+                                   "on a forked stream",
                     "kernel_share_of_step": prof[kname]["ms"] / sum(v["ms"] for v in prof.values()),
                     "all_kernels_ms": {k: v["ms"] / v["launches"] for k, v in prof.items()}}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,

@@ -125,6 +125,45 @@ nv12_resize_kernel(PtrBatch lumas, PtrBatch chromas, size_t pitch, int width, in
   }
 }
 
+// Histogram and Resize of the configs[1] DAG are independent readers of the same surfaces: the
+// histogram kernel is bound by instruction issue (one persistent CTA per SM, most registers), the
+// resize kernel by memory latency (few registers).  When both are requested the resize runs on a
+// side stream forked from / joined to the caller's stream with events, so its CTAs share the SMs
+// with the histogram CTAs instead of queueing behind them.  One side stream per calling thread
+// and device (pipeline instances call from their own threads).
+struct SideStream {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  ~SideStream() {
+    // the owning thread is going away; the context may already be gone at process exit
+    if (stream) {
+      cudaEventDestroy(fork);
+      cudaEventDestroy(join);
+      cudaStreamDestroy(stream);
+      cudaGetLastError();
+    }
+  }
+};
+
+SideStream* side_stream() {
+  static thread_local SideStream side[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = side[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      s.stream = nullptr;
+      return nullptr;
+    }
+    s.dev = dev;
+  }
+  return &s;
+}
+
 }  // namespace
 }  // namespace scn
 
@@ -150,7 +189,19 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
     if (e != cudaSuccess) return (int)e;
   }
   const int quads = (width + 3) / 4;
-  for (int i0 = 0; i0 < n; i0 += SCN_MAX_PTRS) {
+  // fork: the resize kernels of this call go to the side stream (see SideStream)
+  SideStream* side = (do_hist && do_resize) ? side_stream() : nullptr;
+  cudaStream_t rst = st;
+  if (side) {
+    if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+      cudaGetLastError();
+      side = nullptr;
+    } else {
+      rst = side->stream;
+    }
+  }
+  int rc = 0;
+  for (int i0 = 0; i0 < n && rc == 0; i0 += SCN_MAX_PTRS) {
     const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
     PtrBatch l, c;
     MutPtrBatch d;
@@ -161,33 +212,41 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
       d.p[i] = do_resize ? host_dst_ptrs[i0 + i] : nullptr;
       if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i]) & 3) vec_ok = 0;
     }
-    const bool use_csa = do_hist && nvcsa::eligible(l.p, c.p, cnt, pitch, width, height);
-    if (use_csa) {
-      int rc = nvcsa::launch(l.p, c.p, cnt, pitch, width, height, hist_out + (size_t)i0 * 48, st);
-      if (rc) return rc;
+    // the histogram kernel goes first: its persistent CTAs take one slot per SM and the resize
+    // CTAs fill in around them (the other order makes the histogram wait for the resize grid)
+    if (do_hist) {
+      if (nvcsa::eligible(l.p, c.p, cnt, pitch, width, height)) {
+        rc = nvcsa::launch(l.p, c.p, cnt, pitch, width, height, hist_out + (size_t)i0 * 48, st);
+      } else {
+        const int gx = (quads + HT - 1) / HT;
+        int gy = (sm_count() * 8 + gx * cnt - 1) / (gx * cnt);
+        if (gy < 1) gy = 1;
+        if (gy > height) gy = height;
+        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
+        {
+          LaunchScope ls("nv12_hist_kernel", st);
+          nv12_hist_kernel<<<grid, HT, 0, st>>>(l, c, pitch, width, height, quads, vec_ok, hist_out + (size_t)i0 * 48);
+        }
+        rc = launch_status();
+      }
+      if (rc) break;
     }
-    const int gx = (quads + HT - 1) / HT;
-    int gy = (sm_count() * 8 + gx * cnt - 1) / (gx * cnt);
-    if (gy < 1) gy = 1;
-    if (gy > height) gy = height;
-    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
-    if (do_hist && !use_csa) {
-      LaunchScope ls("nv12_hist_kernel", st);
-      nv12_hist_kernel<<<grid, HT, 0, st>>>(l, c, pitch, width, height, quads, vec_ok,
-                                          hist_out + (size_t)i0 * 48);
-    }
-    int rc = launch_status();
-    if (rc) return rc;
     if (do_resize) {
       dim3 g2((unsigned)((dst_w * dst_h + 255) / 256), (unsigned)cnt);
       {
-        LaunchScope ls("nv12_resize_kernel", st);
-        nv12_resize_kernel<<<g2, 256, 0, st>>>(l, c, pitch, width, height, d, (const uint8_t*)plan,
-                                             dst_w, dst_h, area2x ? 1 : 0);
+        LaunchScope ls("nv12_resize_kernel", rst);
+        nv12_resize_kernel<<<g2, 256, 0, rst>>>(l, c, pitch, width, height, d, (const uint8_t*)plan, dst_w, dst_h,
+                                              area2x ? 1 : 0);
       }
       rc = launch_status();
-      if (rc) return rc;
     }
   }
-  return 0;
+  // join, also on the error path: the caller's stream must not run ahead of the side stream
+  if (side) {
+    if (cudaEventRecord(side->join, side->stream) != cudaSuccess || cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaStreamSynchronize(side->stream);
+    }
+  }
+  return rc;
 }

@@ -22,7 +22,10 @@
 namespace scn {
 namespace nvcsa {
 
-constexpr int kThreads = 256;
+#ifndef NVCSA_THREADS
+#define NVCSA_THREADS 256
+#endif
+constexpr int kThreads = NVCSA_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kPlanes = 10;
 constexpr int kHi = kPlanes - 3;   // planes 3..9
@@ -120,17 +123,20 @@ __device__ __forceinline__ void pixel_pair(S3& s, float yA, float yB, float cbA,
   s.b = fma2(qb, splat(w), s.b);
 }
 
+// `lut_lo` is csa::kLutLo held in a vector register: PRMT takes only one immediate, and as a literal
+// (or any value ptxas can prove uniform) the low LUT word sits in a uniform register and is copied
+// with an IMAD before every PRMT -- 36 issue slots per step
 template <int K>
-__device__ __forceinline__ void count4(Acc& A, Acc& B, uint32_t z, uint32_t& cA, uint32_t& cB) {
-  push8<K>(A, prmt(csa::kLutLo, csa::kLutHiA, z), cA);
-  push8<K>(B, prmt(csa::kLutLo, csa::kLutHiB, z ^ 0x8888u), cB);
+__device__ __forceinline__ void count4(Acc& A, Acc& B, uint32_t z, uint32_t& cA, uint32_t& cB, uint32_t lut_lo) {
+  push8<K>(A, prmt(lut_lo, csa::kLutHiA, z), cA);
+  push8<K>(B, prmt(lut_lo, csa::kLutHiB, z ^ 0x8888u), cB);
 }
 
 // 8 pixels: luma words yA, yB (4 px each) with their chroma words cA, cB (2 Cb,Cr pairs each);
 // feeds pushes K and K+1 of every accumulator
 template <int K>
 __device__ __forceinline__ void eight(Acc (&A)[3], Acc (&B)[3], uint32_t (&cyA)[3], uint32_t (&cyB)[3], uint32_t yA,
-                                      uint32_t yB, uint32_t cA, uint32_t cB) {
+                                      uint32_t yB, uint32_t cA, uint32_t cB, uint32_t lut_lo) {
   const f2 bias = splat(-(kMagic + 128.0f));
   float cb0A, cb0B, cr0A, cr0B, cb1A, cb1B, cr1A, cr1B;
   unpack2(add2(pack2(byte_magic(cA, 0x7440u), byte_magic(cB, 0x7440u)), bias), cb0A, cb0B);
@@ -144,20 +150,26 @@ __device__ __forceinline__ void eight(Acc (&A)[3], Acc (&B)[3], uint32_t (&cyA)[
   pixel_pair<3>(s, byte_magic(yA, 0x7443u), byte_magic(yB, 0x7443u), cb1A, cr1A, cb1B, cr1B);
   float lo, hi;
   unpack2(s.r, lo, hi);
-  count4<K>(A[0], B[0], __float_as_uint(lo), cyA[0], cyB[0]);
-  count4<K + 1>(A[0], B[0], __float_as_uint(hi), cyA[0], cyB[0]);
+  count4<K>(A[0], B[0], __float_as_uint(lo), cyA[0], cyB[0], lut_lo);
+  count4<K + 1>(A[0], B[0], __float_as_uint(hi), cyA[0], cyB[0], lut_lo);
   unpack2(s.g, lo, hi);
-  count4<K>(A[1], B[1], __float_as_uint(lo), cyA[1], cyB[1]);
-  count4<K + 1>(A[1], B[1], __float_as_uint(hi), cyA[1], cyB[1]);
+  count4<K>(A[1], B[1], __float_as_uint(lo), cyA[1], cyB[1], lut_lo);
+  count4<K + 1>(A[1], B[1], __float_as_uint(hi), cyA[1], cyB[1], lut_lo);
   unpack2(s.b, lo, hi);
-  count4<K>(A[2], B[2], __float_as_uint(lo), cyA[2], cyB[2]);
-  count4<K + 1>(A[2], B[2], __float_as_uint(hi), cyA[2], cyB[2]);
+  count4<K>(A[2], B[2], __float_as_uint(lo), cyA[2], cyB[2], lut_lo);
+  count4<K + 1>(A[2], B[2], __float_as_uint(hi), cyA[2], cyB[2], lut_lo);
 }
 
 __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >> 1
   return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1);
 }
 
+// csa::kLutLo once per lane: loaded with a per-lane index so the value is not provably uniform
+__device__ const uint32_t g_lut_lo[32] = {
+    csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo,
+    csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo,
+    csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo,
+    csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo, csa::kLutLo};
 __device__ uint4 g_zero_page[1];  // what inactive lanes load (zero-initialised module memory)
 
 struct Params {
@@ -191,6 +203,11 @@ nv12_hist_csa_kernel(const Params prm, int32_t* __restrict__ out) {
   uint64_t g0 = prm.total_steps * gwarp / nwarps;
   const uint64_t g1 = prm.total_steps * (gwarp + 1) / nwarps;
   const int last_crow = (prm.height >> 1) - 1;
+#ifdef NVCSA_LITERAL_LUT
+  const uint32_t lut_lo = csa::kLutLo;
+#else
+  const uint32_t lut_lo = g_lut_lo[lane];
+#endif
 
   while (g0 < g1) {
     const uint32_t frame = (uint32_t)(g0 / prm.steps_per_frame);
@@ -246,10 +263,10 @@ nv12_hist_csa_kernel(const Params prm, int32_t* __restrict__ out) {
       // odd luma row: rounded average of the two neighbouring chroma rows (image.cu:133-151)
       const uint4 ca = make_uint4(avg4(c0.x, c1.x), avg4(c0.y, c1.y), avg4(c0.z, c1.z), avg4(c0.w, c1.w));
       uint32_t cA[3], cB[3];
-      eight<0>(A, B, cA, cB, ya.x, ya.y, c0.x, c0.y);
-      eight<2>(A, B, cA, cB, ya.z, ya.w, c0.z, c0.w);
-      eight<4>(A, B, cA, cB, yb.x, yb.y, ca.x, ca.y);
-      eight<6>(A, B, cA, cB, yb.z, yb.w, ca.z, ca.w);
+      eight<0>(A, B, cA, cB, ya.x, ya.y, c0.x, c0.y, lut_lo);
+      eight<2>(A, B, cA, cB, ya.z, ya.w, c0.z, c0.w, lut_lo);
+      eight<4>(A, B, cA, cB, yb.x, yb.y, ca.x, ca.y, lut_lo);
+      eight<6>(A, B, cA, cB, yb.z, yb.w, ca.z, ca.w, lut_lo);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         fold_step(A[c], cA[c], (int)step);
