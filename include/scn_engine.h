@@ -133,6 +133,50 @@ SCN_ENGINE_API int64_t scn_h264_synth(const uint8_t* yuv, int width, int height,
 /* NVDEC probe: info[0..5] = available, h264_supported, engines, max_w, max_h, min_w. */
 SCN_ENGINE_API int scn_nvdec_caps(int gpu_id, int info[6]);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tables on disk: a Scanner database directory in the reference's layout (db_metadata.bin,
+ * tables/<id>/descriptor.bin, <col>_<item>.bin + _metadata.bin / _video_metadata.bin; reference
+ * scanner/engine/metadata.h:37-86, metadata.proto:6-23,55-126).  POSIX file systems only.
+ *   scn_db_ingest_video   what Client.ingest_videos does per file (ingest.cpp:175-380): demux an
+ *                         .mp4/.mov (or take a raw Annex-B .h264), index it, write the video table
+ *   scn_db_add_video_stream  bind a stored video table to an engine as an H.264 input stream using
+ *                         the stored sample/keyframe index (no rescan) -- load_worker's view of it
+ *   scn_db_save_job       write the rows a job left in memory as a new table (one item per task,
+ *                         column 0 = index column; frame-valued sinks are stored uncompressed with
+ *                         a RAW VideoDescriptor, column_sink.cpp:159-176).  Returns the table id.
+ *   scn_db_read_rows      rows of a stored column back to host memory (Column.load)
+ */
+typedef struct scn_db scn_db;
+typedef struct scn_rows scn_rows;
+SCN_ENGINE_API scn_db* scn_db_open(const char* path);
+SCN_ENGINE_API void scn_db_close(scn_db* db);
+SCN_ENGINE_API int scn_db_ingest_video(scn_db* db, const char* table, const char* video_path);
+SCN_ENGINE_API int scn_db_ingest_h264(scn_db* db, const char* table, const uint8_t* bytes, size_t size, int fps_num,
+                                      int fps_den);
+SCN_ENGINE_API int scn_db_has_table(scn_db* db, const char* table);
+SCN_ENGINE_API int scn_db_delete_table(scn_db* db, const char* table);
+SCN_ENGINE_API int scn_db_list_tables(scn_db* db, char* buf, size_t cap); /* names, one per line */
+/* info: {table id, rows, columns (incl. index), items, job id, width, height, keyframes (-1: RAW)};
+ * columns (optional): "name:type:type_name" per line */
+SCN_ENGINE_API int scn_db_table_info(scn_db* db, const char* table, int64_t info[8], char* columns, size_t cap);
+SCN_ENGINE_API int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const char* table);
+SCN_ENGINE_API int scn_db_save_job(scn_db* db, scn_job* j, const char* table, const int* sinks,
+                                   const char* const* column_names, const char* const* type_names, int n_columns,
+                                   int job_id);
+SCN_ENGINE_API scn_rows* scn_db_read_rows(scn_db* db, const char* table, const char* column, const int64_t* rows,
+                                          int64_t n);
+SCN_ENGINE_API int64_t scn_rows_count(const scn_rows* r);
+SCN_ENGINE_API int scn_rows_get(const scn_rows* r, int64_t i, const uint8_t** data, uint64_t* size, int shape[4]);
+SCN_ENGINE_API void scn_rows_free(scn_rows* r);
+
+/* ISO base media container (the part of libavformat ingest needs, ingest.cpp:54-168,228-300):
+ * scn_mp4_demux extracts the first H.264 track as an Annex-B stream (info: width, height, timescale,
+ * duration, samples, sync samples); scn_mp4_mux wraps an Annex-B stream into a non-fragmented .mp4.
+ * Both return the byte count needed; the output is written only if cap is large enough. */
+SCN_ENGINE_API int64_t scn_mp4_mux(const uint8_t* annexb, size_t size, int fps_num, int fps_den, uint8_t* out,
+                                   size_t cap);
+SCN_ENGINE_API int64_t scn_mp4_demux(const uint8_t* file, size_t size, uint8_t* out, size_t cap, int64_t info[6]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,9 @@
 
 #include "nvdec.h"
 #include "pipeline.h"
+#include "mp4.h"
 #include "scn_engine.h"
+#include "storage.h"
 
 using namespace scanner;
 using namespace scanner::internal;
@@ -18,6 +20,14 @@ struct scn_graph {
 };
 struct scn_job {
   Job j;
+};
+struct scn_db {
+  std::unique_ptr<Database> impl;
+};
+struct scn_rows {
+  std::vector<u8> data;
+  std::vector<u64> sizes, offsets;
+  std::vector<i32> shapes;
 };
 
 namespace {
@@ -334,6 +344,214 @@ int scn_nvdec_caps(int gpu_id, int info[6]) {
   info[5] = c.min_width;
   if (!c.available) t_error = c.error;
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// database directory (include/scn_engine.h "tables on disk")
+scn_db* scn_db_open(const char* path) {
+  if (!path) {
+    fail("null path");
+    return nullptr;
+  }
+  std::unique_ptr<Database> db;
+  Result r = Database::open(path, db);
+  if (!r.success()) {
+    fail(r.msg());
+    return nullptr;
+  }
+  scn_db* h = new scn_db();
+  h->impl = std::move(db);
+  return h;
+}
+void scn_db_close(scn_db* db) { delete db; }
+
+int scn_db_ingest_video(scn_db* db, const char* table, const char* video_path) {
+  if (!db || !table || !video_path) return fail("bad arguments");
+  return from_result(db->impl->ingest_video(table, video_path));
+}
+int scn_db_ingest_h264(scn_db* db, const char* table, const uint8_t* bytes, size_t size, int fps_num, int fps_den) {
+  if (!db || !table || !bytes || !size) return fail("bad arguments");
+  return from_result(db->impl->ingest_h264(table, bytes, size, fps_den > 0 ? fps_den : 1, fps_num > 0 ? fps_num : 25));
+}
+int scn_db_has_table(scn_db* db, const char* table) { return db && table && db->impl->has_table(table) ? 1 : 0; }
+int scn_db_delete_table(scn_db* db, const char* table) {
+  if (!db || !table) return fail("bad arguments");
+  return from_result(db->impl->delete_table(table));
+}
+int scn_db_list_tables(scn_db* db, char* buf, size_t cap) {
+  if (!db) return fail("null database");
+  std::string s;
+  for (const std::string& n : db->impl->table_names()) s += n + "\n";
+  return copy_out(s, buf, cap);
+}
+
+int scn_db_table_info(scn_db* db, const char* table, int64_t info[8], char* columns, size_t cap) {
+  if (!db || !table || !info) return fail("bad arguments");
+  tables::TableDescriptor td;
+  Result r = db->impl->read_table(table, td);
+  if (!r.success()) return fail(r.msg());
+  for (int i = 0; i < 8; ++i) info[i] = 0;
+  info[0] = td.id();
+  info[1] = td.end_rows_size() ? td.end_rows(td.end_rows_size() - 1) : 0;
+  info[2] = td.columns_size();
+  info[3] = td.end_rows_size();
+  info[4] = td.job_id();
+  std::string cols;
+  bool video = false;
+  for (const auto& c : td.columns()) {
+    cols += c.name() + ":" + std::to_string(c.type()) + ":" + c.type_name() + "\n";
+    if (c.type() == (int)proto::Video) video = true;
+  }
+  if (video) {
+    tables::VideoDescriptor vd;
+    std::string file;
+    if (db->impl->read_video(table, vd, file).success()) {
+      info[5] = vd.width();
+      info[6] = vd.height();
+      info[7] = vd.codec_type() == 0 ? vd.keyframe_indices_size() : -1;  // -1: stored uncompressed
+    }
+  }
+  if (columns) return copy_out(cols, columns, cap);
+  return 0;
+}
+
+int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const char* table) {
+  if (!db || !e || !table) return fail("bad arguments");
+  tables::VideoDescriptor vd;
+  std::string file;
+  Result r = db->impl->read_video(table, vd, file);
+  if (!r.success()) return fail(r.msg());
+  std::unique_ptr<InputStream> s(new InputStream());
+  s->kind = InputStream::H264;
+  r = index_from_descriptor(vd, s->index);
+  if (!r.success()) return fail(r.msg());
+  FILE* f = fopen(file.c_str(), "rb");
+  if (!f) return fail("cannot open " + file);
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  s->encoded.resize((size_t)n);
+  const size_t got = n ? fread(s->encoded.data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  if (got != (size_t)n) return fail("short read of " + file);
+  if (!s->index.sample_offsets.empty() &&
+      s->index.sample_offsets.back() + s->index.sample_sizes.back() > (u64)n)
+    return fail("video descriptor of table " + std::string(table) + " points past the end of " + file);
+  return e->impl->add_stream(std::move(s));
+}
+
+int scn_db_save_job(scn_db* db, scn_job* j, const char* table, const int* sinks, const char* const* column_names,
+                    const char* const* type_names, int n_columns, int job_id) {
+  if (!db || !j || !table || !sinks || !column_names || n_columns <= 0) return fail("bad arguments");
+  std::vector<ColumnSpec> cols;
+  std::vector<const std::vector<TaskOutput>*> outs;
+  size_t n_tasks = 0;
+  for (int c = 0; c < n_columns; ++c) {
+    auto it = j->j.outputs.find(sinks[c]);
+    if (it == j->j.outputs.end()) return fail("op " + std::to_string(sinks[c]) + " is not a sink of this job");
+    outs.push_back(&it->second);
+    if (c == 0) n_tasks = it->second.size();
+    else if (it->second.size() != n_tasks) return fail("sinks of one job must have the same number of tasks");
+    bool is_frame = false;
+    for (const TaskOutput& t : it->second)
+      for (size_t i = 0; i < t.sizes.size(); ++i)
+        if (t.shapes[4 * i + 3] >= 0) is_frame = true;
+    ColumnSpec cs;
+    cs.name = column_names[c];
+    cs.type = is_frame ? proto::Video : proto::Bytes;
+    cs.type_name = type_names && type_names[c] ? type_names[c] : "";
+    cols.push_back(cs);
+  }
+  i32 id = -1;
+  Result r = db->impl->new_table(table, cols, job_id, id);
+  if (!r.success()) return fail(r.msg());
+  std::vector<i64> end_rows;
+  i64 row = 0;
+  for (size_t t = 0; t < n_tasks && r.success(); ++t) {
+    const i64 n = (i64)(*outs[0])[t].sizes.size();
+    r = db->impl->write_index_item(id, (i32)t, row, row + n);
+    for (int c = 0; c < n_columns && r.success(); ++c) {
+      const TaskOutput& to = (*outs[c])[t];
+      if ((i64)to.sizes.size() != n) {
+        r.set_success(false);
+        r.set_msg("columns of one task disagree on the number of rows");
+        break;
+      }
+      ItemColumn ic;
+      ic.data = to.data.data();
+      ic.bytes = to.data.size();
+      ic.sizes = &to.sizes;
+      ic.shapes = &to.shapes;
+      r = db->impl->write_item(id, c + 1, (i32)t, ic, cols[c].type == proto::Video);
+    }
+    row += n;
+    end_rows.push_back(row);
+  }
+  if (r.success()) r = db->impl->commit_table(id, end_rows);
+  if (!r.success()) {
+    db->impl->delete_table(table);
+    return fail(r.msg());
+  }
+  return id;
+}
+
+scn_rows* scn_db_read_rows(scn_db* db, const char* table, const char* column, const int64_t* rows, int64_t n) {
+  if (!db || !table || !column || (n > 0 && !rows)) {
+    fail("bad arguments");
+    return nullptr;
+  }
+  std::unique_ptr<scn_rows> out(new scn_rows());
+  std::vector<i64> want(rows, rows + (n > 0 ? n : 0));
+  Result r = db->impl->read_rows(table, column, want, out->data, out->sizes, out->shapes);
+  if (!r.success()) {
+    fail(r.msg());
+    return nullptr;
+  }
+  u64 off = 0;
+  for (u64 s : out->sizes) {
+    out->offsets.push_back(off);
+    off += s;
+  }
+  return out.release();
+}
+int64_t scn_rows_count(const scn_rows* r) { return r ? (int64_t)r->sizes.size() : 0; }
+int scn_rows_get(const scn_rows* r, int64_t i, const uint8_t** data, uint64_t* size, int shape[4]) {
+  if (!r || i < 0 || (size_t)i >= r->sizes.size()) return fail("row out of range");
+  if (data) *data = r->data.data() + r->offsets[(size_t)i];
+  if (size) *size = r->sizes[(size_t)i];
+  if (shape)
+    for (int k = 0; k < 4; ++k) shape[k] = r->shapes[(size_t)i * 4 + k];
+  return 0;
+}
+void scn_rows_free(scn_rows* r) { delete r; }
+
+// ---- mp4 container helpers (ingest reads .mp4; tests and benchmarks write it)
+int64_t scn_mp4_mux(const uint8_t* annexb, size_t size, int fps_num, int fps_den, uint8_t* out, size_t cap) {
+  if (!annexb || !size) return fail("bad arguments");
+  H264Index idx;
+  Result r = index_bytestream(annexb, size, idx);
+  if (!r.success()) return fail(r.msg());
+  std::vector<u8> file;
+  r = mux_mp4(annexb, size, idx, fps_num, fps_den, file);
+  if (!r.success()) return fail(r.msg());
+  if (out && cap >= file.size()) memcpy(out, file.data(), file.size());
+  return (int64_t)file.size();
+}
+int64_t scn_mp4_demux(const uint8_t* file, size_t size, uint8_t* out, size_t cap, int64_t info[6]) {
+  if (!file || !size) return fail("bad arguments");
+  Mp4Track t;
+  Result r = demux_mp4(file, size, t);
+  if (!r.success()) return fail(r.msg());
+  if (info) {
+    info[0] = t.width;
+    info[1] = t.height;
+    info[2] = t.timescale;
+    info[3] = (int64_t)t.duration;
+    info[4] = t.samples;
+    info[5] = t.sync_samples;
+  }
+  if (out && cap >= t.annexb.size()) memcpy(out, t.annexb.data(), t.annexb.size());
+  return (int64_t)t.annexb.size();
 }
 
 }  // extern "C"

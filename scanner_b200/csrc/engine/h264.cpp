@@ -206,7 +206,7 @@ void emit_nal(std::vector<u8>& out, int ref_idc, int type, const std::vector<u8>
 
 }  // namespace
 
-Result index_bytestream(const u8* data, size_t size, H264Index& out) {
+Result index_bytestream(const u8* data, size_t size, H264Index& out, bool parameter_sets_only) {
   Result r;
   out = H264Index();
   std::vector<Nal> nals;
@@ -277,6 +277,10 @@ Result index_bytestream(const u8* data, size_t size, H264Index& out) {
   close_au(size);
   if (!have_sps || !have_pps) {
     RESULT_ERROR(&r, "stream has no SPS/PPS");
+    return r;
+  }
+  if (parameter_sets_only) {
+    r.set_success(true);
     return r;
   }
   if (out.sample_offsets.empty() || out.keyframe_indices.empty() || out.keyframe_indices[0] != 0) {

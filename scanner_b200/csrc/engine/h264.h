@@ -31,7 +31,9 @@ struct H264Index {
 
 // Scans an Annex-B byte stream.  A new access unit starts at the first SPS/PPS/SEI/AUD NAL after
 // a VCL NAL, or at a VCL NAL whose first_mb_in_slice is 0.
-Result index_bytestream(const u8* data, size_t size, H264Index& out);
+// parameter_sets_only: accept a buffer holding just SPS/PPS (a stored descriptor's metadata
+// packets) and fill the picture geometry without requiring any picture.
+Result index_bytestream(const u8* data, size_t size, H264Index& out, bool parameter_sets_only = false);
 
 enum class SynthNonKey { Pcm = 0, Skip = 1 };
 

@@ -1,0 +1,541 @@
+// storage.cpp -- see storage.h.
+#include "storage.h"
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+#include "mp4.h"
+
+namespace scanner {
+namespace internal {
+namespace {
+
+Result ok() {
+  Result r;
+  r.set_success(true);
+  return r;
+}
+
+bool mkdirs(const std::string& path) {
+  std::string cur;
+  for (size_t i = 0; i <= path.size(); ++i) {
+    if (i == path.size() || path[i] == '/') {
+      if (!cur.empty() && cur != "/") {
+        if (mkdir(cur.c_str(), 0755) != 0 && errno != EEXIST) return false;
+      }
+    }
+    if (i < path.size()) cur.push_back(path[i]);
+  }
+  return true;
+}
+
+bool read_file(const std::string& path, std::string& out) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return false;
+  const std::streamsize n = f.tellg();
+  f.seekg(0);
+  out.resize((size_t)n);
+  if (n) f.read(&out[0], n);
+  return (bool)f;
+}
+
+// write to a temporary name, then rename: a reader never sees a half-written descriptor
+bool write_file_atomic(const std::string& path, const void* data, size_t n) {
+  const std::string tmp = path + ".tmp";
+  {
+    std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+    if (!f) return false;
+    if (n) f.write((const char*)data, (std::streamsize)n);
+    if (!f) return false;
+  }
+  return rename(tmp.c_str(), path.c_str()) == 0;
+}
+
+void remove_tree(const std::string& dir) {
+  DIR* d = opendir(dir.c_str());
+  if (!d) return;
+  while (dirent* e = readdir(d)) {
+    const std::string name = e->d_name;
+    if (name == "." || name == "..") continue;
+    const std::string p = dir + "/" + name;
+    struct stat st;
+    if (lstat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) remove_tree(p);
+    else unlink(p.c_str());
+  }
+  closedir(d);
+  rmdir(dir.c_str());
+}
+
+i64 now_seconds() {
+  return std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch())
+      .count();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+Result Database::open(const std::string& path, std::unique_ptr<Database>& out) {
+  Result r = ok();
+  std::unique_ptr<Database> db(new Database());
+  db->root_ = path;
+  if (db->root_.empty()) {
+    RESULT_ERROR(&r, "database path is empty");
+    return r;
+  }
+  if (db->root_.back() != '/') db->root_.push_back('/');
+  if (!mkdirs(db->root_ + "tables")) {
+    RESULT_ERROR(&r, "cannot create database directory %s: %s", db->root_.c_str(), strerror(errno));
+    return r;
+  }
+  r = db->load_meta();
+  if (r.success()) out = std::move(db);
+  return r;
+}
+
+Result Database::load_meta() {
+  Result r = ok();
+  std::string bytes;
+  const std::string p = root_ + "db_metadata.bin";
+  if (!read_file(p, bytes)) {  // fresh database (reference: master creates it on first start)
+    meta_ = tables::DatabaseDescriptor();
+    return save_meta();
+  }
+  if (!meta_.ParseFromString(bytes)) RESULT_ERROR(&r, "%s is not a DatabaseDescriptor", p.c_str());
+  return r;
+}
+
+Result Database::save_meta() const {
+  Result r = ok();
+  const std::string s = meta_.SerializeAsString();
+  if (!write_file_atomic(root_ + "db_metadata.bin", s.data(), s.size()))
+    RESULT_ERROR(&r, "cannot write %sdb_metadata.bin: %s", root_.c_str(), strerror(errno));
+  return r;
+}
+
+std::vector<std::string> Database::table_names() const {
+  std::lock_guard<std::mutex> g(mu_);
+  std::vector<std::string> out;
+  for (const auto& t : meta_.tables())
+    if (t.committed()) out.push_back(t.name());
+  return out;
+}
+
+i32 Database::table_id(const std::string& name) const {
+  std::lock_guard<std::mutex> g(mu_);
+  for (const auto& t : meta_.tables())
+    if (t.committed() && t.name() == name) return t.id();
+  return -1;
+}
+
+bool Database::has_table(const std::string& name) const { return table_id(name) >= 0; }
+
+std::string Database::table_dir(i32 id) const { return root_ + "tables/" + std::to_string(id); }
+
+std::string Database::item_base(i32 table_id, i32 column_id, i32 item_id) const {
+  return table_dir(table_id) + "/" + std::to_string(column_id) + "_" + std::to_string(item_id);
+}
+
+Result Database::delete_table(const std::string& name) {
+  Result r = ok();
+  i32 id = -1;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto* ts = meta_.mutable_tables();
+    for (size_t i = 0; i < ts->size(); ++i)
+      if ((*ts)[i].name() == name) {
+        id = (*ts)[i].id();
+        ts->erase(ts->begin() + (long)i);
+        break;
+      }
+    if (id < 0) {
+      RESULT_ERROR(&r, "table %s does not exist", name.c_str());
+      return r;
+    }
+    r = save_meta();
+  }
+  remove_tree(table_dir(id));
+  return r;
+}
+
+Result Database::new_table(const std::string& name, const std::vector<ColumnSpec>& columns, i32 job_id,
+                           i32& table_id) {
+  Result r = ok();
+  std::lock_guard<std::mutex> g(mu_);
+  for (const auto& t : meta_.tables())
+    if (t.name() == name) {
+      RESULT_ERROR(&r, "table %s already exists", name.c_str());
+      return r;
+    }
+  table_id = meta_.next_table_id();
+  meta_.set_next_table_id(table_id + 1);
+  tables::DbTable* t = meta_.add_tables();
+  t->set_id(table_id);
+  t->set_name(name);
+  t->set_committed(false);
+  tables::TableDescriptor td;
+  td.set_id(table_id);
+  td.set_name(name);
+  td.set_job_id(job_id);
+  td.set_timestamp(now_seconds());
+  {
+    tables::ColumnDescriptor* c = td.add_columns();  // column 0 is always the index column
+    c->set_id(0);
+    c->set_name("index");
+    c->set_type((int)proto::Bytes);
+  }
+  for (size_t i = 0; i < columns.size(); ++i) {
+    tables::ColumnDescriptor* c = td.add_columns();
+    c->set_id((i32)i + 1);
+    c->set_name(columns[i].name);
+    c->set_type((int)columns[i].type);
+    c->set_type_name(columns[i].type_name);
+  }
+  pending_[table_id] = td;
+  if (!mkdirs(table_dir(table_id))) {
+    RESULT_ERROR(&r, "cannot create %s: %s", table_dir(table_id).c_str(), strerror(errno));
+    return r;
+  }
+  return save_meta();
+}
+
+Result Database::write_index_item(i32 table_id, i32 item_id, i64 row0, i64 row1) {
+  // reference ingest.cpp:321-345: row i = little-endian int64 i, metadata = n then n sizes of 8
+  std::vector<i64> idx;
+  for (i64 i = row0; i < row1; ++i) idx.push_back(i);
+  std::vector<u64> sizes(idx.size(), 8);
+  ItemColumn c;
+  c.data = (const u8*)idx.data();
+  c.bytes = idx.size() * 8;
+  c.sizes = &sizes;
+  return write_item(table_id, 0, item_id, c, false);
+}
+
+Result Database::write_item(i32 table_id, i32 column_id, i32 item_id, const ItemColumn& col, bool is_video) {
+  Result r = ok();
+  const std::string base = item_base(table_id, column_id, item_id);
+  {
+    std::ofstream f(base + ".bin", std::ios::binary | std::ios::trunc);
+    if (col.bytes) f.write((const char*)col.data, (std::streamsize)col.bytes);
+    if (!f) {
+      RESULT_ERROR(&r, "cannot write %s.bin: %s", base.c_str(), strerror(errno));
+      return r;
+    }
+  }
+  const std::vector<u64> none;
+  const std::vector<u64>& sizes = col.sizes ? *col.sizes : none;
+  if (!is_video) {
+    std::string m;
+    const u64 n = sizes.size();
+    m.append((const char*)&n, 8);
+    if (n) m.append((const char*)sizes.data(), 8 * sizes.size());
+    if (!write_file_atomic(base + "_metadata.bin", m.data(), m.size()))
+      RESULT_ERROR(&r, "cannot write %s_metadata.bin: %s", base.c_str(), strerror(errno));
+    return r;
+  }
+  // frame column stored uncompressed (reference column_sink.cpp:159-176): codec RAW, one "sample"
+  // per frame so rows stay addressable; null rows have size 0
+  tables::VideoDescriptor vd;
+  vd.set_table_id(table_id);
+  vd.set_column_id(column_id);
+  vd.set_item_id(item_id);
+  vd.set_frames((i64)sizes.size());
+  vd.set_codec_type(2);
+  vd.set_chroma_format(1);
+  u64 off = 0;
+  bool have_shape = false;
+  for (size_t i = 0; i < sizes.size(); ++i) {
+    vd.add_sample_offsets(off);
+    vd.add_sample_sizes(sizes[i]);
+    off += sizes[i];
+    if (!have_shape && sizes[i] && col.shapes && col.shapes->size() >= 4 * (i + 1)) {
+      vd.set_height((*col.shapes)[4 * i + 0]);
+      vd.set_width((*col.shapes)[4 * i + 1]);
+      vd.set_channels((*col.shapes)[4 * i + 2]);
+      vd.set_frame_type((*col.shapes)[4 * i + 3]);
+      have_shape = true;
+    }
+  }
+  vd.set_num_encoded_videos(1);
+  vd.add_frames_per_video((i64)sizes.size());
+  vd.add_keyframes_per_video((i64)sizes.size());
+  vd.add_size_per_video((i64)off);
+  vd.set_data_path(base + ".bin");
+  const std::string s = vd.SerializeAsString();
+  if (!write_file_atomic(base + "_video_metadata.bin", s.data(), s.size()))
+    RESULT_ERROR(&r, "cannot write %s_video_metadata.bin: %s", base.c_str(), strerror(errno));
+  return r;
+}
+
+Result Database::commit_table(i32 table_id, const std::vector<i64>& end_rows) {
+  Result r = ok();
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = pending_.find(table_id);
+  if (it == pending_.end()) {
+    RESULT_ERROR(&r, "table id %d is not being written", table_id);
+    return r;
+  }
+  tables::TableDescriptor& td = it->second;
+  td.clear_end_rows();
+  for (i64 e : end_rows) td.add_end_rows(e);
+  const std::string s = td.SerializeAsString();
+  if (!write_file_atomic(table_dir(table_id) + "/descriptor.bin", s.data(), s.size())) {
+    RESULT_ERROR(&r, "cannot write the descriptor of table %d: %s", table_id, strerror(errno));
+    return r;
+  }
+  for (auto& t : *meta_.mutable_tables())
+    if (t.id() == table_id) t.set_committed(true);
+  pending_.erase(it);
+  return save_meta();
+}
+
+// ---------------------------------------------------------------------------------------------
+Result Database::ingest_video(const std::string& table, const std::string& video_path) {
+  Result r = ok();
+  std::string bytes;
+  if (!read_file(video_path, bytes)) {
+    RESULT_ERROR(&r, "cannot read %s: %s", video_path.c_str(), strerror(errno));
+    return r;
+  }
+  const u8* p = (const u8*)bytes.data();
+  if (looks_like_mp4(p, bytes.size())) {
+    Mp4Track trk;
+    r = demux_mp4(p, bytes.size(), trk);
+    if (!r.success()) return r;
+    // time base of one tick (reference stores the codec context's time_base, ingest.cpp:303-304)
+    return ingest_h264(table, trk.annexb.data(), trk.annexb.size(), 1, (i32)trk.timescale);
+  }
+  return ingest_h264(table, p, bytes.size(), 1, 25);
+}
+
+Result Database::ingest_h264(const std::string& table, const u8* annexb, size_t size, i32 tb_num, i32 tb_den) {
+  H264Index idx;
+  Result r = index_bytestream(annexb, size, idx);
+  if (!r.success()) return r;
+  if (idx.frames() == 0) {
+    RESULT_ERROR(&r, "no H.264 pictures found while ingesting table %s", table.c_str());
+    return r;
+  }
+  i32 id = -1;
+  r = new_table(table, {ColumnSpec{"frame", proto::Video, ""}}, -1, id);
+  if (!r.success()) return r;
+  const std::string base = item_base(id, 1, 0);
+  {
+    std::ofstream f(base + ".bin", std::ios::binary | std::ios::trunc);
+    f.write((const char*)annexb, (std::streamsize)size);
+    if (!f) {
+      RESULT_ERROR(&r, "cannot write %s.bin: %s", base.c_str(), strerror(errno));
+      return r;
+    }
+  }
+  tables::VideoDescriptor vd;  // reference ingest.cpp:211-224, 347-366
+  vd.set_table_id(id);
+  vd.set_column_id(1);
+  vd.set_item_id(0);
+  vd.set_frames(idx.frames());
+  vd.set_width(idx.width);
+  vd.set_height(idx.height);
+  vd.set_channels(3);
+  vd.set_frame_type((int)proto::U8);
+  vd.set_codec_type(0);
+  vd.set_chroma_format(1);
+  vd.set_time_base_num(tb_num);
+  vd.set_time_base_denom(tb_den);
+  vd.set_num_encoded_videos(1);
+  vd.add_frames_per_video(idx.frames());
+  vd.add_keyframes_per_video((i64)idx.keyframe_indices.size());
+  vd.add_size_per_video((i64)size);
+  for (u64 v : idx.sample_offsets) vd.add_sample_offsets(v);
+  for (u64 v : idx.sample_sizes) vd.add_sample_sizes(v);
+  for (i64 v : idx.keyframe_indices) vd.add_keyframe_indices((u64)v);
+  vd.mutable_metadata_packets()->assign((const char*)idx.metadata_packets.data(), idx.metadata_packets.size());
+  vd.set_data_path(base + ".bin");
+  vd.set_inplace(false);
+  const std::string s = vd.SerializeAsString();
+  if (!write_file_atomic(base + "_video_metadata.bin", s.data(), s.size())) {
+    RESULT_ERROR(&r, "cannot write %s_video_metadata.bin: %s", base.c_str(), strerror(errno));
+    return r;
+  }
+  r = write_index_item(id, 0, 0, idx.frames());
+  if (!r.success()) return r;
+  return commit_table(id, {idx.frames()});
+}
+
+// ---------------------------------------------------------------------------------------------
+Result Database::read_table(const std::string& table, tables::TableDescriptor& out) const {
+  Result r = ok();
+  const i32 id = table_id(table);
+  if (id < 0) {
+    RESULT_ERROR(&r, "table %s does not exist", table.c_str());
+    return r;
+  }
+  std::string bytes;
+  const std::string p = table_dir(id) + "/descriptor.bin";
+  if (!read_file(p, bytes) || !out.ParseFromString(bytes)) RESULT_ERROR(&r, "cannot read %s", p.c_str());
+  return r;
+}
+
+Result Database::read_video(const std::string& table, tables::VideoDescriptor& out, std::string& data_file,
+                            const std::string& column) const {
+  tables::TableDescriptor td;
+  Result r = read_table(table, td);
+  if (!r.success()) return r;
+  i32 col = -1;
+  for (const auto& c : td.columns())
+    if (c.type() == (int)proto::Video && (column.empty() || c.name() == column)) {
+      col = c.id();
+      break;
+    }
+  if (col < 0) {
+    RESULT_ERROR(&r, "table %s has no video column %s", table.c_str(), column.c_str());
+    return r;
+  }
+  const std::string base = item_base(td.id(), col, 0);
+  std::string bytes;
+  if (!read_file(base + "_video_metadata.bin", bytes) || !out.ParseFromString(bytes)) {
+    RESULT_ERROR(&r, "cannot read %s_video_metadata.bin", base.c_str());
+    return r;
+  }
+  // the stored data_path is absolute for the writer's mount point; the file next to the
+  // descriptor is authoritative (a database directory can be moved)
+  data_file = base + ".bin";
+  return r;
+}
+
+Result Database::read_rows(const std::string& table, const std::string& column, const std::vector<i64>& rows,
+                           std::vector<u8>& data, std::vector<u64>& sizes, std::vector<i32>& shapes) const {
+  tables::TableDescriptor td;
+  Result r = read_table(table, td);
+  if (!r.success()) return r;
+  const tables::ColumnDescriptor* cd = nullptr;
+  for (const auto& c : td.columns())
+    if (c.name() == column) cd = &c;
+  if (!cd) {
+    RESULT_ERROR(&r, "table %s has no column %s", table.c_str(), column.c_str());
+    return r;
+  }
+  const bool video = cd->type() == (int)proto::Video;
+  // item -> (row offsets, sizes) loaded lazily
+  struct Item {
+    std::vector<u64> offs, sizes;
+    i32 shape[4] = {0, 0, 0, -1};
+    std::ifstream f;
+  };
+  std::map<i32, Item> items;
+  data.clear();
+  sizes.clear();
+  shapes.clear();
+  const i64 total = td.end_rows_size() ? td.end_rows(td.end_rows_size() - 1) : 0;
+  for (i64 row : rows) {
+    if (row < 0 || row >= total) {
+      RESULT_ERROR(&r, "row %ld is outside table %s (%ld rows)", (long)row, table.c_str(), (long)total);
+      return r;
+    }
+    i32 item = 0;
+    while (item < td.end_rows_size() && row >= td.end_rows(item)) ++item;
+    const i64 first = item ? td.end_rows(item - 1) : 0;
+    auto it = items.find(item);
+    if (it == items.end()) {
+      Item& I = items[item];
+      const std::string base = item_base(td.id(), cd->id(), item);
+      std::string bytes;
+      if (video) {
+        tables::VideoDescriptor vd;
+        if (!read_file(base + "_video_metadata.bin", bytes) || !vd.ParseFromString(bytes)) {
+          RESULT_ERROR(&r, "cannot read %s_video_metadata.bin", base.c_str());
+          return r;
+        }
+        if (vd.codec_type() != 2) {
+          RESULT_ERROR(&r, "column %s of table %s is compressed video: decode it through a job", column.c_str(),
+                       table.c_str());
+          return r;
+        }
+        I.offs = vd.sample_offsets();
+        I.sizes = vd.sample_sizes();
+        I.shape[0] = vd.height();
+        I.shape[1] = vd.width();
+        I.shape[2] = vd.channels();
+        I.shape[3] = vd.frame_type();
+      } else {
+        if (!read_file(base + "_metadata.bin", bytes) || bytes.size() < 8) {
+          RESULT_ERROR(&r, "cannot read %s_metadata.bin", base.c_str());
+          return r;
+        }
+        u64 n;
+        memcpy(&n, bytes.data(), 8);
+        if (bytes.size() < 8 + 8 * n) {
+          RESULT_ERROR(&r, "%s_metadata.bin is truncated", base.c_str());
+          return r;
+        }
+        I.sizes.resize(n);
+        if (n) memcpy(I.sizes.data(), bytes.data() + 8, 8 * n);
+        u64 off = 0;
+        for (u64 s : I.sizes) {
+          I.offs.push_back(off);
+          off += s;
+        }
+      }
+      I.f.open(base + ".bin", std::ios::binary);
+      if (!I.f) {
+        RESULT_ERROR(&r, "cannot open %s.bin", base.c_str());
+        return r;
+      }
+      it = items.find(item);
+    }
+    Item& I = it->second;
+    const size_t k = (size_t)(row - first);
+    if (k >= I.sizes.size()) {
+      RESULT_ERROR(&r, "item %d of %s.%s holds %zu rows, row %ld wanted", item, table.c_str(), column.c_str(),
+                   I.sizes.size(), (long)row);
+      return r;
+    }
+    const size_t at = data.size();
+    data.resize(at + I.sizes[k]);
+    if (I.sizes[k]) {
+      I.f.seekg((std::streamoff)I.offs[k]);
+      I.f.read((char*)data.data() + at, (std::streamsize)I.sizes[k]);
+      if (!I.f) {
+        RESULT_ERROR(&r, "short read in item %d of %s.%s", item, table.c_str(), column.c_str());
+        return r;
+      }
+    }
+    sizes.push_back(I.sizes[k]);
+    shapes.insert(shapes.end(), I.shape, I.shape + 4);
+  }
+  return r;
+}
+
+Result index_from_descriptor(const tables::VideoDescriptor& vd, H264Index& out) {
+  Result r = ok();
+  if (vd.codec_type() != 0) {
+    RESULT_ERROR(&r, "video column is not H.264 (codec type %d)", vd.codec_type());
+    return r;
+  }
+  // coded size and cropping come from the stored SPS
+  H264Index meta;
+  const std::string& mp = vd.metadata_packets();
+  r = index_bytestream((const u8*)mp.data(), mp.size(), meta, true);
+  if (!r.success()) return r;
+  out = H264Index();
+  out.width = vd.width();
+  out.height = vd.height();
+  out.coded_width = meta.coded_width;
+  out.coded_height = meta.coded_height;
+  out.sample_offsets = vd.sample_offsets();
+  out.sample_sizes = vd.sample_sizes();
+  for (u64 k : vd.keyframe_indices()) out.keyframe_indices.push_back((i64)k);
+  out.metadata_packets.assign(mp.begin(), mp.end());
+  if ((i64)out.sample_offsets.size() != vd.frames() || out.sample_sizes.size() != out.sample_offsets.size()) {
+    RESULT_ERROR(&r, "video descriptor is inconsistent: %ld frames, %zu offsets, %zu sizes", (long)vd.frames(),
+                 out.sample_offsets.size(), out.sample_sizes.size());
+  }
+  return r;
+}
+
+}  // namespace internal
+}  // namespace scanner

@@ -50,6 +50,22 @@ SIGNATURES = {
     "scn_engine_stats_json": (_I, [_VP, _CP, _SZ]),
     "scn_h264_synth": (_I64, [_VP, _I, _I, _I64, _I, _I, _VP, _SZ]),
     "scn_nvdec_caps": (_I, [_I, _IP]),
+    "scn_db_open": (_VP, [_CP]),
+    "scn_db_close": (None, [_VP]),
+    "scn_db_ingest_video": (_I, [_VP, _CP, _CP]),
+    "scn_db_ingest_h264": (_I, [_VP, _CP, _VP, _SZ, _I, _I]),
+    "scn_db_has_table": (_I, [_VP, _CP]),
+    "scn_db_delete_table": (_I, [_VP, _CP]),
+    "scn_db_list_tables": (_I, [_VP, _CP, _SZ]),
+    "scn_db_table_info": (_I, [_VP, _CP, _c.POINTER(_I64), _CP, _SZ]),
+    "scn_db_add_video_stream": (_I64, [_VP, _VP, _CP]),
+    "scn_db_save_job": (_I, [_VP, _VP, _CP, _IP, _c.POINTER(_CP), _c.POINTER(_CP), _I, _I]),
+    "scn_db_read_rows": (_VP, [_VP, _CP, _CP, _c.POINTER(_I64), _I64]),
+    "scn_rows_count": (_I64, [_VP]),
+    "scn_rows_get": (_I, [_VP, _I64, _c.POINTER(_VP), _c.POINTER(_c.c_uint64), _IP]),
+    "scn_rows_free": (None, [_VP]),
+    "scn_mp4_mux": (_I64, [_VP, _SZ, _I, _I, _VP, _SZ]),
+    "scn_mp4_demux": (_I64, [_VP, _SZ, _VP, _SZ, _c.POINTER(_I64)]),
 }
 
 _lib = None
@@ -134,6 +150,121 @@ def h264_synth(yuv_frames, width, height, gop=30, non_key="pcm", frames=None):
     got = lib().scn_h264_synth(arr.ctypes.data, width, height, n, gop, mode, out.ctypes.data, out.size)
     assert got == need
     return out.tobytes()
+
+
+def mp4_mux(annexb, fps_num=25, fps_den=1):
+    """H.264 Annex-B bytes -> the bytes of a non-fragmented .mp4 holding that one track."""
+    buf = np.frombuffer(bytes(annexb), np.uint8)
+    need = check(lib().scn_mp4_mux(buf.ctypes.data, buf.size, fps_num, fps_den, None, 0), "scn_mp4_mux")
+    out = np.empty(need, np.uint8)
+    check(lib().scn_mp4_mux(buf.ctypes.data, buf.size, fps_num, fps_den, out.ctypes.data, out.size), "scn_mp4_mux")
+    return out.tobytes()
+
+
+def mp4_demux(data):
+    """.mp4/.mov bytes -> (Annex-B stream of the first H.264 track, info dict)."""
+    buf = np.frombuffer(bytes(data), np.uint8)
+    info = (ctypes.c_int64 * 6)()
+    need = check(lib().scn_mp4_demux(buf.ctypes.data, buf.size, None, 0, info), "scn_mp4_demux")
+    out = np.empty(need, np.uint8)
+    check(lib().scn_mp4_demux(buf.ctypes.data, buf.size, out.ctypes.data, out.size, info), "scn_mp4_demux")
+    keys = ["width", "height", "timescale", "duration", "samples", "sync_samples"]
+    return out.tobytes(), dict(zip(keys, list(info)))
+
+
+class Database:
+    """A Scanner database directory (reference layout: db_metadata.bin, tables/<id>/...)."""
+
+    def __init__(self, path):
+        self._h = lib().scn_db_open(os.path.abspath(path).encode())
+        if not self._h:
+            raise EngineError(f"scn_db_open({path}): {lib().scn_last_error().decode()}")
+        self.path = os.path.abspath(path)
+
+    def close(self):
+        if self._h:
+            lib().scn_db_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ingest_video(self, table, video_path):
+        check(lib().scn_db_ingest_video(self._h, table.encode(), os.path.abspath(video_path).encode()),
+              f"ingest_video({video_path})")
+
+    def ingest_h264(self, table, data, fps_num=25, fps_den=1):
+        buf = np.frombuffer(bytes(data), np.uint8)
+        check(lib().scn_db_ingest_h264(self._h, table.encode(), buf.ctypes.data, buf.size, fps_num, fps_den),
+              f"ingest_h264({table})")
+
+    def has_table(self, table):
+        return bool(lib().scn_db_has_table(self._h, table.encode()))
+
+    def delete_table(self, table):
+        check(lib().scn_db_delete_table(self._h, table.encode()), f"delete_table({table})")
+
+    def tables(self):
+        buf = ctypes.create_string_buffer(1 << 20)
+        check(lib().scn_db_list_tables(self._h, buf, len(buf)), "scn_db_list_tables")
+        return [t for t in buf.value.decode().split("\n") if t]
+
+    def table_info(self, table):
+        info = (ctypes.c_int64 * 8)()
+        cols = ctypes.create_string_buffer(1 << 16)
+        check(lib().scn_db_table_info(self._h, table.encode(), info, cols, len(cols)), f"table_info({table})")
+        d = dict(zip(["id", "rows", "num_columns", "items", "job_id", "width", "height", "keyframes"], list(info)))
+        d["columns"] = []
+        for line in cols.value.decode().splitlines():
+            n, t, tn = line.split(":", 2)
+            d["columns"].append({"name": n, "type": "Video" if int(t) == 1 else "Bytes", "type_name": tn})
+        return d
+
+    def add_video_stream(self, engine, table):
+        return check(lib().scn_db_add_video_stream(self._h, engine._h, table.encode()), f"add_video_stream({table})")
+
+    def save_job(self, job, table, columns, job_id=-1):
+        """columns: [(sink op index, column name, type name)] -> table id"""
+        n = len(columns)
+        sinks = (ctypes.c_int * n)(*[c[0] for c in columns])
+        names = (ctypes.c_char_p * n)(*[c[1].encode() for c in columns])
+        types = (ctypes.c_char_p * n)(*[(c[2] or "").encode() for c in columns])
+        return check(lib().scn_db_save_job(self._h, job._h, table.encode(), sinks, names, types, n, job_id),
+                     f"save_job({table})")
+
+    def read_rows(self, table, column, rows=None):
+        """-> list of rows: bytes for byte columns, ndarrays for frame columns, None for null rows."""
+        if rows is None:
+            rows = range(self.table_info(table)["rows"])
+        rows = list(rows)
+        arr = (ctypes.c_int64 * max(1, len(rows)))(*rows)
+        h = lib().scn_db_read_rows(self._h, table.encode(), column.encode(), arr, len(rows))
+        if not h:
+            raise EngineError(f"read_rows({table}.{column}): {lib().scn_last_error().decode()}")
+        try:
+            out = []
+            for i in range(lib().scn_rows_count(h)):
+                data, size, shape = ctypes.c_void_p(), ctypes.c_uint64(), (ctypes.c_int * 4)()
+                check(lib().scn_rows_get(h, i, ctypes.byref(data), ctypes.byref(size), shape), "scn_rows_get")
+                out.append(_row_to_python(data.value, size.value, list(shape)))
+            return out
+        finally:
+            lib().scn_rows_free(h)
+
+
+_FRAME_DTYPES = {0: np.uint8, 1: np.float32, 2: np.float64, 3: np.uint16}
+
+
+def _row_to_python(addr, size, shape):
+    if size == 0:
+        return None
+    raw = ctypes.string_at(addr, size)
+    if shape[3] >= 0:
+        return np.frombuffer(raw, _FRAME_DTYPES[shape[3]]).reshape(shape[0], shape[1], shape[2]).copy()
+    return raw
 
 
 class Engine:

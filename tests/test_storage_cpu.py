@@ -1,0 +1,243 @@
+"""Tables on disk and .mp4 ingest, CPU only.
+
+Independent readers pin the formats:
+  * FFmpeg (cv2.VideoCapture) must open the .mp4 files our muxer writes and decode the same pictures
+    it decodes from the raw Annex-B stream -- so the demuxer is tested on files a third party accepts;
+  * the real protobuf runtime (google.protobuf, message types declared here with the reference's
+    field numbers, scanner/metadata.proto:6-23,55-126) must parse every descriptor we write."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import synth
+from scanner_b200 import engine as E
+from scanner_b200 import protolite
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TEST_ARGS = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
+
+
+# ------------------------------------------------------------------ protobuf-runtime message types
+def _reference_messages():
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="ref_metadata_subset.proto", package="refmeta", syntax="proto3")
+
+    def msg(name, fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, ftype, rep, tname in fields:
+            f = m.field.add(name=fname, number=num, type=ftype,
+                            label=F.LABEL_REPEATED if rep else F.LABEL_OPTIONAL)
+            if tname:
+                f.type_name = ".refmeta." + tname
+    msg("DbEntry", [("id", 1, F.TYPE_INT32, 0, None), ("name", 2, F.TYPE_STRING, 0, None),
+                    ("committed", 3, F.TYPE_BOOL, 0, None)])
+    msg("DatabaseDescriptor", [("next_bulk_job_id", 1, F.TYPE_INT32, 0, None), ("next_table_id", 2, F.TYPE_INT32, 0, None),
+                               ("bulk_jobs", 3, F.TYPE_MESSAGE, 1, "DbEntry"), ("tables", 4, F.TYPE_MESSAGE, 1, "DbEntry")])
+    msg("Column", [("id", 1, F.TYPE_INT32, 0, None), ("name", 2, F.TYPE_STRING, 0, None),
+                   ("type", 3, F.TYPE_INT32, 0, None), ("type_name", 4, F.TYPE_STRING, 0, None)])
+    msg("TableDescriptor", [("id", 1, F.TYPE_INT32, 0, None), ("name", 2, F.TYPE_STRING, 0, None),
+                            ("columns", 3, F.TYPE_MESSAGE, 1, "Column"), ("end_rows", 4, F.TYPE_INT64, 1, None),
+                            ("job_id", 6, F.TYPE_INT32, 0, None), ("timestamp", 7, F.TYPE_INT64, 0, None)])
+    msg("VideoDescriptor", [
+        ("table_id", 1, F.TYPE_INT32, 0, None), ("column_id", 2, F.TYPE_INT32, 0, None),
+        ("item_id", 3, F.TYPE_INT32, 0, None), ("frames", 4, F.TYPE_INT64, 0, None),
+        ("width", 5, F.TYPE_INT32, 0, None), ("height", 6, F.TYPE_INT32, 0, None),
+        ("codec_type", 7, F.TYPE_INT32, 0, None), ("chroma_format", 8, F.TYPE_INT32, 0, None),
+        ("sample_offsets", 9, F.TYPE_UINT64, 1, None), ("sample_sizes", 10, F.TYPE_UINT64, 1, None),
+        ("keyframe_indices", 11, F.TYPE_UINT64, 1, None), ("metadata_packets", 12, F.TYPE_BYTES, 0, None),
+        ("frame_type", 13, F.TYPE_INT32, 0, None), ("channels", 14, F.TYPE_INT32, 0, None),
+        ("time_base_num", 15, F.TYPE_INT32, 0, None), ("time_base_denom", 16, F.TYPE_INT32, 0, None),
+        ("num_encoded_videos", 17, F.TYPE_INT64, 0, None), ("frames_per_video", 18, F.TYPE_INT64, 1, None),
+        ("keyframes_per_video", 19, F.TYPE_INT64, 1, None), ("size_per_video", 20, F.TYPE_INT64, 1, None),
+        ("data_path", 21, F.TYPE_STRING, 0, None), ("inplace", 22, F.TYPE_BOOL, 0, None)])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, "GetMessageClass", None)
+    out = {}
+    for n in ("DatabaseDescriptor", "TableDescriptor", "VideoDescriptor"):
+        d = pool.FindMessageTypeByName("refmeta." + n)
+        out[n] = get(d) if get else message_factory.MessageFactory(pool).GetPrototype(d)
+    return out
+
+
+REF = _reference_messages()
+
+
+def parse_ref(kind, path):
+    m = REF[kind]()
+    m.ParseFromString(open(path, "rb").read())
+    return m
+
+
+# ------------------------------------------------------------------------------------- fixtures
+@pytest.fixture(scope="module", autouse=True)
+def plugin():
+    oracle.build()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
+    so = os.path.join(ROOT, "build", "tests", "libtest_plugin_ops.so")
+    if "TestWindow" not in E.list_ops():
+        E.load_op_library(so)
+
+
+def make_stream(seed, n, h, w, gop, non_key="pcm"):
+    rng = np.random.default_rng(seed)
+    k = n if non_key == "pcm" else (n + gop - 1) // gop
+    yuv = rng.integers(0, 256, (k, h * w * 3 // 2), dtype=np.uint8)
+    return E.h264_synth(yuv, w, h, gop=gop, non_key=non_key, frames=n), yuv
+
+
+def cv2_frames(path):
+    import cv2
+    cap = cv2.VideoCapture(path)
+    assert cap.isOpened(), path
+    out = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        out.append(f)
+    return out
+
+
+# ------------------------------------------------------------------------------------- container
+@pytest.mark.parametrize("h,w,n,gop,mode", [(48, 64, 12, 4, "pcm"), (96, 128, 9, 3, "skip"), (270, 480, 5, 5, "pcm")])
+def test_mp4_written_here_is_read_by_ffmpeg_and_demuxes_back(tmp_path, h, w, n, gop, mode):
+    stream, _ = make_stream(3, n, h, w, gop, mode)
+    mp4 = E.mp4_mux(stream, 30, 1)
+    raw_path, mp4_path = str(tmp_path / "a.h264"), str(tmp_path / "a.mp4")
+    open(raw_path, "wb").write(stream)
+    open(mp4_path, "wb").write(mp4)
+    from_raw, from_mp4 = cv2_frames(raw_path), cv2_frames(mp4_path)
+    assert len(from_mp4) == n == len(from_raw)
+    for a, b in zip(from_raw, from_mp4):
+        assert (a == b).all()
+    # our demuxer gives back the elementary stream byte for byte (parameter sets re-inserted in
+    # front of every sync sample, which is where the synthetic encoder puts them)
+    back, info = E.mp4_demux(mp4)
+    assert info == {"width": w, "height": h, "timescale": 30, "duration": n, "samples": n,
+                    "sync_samples": (n + gop - 1) // gop}
+    assert back == stream
+
+
+def test_mp4_errors_are_reported():
+    stream, _ = make_stream(4, 4, 48, 64, 2)
+    mp4 = E.mp4_mux(stream)
+    with pytest.raises(E.EngineError, match="moov"):
+        E.mp4_demux(mp4[:len(mp4) // 2])          # index (moov) cut off
+    broken = bytearray(mp4)
+    i = broken.find(b"avc1", broken.find(b"stsd"))   # the sample entry, not the ftyp brand
+    broken[i:i + 4] = b"hev1"
+    with pytest.raises(E.EngineError, match="hev1"):
+        E.mp4_demux(bytes(broken))
+    with pytest.raises(E.EngineError):
+        E.mp4_demux(b"\x00\x00\x00\x08free" + b"\x00" * 32)
+
+
+# ------------------------------------------------------------------------------------- ingest
+def test_ingest_mp4_writes_the_reference_table_layout(tmp_path):
+    n, h, w, gop = 10, 48, 64, 5
+    stream, _ = make_stream(5, n, h, w, gop)
+    mp4_path = str(tmp_path / "clip.mp4")
+    open(mp4_path, "wb").write(E.mp4_mux(stream, 24, 1))
+    db = E.Database(str(tmp_path / "db"))
+    db.ingest_video("clip", mp4_path)
+    assert db.tables() == ["clip"] and db.has_table("clip")
+    info = db.table_info("clip")
+    assert info["rows"] == n and info["width"] == w and info["height"] == h and info["keyframes"] == 2
+    assert [c["name"] for c in info["columns"]] == ["index", "frame"] and info["columns"][1]["type"] == "Video"
+
+    root = str(tmp_path / "db")
+    meta = parse_ref("DatabaseDescriptor", os.path.join(root, "db_metadata.bin"))
+    assert meta.next_table_id == 1 and [(t.id, t.name, t.committed) for t in meta.tables] == [(0, "clip", True)]
+    td = parse_ref("TableDescriptor", os.path.join(root, "tables/0/descriptor.bin"))
+    assert td.name == "clip" and list(td.end_rows) == [n] and td.job_id == -1
+    assert [(c.id, c.name, c.type) for c in td.columns] == [(0, "index", 0), (1, "frame", 1)]
+    vd = parse_ref("VideoDescriptor", os.path.join(root, "tables/0/1_0_video_metadata.bin"))
+    assert (vd.frames, vd.width, vd.height, vd.channels, vd.codec_type, vd.chroma_format) == (n, w, h, 3, 0, 1)
+    assert (vd.time_base_num, vd.time_base_denom) == (1, 24)
+    assert list(vd.keyframe_indices) == [0, 5] and list(vd.frames_per_video) == [n]
+    data = open(os.path.join(root, "tables/0/1_0.bin"), "rb").read()
+    assert data == stream and list(vd.size_per_video) == [len(data)]
+    # every sample is one access unit of the stored stream; IDR samples start with the SPS
+    offs, sizes = list(vd.sample_offsets), list(vd.sample_sizes)
+    assert len(offs) == n and offs[0] == 0 and all(offs[i] + sizes[i] == offs[i + 1] for i in range(n - 1))
+    assert offs[-1] + sizes[-1] == len(data)
+    for k in vd.keyframe_indices:
+        assert data[offs[k]:offs[k] + 5] == b"\x00\x00\x00\x01\x67"
+    assert vd.metadata_packets.startswith(b"\x00\x00\x00\x01\x67")
+    # index column: row i = int64 i, metadata = n then n sizes (reference ingest.cpp:321-345)
+    idx = open(os.path.join(root, "tables/0/0_0.bin"), "rb").read()
+    assert idx == b"".join(struct.pack("<q", i) for i in range(n))
+    m = open(os.path.join(root, "tables/0/0_0_metadata.bin"), "rb").read()
+    assert struct.unpack(f"<{n + 1}Q", m) == (n,) + (8,) * n
+    assert db.read_rows("clip", "index", [0, 7]) == [struct.pack("<q", 0), struct.pack("<q", 7)]
+    with pytest.raises(E.EngineError, match="compressed"):
+        db.read_rows("clip", "frame", [0])
+    with pytest.raises(E.EngineError, match="already exists"):
+        db.ingest_video("clip", mp4_path)
+    with pytest.raises(E.EngineError, match="cannot read"):
+        db.ingest_video("other", str(tmp_path / "missing.mp4"))
+
+    # the stored table binds to an engine as an H.264 stream without rescanning
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    sid = db.add_video_stream(eng, "clip")
+    si = eng.stream_info(sid)
+    assert (si["is_video"], si["width"], si["height"], si["keyframes"]) == (1, w, h, 2) and eng.stream_rows(sid) == n
+    eng.close()
+    db.close()
+
+    # a second process / session sees the committed table; raw .h264 files ingest too
+    db2 = E.Database(root)
+    assert db2.tables() == ["clip"]
+    raw_path = str(tmp_path / "clip.h264")
+    open(raw_path, "wb").write(stream)
+    db2.ingest_video("raw", raw_path)
+    assert db2.table_info("raw")["id"] == 1 and sorted(db2.tables()) == ["clip", "raw"]
+    db2.delete_table("clip")
+    assert db2.tables() == ["raw"] and not os.path.exists(os.path.join(root, "tables/0"))
+    db2.close()
+
+
+# ------------------------------------------------------------------------------------- job output tables
+def test_job_outputs_saved_as_tables_and_read_back(tmp_path):
+    n, h, w = 11, 24, 32
+    frames = np.stack([synth.rand_frame(200 + i, h, w) for i in range(n)])
+    eng = E.Engine(gpus=[], cpu_instances=2)
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("TestHistogramOracle", [(src, "frame")])
+    rz = g.add_op("TestResizeOracle", [(src, "frame")])
+    s_h, s_r = g.add_sink((hs, "histogram")), g.add_sink((rz, "frame"))
+    j = E.Job()
+    j.bind_source(src, eng.add_raw_frames(frames))
+    j.set_stream_args(rz, protolite.encode(TEST_ARGS["TestSizeArgs"], {"width": 16, "height": 12}))
+    eng.run(g, [j], 2, 4)
+    db = E.Database(str(tmp_path / "db"))
+    tid = db.save_job(j, "out", [(s_h, "histogram", "Histogram"), (s_r, "frame", "")], job_id=7)
+    assert tid == 0
+    info = db.table_info("out")
+    assert info["rows"] == n and info["items"] == 3 and info["job_id"] == 7 and info["keyframes"] == -1
+    assert [(c["name"], c["type"], c["type_name"]) for c in info["columns"]] == \
+        [("index", "Bytes", ""), ("histogram", "Bytes", "Histogram"), ("frame", "Video", "")]
+    td = parse_ref("TableDescriptor", str(tmp_path / "db/tables/0/descriptor.bin"))
+    assert list(td.end_rows) == [4, 8, 11]
+    vd = parse_ref("VideoDescriptor", str(tmp_path / "db/tables/0/2_1_video_metadata.bin"))
+    assert (vd.codec_type, vd.frames, vd.height, vd.width, vd.channels, vd.frame_type) == (2, 4, 12, 16, 3, 0)
+    hist = db.read_rows("out", "histogram")
+    res = db.read_rows("out", "frame", [0, 5, 10])
+    for i in range(n):
+        assert hist[i] == oracle.hist16(frames[i]).tobytes() == j.output_row(s_h, i)
+    for k, i in enumerate([0, 5, 10]):
+        assert res[k].shape == (12, 16, 3) and (res[k] == oracle.resize(frames[i], 16, 12)).all()
+    assert db.read_rows("out", "index", [9]) == [struct.pack("<q", 9)]
+    with pytest.raises(E.EngineError, match="outside"):
+        db.read_rows("out", "histogram", [n])
+    with pytest.raises(E.EngineError, match="no column"):
+        db.read_rows("out", "nope", [0])
+    eng.close()
+    db.close()
