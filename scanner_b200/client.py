@@ -4,8 +4,11 @@ Keeps the names and call shapes of the reference's Python API for the hot path s
 the same (python/scannerpy/client.py:1282-1590 `Client.run`, op.py:121-314 `sc.ops.<Name>(...)`,
 streams.py `sc.streams.Stride/Range/Gather/...`, storage.py:250-372 `NamedVideoStream`,
 `NamedStream`, common.py:78-234 `PerfParams`).  The transport underneath is not gRPC: the graph is
-handed to libscn_engine.so through its C ABI.  Not reproduced: the database / table catalogue,
-Slice/Unslice, Python kernels, multi-node master.
+handed to libscn_engine.so through its C ABI.  With `Client(db_path=...)` named streams live in a
+database directory in the reference's on-disk layout (engine.Database): videos are ingested from
+.mp4 / .h264 files once and re-bound from their stored index afterwards, outputs are committed as
+tables and can be loaded by a later session.  Not reproduced: Slice/Unslice, Python kernels,
+multi-node master.
 
     sc = Client(gpus=[0])
     video = NamedVideoStream(sc, 'clip', path='clip.h264')         # Annex-B elementary stream
@@ -171,21 +174,44 @@ class IOGenerator:
 
 # ------------------------------------------------------------------------------------------------
 class NamedVideoStream:
-    """A stored video.  path: an H.264 Annex-B file; data: the bytes; frames: (n,h,w,3) uint8 RAW frames."""
+    """A stored video.  path: an .mp4/.mov or an H.264 Annex-B file; data: the bytes of either;
+    frames: (n,h,w,3) uint8 RAW frames (kept in memory only).  With a database the video becomes
+    (or already is) the table `name` and is bound from its stored index."""
 
-    def __init__(self, sc, name, path=None, data=None, frames=None):
+    def __init__(self, sc, name, path=None, data=None, frames=None, inplace=False):
         self._sc, self._name = sc, name
+        db = sc._db
         if name in sc._streams and path is None and data is None and frames is None:
             self._sid = sc._streams[name]
+            return
+        if frames is not None:
+            self._sid = sc._engine.add_raw_frames(frames)
+        elif db is not None:
+            if not db.has_table(name):
+                if path is None and data is None:
+                    raise ScannerException(f"video table {name} does not exist and no path was given")
+                try:
+                    if path is not None:
+                        db.ingest_video(name, path)
+                    else:
+                        stream = E.mp4_demux(data)[0] if _is_mp4(data) else data
+                        db.ingest_h264(name, stream)
+                except E.EngineError as e:
+                    raise ScannerException(str(e)) from e
+            self._sid = db.add_video_stream(sc._engine, name)
         else:
-            if frames is not None:
-                self._sid = sc._engine.add_raw_frames(frames)
-            else:
-                if data is None:
-                    with open(path, "rb") as f:
-                        data = f.read()
+            if data is None:
+                if path is None:
+                    raise ScannerException(f"stream {name} is not known to this client")
+                with open(path, "rb") as f:
+                    data = f.read()
+            try:
+                if _is_mp4(data):
+                    data = E.mp4_demux(data)[0]
                 self._sid = sc._engine.add_h264(data)
-            sc._streams[name] = self._sid
+            except E.EngineError as e:
+                raise ScannerException(str(e)) from e
+        sc._streams[name] = self._sid
 
     def name(self):
         return self._name
@@ -196,9 +222,20 @@ class NamedVideoStream:
     def info(self):
         return self._sc._engine.stream_info(self._sid)
 
+    def exists(self):
+        return True
+
+    def committed(self):
+        return True
+
+
+def _is_mp4(data):
+    return len(data) >= 12 and bytes(data[4:8]) in (b"ftyp", b"moov", b"mdat", b"free", b"skip", b"wide", b"styp")
+
 
 class NamedStream:
-    """An output column (or a byte-row input when created with rows=[...])."""
+    """An output column (or a byte-row input when created with rows=[...]).  With a database it is
+    the table `name` with one data column, readable by later sessions."""
 
     def __init__(self, sc, name, rows=None):
         self._sc, self._name, self._job, self._sink, self._type = sc, name, None, None, None
@@ -210,20 +247,39 @@ class NamedStream:
     def name(self):
         return self._name
 
+    def _stored(self):
+        db = self._sc._db
+        return db is not None and db.has_table(self._name)
+
+    def exists(self):
+        return self._job is not None or self._sid is not None or self._stored()
+
+    committed = exists
+
     def len(self):
-        if self._job is None:
+        if self._job is not None:
+            return self._job.output_rows(self._sink)
+        if self._sid is not None:
             return self._sc._engine.stream_rows(self._sid)
-        return self._job.output_rows(self._sink)
+        if self._stored():
+            return self._sc._db.table_info(self._name)["rows"]
+        raise ScannerException(f"stream {self._name} does not exist")
 
     def load(self, ty=None, rows=None):
         """Generator over rows, deserialised like scannerpy.types (types.py:91-132): frame columns
         as ndarrays, `Histogram` as a list of three int32 arrays, anything else as bytes."""
-        if self._job is None:
+        if self._job is not None:
+            ty = ty or self._type
+            idx = range(self.len()) if rows is None else rows
+            fetched = (self._job.output_row(self._sink, i) for i in idx)
+        elif self._stored():
+            info = self._sc._db.table_info(self._name)
+            col = info["columns"][1]
+            ty = ty or col["type_name"] or None
+            fetched = iter(self._sc._db.read_rows(self._name, col["name"], rows))
+        else:
             raise ScannerException(f"stream {self._name} has not been written by a job")
-        ty = ty or self._type
-        idx = range(self.len()) if rows is None else rows
-        for i in idx:
-            r = self._job.output_row(self._sink, i)
+        for r in fetched:
             if r is None or isinstance(r, np.ndarray):
                 yield r
             elif ty == "Histogram":
@@ -234,17 +290,22 @@ class NamedStream:
 
     def delete(self, sc=None):
         self._job = None
+        if self._stored():
+            self._sc._db.delete_table(self._name)
 
 
 # ------------------------------------------------------------------------------------------------
 class Client:
     """In-process stand-in for scannerpy.Client: same graph-building surface, runs on local GPUs."""
 
-    def __init__(self, gpus=None, instances_per_gpu=0, cpu_instances=1, load_stdlib=True, **_ignored):
+    def __init__(self, gpus=None, instances_per_gpu=0, cpu_instances=1, load_stdlib=True, db_path=None,
+                 **_ignored):
         import torch
         if gpus is None:
             gpus = list(range(torch.cuda.device_count())) if torch.cuda.is_available() else []
         self._engine = E.Engine(gpus, instances_per_gpu, cpu_instances)
+        self._db = E.Database(db_path) if db_path else None
+        self._bulk_jobs = 0
         self._streams = {}
         self._op_protos = {}
         self.ops, self.streams, self.io = OpGenerator(self), StreamsGenerator(self), IOGenerator(self)
@@ -254,6 +315,38 @@ class Client:
                                                           "stdlib_args.proto")).read())
             self._op_protos["Blur"] = {"init": std["BlurArgs"]}
             self._op_protos["Resize"] = {"stream": std["ResizeArgs"]}
+
+    # ---- table catalogue (reference client.py: ingest_videos :1009-1078, has_table, delete_table)
+    def _need_db(self):
+        if self._db is None:
+            raise ScannerException("this Client was created without db_path: there is no table catalogue")
+        return self._db
+
+    def ingest_videos(self, videos, inplace=False, force=False):
+        """videos: [(table name, path)] -> (ingested NamedVideoStreams, [(path, error message)])."""
+        db, done, failed = self._need_db(), [], []
+        for name, path in videos:
+            try:
+                if db.has_table(name):
+                    if not force:
+                        raise ScannerException(f"table {name} already exists")
+                    db.delete_table(name)
+                    self._streams.pop(name, None)
+                db.ingest_video(name, path)
+                done.append(NamedVideoStream(self, name))
+            except (E.EngineError, ScannerException) as e:
+                failed.append((path, str(e)))
+        return done, failed
+
+    def has_table(self, name):
+        return self._need_db().has_table(name)
+
+    def table_names(self):
+        return self._need_db().tables()
+
+    def delete_table(self, name):
+        self._need_db().delete_table(name)
+        self._streams.pop(name, None)
 
     def load_op(self, so_path, proto_path=None, protos=None):
         """Load an op library (reference Client.load_op, client.py:514-537).  `protos` maps op name to
@@ -291,6 +384,24 @@ class Client:
 
         for o in outputs:
             visit(o)
+        # ---- output tables that already exist (reference CacheMode, client.py:1325-1370)
+        out_nodes = [n for n in order if n.kind == "output"]
+        skip = set()
+        if self._db is not None and out_nodes:
+            for j in range(len(out_nodes[0].streams)):
+                present = [n.streams[j].name() for n in out_nodes if self._db.has_table(n.streams[j].name())]
+                if not present:
+                    continue
+                if cache_mode == CacheMode.Error:
+                    raise ScannerException(f"output stream {present[0]} already exists (CacheMode.Error)")
+                if cache_mode == CacheMode.Overwrite:
+                    for name in present:
+                        self._db.delete_table(name)
+                elif len(present) == len(out_nodes):
+                    skip.add(j)  # CacheMode.Ignore: every output of this job is already stored
+                else:
+                    for name in present:
+                        self._db.delete_table(name)
         g = E.Graph()
         index, n_jobs = {}, None
         for node in order:
@@ -310,8 +421,11 @@ class Client:
             elif node.kind == "output":
                 c = node.inputs[0]
                 index[id(node)] = g.add_sink((index[id(c._op)], c._col), node.streams[0].name())
-        jobs = []
+        jobs, job_of = [], {}
         for j in range(n_jobs):
+            if j in skip:
+                continue
+            job_of[j] = len(jobs)
             job = E.Job()
             for node in order:
                 if node.kind == "input":
@@ -323,15 +437,26 @@ class Client:
                     job.set_stream_args(index[id(node)], node.per_stream[j if len(node.per_stream) > 1 else 0])
             jobs.append(job)
         try:
-            self._engine.run(g, jobs, perf_params.work_packet_size, perf_params.io_packet_size, out_dir)
+            if jobs:
+                self._engine.run(g, jobs, perf_params.work_packet_size, perf_params.io_packet_size, out_dir)
         except E.EngineError as e:
             raise ScannerException(str(e)) from e
-        for node in order:
-            if node.kind == "output":
-                src_col = node.inputs[0]
-                for j, s in enumerate(node.streams):
-                    s._job, s._sink = jobs[j], index[id(node)]
-                    s._type = "Histogram" if src_col._col == "histogram" else None
+        bulk_job_id = self._bulk_jobs
+        self._bulk_jobs += 1
+        for node in out_nodes:
+            src_col = node.inputs[0]
+            type_name = "Histogram" if src_col._col == "histogram" else ""
+            for j, s in enumerate(node.streams):
+                if j in skip:
+                    s._job = None  # served from the stored table
+                    continue
+                s._job, s._sink = jobs[job_of[j]], index[id(node)]
+                s._type = type_name or None
+                if self._db is not None:
+                    try:
+                        self._db.save_job(s._job, s.name(), [(s._sink, src_col._col, type_name)], bulk_job_id)
+                    except E.EngineError as e:
+                        raise ScannerException(str(e)) from e
         self._last_graph = g
         return len(jobs)
 
@@ -340,3 +465,5 @@ class Client:
 
     def stop(self):
         self._engine.close()
+        if self._db is not None:
+            self._db.close()

@@ -84,3 +84,74 @@ def test_errors_are_scanner_exceptions(sc):
     a = sp.NamedStream(sc, "ints_d", rows=rows)
     with pytest.raises(sp.ScannerException, match="does not take argument"):
         sc.ops.TestAffine(col=sc.io.Input([a]), bogus=1)
+
+
+# ------------------------------------------------------------------------------------------------
+def _db_client(path):
+    c = sp.Client(gpus=[], cpu_instances=2, db_path=str(path))
+    from scanner_b200 import protolite
+    msgs = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
+    c._op_protos["TestAffine"] = {"init": msgs["TestScaleArgs"], "stream": msgs["TestOffsetArgs"]}
+    return c
+
+
+def test_database_backed_streams_persist_and_cache_modes(sc, tmp_path):
+    """Outputs are committed as tables (reference storage.py NamedStream / CacheMode, client.py:1325-1370)
+    and a later session loads them without re-running."""
+    rows = [struct.pack("<q", i) for i in range(30)]
+    c1 = _db_client(tmp_path / "db")
+    src = sp.NamedStream(c1, "ints", rows=rows)
+    out = sp.NamedStream(c1, "ints_scaled")
+    assert not out.exists()
+    aff = c1.ops.TestAffine(col=c1.io.Input([src]), scale=3, offset=[7])
+    assert c1.run(c1.io.Output(aff, [out]), sp.PerfParams.manual(4, 8)) == 1
+    want = [3 * i + 7 for i in range(30)]
+    assert [struct.unpack("<q", r)[0] for r in out.load()] == want
+    assert c1.table_names() == ["ints_scaled"] and out.exists()
+    # the same output again: Error refuses, Ignore skips the job, Overwrite recomputes
+    with pytest.raises(sp.ScannerException, match="already exists"):
+        c1.run(c1.io.Output(aff, [out]), sp.PerfParams.manual(4, 8))
+    assert c1.run(c1.io.Output(aff, [out]), sp.PerfParams.manual(4, 8), cache_mode=sp.CacheMode.Ignore) == 0
+    assert [struct.unpack("<q", r)[0] for r in out.load(rows=[0, 29])] == [want[0], want[29]]
+    aff2 = c1.ops.TestAffine(col=c1.io.Input([src]), scale=5, offset=[1])
+    assert c1.run(c1.io.Output(aff2, [out]), sp.PerfParams.manual(4, 8), cache_mode=sp.CacheMode.Overwrite) == 1
+    assert [struct.unpack("<q", r)[0] for r in out.load()] == [5 * i + 1 for i in range(30)]
+    c1.stop()
+
+    c2 = _db_client(tmp_path / "db")          # a later session
+    again = sp.NamedStream(c2, "ints_scaled")
+    assert again.exists() and again.len() == 30
+    assert [struct.unpack("<q", r)[0] for r in again.load()] == [5 * i + 1 for i in range(30)]
+    again.delete()
+    assert c2.table_names() == [] and not sp.NamedStream(c2, "ints_scaled").exists()
+    with pytest.raises(sp.ScannerException, match="without db_path"):
+        sc.has_table("x")
+    c2.stop()
+
+
+def test_ingest_videos_from_mp4_and_h264_files(tmp_path):
+    """Client.ingest_videos (reference client.py:1009-1078): tables appear, failures are reported per
+    file, a stored video re-binds by name in a later session (decode itself needs a GPU)."""
+    rng = np.random.default_rng(8)
+    n, h, w = 8, 48, 64
+    yuv = rng.integers(0, 256, (n, h * w * 3 // 2), dtype=np.uint8)
+    stream = E.h264_synth(yuv, w, h, gop=4)
+    mp4, raw = tmp_path / "a.mp4", tmp_path / "b.h264"
+    mp4.write_bytes(E.mp4_mux(stream, 25, 1))
+    raw.write_bytes(stream)
+    c = sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False)
+    done, failed = c.ingest_videos([("a", str(mp4)), ("b", str(raw)), ("c", str(tmp_path / "nope.mp4"))])
+    assert [v.name() for v in done] == ["a", "b"] and len(failed) == 1 and "nope.mp4" in failed[0][0]
+    assert all(v.len() == n and v.info()["width"] == w for v in done)
+    _, failed = c.ingest_videos([("a", str(mp4))])
+    assert "already exists" in failed[0][1]
+    done, failed = c.ingest_videos([("a", str(raw))], force=True)
+    assert not failed and done[0].len() == n
+    c.stop()
+    c2 = sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False)
+    assert sorted(c2.table_names()) == ["a", "b"]
+    v = sp.NamedVideoStream(c2, "b")       # by name only: bound from the stored descriptor
+    assert v.len() == n and v.info()["keyframes"] == 2
+    with pytest.raises(sp.ScannerException, match="does not exist"):
+        sp.NamedVideoStream(c2, "zzz")
+    c2.stop()

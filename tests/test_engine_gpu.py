@@ -308,6 +308,36 @@ def test_client_surface_on_gpu_like_tutorial_00():
     sc.stop()
 
 
+def test_mp4_ingest_to_stored_histograms_through_the_database(tmp_path):
+    """The whole path on disk formats: .mp4 file -> Client.ingest_videos (demux + index + video table)
+    -> NVDEC decode from the stored stream -> GPU Histogram / Resize -> output tables -> a later
+    session loads them.  Every value equals the oracle on the source planes."""
+    import scanner_b200 as sp
+    n, gop = 20, 5
+    data, want = make_clip(41, n, 96, 128, gop)
+    (tmp_path / "clip.mp4").write_bytes(E.mp4_mux(data, 30, 1))
+    sc = sp.Client(gpus=[0], instances_per_gpu=2, db_path=str(tmp_path / "db"))
+    done, failed = sc.ingest_videos([("clip", str(tmp_path / "clip.mp4"))])
+    assert not failed and done[0].len() == n
+    frames = sc.io.Input([sp.NamedVideoStream(sc, "clip")])
+    gathered = sc.streams.Gather(frames, [[1, 4, 5, 13, 19]])
+    hists = sc.ops.Histogram(frame=gathered, device=sp.DeviceType.GPU)
+    small = sc.ops.Resize(frame=gathered, device=sp.DeviceType.GPU, width=[32], height=[24])
+    o_h, o_r = sp.NamedStream(sc, "clip_hist"), sp.NamedStream(sc, "clip_small")
+    sc.run([sc.io.Output(hists, [o_h]), sc.io.Output(small, [o_r])], sp.PerfParams.manual(2, 4))
+    assert sc.stats()["counters"]["frames_delivered_nv12"] == 5
+    sc.stop()
+    sc2 = sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False)
+    assert sorted(sc2.table_names()) == ["clip", "clip_hist", "clip_small"]
+    hist = list(sp.NamedStream(sc2, "clip_hist").load())
+    small = list(sp.NamedStream(sc2, "clip_small").load())
+    assert len(hist) == len(small) == 5
+    for k, row in enumerate([1, 4, 5, 13, 19]):
+        assert (np.stack(hist[k]) == oracle.hist16(want[row])).all()
+        assert (small[k] == oracle.resize(want[row], 32, 24)).all()
+    sc2.stop()
+
+
 def test_decode_to_device_matches_engine_path(eng):
     import torch
     data, want = make_clip(31, 20, 96, 128, 6)
