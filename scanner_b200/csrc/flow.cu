@@ -12,6 +12,7 @@
 // double like OpenCV's (the determinant cancels catastrophically in float).
 // All kernels are plain per-pixel / separable memory-bound passes (no tensor cores).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "scn_common.cuh"
@@ -214,6 +215,233 @@ __global__ void box_h_solve_kernel(const double* __restrict__ V, int w, int h, i
   flow[((size_t)y * w + x) * 2 + 1] = (float)((g22 * h1 - g12 * h2) * idet);
 }
 
+
+// ---- fused, shared-memory tiled forms of the three separable stages -------------------------------
+// The per-row kernels above make two global round trips per stage (h pass, v pass) with one pixel
+// per thread and a clamp/reflect per tap.  The fused kernels load a tile with its halo once
+// (border handling happens while loading), run both passes out of shared memory and keep the
+// summation order of the two-pass kernels, so their results are bit-identical to them
+// (tests/test_flow_gpu.py compares the two paths).  256 threads per CTA.
+constexpr int FT = 256;
+
+// GaussianBlur: tile (TH + 2r) x (TW + 2r) in, h pass into hbuf, v pass out.  Threads are laid out
+// 64 x 4 (column, row phase) so no index needs a division.
+constexpr int GTW = 64, GTH = 32;
+__global__ void __launch_bounds__(FT)
+gauss_fused_kernel(const float* __restrict__ src, int w, int h, GaussK gk, float* __restrict__ dst) {
+  extern __shared__ float fsm[];
+  const int r = gk.radius, iw = GTW + 2 * r, ih = GTH + 2 * r;
+  float* in = fsm;             // ih x iw
+  float* hb = fsm + ih * iw;   // ih x GTW
+  const int x0 = blockIdx.x * GTW, y0 = blockIdx.y * GTH;
+  const int tx = threadIdx.x & 63, tq = threadIdx.x >> 6;
+  // tile load, 8 independent global loads in flight per thread before the first shared store (a
+  // plain load->store loop serialises on the load latency: r01 ncu long_scoreboard 3-9 per issue)
+  for (int i = tx; i < iw; i += 64) {
+    const int sx = reflect101(x0 - r + i, w);
+    for (int j0 = tq; j0 < ih; j0 += 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + 4 * u;
+        v[u] = j < ih ? src[(size_t)reflect101(y0 - r + j, h) * w + sx] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + 4 * u;
+        if (j < ih) in[j * iw + i] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tq; j < ih; j += 4) {
+    const float* row = in + j * iw + tx;
+    float s = 0.f;
+    for (int i = 0; i <= 2 * r; ++i) s += gk.k[i] * row[i];
+    hb[j * GTW + tx] = s;
+  }
+  __syncthreads();
+  const int x = x0 + tx;
+  if (x >= w) return;
+  for (int ty = tq; ty < GTH; ty += 4) {
+    const int y = y0 + ty;
+    if (y >= h) break;
+    float s = 0.f;
+    for (int i = 0; i <= 2 * r; ++i) s += gk.k[i] * hb[(ty + i) * GTW + tx];
+    dst[(size_t)y * w + x] = s;
+  }
+}
+
+// Polynomial expansion: v pass (3 values per pixel) into shared memory, h pass to 5 coefficients.
+constexpr int PTW = 64, PTH = 32;
+__global__ void __launch_bounds__(FT)
+poly_fused_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* __restrict__ dst5) {
+  extern __shared__ float fsm[];
+  const int n = pk.n, iw = PTW + 2 * n, ih = PTH + 2 * n;
+  float* in = fsm;            // ih x iw
+  float* t3 = fsm + ih * iw;  // PTH x iw x 3
+  const int x0 = blockIdx.x * PTW, y0 = blockIdx.y * PTH;
+  const int tx = threadIdx.x & 63, tq = threadIdx.x >> 6;
+  for (int i = tx; i < iw; i += 64) {
+    const int sx = clampi(x0 - n + i, 0, w - 1);
+    for (int j0 = tq; j0 < ih; j0 += 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + 4 * u;
+        v[u] = j < ih ? src[(size_t)clampi(y0 - n + j, 0, h - 1) * w + sx] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + 4 * u;
+        if (j < ih) in[j * iw + i] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  for (int jy = tq; jy < PTH; jy += 4)
+    for (int i = tx; i < iw; i += 64) {
+      const float* c = in + (jy + n) * iw + i;
+      float t0 = c[0] * pk.g[0], t1 = 0.f, t2 = 0.f;
+      for (int k = 1; k <= n; ++k) {
+        const float sp = c[k * iw], sm = c[-k * iw];
+        t0 += pk.g[k] * (sp + sm);
+        t1 += pk.xg[k] * (sp - sm);
+        t2 += pk.xxg[k] * (sp + sm);
+      }
+      float* d = t3 + ((size_t)jy * iw + i) * 3;
+      d[0] = t0;
+      d[1] = t1;
+      d[2] = t2;
+    }
+  __syncthreads();
+  const int x = x0 + tx;
+  if (x >= w) return;
+  for (int ty = tq; ty < PTH; ty += 4) {
+    const int y = y0 + ty;
+    if (y >= h) break;
+    const float* c0 = t3 + ((size_t)ty * iw + tx + n) * 3;
+    float b1 = c0[0] * pk.g[0], b2 = 0.f, b3 = c0[1] * pk.g[0], b4 = 0.f, b5 = c0[2] * pk.g[0], b6 = 0.f;
+    for (int k = 1; k <= n; ++k) {
+      const float* p = c0 + k * 3;
+      const float* m = c0 - k * 3;
+      const float tg = p[0] + m[0];
+      b1 += tg * pk.g[k];
+      b2 += (p[0] - m[0]) * pk.xg[k];
+      b4 += tg * pk.xxg[k];
+      b3 += (p[1] + m[1]) * pk.g[k];
+      b6 += (p[1] - m[1]) * pk.xg[k];
+      b5 += (p[2] + m[2]) * pk.g[k];
+    }
+    float* d = dst5 + ((size_t)y * w + x) * 5;
+    d[1] = b2 * pk.ig11;
+    d[0] = b3 * pk.ig11;
+    d[3] = b1 * pk.ig03 + b4 * pk.ig33;
+    d[2] = b1 * pk.ig03 + b5 * pk.ig33;
+    d[4] = b6 * pk.ig55;
+  }
+}
+
+// winSize x winSize box average of M (double sums, clamped borders) + the 2x2 solve.  MW = window
+// half-width at compile time (winSize 15 -> 7).  Both passes are register-blocked by 4: a thread
+// converts 2 MW + 4 inputs once and forms four overlapping (2 MW + 1)-term sums from them, each in the
+// two-pass kernels' order.  The vertical sums are kept with an odd row stride so that the 16 rows a
+// half-warp reads in the horizontal pass fall into distinct shared-memory banks.
+constexpr int BTW = 64, BTH = 16;
+template <int MW>
+__global__ void __launch_bounds__(FT)
+box_solve_fused_kernel(const float* __restrict__ M, int w, int h, double scale, float* __restrict__ flow) {
+  extern __shared__ double dsm[];
+  constexpr int iw = BTW + 2 * MW, ih = BTH + 2 * MW, rowf = iw * 5, vstride = rowf | 1, taps = 2 * MW + 1;
+  double* V = dsm;                                                    // BTH x vstride doubles
+  float* in = reinterpret_cast<float*>(dsm + (size_t)BTH * vstride);  // ih x rowf floats
+  const int x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH;
+  for (int q = threadIdx.x; q < rowf; q += FT) {
+    const int i = q / 5, c = q - i * 5;
+    const size_t sx = (size_t)clampi(x0 - MW + i, 0, w - 1) * 5 + c;
+    for (int j0 = 0; j0 < ih; j0 += 10) {  // 10 independent loads in flight, then the 10 stores
+      float v[10];
+#pragma unroll
+      for (int u = 0; u < 10; ++u)
+        v[u] = j0 + u < ih ? M[(size_t)clampi(y0 - MW + j0 + u, 0, h - 1) * w * 5 + sx] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 10; ++u)
+        if (j0 + u < ih) in[(j0 + u) * rowf + q] = v[u];
+    }
+  }
+  __syncthreads();
+  // vertical: item = (group of 4 rows, column-channel q)
+  for (int e = threadIdx.x; e < (BTH / 4) * rowf; e += FT) {
+    const int g4 = e / rowf, q = e - g4 * rowf;
+    const float* col = in + (g4 * 4) * rowf + q;
+    double v[taps + 3];
+#pragma unroll
+    for (int k = 0; k < taps + 3; ++k) v[k] = (double)col[k * rowf];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < taps; ++k) sum += v[o + k];
+      V[(size_t)(g4 * 4 + o) * vstride + q] = sum;
+    }
+  }
+  __syncthreads();
+  // horizontal + solve: thread = (row ty, group of 4 columns)
+  const int ty = threadIdx.x & (BTH - 1), gx = threadIdx.x / BTH;  // 16 rows x 16 groups = 256 threads
+  const int y = y0 + ty;
+  if (y >= h) return;
+  const double* p = V + (size_t)ty * vstride + (gx * 4) * 5;
+  double hs[4][5];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) hs[o][c] = 0.0;
+#pragma unroll
+  for (int k = 0; k < taps + 3; ++k) {
+    double vk[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) vk[c] = p[k * 5 + c];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (k - o >= 0 && k - o < taps) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) hs[o][c] += vk[c];
+      }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int x = x0 + gx * 4 + o;
+    if (x >= w) break;
+    const double g11 = hs[o][0] * scale, g12 = hs[o][1] * scale, g22 = hs[o][2] * scale, h1 = hs[o][3] * scale,
+                 h2 = hs[o][4] * scale;
+    const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+    flow[((size_t)y * w + x) * 2] = (float)((g11 * h2 - g12 * h1) * idet);
+    flow[((size_t)y * w + x) * 2 + 1] = (float)((g22 * h1 - g12 * h2) * idet);
+  }
+}
+
+constexpr size_t kFusedSmemCap = 160 * 1024;
+inline size_t gauss_smem(int r) { return ((size_t)(GTH + 2 * r) * (GTW + 2 * r) + (size_t)(GTH + 2 * r) * GTW) * 4; }
+inline size_t poly_smem(int n) { return ((size_t)(PTH + 2 * n) * (PTW + 2 * n) + (size_t)PTH * (PTW + 2 * n) * 3) * 4; }
+constexpr int kBoxMW = 7;  // the fused box kernel is instantiated for winSize 15 (the reference's)
+inline size_t box_smem(int m) {
+  return (size_t)BTH * (((BTW + 2 * m) * 5) | 1) * 8 + (size_t)(BTH + 2 * m) * (BTW + 2 * m) * 5 * 4;
+}
+// SCN_FLOW_UNFUSED=1 selects the two-pass kernels (kept as the reference the fused ones are tested against)
+inline bool use_fused() {
+  static const bool v = [] {
+    const char* e = getenv("SCN_FLOW_UNFUSED");
+    if (e && e[0] == '1') return false;
+    return cudaFuncSetAttribute(gauss_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemCap) ==
+               cudaSuccess &&
+           cudaFuncSetAttribute(poly_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemCap) ==
+               cudaSuccess &&
+           cudaFuncSetAttribute(box_solve_fused_kernel<kBoxMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kFusedSmemCap) == cudaSuccess;
+  }();
+  return v;
+}
+
 // ---- host-side constants --------------------------------------------------------------------
 void make_gauss(int ksize, double sigma, GaussK& gk) {
   static const float small_tab[4][7] = {{1.f},
@@ -405,13 +633,19 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
       GaussK gk;
       make_gauss(lv[k].smooth, lv[k].sigma, gk);
       for (int i = 0; i < 2; ++i) {
-        {
-          LaunchScope ls("flow_gauss_h_kernel", st);
-          gauss_h_kernel<<<grid2(width, height), T, 0, st>>>(ws.gray[i], width, height, gk, ws.tmp);
-        }
-        {
-          LaunchScope ls("flow_gauss_v_kernel", st);
-          gauss_v_kernel<<<grid2(width, height), T, 0, st>>>(ws.tmp, width, height, gk, ws.blur);
+        if (use_fused() && gauss_smem(gk.radius) <= kFusedSmemCap) {
+          LaunchScope ls("flow_gauss_fused_kernel", st);
+          gauss_fused_kernel<<<dim3((unsigned)((width + GTW - 1) / GTW), (unsigned)((height + GTH - 1) / GTH)), FT,
+                               gauss_smem(gk.radius), st>>>(ws.gray[i], width, height, gk, ws.blur);
+        } else {
+          {
+            LaunchScope ls("flow_gauss_h_kernel", st);
+            gauss_h_kernel<<<grid2(width, height), T, 0, st>>>(ws.gray[i], width, height, gk, ws.tmp);
+          }
+          {
+            LaunchScope ls("flow_gauss_v_kernel", st);
+            gauss_v_kernel<<<grid2(width, height), T, 0, st>>>(ws.tmp, width, height, gk, ws.blur);
+          }
         }
         const float* I = ws.blur;
         if (w != width || h != height) {
@@ -420,13 +654,19 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
                                                           (double)height / h, 1.f);
           I = ws.I;
         }
-        {
-          LaunchScope ls("flow_poly_v_kernel", st);
-          poly_v_kernel<<<grid2(w, h), T, 0, st>>>(I, w, h, pk, ws.poly3);
-        }
-        {
-          LaunchScope ls("flow_poly_h_kernel", st);
-          poly_h_kernel<<<grid2(w, h), T, 0, st>>>(ws.poly3, w, h, pk, ws.R[i]);
+        if (use_fused() && poly_smem(pk.n) <= kFusedSmemCap) {
+          LaunchScope ls("flow_poly_fused_kernel", st);
+          poly_fused_kernel<<<dim3((unsigned)((w + PTW - 1) / PTW), (unsigned)((h + PTH - 1) / PTH)), FT,
+                              poly_smem(pk.n), st>>>(I, w, h, pk, ws.R[i]);
+        } else {
+          {
+            LaunchScope ls("flow_poly_v_kernel", st);
+            poly_v_kernel<<<grid2(w, h), T, 0, st>>>(I, w, h, pk, ws.poly3);
+          }
+          {
+            LaunchScope ls("flow_poly_h_kernel", st);
+            poly_h_kernel<<<grid2(w, h), T, 0, st>>>(ws.poly3, w, h, pk, ws.R[i]);
+          }
         }
       }
       {
@@ -435,13 +675,19 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
       }
       const int m = win_size / 2;
       for (int it = 0; it < num_iters; ++it) {
-        {
-          LaunchScope ls("flow_box_v_kernel", st);
-          box_v_kernel<<<grid2(w * 5, h), T, 0, st>>>(ws.M, w, h, m, ws.V);
-        }
-        {
-          LaunchScope ls("flow_box_h_solve_kernel", st);
-          box_h_solve_kernel<<<grid2(w, h), T, 0, st>>>(ws.V, w, h, m, 1.0 / ((double)win_size * win_size), flow);
+        if (use_fused() && m == kBoxMW) {
+          LaunchScope ls("flow_box_solve_fused_kernel", st);
+          box_solve_fused_kernel<kBoxMW><<<dim3((unsigned)((w + BTW - 1) / BTW), (unsigned)((h + BTH - 1) / BTH)), FT,
+                                           box_smem(m), st>>>(ws.M, w, h, 1.0 / ((double)win_size * win_size), flow);
+        } else {
+          {
+            LaunchScope ls("flow_box_v_kernel", st);
+            box_v_kernel<<<grid2(w * 5, h), T, 0, st>>>(ws.M, w, h, m, ws.V);
+          }
+          {
+            LaunchScope ls("flow_box_h_solve_kernel", st);
+            box_h_solve_kernel<<<grid2(w, h), T, 0, st>>>(ws.V, w, h, m, 1.0 / ((double)win_size * win_size), flow);
+          }
         }
         if (it < num_iters - 1) {
           LaunchScope ls("flow_update_matrices_kernel", st);

@@ -76,3 +76,30 @@ def test_optical_flow_op_stencil_through_the_engine():
             want = oracle.optical_flow(frames[i], frames[min(i + 1, n - 1)])
             assert np.abs(got - want).max() <= 2e-3, (i, wps)
     eng.close()
+
+
+def test_fused_tiled_kernels_equal_the_two_pass_kernels_bit_for_bit():
+    """The shared-memory tiled Gaussian / polynomial-expansion / box+solve kernels keep the summation
+    order of the per-row two-pass kernels (SCN_FLOW_UNFUSED=1): same bits, including at image borders
+    and for sizes that are not multiples of the tiles."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, '.');"
+        "from scanner_b200 import kernels;"
+        "g = torch.Generator(device='cuda').manual_seed(11);"
+        "outs = [];"
+        "\nfor (h, w) in [(270, 480), (97, 131), (1080, 1920)]:"
+        "\n    a = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, device='cuda', generator=g)"
+        "\n    b = torch.roll(a, shifts=(1, 2), dims=(1, 2)).contiguous()"
+        "\n    outs.append(kernels.optical_flow(a, b).cpu().numpy())"
+        "\nnp.savez(sys.argv[1], *outs)")
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        for mode, name in (("0", "fused.npz"), ("1", "unfused.npz")):
+            env = dict(os.environ, SCN_FLOW_UNFUSED=mode)
+            subprocess.check_call([sys.executable, "-c", code, os.path.join(d, name)], env=env,
+                                  cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        f, u = np.load(os.path.join(d, "fused.npz")), np.load(os.path.join(d, "unfused.npz"))
+        for k in f.files:
+            assert f[k].shape == u[k].shape and np.array_equal(f[k], u[k]), k
