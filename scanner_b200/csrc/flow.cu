@@ -53,7 +53,7 @@ __global__ void gauss_h_kernel(const float* __restrict__ src, int w, int h, Gaus
   if (x >= w) return;
   const float* row = src + (size_t)y * w;
   float s = 0.f;
-  for (int i = -gk.radius; i <= gk.radius; ++i) s += gk.k[i + gk.radius] * row[reflect101(x + i, w)];
+  for (int i = -gk.radius; i <= gk.radius; ++i) s = __fmaf_rn(gk.k[i + gk.radius], row[reflect101(x + i, w)], s);
   dst[(size_t)y * w + x] = s;
 }
 
@@ -61,7 +61,7 @@ __global__ void gauss_v_kernel(const float* __restrict__ src, int w, int h, Gaus
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= w) return;
   float s = 0.f;
-  for (int i = -gk.radius; i <= gk.radius; ++i) s += gk.k[i + gk.radius] * src[(size_t)reflect101(y + i, h) * w + x];
+  for (int i = -gk.radius; i <= gk.radius; ++i) s = __fmaf_rn(gk.k[i + gk.radius], src[(size_t)reflect101(y + i, h) * w + x], s);
   dst[(size_t)y * w + x] = s;
 }
 
@@ -100,9 +100,9 @@ __global__ void poly_v_kernel(const float* __restrict__ src, int w, int h, PolyK
   float t0 = src[(size_t)y * w + x] * pk.g[0], t1 = 0.f, t2 = 0.f;
   for (int k = 1; k <= pk.n; ++k) {
     const float sp = src[(size_t)clampi(y + k, 0, h - 1) * w + x], sm = src[(size_t)clampi(y - k, 0, h - 1) * w + x];
-    t0 += pk.g[k] * (sp + sm);
-    t1 += pk.xg[k] * (sp - sm);
-    t2 += pk.xxg[k] * (sp + sm);
+    t0 = __fmaf_rn(pk.g[k], sp + sm, t0);
+    t1 = __fmaf_rn(pk.xg[k], sp - sm, t1);
+    t2 = __fmaf_rn(pk.xxg[k], sp + sm, t2);
   }
   float* d = dst3 + ((size_t)y * w + x) * 3;
   d[0] = t0;
@@ -121,18 +121,18 @@ __global__ void poly_h_kernel(const float* __restrict__ src3, int w, int h, Poly
     const float* p = row + (size_t)clampi(x + k, 0, w - 1) * 3;
     const float* m = row + (size_t)clampi(x - k, 0, w - 1) * 3;
     const float tg = p[0] + m[0];
-    b1 += tg * pk.g[k];
-    b2 += (p[0] - m[0]) * pk.xg[k];
-    b4 += tg * pk.xxg[k];
-    b3 += (p[1] + m[1]) * pk.g[k];
-    b6 += (p[1] - m[1]) * pk.xg[k];
-    b5 += (p[2] + m[2]) * pk.g[k];
+    b1 = __fmaf_rn(tg, pk.g[k], b1);
+    b2 = __fmaf_rn(p[0] - m[0], pk.xg[k], b2);
+    b4 = __fmaf_rn(tg, pk.xxg[k], b4);
+    b3 = __fmaf_rn(p[1] + m[1], pk.g[k], b3);
+    b6 = __fmaf_rn(p[1] - m[1], pk.xg[k], b6);
+    b5 = __fmaf_rn(p[2] + m[2], pk.g[k], b5);
   }
   float* d = dst5 + ((size_t)y * w + x) * 5;
   d[1] = b2 * pk.ig11;
   d[0] = b3 * pk.ig11;
-  d[3] = b1 * pk.ig03 + b4 * pk.ig33;
-  d[2] = b1 * pk.ig03 + b5 * pk.ig33;
+  d[3] = __fmaf_rn(b4, pk.ig33, __fmul_rn(b1, pk.ig03));
+  d[2] = __fmaf_rn(b5, pk.ig33, __fmul_rn(b1, pk.ig03));
   d[4] = b6 * pk.ig55;
 }
 
@@ -227,10 +227,11 @@ constexpr int FT = 256;
 // GaussianBlur: tile (TH + 2r) x (TW + 2r) in, h pass into hbuf, v pass out.  Threads are laid out
 // 64 x 4 (column, row phase) so no index needs a division.
 constexpr int GTW = 64, GTH = 32;
+template <int R>  // R > 0: radius known at compile time (taps unrolled, coefficients read in place); 0: generic
 __global__ void __launch_bounds__(FT)
 gauss_fused_kernel(const float* __restrict__ src, int w, int h, GaussK gk, float* __restrict__ dst) {
   extern __shared__ float fsm[];
-  const int r = gk.radius, iw = GTW + 2 * r, ih = GTH + 2 * r;
+  const int r = R > 0 ? R : gk.radius, iw = GTW + 2 * r, ih = GTH + 2 * r;
   float* in = fsm;             // ih x iw
   float* hb = fsm + ih * iw;   // ih x GTW
   const int x0 = blockIdx.x * GTW, y0 = blockIdx.y * GTH;
@@ -257,7 +258,8 @@ gauss_fused_kernel(const float* __restrict__ src, int w, int h, GaussK gk, float
   for (int j = tq; j < ih; j += 4) {
     const float* row = in + j * iw + tx;
     float s = 0.f;
-    for (int i = 0; i <= 2 * r; ++i) s += gk.k[i] * row[i];
+#pragma unroll
+    for (int i = 0; i <= 2 * r; ++i) s = __fmaf_rn(gk.k[i], row[i], s);
     hb[j * GTW + tx] = s;
   }
   __syncthreads();
@@ -267,17 +269,19 @@ gauss_fused_kernel(const float* __restrict__ src, int w, int h, GaussK gk, float
     const int y = y0 + ty;
     if (y >= h) break;
     float s = 0.f;
-    for (int i = 0; i <= 2 * r; ++i) s += gk.k[i] * hb[(ty + i) * GTW + tx];
+#pragma unroll
+    for (int i = 0; i <= 2 * r; ++i) s = __fmaf_rn(gk.k[i], hb[(ty + i) * GTW + tx], s);
     dst[(size_t)y * w + x] = s;
   }
 }
 
 // Polynomial expansion: v pass (3 values per pixel) into shared memory, h pass to 5 coefficients.
 constexpr int PTW = 64, PTH = 32;
+template <int N>  // N > 0: polyN known at compile time; 0: generic
 __global__ void __launch_bounds__(FT)
 poly_fused_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* __restrict__ dst5) {
   extern __shared__ float fsm[];
-  const int n = pk.n, iw = PTW + 2 * n, ih = PTH + 2 * n;
+  const int n = N > 0 ? N : pk.n, iw = PTW + 2 * n, ih = PTH + 2 * n;
   float* in = fsm;            // ih x iw
   float* t3 = fsm + ih * iw;  // PTH x iw x 3
   const int x0 = blockIdx.x * PTW, y0 = blockIdx.y * PTH;
@@ -303,11 +307,12 @@ poly_fused_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* 
     for (int i = tx; i < iw; i += 64) {
       const float* c = in + (jy + n) * iw + i;
       float t0 = c[0] * pk.g[0], t1 = 0.f, t2 = 0.f;
+#pragma unroll
       for (int k = 1; k <= n; ++k) {
         const float sp = c[k * iw], sm = c[-k * iw];
-        t0 += pk.g[k] * (sp + sm);
-        t1 += pk.xg[k] * (sp - sm);
-        t2 += pk.xxg[k] * (sp + sm);
+        t0 = __fmaf_rn(pk.g[k], sp + sm, t0);
+        t1 = __fmaf_rn(pk.xg[k], sp - sm, t1);
+        t2 = __fmaf_rn(pk.xxg[k], sp + sm, t2);
       }
       float* d = t3 + ((size_t)jy * iw + i) * 3;
       d[0] = t0;
@@ -322,22 +327,23 @@ poly_fused_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* 
     if (y >= h) break;
     const float* c0 = t3 + ((size_t)ty * iw + tx + n) * 3;
     float b1 = c0[0] * pk.g[0], b2 = 0.f, b3 = c0[1] * pk.g[0], b4 = 0.f, b5 = c0[2] * pk.g[0], b6 = 0.f;
+#pragma unroll
     for (int k = 1; k <= n; ++k) {
       const float* p = c0 + k * 3;
       const float* m = c0 - k * 3;
       const float tg = p[0] + m[0];
-      b1 += tg * pk.g[k];
-      b2 += (p[0] - m[0]) * pk.xg[k];
-      b4 += tg * pk.xxg[k];
-      b3 += (p[1] + m[1]) * pk.g[k];
-      b6 += (p[1] - m[1]) * pk.xg[k];
-      b5 += (p[2] + m[2]) * pk.g[k];
+      b1 = __fmaf_rn(tg, pk.g[k], b1);
+      b2 = __fmaf_rn(p[0] - m[0], pk.xg[k], b2);
+      b4 = __fmaf_rn(tg, pk.xxg[k], b4);
+      b3 = __fmaf_rn(p[1] + m[1], pk.g[k], b3);
+      b6 = __fmaf_rn(p[1] - m[1], pk.xg[k], b6);
+      b5 = __fmaf_rn(p[2] + m[2], pk.g[k], b5);
     }
     float* d = dst5 + ((size_t)y * w + x) * 5;
     d[1] = b2 * pk.ig11;
     d[0] = b3 * pk.ig11;
-    d[3] = b1 * pk.ig03 + b4 * pk.ig33;
-    d[2] = b1 * pk.ig03 + b5 * pk.ig33;
+    d[3] = __fmaf_rn(b4, pk.ig33, __fmul_rn(b1, pk.ig03));
+    d[2] = __fmaf_rn(b5, pk.ig33, __fmul_rn(b1, pk.ig03));
     d[4] = b6 * pk.ig55;
   }
 }
@@ -432,10 +438,12 @@ inline bool use_fused() {
   static const bool v = [] {
     const char* e = getenv("SCN_FLOW_UNFUSED");
     if (e && e[0] == '1') return false;
-    return cudaFuncSetAttribute(gauss_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemCap) ==
-               cudaSuccess &&
-           cudaFuncSetAttribute(poly_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemCap) ==
-               cudaSuccess &&
+    auto big = [](const void* f) {
+      return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemCap) == cudaSuccess;
+    };
+    return big((const void*)gauss_fused_kernel<0>) && big((const void*)gauss_fused_kernel<1>) &&
+           big((const void*)gauss_fused_kernel<3>) && big((const void*)gauss_fused_kernel<8>) &&
+           big((const void*)poly_fused_kernel<0>) && big((const void*)poly_fused_kernel<5>) &&
            cudaFuncSetAttribute(box_solve_fused_kernel<kBoxMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kFusedSmemCap) == cudaSuccess;
   }();
@@ -635,8 +643,15 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
       for (int i = 0; i < 2; ++i) {
         if (use_fused() && gauss_smem(gk.radius) <= kFusedSmemCap) {
           LaunchScope ls("flow_gauss_fused_kernel", st);
-          gauss_fused_kernel<<<dim3((unsigned)((width + GTW - 1) / GTW), (unsigned)((height + GTH - 1) / GTH)), FT,
-                               gauss_smem(gk.radius), st>>>(ws.gray[i], width, height, gk, ws.blur);
+          const dim3 gg((unsigned)((width + GTW - 1) / GTW), (unsigned)((height + GTH - 1) / GTH));
+          const size_t sm = gauss_smem(gk.radius);
+          // the radii of the reference's pyramid (pyrScale 0.5: ksize 3, 3, 7, 17) are instantiated
+          switch (gk.radius) {
+            case 1: gauss_fused_kernel<1><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
+            case 3: gauss_fused_kernel<3><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
+            case 8: gauss_fused_kernel<8><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
+            default: gauss_fused_kernel<0><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
+          }
         } else {
           {
             LaunchScope ls("flow_gauss_h_kernel", st);
@@ -656,8 +671,9 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
         }
         if (use_fused() && poly_smem(pk.n) <= kFusedSmemCap) {
           LaunchScope ls("flow_poly_fused_kernel", st);
-          poly_fused_kernel<<<dim3((unsigned)((w + PTW - 1) / PTW), (unsigned)((h + PTH - 1) / PTH)), FT,
-                              poly_smem(pk.n), st>>>(I, w, h, pk, ws.R[i]);
+          const dim3 pg((unsigned)((w + PTW - 1) / PTW), (unsigned)((h + PTH - 1) / PTH));
+          if (pk.n == 5) poly_fused_kernel<5><<<pg, FT, poly_smem(pk.n), st>>>(I, w, h, pk, ws.R[i]);
+          else poly_fused_kernel<0><<<pg, FT, poly_smem(pk.n), st>>>(I, w, h, pk, ws.R[i]);
         } else {
           {
             LaunchScope ls("flow_poly_v_kernel", st);
