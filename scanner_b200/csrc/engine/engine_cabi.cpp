@@ -267,7 +267,7 @@ int scn_job_output_row(scn_job* j, int sink, int64_t row, const uint8_t** data, 
   size_t idx;
   const TaskOutput* t = locate(j, sink, row, idx);
   if (!t) return fail("row out of range");
-  if (data) *data = t->data.data() + t->offsets[idx];
+  if (data) *data = t->row(idx);
   if (size) *size = t->sizes[idx];
   if (shape)
     for (int k = 0; k < 4; ++k) shape[k] = t->shapes[idx * 4 + k];
@@ -283,7 +283,7 @@ int scn_job_output_copy(scn_job* j, int sink, int64_t row0, int64_t n, uint8_t* 
     if (t->sizes[idx] != row_bytes) return fail("row " + std::to_string(row0 + i) + " has " +
                                                 std::to_string(t->sizes[idx]) + " bytes, expected " +
                                                 std::to_string(row_bytes));
-    memcpy(dst + (size_t)i * row_bytes, t->data.data() + t->offsets[idx], row_bytes);
+    memcpy(dst + (size_t)i * row_bytes, t->row(idx), row_bytes);
   }
   return 0;
 }
@@ -478,8 +478,16 @@ int scn_db_save_job(scn_db* db, scn_job* j, const char* table, const int* sinks,
         break;
       }
       ItemColumn ic;
-      ic.data = to.data.data();
-      ic.bytes = to.data.size();
+      std::vector<u8> flat;  // rows kept in page-locked blocks are gathered for the writer
+      if (to.held.empty()) {
+        ic.data = to.data.data();
+        ic.bytes = to.data.size();
+      } else {
+        flat.reserve(to.total_bytes());
+        for (size_t i = 0; i < to.sizes.size(); ++i) flat.insert(flat.end(), to.row(i), to.row(i) + to.sizes[i]);
+        ic.data = flat.data();
+        ic.bytes = flat.size();
+      }
       ic.sizes = &to.sizes;
       ic.shapes = &to.shapes;
       r = db->impl->write_item(id, c + 1, (i32)t, ic, cols[c].type == proto::Video);

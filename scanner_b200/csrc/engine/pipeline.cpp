@@ -198,6 +198,12 @@ struct SourceCursor {
 
 }  // namespace
 
+void TaskOutput::release() {
+  if (!held.empty()) delete_elements(CPU_DEVICE, held);
+  held.clear();
+  ext.clear();
+}
+
 void Engine::instance_main(Instance* inst) {
   RunState& rs = *run_;
   const i32 gpu = inst->gpu_id;
@@ -426,14 +432,17 @@ void Engine::instance_main(Instance* inst) {
             to.offsets.push_back(to.data.size());
             to.sizes.push_back(n);
             to.shapes.insert(to.shapes.end(), shape, shape + 4);
-            if (n) to.data.insert(to.data.end(), src, src + n);
+            if (n >= TaskOutput::kLargeRow) {
+              to.ext.resize(to.sizes.size(), nullptr);
+              to.ext.back() = src;
+              to.held.push_back(e);  // the reference this element holds on its block moves to the task
+              e = Element();
+            } else if (n) {
+              to.data.insert(to.data.end(), src, src + n);
+            }
           }
-          if (cb.device.is_gpu()) {
-            delete_elements(CPU_DEVICE, host);
-            delete_elements(cb.device, cb.elements);
-          } else {
-            delete_elements(CPU_DEVICE, cb.elements);
-          }
+          delete_elements(CPU_DEVICE, host);  // rows kept above were replaced by null elements
+          if (cb.device.is_gpu()) delete_elements(cb.device, cb.elements);
         }
       }
       // close decoder intervals left open by a task that did not need their tail
@@ -479,7 +488,17 @@ void Engine::instance_main(Instance* inst) {
         for (i64 row = t.row0; row < t.row1; ++row) idx.push_back(row);
         write_col(0, isz, (const u8*)idx.data(), idx.size() * 8);
         i32 col = 1;
-        for (auto& kv : outs) write_col(col++, kv.second->sizes, kv.second->data.data(), kv.second->data.size());
+        for (auto& kv : outs) {
+          const TaskOutput& to = *kv.second;
+          if (to.held.empty()) {
+            write_col(col++, to.sizes, to.data.data(), to.data.size());
+          } else {  // rows kept in page-locked blocks: gather them for the writer
+            std::vector<u8> flat;
+            flat.reserve(to.total_bytes());
+            for (size_t i = 0; i < to.sizes.size(); ++i) flat.insert(flat.end(), to.row(i), to.row(i) + to.sizes[i]);
+            write_col(col++, to.sizes, flat.data(), flat.size());
+          }
+        }
       }
       rs.profiler.add_interval("task", task_start, now());
     }

@@ -62,12 +62,45 @@ struct InputStream {
   i64 rows() const { return kind == H264 ? index.frames() : (i64)sizes.size(); }
 };
 
-// Rows a sink stored for one task, host memory.
+// Rows a sink stored for one task, host memory.  Small rows are appended to `data`; rows of
+// kLargeRow bytes or more (frames, flow fields) stay in the page-locked block the post-evaluate
+// stage copied them into -- the element is kept instead of being copied again into a growing vector
+// whose fresh pages fault in at ~1 GB/s (a 1080p flow field is 16.6 MB per row).
 struct TaskOutput {
+  static constexpr size_t kLargeRow = 64 * 1024;
   bool done = false;
   std::vector<u8> data;
   std::vector<u64> offsets, sizes;
-  std::vector<i32> shapes;  // 4 per row: h, w, c, frame type (-1 for byte rows)
+  std::vector<i32> shapes;       // 4 per row: h, w, c, frame type (-1 for byte rows)
+  std::vector<const u8*> ext;    // per row: non-null = the row lives in a held host block
+  Elements held;                 // host elements that keep those blocks alive
+
+  TaskOutput() = default;
+  TaskOutput(const TaskOutput&) = delete;
+  TaskOutput& operator=(const TaskOutput&) = delete;
+  TaskOutput(TaskOutput&& o) noexcept { *this = std::move(o); }
+  TaskOutput& operator=(TaskOutput&& o) noexcept {
+    if (this != &o) {
+      release();
+      done = o.done;
+      data = std::move(o.data);
+      offsets = std::move(o.offsets);
+      sizes = std::move(o.sizes);
+      shapes = std::move(o.shapes);
+      ext = std::move(o.ext);
+      held = std::move(o.held);
+      o.held.clear();
+    }
+    return *this;
+  }
+  ~TaskOutput() { release(); }
+  void release();  // frees the held blocks (pipeline.cpp)
+  const u8* row(size_t i) const { return i < ext.size() && ext[i] ? ext[i] : data.data() + offsets[i]; }
+  size_t total_bytes() const {
+    size_t n = 0;
+    for (u64 s : sizes) n += s;
+    return n;
+  }
 };
 
 struct Job {
