@@ -28,7 +28,13 @@ class Profiler {
     std::string key;
     i64 start_ns;
     i64 end_ns;
+    i32 worker;  // pipeline instance that recorded it (thread_worker() of the calling thread)
   };
+  // id the engine gives each pipeline-instance thread; -1 outside of one
+  static i32& thread_worker() {
+    static thread_local i32 w = -1;
+    return w;
+  }
   explicit Profiler(timepoint_t base = now()) : base_(base) {}
 
   void add_interval(const std::string& key, timepoint_t start, timepoint_t end,
@@ -40,7 +46,7 @@ class Profiler {
     std::lock_guard<std::mutex> g(mu_);
     totals_ns_[key] += ns(end) - ns(start);
     counts_[key] += 1;
-    if (keep_records_) records_.push_back({key, ns(start), ns(end)});
+    if (keep_records_) records_.push_back({key, ns(start), ns(end), thread_worker()});
   }
   void increment(const std::string& key, i64 value) {
     std::lock_guard<std::mutex> g(mu_);

@@ -120,6 +120,13 @@ SCN_ENGINE_API int scn_job_output_copy(scn_job* j, int sink_op, int64_t row0, in
                                        size_t row_bytes);
 
 /* JSON: profiler interval totals / counters of the last run (frames_decoded, frames_used, ...). */
+/* Tracing (reference util/profiler.{h,cpp} interval records + scannerpy Profile.write_trace,
+ * profiler.py): with tracing on, every profiler interval of a run (task, get_frames, op:<Name>,
+ * evaluate:<Name>, op_marshal, ...) is kept with the pipeline instance that recorded it;
+ * scn_engine_write_trace writes the last run as a Chrome trace-event JSON file (chrome://tracing,
+ * Perfetto): pid = GPU id (-1 for CPU instances), tid = pipeline instance, times in microseconds. */
+SCN_ENGINE_API int scn_engine_set_trace(scn_engine* e, int on);
+SCN_ENGINE_API int scn_engine_write_trace(scn_engine* e, const char* path);
 SCN_ENGINE_API int scn_engine_stats_json(scn_engine* e, char* host_buf, size_t cap);
 
 /* ---- synthetic H.264 (tests / bench input generation; no encoder exists offline) ----------- */

@@ -294,6 +294,19 @@ class NamedStream:
             self._sc._db.delete_table(self._name)
 
 
+class Profile:
+    def __init__(self, sc):
+        self._sc = sc
+
+    def statistics(self):
+        return self._sc._engine.stats()
+
+    def write_trace(self, path):
+        if not self._sc._profiling:
+            raise ScannerException("create the Client with profiling=True to record a trace")
+        self._sc._engine.write_trace(path)
+
+
 # ------------------------------------------------------------------------------------------------
 class Client:
     """In-process stand-in for scannerpy.Client: same graph-building surface, runs on local GPUs."""
@@ -304,6 +317,9 @@ class Client:
         if gpus is None:
             gpus = list(range(torch.cuda.device_count())) if torch.cuda.is_available() else []
         self._engine = E.Engine(gpus, instances_per_gpu, cpu_instances)
+        self._profiling = bool(_ignored.get("profiling", False))
+        if self._profiling:
+            self._engine.set_trace(True)
         self._db = E.Database(db_path) if db_path else None
         self._bulk_jobs = 0
         self._streams = {}
@@ -462,6 +478,11 @@ class Client:
 
     def stats(self):
         return self._engine.stats()
+
+    def get_profile(self, job_id=None):
+        """Like scannerpy's `sc.get_profile(job_id)` for the last run: `.statistics()` and, if the
+        client was created with profiling=True, `.write_trace(path)` (Chrome trace events)."""
+        return Profile(self)
 
     def stop(self):
         self._engine.close()

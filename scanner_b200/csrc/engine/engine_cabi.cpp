@@ -288,6 +288,16 @@ int scn_job_output_copy(scn_job* j, int sink, int64_t row0, int64_t n, uint8_t* 
   return 0;
 }
 
+int scn_engine_set_trace(scn_engine* e, int on) {
+  if (!e) return fail("null engine");
+  e->impl->set_trace(on != 0);
+  return 0;
+}
+int scn_engine_write_trace(scn_engine* e, const char* path) {
+  if (!e || !path) return fail("bad arguments");
+  return from_result(e->impl->write_trace(path));
+}
+
 int scn_engine_stats_json(scn_engine* e, char* buf, size_t cap) {
   if (!e) return fail("null engine");
   const RunStats& s = e->impl->stats();

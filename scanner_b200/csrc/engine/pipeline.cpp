@@ -90,6 +90,7 @@ struct Engine::Instance {
   Engine* eng;
   i32 gpu_id;
   i32 node_id;
+  i32 index = 0;  // position in this run's instance list (trace tid)
   std::thread th;
 };
 
@@ -226,6 +227,7 @@ void Engine::instance_main(Instance* inst) {
     set_thread_stream(gpu, slot.stream);
   }
   cudaStream_t stream = slot.stream;
+  Profiler::thread_worker() = inst->index;
   const DeviceHandle gpu_dev(DeviceType::GPU, gpu);
   {
     EvaluateWorker ew(*rs.graph, rs.an, gpu, inst->node_id, &rs.profiler);
@@ -517,6 +519,37 @@ void Engine::instance_main(Instance* inst) {
   }
 }
 
+Result Engine::write_trace(const std::string& path) const {
+  Result r;
+  std::ofstream f(path, std::ios::trunc);
+  if (!f) {
+    RESULT_ERROR(&r, "cannot write %s", path.c_str());
+    return r;
+  }
+  auto esc = [](const std::string& s) {
+    std::string o;
+    for (char c : s) {
+      if (c == '"' || c == '\\') o.push_back('\\');
+      o.push_back(c);
+    }
+    return o;
+  };
+  f << "{\"displayTimeUnit\": \"ms\", \"traceEvents\": [\n";
+  bool first = true;
+  for (const TraceEvent& e : stats_.trace) {
+    char buf[96];
+    snprintf(buf, sizeof(buf), "\"ts\": %.3f, \"dur\": %.3f", (double)e.start_ns * 1e-3,
+             (double)(e.end_ns - e.start_ns) * 1e-3);
+    f << (first ? "" : ",\n") << "{\"name\": \"" << esc(e.key) << "\", \"ph\": \"X\", " << buf
+      << ", \"pid\": " << e.node << ", \"tid\": " << e.worker << "}";
+    first = false;
+  }
+  f << "\n]}\n";
+  r.set_success((bool)f);
+  if (!f) r.set_msg("short write to " + path);
+  return r;
+}
+
 Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows, i32 gpu_id, u8* dst) {
   Result r;
   InputStream* st = stream(stream_id);
@@ -635,6 +668,8 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   // never more instances than tasks
   while (instances.size() > std::max<size_t>(1, rs.tasks.size())) instances.pop_back();
 
+  rs.profiler.keep_records(trace_);
+  for (size_t i = 0; i < instances.size(); ++i) instances[i]->index = (i32)i;
   const auto t0 = std::chrono::steady_clock::now();
   for (auto& inst : instances) inst->th = std::thread([this, p = inst.get()] { instance_main(p); });
   for (auto& inst : instances) inst->th.join();
@@ -663,6 +698,12 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   stats_.counters["instances"] = (i64)instances.size();
   stats_.interval_ns = rs.profiler.interval_totals_ns();
   stats_.interval_counts = rs.profiler.interval_counts();
+  for (const Profiler::TaskRecord& rec : rs.profiler.records()) {
+    const i32 w = rec.worker;
+    // trace "process" = the device the instance drives (-1: CPU instance)
+    const i32 node = (w >= 0 && (size_t)w < instances.size()) ? instances[(size_t)w]->gpu_id : -1;
+    stats_.trace.push_back({rec.key, rec.start_ns, rec.end_ns, w, node});
+  }
   if (rs.failed.load()) {
     RESULT_ERROR(&r, "%s", rs.error.c_str());
     return r;

@@ -113,7 +113,14 @@ struct Job {
   std::map<i32, std::vector<TaskOutput>> outputs;  // sink op -> per task
 };
 
+struct TraceEvent {
+  std::string key;
+  i64 start_ns, end_ns;
+  i32 worker, node;
+};
+
 struct RunStats {
+  std::vector<TraceEvent> trace;  // filled when tracing is on (Engine::set_trace)
   std::map<std::string, i64> counters;
   std::map<std::string, i64> interval_ns;
   std::map<std::string, i64> interval_counts;
@@ -137,6 +144,13 @@ class Engine {
   Result decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows, i32 gpu_id, u8* dst);
 
   const RunStats& stats() const { return stats_; }
+  // Keep every profiler interval of the next runs with the instance that recorded it (reference
+  // Profiler records, util/profiler.h; off by default: a long job records millions of intervals).
+  void set_trace(bool on) { trace_ = on; }
+  // The last run's intervals as a Chrome trace-event file (what scannerpy's Profile.write_trace
+  // produces from the reference's profiler files, profiler.py): one "X" event per interval,
+  // pid = GPU id (-1: CPU instance), tid = pipeline instance.
+  Result write_trace(const std::string& path) const;
   const std::vector<i32>& gpu_ids() const { return gpu_ids_; }
 
  private:
@@ -151,6 +165,7 @@ class Engine {
   std::map<i64, std::unique_ptr<InputStream>> streams_;
   i64 next_stream_id_ = 1;
   RunStats stats_;
+  bool trace_ = false;
 
   // state of the run in flight
   struct RunState;

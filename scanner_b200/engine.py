@@ -50,6 +50,8 @@ SIGNATURES = {
     "scn_engine_stats_json": (_I, [_VP, _CP, _SZ]),
     "scn_h264_synth": (_I64, [_VP, _I, _I, _I64, _I, _I, _VP, _SZ]),
     "scn_nvdec_caps": (_I, [_I, _IP]),
+    "scn_engine_set_trace": (_I, [_VP, _I]),
+    "scn_engine_write_trace": (_I, [_VP, _CP]),
     "scn_db_open": (_VP, [_CP]),
     "scn_db_close": (None, [_VP]),
     "scn_db_ingest_video": (_I, [_VP, _CP, _CP]),
@@ -300,6 +302,14 @@ class Engine:
         sizes = np.array([len(r) for r in rows], np.uint64)
         data = np.frombuffer(b"".join(bytes(r) for r in rows) or b"\0", np.uint8)
         return check(lib().scn_stream_add_bytes(self._h, data.ctypes.data, sizes.ctypes.data, len(rows)), "add_bytes")
+
+    def set_trace(self, on=True):
+        """Keep every profiler interval of the following runs (see write_trace)."""
+        check(lib().scn_engine_set_trace(self._h, 1 if on else 0), "set_trace")
+
+    def write_trace(self, path):
+        """The last run as a Chrome trace-event JSON file (pid = GPU, tid = pipeline instance)."""
+        check(lib().scn_engine_write_trace(self._h, os.path.abspath(path).encode()), "write_trace")
 
     def stream_rows(self, sid):
         return check(lib().scn_stream_rows(self._h, sid), "stream_rows")

@@ -351,3 +351,34 @@ def test_h264_needs_gpu_instance_no_software_fallback(eng):
     j.bind_source(src, sid)
     with pytest.raises(E.EngineError, match="NVDEC"):
         eng.run(g, [j], 2, 2)
+
+
+def test_trace_file_has_one_event_per_interval_and_instance_ids(eng, tmp_path):
+    """scn_engine_write_trace: Chrome trace events of the last run (reference Profiler records +
+    scannerpy Profile.write_trace)."""
+    import json
+    eng.set_trace(True)
+
+    def build(g, src):
+        w = g.add_op("TestWindow", [(src, "column")])
+        return (g.add_sink((w, "window")),), {}
+    run_simple(eng, 40, build, wps=5, ios=10)
+    path = str(tmp_path / "run.trace")
+    eng.write_trace(path)
+    ev = json.load(open(path))["traceEvents"]
+    st = eng.stats()
+    names = {e["name"] for e in ev}
+    assert {"task", "op:TestWindow", "evaluate:TestWindow"} <= names
+    assert sum(1 for e in ev if e["name"] == "task") == st["counters"]["tasks"] == 4
+    for k, n in st["interval_counts"].items():
+        assert sum(1 for e in ev if e["name"] == k) == n
+    assert all(e["ph"] == "X" and e["dur"] >= 0 and e["pid"] == -1 and 0 <= e["tid"] < 3 for e in ev)
+    # an op interval lies inside a task interval of the same instance
+    tasks = [(e["tid"], e["ts"], e["ts"] + e["dur"]) for e in ev if e["name"] == "task"]
+    for e in ev:
+        if e["name"] == "op:TestWindow":
+            assert any(t == e["tid"] and a <= e["ts"] and e["ts"] + e["dur"] <= b + 1e-3 for t, a, b in tasks)
+    eng.set_trace(False)
+    run_simple(eng, 10, build, wps=5, ios=10)
+    eng.write_trace(path)
+    assert json.load(open(path))["traceEvents"] == []
