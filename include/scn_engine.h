@@ -97,6 +97,21 @@ SCN_ENGINE_API int scn_job_bind_source(scn_job* j, int source_op, int64_t stream
  * proto3 bytes of the matching message of scanner/sampler_args.proto. */
 SCN_ENGINE_API int scn_job_set_sampler(scn_job* j, int op, const char* function, const uint8_t* args,
                                        size_t args_size);
+/* Slice / Unslice (reference sc.streams.Slice / Unslice; dag_analysis.cpp:70-271, sampler.cpp:500-770):
+ * a Slice op cuts its input into groups with a partitioner ("Strided" {stride, group_size},
+ * "StridedRange" {stride, starts, ends}, "Gather" {groups{rows}}: the reference's
+ * sampler_args.proto messages); ops between Slice and Unslice see every group as an independent
+ * stream (state reset, stencils clamped at the group's edges, one task never spans two groups);
+ * Unslice concatenates the groups and may only feed sinks.  Inside the slice a Sample/Space op or a
+ * kernel op may be given one argument per group (the reference's SliceList). */
+SCN_ENGINE_API int scn_graph_add_slice(scn_graph* g, int input_op, const char* input_column);
+SCN_ENGINE_API int scn_graph_add_unslice(scn_graph* g, int input_op, const char* input_column);
+SCN_ENGINE_API int scn_job_set_partitioner(scn_job* j, int slice_op, const char* name, const uint8_t* args,
+                                           size_t size);
+SCN_ENGINE_API int scn_job_set_group_sampler(scn_job* j, int op, int group, const char* function,
+                                             const uint8_t* args, size_t size);
+SCN_ENGINE_API int scn_job_set_group_stream_args(scn_job* j, int op, int group, const uint8_t* args, size_t size);
+
 SCN_ENGINE_API int scn_job_set_stream_args(scn_job* j, int op, const uint8_t* args, size_t args_size);
 
 /* ---- run ----------------------------------------------------------------------------------- */

@@ -11,7 +11,7 @@ missing or no device is present.
 """
 from . import cabi  # noqa: F401
 from .client import (CacheMode, Client, DeviceType, NamedStream, NamedVideoStream, PerfParams,  # noqa: F401
-                     ScannerException)
+                     ScannerException, SliceList)
 
 __all__ = ["cabi", "Client", "DeviceType", "PerfParams", "NamedStream", "NamedVideoStream", "CacheMode",
-           "ScannerException"]
+           "ScannerException", "SliceList"]

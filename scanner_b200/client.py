@@ -65,6 +65,11 @@ class OpColumn:
         self._op, self._col, self._is_frame = op, column, is_frame
 
 
+class SliceList(list):
+    """Per-slice-group arguments (reference scannerpy.common.SliceList): inside a Slice, one entry
+    per group where an un-sliced stream takes one value."""
+
+
 class _Node:
     def __init__(self, kind, name=None, inputs=(), device=DeviceType.CPU, args=b"", batch=-1, stencil=(),
                  warmup=-1, per_stream=None, streams=None, sampler=None):
@@ -104,8 +109,18 @@ class OpGenerator:
             per_stream = None
             if stream_vals:
                 n = len(next(iter(stream_vals.values())))
-                per_stream = [protolite.encode(stream_fields, {k: v[i] for k, v in stream_vals.items()})
-                              for i in range(n)]
+                per_stream = []
+                for i in range(n):
+                    vals = {k: v[i] for k, v in stream_vals.items()}
+                    sliced = [v for v in vals.values() if isinstance(v, SliceList)]
+                    if sliced:  # inside a Slice: one new_stream argument per slice group
+                        groups = max(len(v) for v in sliced)
+                        per_stream.append(SliceList(
+                            protolite.encode(stream_fields,
+                                             {k: (v[g if len(v) > 1 else 0] if isinstance(v, SliceList) else v)
+                                              for k, v in vals.items()}) for g in range(groups)))
+                    else:
+                        per_stream.append(protolite.encode(stream_fields, vals))
             node = _Node("op", name, [c for _, c in cols], DeviceType(device), args, batch, stencil,
                          -1 if bounded_state is None else bounded_state, per_stream)
             node.input_names = [k for k, _ in cols]
@@ -123,18 +138,41 @@ class StreamsGenerator:
         self._sc = sc
 
     def _sample(self, col, fn, msg, per_stream_dicts, kind="sample"):
-        enc = [protolite.encode(protolite.SAMPLER_ARGS[msg], d) if msg else b"" for d in per_stream_dicts]
-        node = _Node(kind, fn, [col], per_stream=enc, sampler=fn)
+        def enc(d):
+            if isinstance(d, SliceList):  # one sampler argument per slice group
+                return SliceList(enc(e) for e in d)
+            return protolite.encode(protolite.SAMPLER_ARGS[msg], d) if msg else b""
+        node = _Node(kind, fn, [col], per_stream=[enc(d) for d in per_stream_dicts], sampler=fn)
         return OpColumn(node, col._col, col._is_frame)
+
+    @staticmethod
+    def _map(v, fn):
+        """fn over a per-stream value, or over every entry of a SliceList"""
+        return SliceList(fn(e) for e in v) if isinstance(v, SliceList) else fn(v)
+
+    @staticmethod
+    def _pair(r):
+        return (r["start"], r["end"]) if isinstance(r, dict) else (r[0], r[1])
+
+    def Slice(self, input, partitions):
+        """partitions: one partitioner per stream (sc.partitioner.all / strided / ranges / ...)."""
+        node = _Node("slice", "Slice", [input], per_stream=list(partitions))
+        return OpColumn(node, input._col, input._is_frame)
+
+    def Unslice(self, input):
+        node = _Node("unslice", "Unslice", [input])
+        return OpColumn(node, input._col, input._is_frame)
 
     def All(self, input):
         return self._sample(input, "All", None, [{}])
 
     def Stride(self, input, strides):
-        return self._sample(input, "Strided", "StridedSamplerArgs", [{"stride": s} for s in strides])
+        return self._sample(input, "Strided", "StridedSamplerArgs", [self._map(s, lambda e: {"stride": e}) for s in strides])
 
     def Range(self, input, ranges):
-        return self.StridedRanges(input, [[r] for r in ranges], [1] * len(ranges))
+        ds = [self._map(r, lambda e: {"stride": 1, "starts": [self._pair(e)[0]], "ends": [self._pair(e)[1]]})
+              for r in ranges]
+        return self._sample(input, "StridedRanges", "StridedRangeSamplerArgs", ds)
 
     def Ranges(self, input, intervals):
         return self.StridedRanges(input, intervals, [1] * len(intervals))
@@ -145,11 +183,11 @@ class StreamsGenerator:
     def StridedRanges(self, input, intervals, strides):
         strides = strides if isinstance(strides, (list, tuple)) else [strides] * len(intervals)
         return self._sample(input, "StridedRanges", "StridedRangeSamplerArgs",
-                            [{"stride": st, "starts": [a for a, _ in iv], "ends": [b for _, b in iv]}
-                             for iv, st in zip(intervals, strides)])
+                            [{"stride": st, "starts": [self._pair(p)[0] for p in iv],
+                              "ends": [self._pair(p)[1] for p in iv]} for iv, st in zip(intervals, strides)])
 
     def Gather(self, input, indices):
-        return self._sample(input, "Gather", "GatherSamplerArgs", [{"rows": list(r)} for r in indices])
+        return self._sample(input, "Gather", "GatherSamplerArgs", [self._map(r, lambda e: {"rows": list(e)}) for r in indices])
 
     def RepeatNull(self, input, spacings):
         return self._sample(input, "SpaceNull", "SpaceNullSamplerArgs", [{"spacing": s} for s in spacings], "space")
@@ -157,6 +195,37 @@ class StreamsGenerator:
     def Repeat(self, input, spacings):
         return self._sample(input, "SpaceRepeat", "SpaceRepeatSamplerArgs", [{"spacing": s} for s in spacings],
                             "space")
+
+
+class Partitioner:
+    """Slice partitioners (reference scannerpy/partitioner.py): how a Slice cuts its input into groups."""
+
+    @staticmethod
+    def _enc(msg, d):
+        return protolite.encode(protolite.SAMPLER_ARGS[msg], d)
+
+    def all(self, group_size=250):
+        return self.strided(1, group_size)
+
+    def strided(self, stride, group_size=250):
+        return ("Strided", self._enc("StridedPartitionerArgs", {"stride": stride, "group_size": group_size}))
+
+    def range(self, start, end):
+        return self.ranges([(start, end)])
+
+    def ranges(self, intervals):
+        return self.strided_ranges(intervals, 1)
+
+    def strided_range(self, start, end, stride):
+        return self.strided_ranges([(start, end)], stride)
+
+    def strided_ranges(self, intervals, stride):
+        return ("StridedRange", self._enc("StridedRangePartitionerArgs", {
+            "stride": stride, "starts": [a for a, _ in intervals], "ends": [b for _, b in intervals]}))
+
+    def gather(self, groups_of_rows):
+        groups = [self._enc("GatherList", {"rows": list(g)}) for g in groups_of_rows]
+        return ("Gather", self._enc("GatherPartitionerArgs", {"groups": groups}))
 
 
 class IOGenerator:
@@ -325,6 +394,7 @@ class Client:
         self._streams = {}
         self._op_protos = {}
         self.ops, self.streams, self.io = OpGenerator(self), StreamsGenerator(self), IOGenerator(self)
+        self.partitioner = Partitioner()
         if load_stdlib:
             E.load_stdlib()
             std = protolite.parse_proto(open(os.path.join(os.path.dirname(E.ENGINE_PATH), "..", "csrc", "ops",
@@ -430,9 +500,10 @@ class Client:
                 ins = [(index[id(c._op)], c._col) for c in node.inputs]
                 index[id(node)] = g.add_op(node.name, ins, int(node.device), node.args, node.batch, node.stencil,
                                            node.warmup)
-            elif node.kind in ("sample", "space"):
+            elif node.kind in ("sample", "space", "slice", "unslice"):
                 c = node.inputs[0]
-                fn = g.add_sample if node.kind == "sample" else g.add_space
+                fn = {"sample": g.add_sample, "space": g.add_space, "slice": g.add_slice, "unslice": g.add_unslice}[
+                    node.kind]
                 index[id(node)] = fn((index[id(c._op)], c._col))
             elif node.kind == "output":
                 c = node.inputs[0]
@@ -448,9 +519,21 @@ class Client:
                     job.bind_source(index[id(node)], node.streams[j]._sid)
                 elif node.kind in ("sample", "space"):
                     args = node.per_stream[j if len(node.per_stream) > 1 else 0]
-                    job.set_sampler(index[id(node)], node.sampler, args)
+                    if isinstance(args, SliceList):
+                        for grp, a in enumerate(args):
+                            job.set_group_sampler(index[id(node)], grp, node.sampler, a)
+                    else:
+                        job.set_sampler(index[id(node)], node.sampler, args)
+                elif node.kind == "slice":
+                    name, args = node.per_stream[j if len(node.per_stream) > 1 else 0]
+                    job.set_partitioner(index[id(node)], name, args)
                 elif node.kind == "op" and node.per_stream:
-                    job.set_stream_args(index[id(node)], node.per_stream[j if len(node.per_stream) > 1 else 0])
+                    args = node.per_stream[j if len(node.per_stream) > 1 else 0]
+                    if isinstance(args, SliceList):
+                        for grp, a in enumerate(args):
+                            job.set_group_stream_args(index[id(node)], grp, a)
+                    else:
+                        job.set_stream_args(index[id(node)], args)
             jobs.append(job)
         try:
             if jobs:

@@ -1,4 +1,5 @@
 // engine_cabi.cpp -- extern "C" surface of include/scn_engine.h over the C++ pipeline.
+#include <algorithm>
 #include <cstring>
 #include <sstream>
 
@@ -243,6 +244,48 @@ int scn_engine_run(scn_engine* e, scn_graph* g, scn_job* const* jobs, int n_jobs
   return from_result(e->impl->run(g->g, js, wps, ios, out_dir ? out_dir : ""));
 }
 
+int scn_graph_add_slice(scn_graph* g, int input_op, const char* column) {
+  if (!g || !column) return fail("bad arguments");
+  GraphOp op;
+  op.kind = OpKind::Sample;
+  op.slice_role = SliceRole::Slice;
+  op.name = "Slice";
+  op.inputs.push_back({input_op, column});
+  g->g.ops.push_back(op);
+  g->analyzed = false;
+  return (int)g->g.ops.size() - 1;
+}
+int scn_graph_add_unslice(scn_graph* g, int input_op, const char* column) {
+  if (!g || !column) return fail("bad arguments");
+  GraphOp op;
+  op.kind = OpKind::Sample;
+  op.slice_role = SliceRole::Unslice;
+  op.name = "Unslice";
+  op.inputs.push_back({input_op, column});
+  g->g.ops.push_back(op);
+  g->analyzed = false;
+  return (int)g->g.ops.size() - 1;
+}
+int scn_job_set_partitioner(scn_job* j, int slice_op, const char* name, const uint8_t* args, size_t size) {
+  if (!j || !name) return fail("bad arguments");
+  j->j.params.partitioners[slice_op] = {name, std::vector<u8>(args, args + (args ? size : 0))};
+  return 0;
+}
+int scn_job_set_group_sampler(scn_job* j, int op, int group, const char* name, const uint8_t* args, size_t size) {
+  if (!j || !name || group < 0) return fail("bad arguments");
+  auto& v = j->j.params.group_samplers[op];
+  if (v.size() <= (size_t)group) v.resize((size_t)group + 1);
+  v[(size_t)group] = {name, std::vector<u8>(args, args + (args ? size : 0))};
+  return 0;
+}
+int scn_job_set_group_stream_args(scn_job* j, int op, int group, const uint8_t* args, size_t size) {
+  if (!j || group < 0) return fail("bad arguments");
+  auto& v = j->j.params.group_stream_args[op];
+  if (v.size() <= (size_t)group) v.resize((size_t)group + 1);
+  v[(size_t)group] = std::vector<u8>(args, args + (args ? size : 0));
+  return 0;
+}
+
 int64_t scn_job_output_rows(scn_job* j, int sink) {
   if (!j) return fail("null job");
   auto it = j->j.outputs.find(sink);
@@ -254,10 +297,11 @@ int64_t scn_job_output_rows(scn_job* j, int sink) {
 
 static const TaskOutput* locate(scn_job* j, int sink, int64_t row, size_t& idx) {
   auto it = j->j.outputs.find(sink);
-  if (it == j->j.outputs.end() || j->j.io_packet <= 0 || row < 0) return nullptr;
-  const size_t task = (size_t)(row / j->j.io_packet);
+  const std::vector<i64>& starts = j->j.task_starts;
+  if (it == j->j.outputs.end() || starts.size() < 2 || row < 0 || row >= starts.back()) return nullptr;
+  const size_t task = (size_t)(std::upper_bound(starts.begin(), starts.end(), row) - starts.begin()) - 1;
   if (task >= it->second.size()) return nullptr;
-  idx = (size_t)(row % j->j.io_packet);
+  idx = (size_t)(row - starts[task]);
   const TaskOutput& t = it->second[task];
   return idx < t.sizes.size() ? &t : nullptr;
 }

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "sampler_args.pb.h"
 
@@ -255,11 +256,132 @@ class SpaceSampler : public DomainSampler {
   i64 spacing_ = 1;
 };
 
+// Unslice inside one task: downstream (concatenated) rows [base, base + count) <-> the group's
+// local rows [0, count).  args: two little-endian i64 (base, count).  Internal.
+class SliceOffsetSampler : public DomainSampler {
+ public:
+  explicit SliceOffsetSampler(const std::vector<u8>& args) {
+    valid_.set_success(args.size() == 16);
+    if (args.size() == 16) {
+      memcpy(&base_, args.data(), 8);
+      memcpy(&count_, args.data() + 8, 8);
+    } else {
+      valid_.set_msg("SliceOffset sampler needs 16 bytes of arguments");
+    }
+  }
+  Result validate() const override { return valid_; }
+  Result get_upstream_rows(const std::vector<i64>& d, std::vector<i64>& u) const override {
+    Result r = ok();
+    for (i64 row : d) {
+      if (row < base_ || row >= base_ + count_) {
+        RESULT_ERROR(&r, "row %ld is outside slice group [%ld, %ld)", (long)row, (long)base_, (long)(base_ + count_));
+        return r;
+      }
+      u.push_back(row - base_);
+    }
+    return r;
+  }
+  Result get_num_downstream_rows(i64 n, i64& out) const override {
+    out = base_ + std::min(n, count_);
+    return ok();
+  }
+  Result get_downstream_rows(const std::vector<i64>& u, std::vector<i64>& d, std::vector<i64>& m) const override {
+    for (size_t i = 0; i < u.size(); ++i)
+      if (u[i] >= 0 && u[i] < count_) {
+        d.push_back(u[i] + base_);
+        m.push_back((i64)i);
+      }
+    return ok();
+  }
+
+ private:
+  Result valid_;
+  i64 base_ = 0, count_ = 0;
+};
+
 }  // namespace
+
+Result make_partition_groups(const std::string& name, const std::vector<u8>& args, i64 num_rows,
+                             std::vector<std::vector<i64>>& groups) {
+  Result r = ok();
+  groups.clear();
+  if (name == "Strided") {  // reference sampler.cpp:505-583
+    StridedPartitionerArgs a;
+    if (!a.ParseFromArray(args.data(), (int)args.size())) {
+      RESULT_ERROR(&r, "Strided partitioner provided with invalid protobuf args");
+      return r;
+    }
+    if (a.stride() <= 0 || a.group_size() <= 0) {
+      RESULT_ERROR(&r, "Strided partitioner stride (%ld) and group size (%ld) must be greater than 0", (long)a.stride(),
+                   (long)a.group_size());
+      return r;
+    }
+    const i64 strided = (num_rows + a.stride() - 1) / a.stride();
+    for (i64 s = 0; s < strided; s += a.group_size()) {
+      groups.emplace_back();
+      for (i64 i = s; i < std::min(strided, s + a.group_size()); ++i) groups.back().push_back(i * a.stride());
+    }
+  } else if (name == "StridedRange" || name == "StridedRanges") {  // :585-700
+    StridedRangePartitionerArgs a;
+    if (!a.ParseFromArray(args.data(), (int)args.size())) {
+      RESULT_ERROR(&r, "StridedRange partitioner provided with invalid protobuf args");
+      return r;
+    }
+    if (a.stride() <= 0) {
+      RESULT_ERROR(&r, "StridedRange stride (%ld) must be greater than zero", (long)a.stride());
+      return r;
+    }
+    if (a.starts_size() != a.ends_size()) {
+      RESULT_ERROR(&r, "StridedRange starts and ends not the same size");
+      return r;
+    }
+    for (int i = 0; i < a.starts_size(); ++i) {
+      if (a.starts(i) > a.ends(i)) {
+        RESULT_ERROR(&r, "StridedRange start (%ld) should not be after end (%ld)", (long)a.starts(i), (long)a.ends(i));
+        return r;
+      }
+      if (a.ends(i) > num_rows) {
+        RESULT_ERROR(&r, "StridedRange end (%ld) should be less than table num rows (%ld)", (long)a.ends(i),
+                     (long)num_rows);
+        return r;
+      }
+      groups.emplace_back();
+      for (i64 row = a.starts(i); row < a.ends(i); row += a.stride()) groups.back().push_back(row);
+    }
+  } else if (name == "Gather") {  // :702-770
+    GatherPartitionerArgs a;
+    if (!a.ParseFromArray(args.data(), (int)args.size())) {
+      RESULT_ERROR(&r, "Gather partitioner provided with invalid protobuf args");
+      return r;
+    }
+    for (const GatherList& g : a.groups()) {
+      groups.emplace_back(g.rows().begin(), g.rows().end());
+      i64 prev = -1;
+      for (i64 row : groups.back()) {
+        if (row < 0 || row >= num_rows) {
+          RESULT_ERROR(&r, "Gather partitioner row %ld is outside [0, %ld)", (long)row, (long)num_rows);
+          return r;
+        }
+        if (row <= prev) {  // rows flow through the pipeline in table order
+          RESULT_ERROR(&r, "Gather partitioner rows of one group must be ascending (%ld after %ld)", (long)row,
+                       (long)prev);
+          return r;
+        }
+        prev = row;
+      }
+    }
+  } else {
+    RESULT_ERROR(&r, "Partitioner %s not found.", name.c_str());
+    return r;
+  }
+  if (groups.empty()) RESULT_ERROR(&r, "Partitioner %s produced no slice groups", name.c_str());
+  return r;
+}
 
 Result make_domain_sampler(const std::string& name, const std::vector<u8>& args,
                            std::unique_ptr<DomainSampler>& out) {
   if (name == "All") out.reset(new AllSampler());
+  else if (name == "SliceOffset") out.reset(new SliceOffsetSampler(args));
   else if (name == "Strided") out.reset(new StridedSampler(args));
   else if (name == "StridedRanges" || name == "StridedRange") out.reset(new StridedRangesSampler(args));
   else if (name == "Gather") out.reset(new GatherSampler(args));
@@ -386,6 +508,45 @@ Result Graph::analyze(GraphAnalysis& an) {
     RESULT_ERROR(&r, "A graph needs at least one Source and one Sink (found %zu / %zu)", n_sources, n_sinks);
     return r;
   }
+  // slice levels (reference dag_analysis.cpp:94-271): one level, inputs of an op share it, an
+  // Unslice only feeds sinks, sinks are unsliced
+  slice_level.assign(n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    const GraphOp& op = ops[i];
+    if (op.inputs.empty()) continue;
+    const i32 in_level = slice_level[op.inputs[0].op_index];
+    for (const OpInput& in : op.inputs) {
+      if (slice_level[in.op_index] != in_level) {
+        RESULT_ERROR(&r, "Input Op %s (%d) specified as input to %s Op (%zu) has a different slice level. Ops within "
+                         "a slice level should only receive inputs from other Ops at the same slice level.",
+                     ops[in.op_index].name.c_str(), in.op_index, op.name.c_str(), i);
+        return r;
+      }
+      if (ops[in.op_index].slice_role == SliceRole::Unslice && op.kind != OpKind::Sink) {
+        RESULT_ERROR(&r, "Unslice Op specified as input to %s Op. Scanner currently only supports Output Ops consuming "
+                         "the results of an Unslice Op.", op.name.c_str());
+        return r;
+      }
+    }
+    i32 level = in_level;
+    if (op.slice_role == SliceRole::Slice) {
+      if (in_level > 0) {
+        RESULT_ERROR(&r, "Nested slicing not currently supported.");
+        return r;
+      }
+      level = 1;
+    } else if (op.slice_role == SliceRole::Unslice) {
+      if (in_level == 0) {
+        RESULT_ERROR(&r, "Unslice received inputs that have not been sliced.");
+        return r;
+      }
+      level = 0;
+    } else if (op.kind == OpKind::Sink && in_level != 0) {
+      RESULT_ERROR(&r, "Final output columns are sliced. Final outputs must be unsliced.");
+      return r;
+    }
+    slice_level[i] = level;
+  }
   // liveness: last consumer of every produced column
   for (size_t i = 0; i < n; ++i) an.last_use[i].assign(ops[i].output_columns.size(), -1);
   for (size_t i = 0; i < n; ++i)
@@ -426,9 +587,34 @@ bool Graph::consumers_accept_layout(i32 source_op, FrameLayout layout) const {
   return any;
 }
 
-Result Graph::domain_sizes(const JobParams& job, std::vector<i64>& rows) const {
+Result Graph::domain_sizes(const JobParams& job, std::vector<i64>& rows, SliceInfo* slices) const {
   Result r;
   rows.assign(ops.size(), 0);
+  SliceInfo local;
+  SliceInfo& si = slices ? *slices : local;
+  si = SliceInfo();
+  // per-group sizes of the ops inside the slice: grows[g][op]
+  std::vector<std::vector<i64>>& grows = si.rows_per_op;
+  auto level = [&](size_t i) { return i < slice_level.size() ? slice_level[i] : 0; };
+  auto sampler_of = [&](size_t i, i32 group, std::unique_ptr<DomainSampler>& s) -> Result {
+    Result e;
+    auto git = job.group_samplers.find((i32)i);
+    if (group >= 0 && git != job.group_samplers.end()) {
+      if (git->second.size() != 1 && (i32)git->second.size() != si.groups) {
+        RESULT_ERROR(&e, "A job specified %zu samplers but there are %d slice groups for %s Op at %zu.",
+                     git->second.size(), si.groups, ops[i].name.c_str(), i);
+        return e;
+      }
+      const auto& sa = git->second[git->second.size() == 1 ? 0 : (size_t)group];
+      return make_domain_sampler(sa.first, sa.second, s);
+    }
+    auto it = job.samplers.find((i32)i);
+    if (it == job.samplers.end()) {
+      RESULT_ERROR(&e, "Job does not provide sampling args for op %zu", i);
+      return e;
+    }
+    return make_domain_sampler(it->second.first, it->second.second, s);
+  };
   for (size_t i = 0; i < ops.size(); ++i) {
     const GraphOp& op = ops[i];
     if (op.kind == OpKind::Source) {
@@ -440,15 +626,75 @@ Result Graph::domain_sizes(const JobParams& job, std::vector<i64>& rows) const {
       rows[i] = it->second;
       continue;
     }
-    const i64 in_rows = rows[op.inputs[0].op_index];
-    if (op.kind == OpKind::Sample || op.kind == OpKind::Space) {
-      auto it = job.samplers.find((i32)i);
-      if (it == job.samplers.end()) {
-        RESULT_ERROR(&r, "Job does not provide sampling args for op %zu", i);
+    const i32 in0 = op.inputs[0].op_index;
+    if (op.slice_role == SliceRole::Slice) {
+      auto it = job.partitioners.find((i32)i);
+      if (it == job.partitioners.end()) {
+        RESULT_ERROR(&r, "Job does not provide a partitioner for Slice op %zu", i);
         return r;
       }
+      std::vector<std::vector<i64>> groups;
+      Result pr = make_partition_groups(it->second.first, it->second.second, rows[in0], groups);
+      if (!pr.success()) return pr;
+      if (si.groups != 0 && si.groups != (i32)groups.size()) {
+        RESULT_ERROR(&r, "A job specified one slice with %d groups and another slice with %zu groups. Scanner "
+                         "currently does not support multiple slices with different numbers of groups in the same job.",
+                     si.groups, groups.size());
+        return r;
+      }
+      if (si.groups == 0) {
+        si.groups = (i32)groups.size();
+        grows.assign(groups.size(), std::vector<i64>(ops.size(), 0));
+      }
+      i64 total = 0;
+      for (size_t g = 0; g < groups.size(); ++g) {
+        grows[g][i] = (i64)groups[g].size();
+        total += grows[g][i];
+      }
+      rows[i] = total;
+      si.slice_rows[(i32)i] = std::move(groups);
+      continue;
+    }
+    if (op.slice_role == SliceRole::Unslice) {
+      i64 total = 0;
+      si.out_base.clear();
+      for (i32 g = 0; g < si.groups; ++g) {
+        si.out_base.push_back(total);
+        total += grows[(size_t)g][in0];
+      }
+      si.out_base.push_back(total);
+      rows[i] = total;
+      continue;
+    }
+    if (level(i) > 0) {  // inside the slice: every group on its own
+      i64 total = 0;
+      for (i32 g = 0; g < si.groups; ++g) {
+        const i64 in_rows = grows[(size_t)g][in0];
+        i64 out = in_rows;
+        if (op.kind == OpKind::Sample || op.kind == OpKind::Space) {
+          std::unique_ptr<DomainSampler> s;
+          Result sr = sampler_of(i, g, s);
+          if (!sr.success()) return sr;
+          sr = s->get_num_downstream_rows(in_rows, out);
+          if (!sr.success()) return sr;
+        } else {
+          for (const OpInput& in : op.inputs)
+            if (grows[(size_t)g][in.op_index] != in_rows) {
+              RESULT_ERROR(&r, "Op %s (%zu) has inputs with different numbers of rows in slice group %d (%ld vs %ld)",
+                           op.name.c_str(), i, g, (long)in_rows, (long)grows[(size_t)g][in.op_index]);
+              return r;
+            }
+        }
+        grows[(size_t)g][i] = out;
+        total += out;
+      }
+      rows[i] = total;
+      continue;
+    }
+    const i64 in_rows = rows[in0];
+    if (op.kind == OpKind::Sample || op.kind == OpKind::Space) {
       std::unique_ptr<DomainSampler> s;
-      Result sr = make_domain_sampler(it->second.first, it->second.second, s);
+      Result sr = sampler_of(i, -1, s);
       if (!sr.success()) return sr;
       sr = s->get_num_downstream_rows(in_rows, rows[i]);
       if (!sr.success()) return sr;
@@ -473,8 +719,39 @@ Result Graph::domain_sizes(const JobParams& job, std::vector<i64>& rows) const {
       }
       sink_rows = rows[i];
     }
+  // level-0 ops of a sliced job keep their global sizes in every group's view
+  for (i32 g = 0; g < si.groups; ++g)
+    for (size_t i = 0; i < ops.size(); ++i)
+      if (level(i) == 0 && ops[i].slice_role != SliceRole::Slice) grows[(size_t)g][i] = rows[i];
   r.set_success(true);
   return r;
+}
+
+void Graph::slice_view(const JobParams& job, const SliceInfo& si, i32 group, JobParams& view, std::vector<i64>& vrows) const {
+  view = job;
+  vrows = si.rows_per_op[(size_t)group];
+  for (size_t i = 0; i < ops.size(); ++i) {
+    const GraphOp& op = ops[i];
+    if (op.slice_role == SliceRole::Slice) {
+      GatherSamplerArgs ga;  // the group's rows, as a Gather over the upstream domain
+      for (i64 row : si.slice_rows.at((i32)i)[(size_t)group]) ga.add_rows(row);
+      const std::string bytes = ga.SerializeAsString();
+      view.samplers[(i32)i] = {"Gather", std::vector<u8>(bytes.begin(), bytes.end())};
+    } else if (op.slice_role == SliceRole::Unslice) {
+      const i64 base = si.out_base[(size_t)group], count = si.out_base[(size_t)group + 1] - base;
+      std::vector<u8> a(16);
+      memcpy(a.data(), &base, 8);
+      memcpy(a.data() + 8, &count, 8);
+      view.samplers[(i32)i] = {"SliceOffset", a};
+    } else {
+      auto gs = job.group_samplers.find((i32)i);
+      if (gs != job.group_samplers.end() && !gs->second.empty())
+        view.samplers[(i32)i] = gs->second[gs->second.size() == 1 ? 0 : (size_t)group];
+      auto ga = job.group_stream_args.find((i32)i);
+      if (ga != job.group_stream_args.end() && !ga->second.empty())
+        view.stream_args[(i32)i] = ga->second[ga->second.size() == 1 ? 0 : (size_t)group];
+    }
+  }
 }
 
 Result Graph::derive_task_streams(const GraphAnalysis& an, const JobParams& job,

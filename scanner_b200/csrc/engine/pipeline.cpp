@@ -71,6 +71,7 @@ struct Engine::RunState {
   struct Task {
     i32 job, task;
     i64 row0, row1;
+    i32 group;  // slice group the rows belong to, -1 if the job is not sliced
   };
   std::vector<Task> tasks;
   std::atomic<size_t> next{0};
@@ -253,8 +254,18 @@ void Engine::instance_main(Instance* inst) {
       std::vector<i64> out_rows;
       for (i64 row = t.row0; row < t.row1; ++row) out_rows.push_back(row);
       std::vector<TaskStream> streams;
-      r = rs.graph->derive_task_streams(rs.an, job.params, job.rows_per_op, out_rows, streams);
-      if (r.success()) r = ew.new_task(job.params, job.rows_per_op, streams);
+      if (t.group >= 0) {
+        // a task of a sliced job sees its group's domain: Slice = gather of the group's rows,
+        // Unslice = offset into the concatenated output, per-group samplers / stream args
+        JobParams view;
+        std::vector<i64> view_rows;
+        rs.graph->slice_view(job.params, job.slices, t.group, view, view_rows);
+        r = rs.graph->derive_task_streams(rs.an, view, view_rows, out_rows, streams);
+        if (r.success()) r = ew.new_task(view, view_rows, streams);
+      } else {
+        r = rs.graph->derive_task_streams(rs.an, job.params, job.rows_per_op, out_rows, streams);
+        if (r.success()) r = ew.new_task(job.params, job.rows_per_op, streams);
+      }
       if (!r.success()) {
         rs.fail(r.msg());
         break;
@@ -639,18 +650,39 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
       }
       job.params.source_rows[kv.first] = s->rows();
     }
-    r = graph.domain_sizes(job.params, job.rows_per_op);
+    r = graph.domain_sizes(job.params, job.rows_per_op, &job.slices);
     if (!r.success()) return r;
     job.total_rows = 0;
     job.outputs.clear();
     for (size_t k = 0; k < graph.ops.size(); ++k)
       if (graph.ops[k].kind == OpKind::Sink) job.total_rows = job.rows_per_op[k];
     job.io_packet = ios;
-    const i64 n_tasks = (job.total_rows + ios - 1) / ios;
+    // tasks: io_packet-sized intervals of the output rows, never across a slice group boundary
+    // (reference master.cpp:1567-1606 enumerates (slice group, row interval) the same way)
+    job.task_starts.clear();
+    std::vector<i32> groups_of_task;
+    if (job.slices.groups > 0 && !job.slices.out_base.empty()) {
+      for (i32 gi = 0; gi < job.slices.groups; ++gi)
+        for (i64 row = job.slices.out_base[(size_t)gi]; row < job.slices.out_base[(size_t)gi + 1]; row += ios) {
+          job.task_starts.push_back(row);
+          groups_of_task.push_back(gi);
+        }
+    } else {
+      for (i64 row = 0; row < job.total_rows; row += ios) {
+        job.task_starts.push_back(row);
+        groups_of_task.push_back(-1);
+      }
+    }
+    const i64 n_tasks = (i64)job.task_starts.size();
+    job.task_starts.push_back(job.total_rows);
     for (size_t k = 0; k < graph.ops.size(); ++k)
       if (graph.ops[k].kind == OpKind::Sink) job.outputs[(i32)k].resize((size_t)n_tasks);
-    for (i64 t = 0; t < n_tasks; ++t)
-      rs.tasks.push_back({(i32)j, (i32)t, t * ios, std::min<i64>(job.total_rows, (t + 1) * ios)});
+    for (i64 t = 0; t < n_tasks; ++t) {
+      i64 end = job.task_starts[(size_t)t + 1];
+      if (groups_of_task[(size_t)t] >= 0) end = std::min(end, job.slices.out_base[(size_t)groups_of_task[(size_t)t] + 1]);
+      end = std::min(end, job.task_starts[(size_t)t] + ios);
+      rs.tasks.push_back({(i32)j, (i32)t, job.task_starts[(size_t)t], end, groups_of_task[(size_t)t]});
+    }
   }
 
   // pipeline instances (reference worker.cpp:1297-1337)

@@ -108,8 +108,11 @@ struct Job {
   JobParams params;
   // filled by the run
   std::vector<i64> rows_per_op;
+  SliceInfo slices;              // groups == 0 unless the graph slices
   i64 total_rows = 0;
   i32 io_packet = 0;
+  std::vector<i64> task_starts;  // first output row of every task, then total_rows (tasks never
+                                 // span slice groups, so they are not all io_packet long)
   std::map<i32, std::vector<TaskOutput>> outputs;  // sink op -> per task
 };
 

@@ -50,6 +50,11 @@ SIGNATURES = {
     "scn_engine_stats_json": (_I, [_VP, _CP, _SZ]),
     "scn_h264_synth": (_I64, [_VP, _I, _I, _I64, _I, _I, _VP, _SZ]),
     "scn_nvdec_caps": (_I, [_I, _IP]),
+    "scn_graph_add_slice": (_I, [_VP, _I, _CP]),
+    "scn_graph_add_unslice": (_I, [_VP, _I, _CP]),
+    "scn_job_set_partitioner": (_I, [_VP, _I, _CP, _VP, _SZ]),
+    "scn_job_set_group_sampler": (_I, [_VP, _I, _I, _CP, _VP, _SZ]),
+    "scn_job_set_group_stream_args": (_I, [_VP, _I, _I, _VP, _SZ]),
     "scn_engine_set_trace": (_I, [_VP, _I]),
     "scn_engine_write_trace": (_I, [_VP, _CP]),
     "scn_db_open": (_VP, [_CP]),
@@ -373,6 +378,12 @@ class Graph:
     def add_space(self, inp):
         return check(lib().scn_graph_add_space(self._h, inp[0], inp[1].encode()), "add_space")
 
+    def add_slice(self, inp):
+        return check(lib().scn_graph_add_slice(self._h, inp[0], inp[1].encode()), "add_slice")
+
+    def add_unslice(self, inp):
+        return check(lib().scn_graph_add_unslice(self._h, inp[0], inp[1].encode()), "add_unslice")
+
     def add_sink(self, inp, name=None):
         return check(lib().scn_graph_add_sink(self._h, inp[0], inp[1].encode(), (name or inp[1]).encode()), "add_sink")
 
@@ -398,6 +409,24 @@ class Job:
         buf = ctypes.create_string_buffer(args, len(args)) if args else None
         check(lib().scn_job_set_sampler(self._h, op, function.encode(), ctypes.cast(buf, ctypes.c_void_p) if buf else None,
                                         len(args)), f"set_sampler({function})")
+
+    def set_partitioner(self, slice_op, name, args):
+        buf = ctypes.create_string_buffer(args, len(args)) if args else None
+        check(lib().scn_job_set_partitioner(self._h, slice_op, name.encode(),
+                                            ctypes.cast(buf, ctypes.c_void_p) if buf else None, len(args)),
+              f"set_partitioner({name})")
+
+    def set_group_sampler(self, op, group, function, args=b""):
+        buf = ctypes.create_string_buffer(args, len(args)) if args else None
+        check(lib().scn_job_set_group_sampler(self._h, op, group, function.encode(),
+                                              ctypes.cast(buf, ctypes.c_void_p) if buf else None, len(args)),
+              f"set_group_sampler({function})")
+
+    def set_group_stream_args(self, op, group, args):
+        buf = ctypes.create_string_buffer(args, len(args)) if args else None
+        check(lib().scn_job_set_group_stream_args(self._h, op, group,
+                                                  ctypes.cast(buf, ctypes.c_void_p) if buf else None, len(args)),
+              "set_group_stream_args")
 
     def set_stream_args(self, op, args):
         buf = ctypes.create_string_buffer(args, len(args)) if args else None

@@ -155,3 +155,87 @@ def test_ingest_videos_from_mp4_and_h264_files(tmp_path):
     with pytest.raises(sp.ScannerException, match="does not exist"):
         sp.NamedVideoStream(c2, "zzz")
     c2.stop()
+
+
+# ------------------------------------------------------------------------------------------------
+def _ints(sc, name, n):
+    return sp.NamedStream(sc, name, rows=[struct.pack("<q", i) for i in range(n)])
+
+
+def _load_ints(stream):
+    return [struct.unpack("<q", r)[0] for r in stream.load()]
+
+
+def test_slice_unslice_keeps_every_row(sc):
+    """reference tests/py_test.py:350-358 test_slice: Slice(all(50)) -> Unslice gives the input back."""
+    src = _ints(sc, "slice_in", 130)
+    col = sc.io.Input([src])
+    sliced = sc.streams.Slice(col, partitions=[sc.partitioner.all(50)])
+    out = sp.NamedStream(sc, "slice_out")
+    sc.run(sc.io.Output(sc.streams.Unslice(sliced), [out]), sp.PerfParams.manual(4, 16))
+    assert out.len() == src.len() == 130 and _load_ints(out) == list(range(130))
+
+
+def test_overlapping_slices_with_a_sampler_per_group(sc):
+    """py_test.py:361-375 test_overlapping_slice: three overlapping ranges, a Range per slice group
+    (SliceList), 30 rows out -- here the values are checked too."""
+    src = _ints(sc, "ovl_in", 40)
+    col = sc.io.Input([src])
+    sliced = sc.streams.Slice(col, partitions=[sc.partitioner.strided_ranges([(0, 15), (5, 25), (15, 35)], 1)])
+    sampled = sc.streams.Range(sliced, ranges=[sp.SliceList([{"start": 0, "end": 10}, {"start": 5, "end": 15},
+                                                             {"start": 5, "end": 15}])])
+    out = sp.NamedStream(sc, "ovl_out")
+    sc.run(sc.io.Output(sc.streams.Unslice(sampled), [out]), sp.PerfParams.manual(3, 6))
+    want = list(range(0, 10)) + list(range(10, 20)) + list(range(20, 30))
+    assert out.len() == 30 and _load_ints(out) == want
+
+
+def test_state_and_stencils_restart_at_slice_boundaries(sc):
+    """Inside a Slice every group is an independent stream: an unbounded-state counter restarts at 0
+    in every group, a stencil window clamps at the group's edges instead of reading its neighbour."""
+    src = _ints(sc, "st_in", 23)
+    col = sc.io.Input([src])
+    sliced = sc.streams.Slice(col, partitions=[sc.partitioner.all(10)])
+    counted = sc.ops.TestIncrementUnbounded(ignore=sliced)
+    window = sc.ops.TestWindow(col=sliced)
+    o1, o2 = sp.NamedStream(sc, "st_cnt"), sp.NamedStream(sc, "st_win")
+    sc.run([sc.io.Output(sc.streams.Unslice(counted), [o1]), sc.io.Output(sc.streams.Unslice(window), [o2])],
+           sp.PerfParams.manual(2, 4))
+    assert _load_ints(o1) == list(range(10)) + list(range(10)) + list(range(3))
+    got = [struct.unpack("<3q", r) for r in o2.load()]
+    want = []
+    for lo, hi in ((0, 10), (10, 20), (20, 23)):
+        for i in range(lo, hi):
+            want.append((max(lo, i - 1), i, min(hi - 1, i + 1)))
+    assert got == want
+
+
+def test_per_slice_stream_args_and_gather_partitioner(sc):
+    """py_test.py:393-404 test_slice_args: one new_stream argument per slice group (SliceList)."""
+    src = _ints(sc, "args_in", 12)
+    col = sc.io.Input([src])
+    sliced = sc.streams.Slice(col, [sc.partitioner.gather([[0, 1, 2], [3, 7], [11]])])
+    aff = sc.ops.TestAffine(col=sliced, scale=10, offset=[sp.SliceList([1, 2, 3])])
+    out = sp.NamedStream(sc, "args_out")
+    sc.run(sc.io.Output(sc.streams.Unslice(aff), [out]), sp.PerfParams.manual(2, 2))
+    assert _load_ints(out) == [1, 11, 21, 32, 72, 113]
+    with pytest.raises(sp.ScannerException, match="ascending"):
+        bad = sc.streams.Slice(col, [sc.partitioner.gather([[5, 2]])])
+        sc.run(sc.io.Output(sc.streams.Unslice(bad), [sp.NamedStream(sc, "args_bad")]), sp.PerfParams.manual(2, 2))
+
+
+def test_slice_errors(sc):
+    src = _ints(sc, "err_in", 10)
+    col = sc.io.Input([src])
+    sliced = sc.streams.Slice(col, partitions=[sc.partitioner.all(5)])
+    with pytest.raises(sp.ScannerException, match="must be unsliced"):
+        sc.run(sc.io.Output(sliced, [sp.NamedStream(sc, "e1")]), sp.PerfParams.manual(2, 2))
+    with pytest.raises(sp.ScannerException, match="not been sliced"):
+        sc.run(sc.io.Output(sc.streams.Unslice(col), [sp.NamedStream(sc, "e2")]), sp.PerfParams.manual(2, 2))
+    un = sc.streams.Unslice(sliced)
+    with pytest.raises(sp.ScannerException, match="only supports Output"):
+        sc.run(sc.io.Output(sc.ops.TestAffine(col=un, scale=1, offset=[0]), [sp.NamedStream(sc, "e3")]),
+               sp.PerfParams.manual(2, 2))
+    with pytest.raises(sp.ScannerException, match="3 samplers but there are 2 slice groups"):
+        bad = sc.streams.Range(sliced, ranges=[sp.SliceList([{"start": 0, "end": 2}] * 3)])
+        sc.run(sc.io.Output(sc.streams.Unslice(bad), [sp.NamedStream(sc, "e4")]), sp.PerfParams.manual(2, 2))
