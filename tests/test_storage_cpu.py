@@ -241,3 +241,24 @@ def test_job_outputs_saved_as_tables_and_read_back(tmp_path):
         db.read_rows("out", "nope", [0])
     eng.close()
     db.close()
+
+
+def test_foreign_mp4_with_another_codec_is_rejected_by_name(tmp_path):
+    """A file written by FFmpeg's own muxer (MPEG-4 part 2 video: no H.264 encoder is available to it
+    here) walks through the box parser up to the sample entry, where the codec is refused by name."""
+    import cv2
+    path = str(tmp_path / "foreign.mp4")
+    w = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25, (128, 96))
+    if not w.isOpened():
+        pytest.skip("this OpenCV build cannot write mp4v")
+    for i in range(12):
+        w.write(np.full((96, 128, 3), i * 20, np.uint8))
+    w.release()
+    data = open(path, "rb").read()
+    with pytest.raises(E.EngineError, match="mp4v.*not H.264"):
+        E.mp4_demux(data)
+    db = E.Database(str(tmp_path / "db"))
+    with pytest.raises(E.EngineError, match="not H.264"):
+        db.ingest_video("foreign", path)
+    assert db.tables() == []
+    db.close()
