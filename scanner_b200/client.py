@@ -401,6 +401,7 @@ class Client:
                                                           "stdlib_args.proto")).read())
             self._op_protos["Blur"] = {"init": std["BlurArgs"]}
             self._op_protos["Resize"] = {"stream": std["ResizeArgs"]}
+            self._op_protos["ImageEncoder"] = {"init": std["ImageEncoderArgs"]}
 
     # ---- table catalogue (reference client.py: ingest_videos :1009-1078, has_table, delete_table)
     def _need_db(self):
