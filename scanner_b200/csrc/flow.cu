@@ -351,43 +351,52 @@ poly_fused_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* 
 // winSize x winSize box average of M (double sums, clamped borders) + the 2x2 solve.  MW = window
 // half-width at compile time (winSize 15 -> 7).  Both passes are register-blocked by 4: a thread
 // converts 2 MW + 4 inputs once and forms four overlapping (2 MW + 1)-term sums from them, each in the
-// two-pass kernels' order.  The vertical sums are kept with an odd row stride so that the 16 rows a
-// half-warp reads in the horizontal pass fall into distinct shared-memory banks.
+// two-pass kernels' order.  The vertical pass reads M straight from global memory (no input tile:
+// 50 KB of shared memory per CTA instead of 97 KB, 4 CTAs per SM); its sums are kept with an odd row
+// stride so that the 16 rows a half-warp reads in the horizontal pass fall into distinct banks.
 constexpr int BTW = 64, BTH = 16;
 template <int MW>
 __global__ void __launch_bounds__(FT)
 box_solve_fused_kernel(const float* __restrict__ M, int w, int h, double scale, float* __restrict__ flow) {
   extern __shared__ double dsm[];
-  constexpr int iw = BTW + 2 * MW, ih = BTH + 2 * MW, rowf = iw * 5, vstride = rowf | 1, taps = 2 * MW + 1;
-  double* V = dsm;                                                    // BTH x vstride doubles
-  float* in = reinterpret_cast<float*>(dsm + (size_t)BTH * vstride);  // ih x rowf floats
+  constexpr int iw = BTW + 2 * MW, rowf = iw * 5, vstride = rowf | 1, taps = 2 * MW + 1;
+  double* V = dsm;  // BTH x vstride doubles: the vertical sums of this tile (with the horizontal halo)
   const int x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH;
-  for (int q = threadIdx.x; q < rowf; q += FT) {
-    const int i = q / 5, c = q - i * 5;
-    const size_t sx = (size_t)clampi(x0 - MW + i, 0, w - 1) * 5 + c;
-    for (int j0 = 0; j0 < ih; j0 += 10) {  // 10 independent loads in flight, then the 10 stores
-      float v[10];
-#pragma unroll
-      for (int u = 0; u < 10; ++u)
-        v[u] = j0 + u < ih ? M[(size_t)clampi(y0 - MW + j0 + u, 0, h - 1) * w * 5 + sx] : 0.f;
-#pragma unroll
-      for (int u = 0; u < 10; ++u)
-        if (j0 + u < ih) in[(j0 + u) * rowf + q] = v[u];
-    }
-  }
-  __syncthreads();
-  // vertical: item = (group of 4 rows, column-channel q)
+  // vertical: item = (group of 4 rows, column-channel q); the 2 MW + 4 inputs come straight from
+  // global memory (neighbouring groups and CTAs re-read them from L1/L2), all loads issued before
+  // the first conversion
   for (int e = threadIdx.x; e < (BTH / 4) * rowf; e += FT) {
     const int g4 = e / rowf, q = e - g4 * rowf;
-    const float* col = in + (g4 * 4) * rowf + q;
+    const int i = q / 5, c = q - i * 5;
+    // 32-bit element indices (the launcher checks w * h * 5 < 2^31); rows away from the top and
+    // bottom edge need no clamp, which was most of this kernel's instructions (r01 ncu: 45 %
+    // IMAD / SHF / VIADDMNMX / SEL index arithmetic)
+    const int stride = w * 5;
+    const int idx0 = clampi(x0 - MW + i, 0, w - 1) * 5 + c;
+    const int ytop = y0 + g4 * 4 - MW;
+    float f[taps + 3];
+    if (ytop >= 0 && ytop + taps + 2 < h) {
+      const float* col = M + idx0 + ytop * stride;
+#pragma unroll
+      for (int k = 0; k < taps + 3; ++k) f[k] = col[k * stride];
+    } else {
+#pragma unroll
+      for (int k = 0; k < taps + 3; ++k) f[k] = M[idx0 + clampi(ytop + k, 0, h - 1) * stride];
+    }
     double v[taps + 3];
 #pragma unroll
-    for (int k = 0; k < taps + 3; ++k) v[k] = (double)col[k * rowf];
+    for (int k = 0; k < taps + 3; ++k) v[k] = (double)f[k];
+    // first window summed directly, the next three slide (+ new - old).  Every addend is a float
+    // held in a double, so the partial sums are exact -- and the sliding results identical to direct
+    // sums -- unless the 2 MW + 4 values span more than ~2^28 in magnitude (OpenCV's own
+    // FarnebackUpdateFlow_Blur slides the same way).
+    double sum = 0.0;
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      double sum = 0.0;
+    for (int k = 0; k < taps; ++k) sum += v[k];
+    V[(size_t)(g4 * 4) * vstride + q] = sum;
 #pragma unroll
-      for (int k = 0; k < taps; ++k) sum += v[o + k];
+    for (int o = 1; o < 4; ++o) {
+      sum = (sum + v[o + taps - 1]) - v[o - 1];
       V[(size_t)(g4 * 4 + o) * vstride + q] = sum;
     }
   }
@@ -399,20 +408,16 @@ box_solve_fused_kernel(const float* __restrict__ M, int w, int h, double scale, 
   const double* p = V + (size_t)ty * vstride + (gx * 4) * 5;
   double hs[4][5];
 #pragma unroll
-  for (int o = 0; o < 4; ++o)
+  for (int c = 0; c < 5; ++c) {
+    double s0 = 0.0;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) hs[o][c] = 0.0;
+    for (int k = 0; k < taps; ++k) s0 += p[k * 5 + c];
+    hs[0][c] = s0;
 #pragma unroll
-  for (int k = 0; k < taps + 3; ++k) {
-    double vk[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) vk[c] = p[k * 5 + c];
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-      if (k - o >= 0 && k - o < taps) {
-#pragma unroll
-        for (int c = 0; c < 5; ++c) hs[o][c] += vk[c];
-      }
+    for (int o = 1; o < 4; ++o) {  // slide: + entering column - leaving column
+      s0 = (s0 + p[(o + taps - 1) * 5 + c]) - p[(o - 1) * 5 + c];
+      hs[o][c] = s0;
+    }
   }
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
@@ -430,9 +435,7 @@ constexpr size_t kFusedSmemCap = 160 * 1024;
 inline size_t gauss_smem(int r) { return ((size_t)(GTH + 2 * r) * (GTW + 2 * r) + (size_t)(GTH + 2 * r) * GTW) * 4; }
 inline size_t poly_smem(int n) { return ((size_t)(PTH + 2 * n) * (PTW + 2 * n) + (size_t)PTH * (PTW + 2 * n) * 3) * 4; }
 constexpr int kBoxMW = 7;  // the fused box kernel is instantiated for winSize 15 (the reference's)
-inline size_t box_smem(int m) {
-  return (size_t)BTH * (((BTW + 2 * m) * 5) | 1) * 8 + (size_t)(BTH + 2 * m) * (BTW + 2 * m) * 5 * 4;
-}
+inline size_t box_smem(int m) { return (size_t)BTH * (((BTW + 2 * m) * 5) | 1) * 8; }
 // SCN_FLOW_UNFUSED=1 selects the two-pass kernels (kept as the reference the fused ones are tested against)
 inline bool use_fused() {
   static const bool v = [] {
@@ -691,7 +694,7 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
       }
       const int m = win_size / 2;
       for (int it = 0; it < num_iters; ++it) {
-        if (use_fused() && m == kBoxMW) {
+        if (use_fused() && m == kBoxMW && (size_t)w * h * 5 < ((size_t)1 << 31)) {
           LaunchScope ls("flow_box_solve_fused_kernel", st);
           box_solve_fused_kernel<kBoxMW><<<dim3((unsigned)((w + BTW - 1) / BTW), (unsigned)((h + BTH - 1) / BTH)), FT,
                                            box_smem(m), st>>>(ws.M, w, h, 1.0 / ((double)win_size * win_size), flow);
