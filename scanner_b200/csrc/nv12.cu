@@ -10,6 +10,49 @@
 namespace scn {
 namespace {
 
+// ---- FMA-pipe colour math (same scheme as nv12_csa.cuh, here down to the 8-bit value) -----------
+//   byte -> float : PRMT builds the bits of 2^23 + byte (no I2F: the conversion unit runs at a quarter
+//                   of the FMA rate and made the first version of this kernel XU-bound)
+//   x  = value * 2^-11 computed with fma.sat (lower clamp), min(x, 1023 * 2^-11) (upper clamp)
+//   u8 = floor(512 * x) == ((unsigned)v) >> 2, taken from the mantissa of fma.rm(x, 512, 2^23) (no F2I)
+// Power-of-two scaling commutes with IEEE rounding, so the bits equal yuv_to_rgb()'s.
+constexpr float kS = 1.0f / 2048.0f;
+constexpr float kCY = 4.0f * 1.1644f * kS, kKR = 4.0f * 1.596f * kS, kKG1 = 4.0f * -0.3918f * kS;
+constexpr float kKG2 = 4.0f * -0.813f * kS, kKB = 4.0f * 2.0172f * kS;
+constexpr float kMagic = 8388608.0f, kTop = 1023.0f * kS;
+
+__device__ __forceinline__ float byte_magic(uint32_t word, uint32_t sel) {
+  return __uint_as_float(prmt(word, 0x4B000000u, sel));
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t to_u8_bits(float x) {  // 0x4B0000vv
+  float r;
+  asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fminf(x, kTop)), "f"(512.0f), "f"(kMagic));
+  return __float_as_uint(r);
+}
+struct RgbBits {
+  uint32_t r, g, b;
+};
+__device__ __forceinline__ RgbBits convert(float ym, float cb, float cr) {  // ym = 2^23 + Y, cb/cr centred
+  const float ly = __fmaf_rn(ym, kCY, -kMagic * kCY);
+  RgbBits o;
+  o.r = to_u8_bits(fma_sat(cr, kKR, ly));
+  o.g = to_u8_bits(fma_sat(cr, kKG2, __fmaf_rn(cb, kKG1, ly)));
+  o.b = to_u8_bits(fma_sat(cb, kKB, ly));
+  return o;
+}
+__device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >> 1
+  return (a | b) - (((a ^ b) & 0xFEFEFEFEu) >> 1);
+}
+// low bytes of four registers -> one word
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return prmt(prmt(a, b, 0x0040u), prmt(c, d, 0x0040u), 0x5410u);
+}
+
 __global__ void __launch_bounds__(256)
 nv12_to_rgb_kernel(PtrBatch lumas, PtrBatch chromas, MutPtrBatch rgbs, size_t pitch, int width,
                    int height, size_t rgb_pitch, int quads_per_row, int vec_ok) {
@@ -20,49 +63,68 @@ nv12_to_rgb_kernel(PtrBatch lumas, PtrBatch chromas, MutPtrBatch rgbs, size_t pi
   const uint8_t* __restrict__ chroma = chromas.p[blockIdx.z];
   uint8_t* __restrict__ rgb = rgbs.p[blockIdx.z];
   const int x0 = q * 4;
-  uint32_t yy[4], cb[2], cr[2];
   const int yc = y >> 1;
   const bool avg = (y & 1) && yc < ((height >> 1) - 1);
-  if (vec_ok) {
-    const uint32_t yw = ld_stream_u32(luma + (size_t)y * pitch + x0);
-    uint32_t cw = __ldg(reinterpret_cast<const uint32_t*>(chroma + (size_t)yc * pitch + x0));
-    yy[0] = yw & 0xFF; yy[1] = (yw >> 8) & 0xFF; yy[2] = (yw >> 16) & 0xFF; yy[3] = yw >> 24;
-    cb[0] = cw & 0xFF; cr[0] = (cw >> 8) & 0xFF; cb[1] = (cw >> 16) & 0xFF; cr[1] = cw >> 24;
-    if (avg) {
-      const uint32_t c2 =
-          __ldg(reinterpret_cast<const uint32_t*>(chroma + (size_t)(yc + 1) * pitch + x0));
-      cb[0] = (cb[0] + (c2 & 0xFF) + 1) >> 1;
-      cr[0] = (cr[0] + ((c2 >> 8) & 0xFF) + 1) >> 1;
-      cb[1] = (cb[1] + ((c2 >> 16) & 0xFF) + 1) >> 1;
-      cr[1] = (cr[1] + (c2 >> 24) + 1) >> 1;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) yy[i] = (x0 + i < width) ? luma[(size_t)y * pitch + x0 + i] : 0;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      cb[i] = cr[i] = 0;
-      if (x0 + 2 * i < width) chroma_at(chroma, pitch, height, y, x0 + 2 * i, cb[i], cr[i]);
-    }
-  }
-  uint8_t px[12];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const Rgb8 c = yuv_to_rgb(yy[i], cb[i >> 1], cr[i >> 1]);
-    px[3 * i + 0] = (uint8_t)c.r;
-    px[3 * i + 1] = (uint8_t)c.g;
-    px[3 * i + 2] = (uint8_t)c.b;
-  }
   uint8_t* o = rgb + (size_t)y * rgb_pitch + (size_t)x0 * 3;
   if (vec_ok && x0 + 4 <= width) {
+    const uint32_t yw = ld_stream_u32(luma + (size_t)y * pitch + x0);
+    uint32_t cw = __ldg(reinterpret_cast<const uint32_t*>(chroma + (size_t)yc * pitch + x0));
+    if (avg) cw = avg4(cw, __ldg(reinterpret_cast<const uint32_t*>(chroma + (size_t)(yc + 1) * pitch + x0)));
+    const float bias = -(kMagic + 128.0f);
+    const float cb0 = byte_magic(cw, 0x7440u) + bias, cr0 = byte_magic(cw, 0x7441u) + bias;
+    const float cb1 = byte_magic(cw, 0x7442u) + bias, cr1 = byte_magic(cw, 0x7443u) + bias;
+    const RgbBits p0 = convert(byte_magic(yw, 0x7440u), cb0, cr0), p1 = convert(byte_magic(yw, 0x7441u), cb0, cr0);
+    const RgbBits p2 = convert(byte_magic(yw, 0x7442u), cb1, cr1), p3 = convert(byte_magic(yw, 0x7443u), cb1, cr1);
     uint32_t* o32 = reinterpret_cast<uint32_t*>(o);
-    o32[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
-    o32[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
-    o32[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
-  } else {
-    for (int i = 0; i < 12; ++i)
-      if (x0 + i / 3 < width) o[i] = px[i];
+    o32[0] = pack4(p0.r, p0.g, p0.b, p1.r);
+    o32[1] = pack4(p1.g, p1.b, p2.r, p2.g);
+    o32[2] = pack4(p2.b, p3.r, p3.g, p3.b);
+    return;
   }
+  // ragged / unaligned tail: scalar reference arithmetic
+  for (int i = 0; i < 4 && x0 + i < width; ++i) {
+    const Rgb8 c = nv12_pixel(luma, chroma, pitch, height, x0 + i, y);
+    o[3 * i + 0] = (uint8_t)c.r;
+    o[3 * i + 1] = (uint8_t)c.g;
+    o[3 * i + 2] = (uint8_t)c.b;
+  }
+}
+
+// 16 pixels per thread: one 128-bit luma load, one 128-bit chroma load per contributing chroma row,
+// three 128-bit stores (48 bytes of RGB).  Needs width % 16 == 0 and 16-byte aligned rows.
+__global__ void __launch_bounds__(128)
+nv12_to_rgb16_kernel(PtrBatch lumas, PtrBatch chromas, MutPtrBatch rgbs, size_t pitch, int height, size_t rgb_pitch,
+                     int units_per_row) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (u >= units_per_row) return;
+  const uint8_t* __restrict__ luma = lumas.p[blockIdx.z];
+  const uint8_t* __restrict__ chroma = chromas.p[blockIdx.z];
+  const int yc = y >> 1;
+  const bool avg = (y & 1) && yc < ((height >> 1) - 1);
+  const uint4 yw = ld_stream_u4(luma + (size_t)y * pitch + (size_t)u * 16);
+  uint4 cw = ld_stream_u4(chroma + (size_t)yc * pitch + (size_t)u * 16);
+  if (avg) {
+    const uint4 c2 = ld_stream_u4(chroma + (size_t)(yc + 1) * pitch + (size_t)u * 16);
+    cw = make_uint4(avg4(cw.x, c2.x), avg4(cw.y, c2.y), avg4(cw.z, c2.z), avg4(cw.w, c2.w));
+  }
+  const uint32_t ys[4] = {yw.x, yw.y, yw.z, yw.w}, cs[4] = {cw.x, cw.y, cw.z, cw.w};
+  uint32_t out[12];
+  const float bias = -(kMagic + 128.0f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float cb0 = byte_magic(cs[k], 0x7440u) + bias, cr0 = byte_magic(cs[k], 0x7441u) + bias;
+    const float cb1 = byte_magic(cs[k], 0x7442u) + bias, cr1 = byte_magic(cs[k], 0x7443u) + bias;
+    const RgbBits p0 = convert(byte_magic(ys[k], 0x7440u), cb0, cr0), p1 = convert(byte_magic(ys[k], 0x7441u), cb0, cr0);
+    const RgbBits p2 = convert(byte_magic(ys[k], 0x7442u), cb1, cr1), p3 = convert(byte_magic(ys[k], 0x7443u), cb1, cr1);
+    out[3 * k + 0] = pack4(p0.r, p0.g, p0.b, p1.r);
+    out[3 * k + 1] = pack4(p1.g, p1.b, p2.r, p2.g);
+    out[3 * k + 2] = pack4(p2.b, p3.r, p3.g, p3.b);
+  }
+  uint4* o = reinterpret_cast<uint4*>(rgbs.p[blockIdx.z] + (size_t)y * rgb_pitch + (size_t)u * 48);
+  o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  o[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  o[2] = make_uint4(out[8], out[9], out[10], out[11]);
 }
 
 // Pitched decoder surface -> packed NV12 element (W x H luma rows, then W x H/2 CbCr rows).
@@ -154,8 +216,16 @@ extern "C" int scn_nv12_to_rgb24(const uint8_t* const* host_luma_ptrs,
       r.p[i] = host_rgb_ptrs[i0 + i];
       if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i] | (uintptr_t)r.p[i]) & 3) vec_ok = 0;
     }
-    dim3 grid((unsigned)((quads + 255) / 256), (unsigned)height, (unsigned)cnt);
-    {
+    int vec16 = ((width & 15) == 0) && ((pitch & 15) == 0) && ((rgb_pitch & 15) == 0);
+    for (int i = 0; i < cnt; ++i)
+      if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i] | (uintptr_t)r.p[i]) & 15) vec16 = 0;
+    if (vec16) {
+      const int units = width / 16;
+      dim3 grid((unsigned)((units + 127) / 128), (unsigned)height, (unsigned)cnt);
+      LaunchScope ls("nv12_to_rgb_kernel", st);
+      nv12_to_rgb16_kernel<<<grid, 128, 0, st>>>(l, c, r, pitch, height, rgb_pitch, units);
+    } else {
+      dim3 grid((unsigned)((quads + 255) / 256), (unsigned)height, (unsigned)cnt);
       LaunchScope ls("nv12_to_rgb_kernel", st);
       nv12_to_rgb_kernel<<<grid, 256, 0, st>>>(l, c, r, pitch, width, height, rgb_pitch, quads,
                                              vec_ok);

@@ -22,6 +22,7 @@ for n, h, w, pitch in [(64, 1080, 1920, 2048), (8, 1080, 1920, 1920), (16, 2160,
     for _ in range(10):
         kernels.nv12_hist_resize(surf, w, h, 224, 224, plan)
         kernels.histogram(rgb)
+        kernels.nv12_to_rgb(surf, w, h)
     torch.cuda.synchronize()
     p = cabi.prof_report()
     L.scn_prof_enable(0)
@@ -32,4 +33,6 @@ for n, h, w, pitch in [(64, 1080, 1920, 2048), (8, 1080, 1920, 1920), (16, 2160,
             out["nv12_hist_GBs"] = round(n * h * w * 1.5 / v / 1e6, 1)
         if k.startswith("hist16"):
             out["rgb_hist_GBs"] = round(n * h * w * 3 / v / 1e6, 1)
+        if k.startswith("nv12_to_rgb"):
+            out["nv12_to_rgb_GBs"] = round(n * h * w * 4.5 / v / 1e6, 1)
     print(out)
