@@ -19,7 +19,9 @@ __device__ __forceinline__ uint32_t pack10(float v) {
   return ((uint32_t)v) >> 2;
 }
 
-__device__ __forceinline__ Rgb8 yuv_to_rgb(uint32_t y, uint32_t cb, uint32_t cr) {
+// The arithmetic as the reference writes it (int -> float conversions, clamp, float -> int):
+// kept as the readable statement of what yuv_to_rgb() below must equal.
+__device__ __forceinline__ Rgb8 yuv_to_rgb_plain(uint32_t y, uint32_t cb, uint32_t cr) {
   const float l = (float)(y << 2);
   const float fcb = (float)((int)(cb << 2) - 512);
   const float fcr = (float)((int)(cr << 2) - 512);
@@ -28,6 +30,35 @@ __device__ __forceinline__ Rgb8 yuv_to_rgb(uint32_t y, uint32_t cb, uint32_t cr)
   o.r = pack10(__fmaf_rn(fcr, 1.596f, ly));
   o.g = pack10(__fmaf_rn(fcr, -0.813f, __fmaf_rn(fcb, -0.3918f, ly)));
   o.b = pack10(__fmaf_rn(fcb, 2.0172f, ly));
+  return o;
+}
+
+// Same values without the conversion unit (I2F / F2I issue at a quarter of the FMA rate): the
+// operands enter as 2^23 + byte bit patterns, the matrix runs in a 2^-11 scaled domain (exact:
+// power-of-two scaling commutes with IEEE rounding), fma.sat is the lower clamp, and the 8-bit
+// result is read from the mantissa of fma.rm(x, 512, 2^23).  Bit-identical to yuv_to_rgb_plain for
+// all 2^24 inputs (tests compare every kernel built on it with the oracle).
+__device__ __forceinline__ Rgb8 yuv_to_rgb(uint32_t y, uint32_t cb, uint32_t cr) {
+  constexpr float s = 1.0f / 2048.0f, magic = 8388608.0f, top = 1023.0f * s;
+  constexpr float cy = 4.0f * 1.1644f * s, kr = 4.0f * 1.596f * s, kg1 = 4.0f * -0.3918f * s;
+  constexpr float kg2 = 4.0f * -0.813f * s, kb = 4.0f * 2.0172f * s;
+  const float ym = __uint_as_float(0x4B000000u | y);
+  const float fcb = __uint_as_float(0x4B000000u | cb) - (magic + 128.0f);
+  const float fcr = __uint_as_float(0x4B000000u | cr) - (magic + 128.0f);
+  const float ly = __fmaf_rn(ym, cy, -magic * cy);
+  float r, g, b;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fcr), "f"(kr), "f"(ly));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(g) : "f"(fcr), "f"(kg2), "f"(__fmaf_rn(fcb, kg1, ly)));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(fcb), "f"(kb), "f"(ly));
+  auto u8bits = [&](float x) {
+    float q;
+    asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(q) : "f"(fminf(x, top)), "f"(512.0f), "f"(magic));
+    return __float_as_uint(q) & 0xFFu;
+  };
+  Rgb8 o;
+  o.r = u8bits(r);
+  o.g = u8bits(g);
+  o.b = u8bits(b);
   return o;
 }
 

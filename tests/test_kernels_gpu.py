@@ -200,3 +200,17 @@ def test_launch_counter_counts():
     before = cabi.lib().scn_launch_count()
     kernels.histogram(dev(synth.rand_frame(1, 8, 8)[None]))
     assert cabi.lib().scn_launch_count() > before
+
+
+def test_generic_nv12_paths_small_and_ragged():
+    """Sizes that miss every vector fast path (odd pitch, width % 4 != 0): the scalar conversion used
+    by the generic NV12 histogram / resize kernels and the ragged tails, against the oracle."""
+    for (h, w, pitch) in [(18, 22, 23), (34, 46, 51), (66, 130, 131)]:
+        surf = _surfaces(70, 2, h, w, pitch)
+        rgb = kernels.nv12_to_rgb(dev(surf), w, h).cpu().numpy()
+        hist, res = kernels.nv12_hist_resize(dev(surf), w, h, 16, 12)
+        for i in range(2):
+            want = oracle.nv12_to_rgb(surf[i, :h], surf[i, h:], w)
+            assert (rgb[i] == want).all()
+            assert (hist[i].cpu().numpy() == oracle.hist16(want)).all()
+            assert (res[i].cpu().numpy() == oracle.resize(want, 16, 12)).all()
