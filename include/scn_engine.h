@@ -185,6 +185,14 @@ SCN_ENGINE_API int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const 
 SCN_ENGINE_API int scn_db_save_job(scn_db* db, scn_job* j, const char* table, const int* sinks,
                                    const char* const* column_names, const char* const* type_names, int n_columns,
                                    int job_id);
+/* Saving during the run (reference SaveWorker, one item per task as tasks finish): reserve a one-column
+ * table, point a sink of the job at it, run with out_dir = the database path, commit.  With
+ * keep_rows = 0 the rows of such sinks leave host memory as soon as their item is on disk (they are
+ * then read with scn_db_read_rows, not scn_job_output_row). */
+SCN_ENGINE_API int scn_db_new_table(scn_db* db, const char* table, const char* column_name, int is_video,
+                                    const char* type_name, int job_id); /* -> table id */
+SCN_ENGINE_API int scn_job_set_sink_table(scn_job* j, int sink, int table_id, int keep_rows);
+SCN_ENGINE_API int scn_db_commit_job_table(scn_db* db, int table_id, scn_job* j);
 SCN_ENGINE_API scn_rows* scn_db_read_rows(scn_db* db, const char* table, const char* column, const int64_t* rows,
                                           int64_t n);
 SCN_ENGINE_API int64_t scn_rows_count(const scn_rows* r);

@@ -536,27 +536,48 @@ class Client:
                     else:
                         job.set_stream_args(index[id(node)], args)
             jobs.append(job)
+        bulk_job_id = self._bulk_jobs
+        self._bulk_jobs += 1
+        # with a database the save stage writes every finished task as an item of the output
+        # stream's table and drops the rows from memory (reference SaveWorker / ColumnSink)
+        reserved = []  # (table id, table name, job)
+        if self._db is not None:
+            try:
+                for node in out_nodes:
+                    src_col = node.inputs[0]
+                    type_name = "Histogram" if src_col._col == "histogram" else ""
+                    for j, s in enumerate(node.streams):
+                        if j in skip:
+                            continue
+                        tid = self._db.new_table(s.name(), src_col._col, src_col._is_frame, type_name, bulk_job_id)
+                        reserved.append((tid, s.name(), jobs[job_of[j]]))
+                        jobs[job_of[j]].set_sink_table(index[id(node)], tid, keep_rows=False)
+            except E.EngineError as e:
+                for _, name, _ in reserved:
+                    self._db.delete_table(name)
+                raise ScannerException(str(e)) from e
+            out_dir = self._db.path
         try:
             if jobs:
                 self._engine.run(g, jobs, perf_params.work_packet_size, perf_params.io_packet_size, out_dir)
+            for tid, _, job in reserved:
+                self._db.commit_job_table(tid, job)
         except E.EngineError as e:
+            for _, name, _ in reserved:
+                try:
+                    self._db.delete_table(name)
+                except E.EngineError:
+                    pass
             raise ScannerException(str(e)) from e
-        bulk_job_id = self._bulk_jobs
-        self._bulk_jobs += 1
         for node in out_nodes:
             src_col = node.inputs[0]
             type_name = "Histogram" if src_col._col == "histogram" else ""
             for j, s in enumerate(node.streams):
-                if j in skip:
+                if j in skip or self._db is not None:
                     s._job = None  # served from the stored table
                     continue
                 s._job, s._sink = jobs[job_of[j]], index[id(node)]
                 s._type = type_name or None
-                if self._db is not None:
-                    try:
-                        self._db.save_job(s._job, s.name(), [(s._sink, src_col._col, type_name)], bulk_job_id)
-                    except E.EngineError as e:
-                        raise ScannerException(str(e)) from e
         self._last_graph = g
         return len(jobs)
 

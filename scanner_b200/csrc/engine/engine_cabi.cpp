@@ -300,7 +300,7 @@ static const TaskOutput* locate(scn_job* j, int sink, int64_t row, size_t& idx) 
   const std::vector<i64>& starts = j->j.task_starts;
   if (it == j->j.outputs.end() || starts.size() < 2 || row < 0 || row >= starts.back()) return nullptr;
   const size_t task = (size_t)(std::upper_bound(starts.begin(), starts.end(), row) - starts.begin()) - 1;
-  if (task >= it->second.size()) return nullptr;
+  if (task >= it->second.size() || it->second[task].dropped) return nullptr;
   idx = (size_t)(row - starts[task]);
   const TaskOutput& t = it->second[task];
   return idx < t.sizes.size() ? &t : nullptr;
@@ -492,6 +492,31 @@ int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const char* table) {
       s->index.sample_offsets.back() + s->index.sample_sizes.back() > (u64)n)
     return fail("video descriptor of table " + std::string(table) + " points past the end of " + file);
   return e->impl->add_stream(std::move(s));
+}
+
+int scn_job_set_sink_table(scn_job* j, int sink, int table_id, int keep_rows) {
+  if (!j || table_id < 0) return fail("bad arguments");
+  j->j.sink_tables[sink] = table_id;
+  j->j.keep_rows = keep_rows != 0;
+  return 0;
+}
+
+int scn_db_new_table(scn_db* db, const char* table, const char* column_name, int is_video, const char* type_name,
+                     int job_id) {
+  if (!db || !table || !column_name) return fail("bad arguments");
+  ColumnSpec cs;
+  cs.name = column_name;
+  cs.type = is_video ? proto::Video : proto::Bytes;
+  cs.type_name = type_name ? type_name : "";
+  i32 id = -1;
+  Result r = db->impl->new_table(table, {cs}, job_id, id);
+  return r.success() ? id : fail(r.msg());
+}
+
+int scn_db_commit_job_table(scn_db* db, int table_id, scn_job* j) {
+  if (!db || !j || j->j.task_starts.size() < 1) return fail("bad arguments");
+  std::vector<i64> end_rows(j->j.task_starts.begin() + 1, j->j.task_starts.end());
+  return from_result(db->impl->commit_table(table_id, end_rows));
 }
 
 int scn_db_save_job(scn_db* db, scn_job* j, const char* table, const int* sinks, const char* const* column_names,

@@ -12,6 +12,7 @@
 
 #include "engine_internal.h"
 #include "nvdec.h"
+#include "storage.h"
 #include "scn_kernels.h"
 
 namespace scanner {
@@ -79,6 +80,7 @@ struct Engine::RunState {
   std::mutex err_mu;
   std::string error;
   Profiler profiler;
+  std::unique_ptr<Database> db;  // open when a job saves sinks into tables of out_dir
   std::atomic<i64> frames_decoded{0}, frames_used{0}, frames_native{0};
 
   void fail(const std::string& msg) {
@@ -481,8 +483,44 @@ void Engine::instance_main(Instance* inst) {
       }
       if (rs.failed.load()) break;
 
-      // ---- column files (reference ColumnSink::write, column_sink.cpp:159-195)
-      if (!rs.out_dir.empty()) {
+      // ---- save stage into database tables (reference SaveWorker::feed + ColumnSink::write,
+      // save_worker.cpp:73-151, column_sink.cpp:71-201): one item per task, then the memory goes
+      if (!job.sink_tables.empty()) {
+        for (auto& kv : outs) {
+          auto st = job.sink_tables.find(kv.first);
+          if (st == job.sink_tables.end()) continue;
+          TaskOutput& to = *kv.second;
+          bool video = false;
+          for (size_t i = 0; i < to.sizes.size(); ++i) video = video || to.shapes[4 * i + 3] >= 0;
+          std::vector<u8> flat;
+          ItemColumn ic;
+          if (to.held.empty()) {
+            ic.data = to.data.data();
+            ic.bytes = to.data.size();
+          } else {
+            flat.reserve(to.total_bytes());
+            for (size_t i = 0; i < to.sizes.size(); ++i) flat.insert(flat.end(), to.row(i), to.row(i) + to.sizes[i]);
+            ic.data = flat.data();
+            ic.bytes = flat.size();
+          }
+          ic.sizes = &to.sizes;
+          ic.shapes = &to.shapes;
+          r = rs.db->write_index_item(st->second, t.task, t.row0, t.row1);
+          if (r.success()) r = rs.db->write_item(st->second, 1, t.task, ic, video);
+          if (!r.success()) {
+            rs.fail(r.msg());
+            break;
+          }
+          rs.profiler.increment("io_write", (i64)ic.bytes);
+          if (!job.keep_rows) {
+            to.release();
+            std::vector<u8>().swap(to.data);
+            to.dropped = true;
+          }
+        }
+        if (rs.failed.load()) break;
+      } else if (!rs.out_dir.empty()) {
+        // ---- plain column files (reference ColumnSink::write, column_sink.cpp:159-195)
         const std::string dir = rs.out_dir + "/tables/" + std::to_string(t.job);
         mkdirs(dir);
         auto write_col = [&](i32 col, const std::vector<u64>& sizes, const u8* data, size_t nbytes) {
@@ -625,6 +663,15 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   rs.wps = wps;
   rs.ios = ios;
   rs.out_dir = out_dir;
+  for (Job* jb : jobs)
+    if (!jb->sink_tables.empty() && !rs.db) {
+      if (out_dir.empty()) {
+        RESULT_ERROR(&r, "a job saves into tables but the run has no database directory (out_dir)");
+        return r;
+      }
+      Result dr = Database::open(out_dir, rs.db);
+      if (!dr.success()) return dr;
+    }
   r = graph.analyze(rs.an);
   if (!r.success()) return r;
 

@@ -74,6 +74,7 @@ struct TaskOutput {
   std::vector<i32> shapes;       // 4 per row: h, w, c, frame type (-1 for byte rows)
   std::vector<const u8*> ext;    // per row: non-null = the row lives in a held host block
   Elements held;                 // host elements that keep those blocks alive
+  bool dropped = false;          // payload written to a table and released (sizes/shapes remain)
 
   TaskOutput() = default;
   TaskOutput(const TaskOutput&) = delete;
@@ -89,6 +90,7 @@ struct TaskOutput {
       shapes = std::move(o.shapes);
       ext = std::move(o.ext);
       held = std::move(o.held);
+      dropped = o.dropped;
       o.held.clear();
     }
     return *this;
@@ -114,6 +116,11 @@ struct Job {
   std::vector<i64> task_starts;  // first output row of every task, then total_rows (tasks never
                                  // span slice groups, so they are not all io_packet long)
   std::map<i32, std::vector<TaskOutput>> outputs;  // sink op -> per task
+  // save stage to disk (reference SaveWorker / ColumnSink, one item per task): sink op -> id of a
+  // table reserved with Database::new_table in the database rooted at the run's out_dir.  With
+  // keep_rows == false the rows of such sinks are dropped from memory once their item is written.
+  std::map<i32, i32> sink_tables;
+  bool keep_rows = true;
 };
 
 struct TraceEvent {

@@ -67,6 +67,9 @@ SIGNATURES = {
     "scn_db_table_info": (_I, [_VP, _CP, _c.POINTER(_I64), _CP, _SZ]),
     "scn_db_add_video_stream": (_I64, [_VP, _VP, _CP]),
     "scn_db_save_job": (_I, [_VP, _VP, _CP, _IP, _c.POINTER(_CP), _c.POINTER(_CP), _I, _I]),
+    "scn_db_new_table": (_I, [_VP, _CP, _CP, _I, _CP, _I]),
+    "scn_job_set_sink_table": (_I, [_VP, _I, _I, _I]),
+    "scn_db_commit_job_table": (_I, [_VP, _I, _VP]),
     "scn_db_read_rows": (_VP, [_VP, _CP, _CP, _c.POINTER(_I64), _I64]),
     "scn_rows_count": (_I64, [_VP]),
     "scn_rows_get": (_I, [_VP, _I64, _c.POINTER(_VP), _c.POINTER(_c.c_uint64), _IP]),
@@ -232,6 +235,14 @@ class Database:
 
     def add_video_stream(self, engine, table):
         return check(lib().scn_db_add_video_stream(self._h, engine._h, table.encode()), f"add_video_stream({table})")
+
+    def new_table(self, table, column, is_video=False, type_name="", job_id=-1):
+        """Reserve a one-column table a job will save into while it runs -> table id."""
+        return check(lib().scn_db_new_table(self._h, table.encode(), column.encode(), 1 if is_video else 0,
+                                            (type_name or "").encode(), job_id), f"new_table({table})")
+
+    def commit_job_table(self, table_id, job):
+        check(lib().scn_db_commit_job_table(self._h, table_id, job._h), "commit_job_table")
 
     def save_job(self, job, table, columns, job_id=-1):
         """columns: [(sink op index, column name, type name)] -> table id"""
@@ -427,6 +438,9 @@ class Job:
         check(lib().scn_job_set_group_stream_args(self._h, op, group,
                                                   ctypes.cast(buf, ctypes.c_void_p) if buf else None, len(args)),
               "set_group_stream_args")
+
+    def set_sink_table(self, sink, table_id, keep_rows=False):
+        check(lib().scn_job_set_sink_table(self._h, sink, table_id, 1 if keep_rows else 0), "set_sink_table")
 
     def set_stream_args(self, op, args):
         buf = ctypes.create_string_buffer(args, len(args)) if args else None

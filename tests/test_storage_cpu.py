@@ -262,3 +262,45 @@ def test_foreign_mp4_with_another_codec_is_rejected_by_name(tmp_path):
         db.ingest_video("foreign", path)
     assert db.tables() == []
     db.close()
+
+
+def test_save_stage_writes_items_while_the_job_runs_and_frees_the_rows(tmp_path):
+    """reference SaveWorker/ColumnSink: every finished task becomes one item of the output table; with
+    keep_rows=False the rows are not held in host memory afterwards."""
+    n, h, w = 13, 16, 24
+    frames = np.stack([synth.rand_frame(300 + i, h, w) for i in range(n)])
+    db = E.Database(str(tmp_path / "db"))
+    eng = E.Engine(gpus=[], cpu_instances=2)
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("TestHistogramOracle", [(src, "frame")])
+    rz = g.add_op("TestResizeOracle", [(src, "frame")])
+    s_h, s_r = g.add_sink((hs, "histogram")), g.add_sink((rz, "frame"))
+    j = E.Job()
+    j.bind_source(src, eng.add_raw_frames(frames))
+    j.set_stream_args(rz, protolite.encode(TEST_ARGS["TestSizeArgs"], {"width": 12, "height": 8}))
+    t_h = db.new_table("hists", "histogram", False, "Histogram", job_id=3)
+    t_r = db.new_table("small", "frame", True, "", job_id=3)
+    assert db.tables() == []                      # reserved, not visible until committed
+    eng.run(g, [j], 5, 5)                         # rows kept in memory: the allocator holds them
+    kept = eng.stats()["counters"]["cpu_bytes_live"]
+    j.set_sink_table(s_h, t_h, keep_rows=False)
+    j.set_sink_table(s_r, t_r, keep_rows=False)
+    eng.run(g, [j], 5, 5, db.path)
+    assert eng.stats()["counters"]["cpu_bytes_live"] <= kept   # (process-wide counter: other tests' objects may live)
+    with pytest.raises(E.EngineError):
+        j.output_row(s_h, 0)                      # the rows live in the table now
+    db.commit_job_table(t_h, j)
+    db.commit_job_table(t_r, j)
+    assert sorted(db.tables()) == ["hists", "small"]
+    info = db.table_info("small")
+    assert (info["rows"], info["items"], info["job_id"], info["keyframes"]) == (n, 3, 3, -1)
+    td = parse_ref("TableDescriptor", str(tmp_path / f"db/tables/{t_h}/descriptor.bin"))
+    assert list(td.end_rows) == [5, 10, 13]
+    hist, small = db.read_rows("hists", "histogram"), db.read_rows("small", "frame")
+    for i in range(n):
+        assert hist[i] == oracle.hist16(frames[i]).tobytes()
+        assert (small[i] == oracle.resize(frames[i], 12, 8)).all()
+    assert db.read_rows("hists", "index", [12]) == [struct.pack("<q", 12)]
+    eng.close()
+    db.close()
