@@ -171,8 +171,8 @@ def test_fused_nv12_hist_resize_vs_oracle(h, w, pitch, dh, dw, n):
         assert (res[i] == orr).all()
 
 
-def test_fused_equals_three_pass_composition():
-    h, w, pitch, n = 1080, 1920, 1920, 8
+@pytest.mark.parametrize("h,w,pitch,n", [(1080, 1920, 1920, 8), (2160, 3840, 4096, 3)])
+def test_fused_equals_three_pass_composition(h, w, pitch, n):
     g = torch.Generator(device="cuda").manual_seed(9)
     surf = torch.randint(0, 256, (n, h * 3 // 2, pitch), dtype=torch.uint8, device="cuda", generator=g)
     hist, res = kernels.nv12_hist_resize(surf, w, h, 224, 224)
@@ -214,3 +214,19 @@ def test_generic_nv12_paths_small_and_ragged():
             assert (rgb[i] == want).all()
             assert (hist[i].cpu().numpy() == oracle.hist16(want)).all()
             assert (res[i].cpu().numpy() == oracle.resize(want, 16, 12)).all()
+
+
+def test_4k_blur_then_histogram_properties():
+    """BASELINE configs[2] at full size: every pixel is counted once per channel, the blurred interior
+    equals the oracle on one frame, and Blur -> Histogram equals the histogram of the oracle's blur."""
+    h, w, n = 2160, 3840, 2
+    g = torch.Generator(device="cuda").manual_seed(21)
+    frames = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    blurred = kernels.blur(frames, 3)
+    hist = kernels.histogram(blurred).cpu().numpy()
+    assert (hist.sum(axis=2) == h * w).all()
+    f0 = frames[0].cpu().numpy()
+    want = oracle.blur(f0, 3)
+    got = blurred[0].cpu().numpy()
+    assert (got[1:-1, 1:-1] == want[1:-1, 1:-1]).all() and (got[0] == 0).all() and (got[:, 0] == 0).all()
+    assert (hist[0] == oracle.hist16(got)).all()
