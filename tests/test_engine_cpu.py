@@ -382,3 +382,117 @@ def test_trace_file_has_one_event_per_interval_and_instance_ids(eng, tmp_path):
     run_simple(eng, 10, build, wps=5, ios=10)
     eng.write_trace(path)
     assert json.load(open(path))["traceEvents"] == []
+
+
+def test_random_pipelines_match_a_python_model(eng):
+    """Differential test of the row algebra: random chains of samplers, space ops, element-wise ops and a
+    stencil op over an int64 column, random packet sizes, against a list-based Python model
+    (REPEAT_EDGE windows over the op's own input domain, Gather/Stride/Range/Repeat semantics of
+    reference sampler.cpp:78-454)."""
+    rng = np.random.default_rng(1234)
+    S = protolite.SAMPLER_ARGS
+
+    def random_case():
+        n = int(rng.integers(5, 60))
+        stages, cur = [], n
+        for _ in range(int(rng.integers(1, 5))):
+            kind = rng.choice(["stride", "gather", "range", "repeat", "twice", "affine"])
+            if cur < 2 and kind in ("stride", "gather", "range"):
+                kind = "twice"
+            if kind == "stride":
+                s = int(rng.integers(1, 5))
+                stages.append(("stride", s))
+                cur = (cur + s - 1) // s
+            elif kind == "gather":
+                rows = sorted(set(int(x) for x in rng.integers(0, cur, int(rng.integers(1, cur + 1)))))
+                stages.append(("gather", rows))
+                cur = len(rows)
+            elif kind == "range":
+                a = int(rng.integers(0, cur))
+                b = int(rng.integers(a + 1, cur + 1))
+                stages.append(("range", a, b))
+                cur = b - a
+            elif kind == "repeat":
+                k = int(rng.integers(2, 4))
+                stages.append(("repeat", k))
+                cur *= k
+            elif kind == "twice":
+                stages.append(("twice",))
+            else:
+                stages.append(("affine", int(rng.choice([-3, -2, -1, 1, 2, 3])), int(rng.integers(-50, 50))))
+        if rng.random() < 0.6:
+            stages.append(("window",))
+            if rng.random() < 0.5 and cur >= 2:
+                s = int(rng.integers(1, 4))
+                stages.append(("stride", s))
+        if rng.random() < 0.3:
+            stages.append(("null", int(rng.integers(2, 4))))
+        wps = int(rng.choice([1, 2, 3, 5]))
+        return n, stages, wps, wps * int(rng.integers(1, 4))
+
+    def model(n, stages):
+        vals = list(range(n))
+        for st in stages:
+            if st[0] == "stride":
+                vals = vals[::st[1]]
+            elif st[0] == "gather":
+                vals = [vals[i] for i in st[1]]
+            elif st[0] == "range":
+                vals = vals[st[1]:st[2]]
+            elif st[0] == "repeat":
+                vals = [v for v in vals for _ in range(st[1])]
+            elif st[0] == "null":
+                vals = [x for v in vals for x in [v] + [None] * (st[1] - 1)]
+            elif st[0] == "twice":
+                vals = [v * 2 for v in vals]
+            elif st[0] == "affine":
+                vals = [v * st[1] + st[2] for v in vals]
+            elif st[0] == "window":
+                m = len(vals)
+                vals = [(vals[max(i - 1, 0)], vals[i], vals[min(i + 1, m - 1)]) for i in range(m)]
+        return vals
+
+    for case in range(200):
+        n, stages, wps, ios = random_case()
+        sid = eng.add_bytes(i64_rows(n))
+        g = E.Graph()
+        src = g.add_source(False)
+        j = E.Job()
+        j.bind_source(src, sid)
+        cur = (src, "column")
+        for st in stages:
+            if st[0] in ("stride", "gather", "range"):
+                op = g.add_sample(cur)
+                if st[0] == "stride":
+                    j.set_sampler(op, "Strided", protolite.encode(S["StridedSamplerArgs"], {"stride": st[1]}))
+                elif st[0] == "gather":
+                    j.set_sampler(op, "Gather", protolite.encode(S["GatherSamplerArgs"], {"rows": st[1]}))
+                else:
+                    j.set_sampler(op, "StridedRanges", protolite.encode(
+                        S["StridedRangeSamplerArgs"], {"stride": 1, "starts": [st[1]], "ends": [st[2]]}))
+                cur = (op, cur[1])
+            elif st[0] in ("repeat", "null"):
+                op = g.add_space(cur)
+                name = "SpaceRepeat" if st[0] == "repeat" else "SpaceNull"
+                j.set_sampler(op, name, protolite.encode(S[name + "SamplerArgs"], {"spacing": st[1]}))
+                cur = (op, cur[1])
+            elif st[0] == "twice":
+                cur = (g.add_op("TestTwoOut", [cur]), "twice")
+            elif st[0] == "affine":
+                op = g.add_op("TestAffine", [cur], args=protolite.encode(TEST_ARGS["TestScaleArgs"], {"scale": st[1]}))
+                j.set_stream_args(op, protolite.encode(TEST_ARGS["TestOffsetArgs"], {"offset": st[2]}))
+                cur = (op, "out")
+            elif st[0] == "window":
+                cur = (g.add_op("TestWindow", [cur]), "window")
+        sink = g.add_sink(cur)
+        eng.run(g, [j], wps, ios)
+        want = model(n, stages)
+        assert j.output_rows(sink) == len(want), (case, n, stages, wps, ios)
+        for i, w in enumerate(want):
+            row = j.output_row(sink, i)
+            if w is None:
+                assert row is None, (case, i, stages)
+            elif isinstance(w, tuple):
+                assert struct.unpack("<3q", row) == w, (case, i, n, stages, wps, ios)
+            else:
+                assert struct.unpack("<q", row)[0] == w, (case, i, n, stages, wps, ios)
