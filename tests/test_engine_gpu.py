@@ -365,3 +365,34 @@ def test_single_rank_sharded_flow_equals_direct():
         d = np.abs(flows[i].cpu().numpy() - ref)
         assert np.quantile(d, 0.999) <= 5e-2 and d.mean() <= 1e-3   # uniform-noise frames: ill-conditioned
     e.close()
+
+
+def test_random_gathers_across_gops_both_element_layouts(eng):
+    """Random row subsets (seeks into the middle of GOPs, adjacent GOPs, the last frame) over two clips
+    at once, the sampled frames going both to a frame sink (which keeps the column RGB24 for every
+    consumer) and to Histogram: both equal the oracle on the source planes."""
+    rng = np.random.default_rng(99)
+    clips = [make_clip(50 + k, 45, 96, 128, 7) for k in range(2)]
+    sids = [eng.add_h264(c[0]) for c in clips]
+    g = E.Graph()
+    src = g.add_source(True)
+    smp = g.add_sample((src, "frame"))
+    hs = g.add_op("Histogram", [(smp, "frame")], device=1)
+    s_f = g.add_sink((smp, "frame"))
+    s_h = g.add_sink((hs, "histogram"))
+    for trial in range(4):
+        jobs, picks = [], []
+        for sid in sids:
+            rows = sorted(set(int(x) for x in rng.integers(0, 45, int(rng.integers(1, 20)))) | ({44} if trial == 0 else set()))
+            j = E.Job()
+            j.bind_source(src, sid)
+            j.set_sampler(smp, "Gather", protolite.encode(protolite.SAMPLER_ARGS["GatherSamplerArgs"], {"rows": rows}))
+            jobs.append(j)
+            picks.append(rows)
+        eng.run(g, jobs, 2, 4)
+        for (data, want), rows, j in zip(clips, picks, jobs):
+            assert j.output_rows(s_f) == len(rows)
+            hist = j.output_array(s_h, 192, np.int32).reshape(len(rows), 3, 16)
+            for k, r in enumerate(rows):
+                assert (j.output_row(s_f, k) == want[r]).all(), (trial, r)
+                assert (hist[k] == oracle.hist16(want[r])).all(), (trial, r)
