@@ -304,3 +304,24 @@ def test_save_stage_writes_items_while_the_job_runs_and_frees_the_rows(tmp_path)
     assert db.read_rows("hists", "index", [12]) == [struct.pack("<q", 12)]
     eng.close()
     db.close()
+
+
+@pytest.mark.parametrize("mode,gop", [("pcm", 4), ("skip", 5)])
+def test_ffmpeg_decodes_the_synthetic_streams_to_the_source_luma(tmp_path, mode, gop):
+    """Pin of the H.264 writer (and of the expected values of every decode test): an independent decoder
+    (FFmpeg through cv2, raw output = the luma plane) reproduces the source planes bit for bit -- the
+    streams are lossless (I_PCM) and P_Skip pictures repeat the last key picture."""
+    import cv2
+    n, h, w = 11, 48, 64
+    stream, yuv = make_stream(9, n, h, w, gop, mode)
+    path = str(tmp_path / "s.h264")
+    open(path, "wb").write(stream)
+    cap = cv2.VideoCapture(path)
+    if not cap.set(cv2.CAP_PROP_CONVERT_RGB, 0):
+        pytest.skip("this OpenCV build cannot return undecorated decoder output")
+    for i in range(n):
+        ok, y = cap.read()
+        assert ok and y.shape == (h, w)
+        src = i if mode == "pcm" else i // gop
+        assert (y == yuv[src, :h * w].reshape(h, w)).all(), i
+    assert not cap.read()[0]
