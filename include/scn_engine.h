@@ -125,7 +125,7 @@ SCN_ENGINE_API int scn_engine_run(scn_engine* e, scn_graph* g, scn_job* const* j
 
 /* ---- results ------------------------------------------------------------------------------- */
 SCN_ENGINE_API int64_t scn_job_output_rows(scn_job* j, int sink_op);
-/* Row `row` of sink `sink_op`: *data/*size point into engine-owned host memory valid until the job
+/* Row `row` of sink `sink_op`: *data and *size point into engine-owned host memory valid until the job
  * is destroyed; shape[0..3] = {h, w, c, frame_type} for frame rows, {0,0,0,-1} for byte rows.
  * A null row has size 0. */
 SCN_ENGINE_API int scn_job_output_row(scn_job* j, int sink_op, int64_t row, const uint8_t** data,

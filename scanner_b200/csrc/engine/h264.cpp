@@ -161,7 +161,6 @@ class BitWriter {
   void align_zero() {
     while (nbits_ & 7) bit(0);
   }
-  bool aligned() const { return (nbits_ & 7) == 0; }
   void bytes(const u8* d, size_t n) {  // only when aligned
     buf_.insert(buf_.end(), d, d + n);
     nbits_ += n * 8;
