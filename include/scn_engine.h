@@ -203,6 +203,9 @@ SCN_ENGINE_API void scn_rows_free(scn_rows* r);
  * scn_mp4_demux extracts the first H.264 track as an Annex-B stream (info: width, height, timescale,
  * duration, samples, sync samples); scn_mp4_mux wraps an Annex-B stream into a non-fragmented .mp4.
  * Both return the byte count needed; the output is written only if cap is large enough. */
+/* NamedVideoStream.save_mp4 (reference storage.py): a stored H.264 video table back into an .mp4 file
+ * (fps <= 0: the table's stored time base). */
+SCN_ENGINE_API int scn_db_export_mp4(scn_db* db, const char* table, const char* out_path, int fps_num, int fps_den);
 SCN_ENGINE_API int64_t scn_mp4_mux(const uint8_t* annexb, size_t size, int fps_num, int fps_den, uint8_t* out,
                                    size_t cap);
 SCN_ENGINE_API int64_t scn_mp4_demux(const uint8_t* file, size_t size, uint8_t* out, size_t cap, int64_t info[6]);

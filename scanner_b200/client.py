@@ -297,6 +297,17 @@ class NamedVideoStream:
     def committed(self):
         return True
 
+    def save_mp4(self, output_name, fps=None):
+        """Write the stored video as `<output_name>.mp4` (reference storage.py NamedVideoStream.save_mp4)."""
+        if self._sc._db is None or not self._sc._db.has_table(self._name):
+            raise ScannerException("save_mp4 needs a database-backed video stream")
+        path = output_name if output_name.endswith(".mp4") else output_name + ".mp4"
+        try:
+            self._sc._db.export_mp4(self._name, path, int(fps) if fps else 0, 1 if fps else 0)
+        except E.EngineError as e:
+            raise ScannerException(str(e)) from e
+        return path
+
 
 def _is_mp4(data):
     return len(data) >= 12 and bytes(data[4:8]) in (b"ftyp", b"moov", b"mdat", b"free", b"skip", b"wide", b"styp")

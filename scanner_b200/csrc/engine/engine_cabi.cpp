@@ -612,6 +612,38 @@ int scn_rows_get(const scn_rows* r, int64_t i, const uint8_t** data, uint64_t* s
 }
 void scn_rows_free(scn_rows* r) { delete r; }
 
+int scn_db_export_mp4(scn_db* db, const char* table, const char* out_path, int fps_num, int fps_den) {
+  if (!db || !table || !out_path) return fail("bad arguments");
+  tables::VideoDescriptor vd;
+  std::string file;
+  Result r = db->impl->read_video(table, vd, file);
+  if (!r.success()) return fail(r.msg());
+  H264Index idx;
+  r = index_from_descriptor(vd, idx);
+  if (!r.success()) return fail(r.msg());
+  FILE* f = fopen(file.c_str(), "rb");
+  if (!f) return fail("cannot open " + file);
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<u8> stream((size_t)n);
+  const size_t got = n ? fread(stream.data(), 1, (size_t)n, f) : 0;
+  fclose(f);
+  if (got != (size_t)n) return fail("short read of " + file);
+  if (fps_num <= 0 || fps_den <= 0) {  // default: the stored time base (ticks per second / ticks per frame 1)
+    fps_num = vd.time_base_denom() > 0 ? vd.time_base_denom() : 25;
+    fps_den = vd.time_base_num() > 0 ? vd.time_base_num() : 1;
+  }
+  std::vector<u8> mp4;
+  r = mux_mp4(stream.data(), stream.size(), idx, fps_num, fps_den, mp4);
+  if (!r.success()) return fail(r.msg());
+  FILE* o = fopen(out_path, "wb");
+  if (!o) return fail(std::string("cannot write ") + out_path);
+  const size_t put = fwrite(mp4.data(), 1, mp4.size(), o);
+  fclose(o);
+  return put == mp4.size() ? 0 : fail(std::string("short write to ") + out_path);
+}
+
 // ---- mp4 container helpers (ingest reads .mp4; tests and benchmarks write it)
 int64_t scn_mp4_mux(const uint8_t* annexb, size_t size, int fps_num, int fps_den, uint8_t* out, size_t cap) {
   if (!annexb || !size) return fail("bad arguments");

@@ -74,6 +74,7 @@ SIGNATURES = {
     "scn_rows_count": (_I64, [_VP]),
     "scn_rows_get": (_I, [_VP, _I64, _c.POINTER(_VP), _c.POINTER(_c.c_uint64), _IP]),
     "scn_rows_free": (None, [_VP]),
+    "scn_db_export_mp4": (_I, [_VP, _CP, _CP, _I, _I]),
     "scn_mp4_mux": (_I64, [_VP, _SZ, _I, _I, _VP, _SZ]),
     "scn_mp4_demux": (_I64, [_VP, _SZ, _VP, _SZ, _c.POINTER(_I64)]),
 }
@@ -210,6 +211,10 @@ class Database:
         buf = np.frombuffer(bytes(data), np.uint8)
         check(lib().scn_db_ingest_h264(self._h, table.encode(), buf.ctypes.data, buf.size, fps_num, fps_den),
               f"ingest_h264({table})")
+
+    def export_mp4(self, table, out_path, fps_num=0, fps_den=0):
+        check(lib().scn_db_export_mp4(self._h, table.encode(), os.path.abspath(out_path).encode(), fps_num, fps_den),
+              f"export_mp4({table})")
 
     def has_table(self, table):
         return bool(lib().scn_db_has_table(self._h, table.encode()))

@@ -152,6 +152,12 @@ def test_ingest_videos_from_mp4_and_h264_files(tmp_path):
     assert sorted(c2.table_names()) == ["a", "b"]
     v = sp.NamedVideoStream(c2, "b")       # by name only: bound from the stored descriptor
     assert v.len() == n and v.info()["keyframes"] == 2
+    # export the stored table as .mp4 again: FFmpeg reads it, and it demuxes to the ingested stream
+    out = v.save_mp4(str(tmp_path / "exported"))
+    import cv2
+    cap = cv2.VideoCapture(out)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n and abs(cap.get(cv2.CAP_PROP_FPS) - 25) < 1e-6
+    assert E.mp4_demux(open(out, "rb").read())[0] == stream
     with pytest.raises(sp.ScannerException, match="does not exist"):
         sp.NamedVideoStream(c2, "zzz")
     c2.stop()
