@@ -374,6 +374,57 @@ class NamedStream:
             self._sc._db.delete_table(self._name)
 
 
+class Column:
+    """A stored column (reference scannerpy/column.py): `load()` yields its rows."""
+
+    def __init__(self, table, desc):
+        self._table, self._desc = table, desc
+
+    def name(self):
+        return self._desc["name"]
+
+    def type(self):
+        return self._desc["type"]
+
+    def load(self, ty=None, rows=None):
+        ty = ty or self._desc["type_name"] or None
+        for r in self._table._db.read_rows(self._table._name, self._desc["name"], rows):
+            if ty == "Histogram" and isinstance(r, (bytes, bytearray)):
+                a = np.frombuffer(r, np.int32)
+                yield [a[0:16], a[16:32], a[32:48]]
+            else:
+                yield r
+
+
+class Table:
+    """A stored table (reference scannerpy/table.py): id, name, rows, columns."""
+
+    def __init__(self, db, name):
+        self._db, self._name = db, name
+        self._info = db.table_info(name)
+
+    def id(self):
+        return self._info["id"]
+
+    def name(self):
+        return self._name
+
+    def num_rows(self):
+        return self._info["rows"]
+
+    def column_names(self):
+        return [c["name"] for c in self._info["columns"]]
+
+    def column(self, name):
+        for c in self._info["columns"]:
+            if c["name"] == name:
+                return Column(self, c)
+        raise ScannerException(f"table {self._name} has no column {name}")
+
+    def committed(self):
+        return True
+
+
 class Profile:
     def __init__(self, sc):
         self._sc = sc
@@ -438,6 +489,19 @@ class Client:
 
     def has_table(self, name):
         return self._need_db().has_table(name)
+
+    def table(self, name):
+        if not self._need_db().has_table(name):
+            raise ScannerException(f"table {name} does not exist")
+        return Table(self._db, name)
+
+    def summarize(self):
+        """Text table of the catalogue (reference client.py summarize): name, id, rows, columns."""
+        lines = [f"{'name':<28} {'id':>4} {'rows':>9}  columns"]
+        for n in sorted(self._need_db().tables()):
+            t = Table(self._db, n)
+            lines.append(f"{n:<28} {t.id():>4} {t.num_rows():>9}  {', '.join(t.column_names())}")
+        return "\n".join(lines)
 
     def table_names(self):
         return self._need_db().tables()

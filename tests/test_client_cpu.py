@@ -119,6 +119,10 @@ def test_database_backed_streams_persist_and_cache_modes(sc, tmp_path):
     c1.stop()
 
     c2 = _db_client(tmp_path / "db")          # a later session
+    t = c2.table("ints_scaled")
+    assert t.num_rows() == 30 and t.column_names() == ["index", "out"] and "ints_scaled" in c2.summarize()
+    assert [struct.unpack("<q", r)[0] for r in t.column("out").load(rows=[3])] == [16]
+    assert [struct.unpack("<q", r)[0] for r in t.column("index").load(rows=[29])] == [29]
     again = sp.NamedStream(c2, "ints_scaled")
     assert again.exists() and again.len() == 30
     assert [struct.unpack("<q", r)[0] for r in again.load()] == [5 * i + 1 for i in range(30)]
