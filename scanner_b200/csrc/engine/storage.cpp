@@ -2,6 +2,8 @@
 #include "storage.h"
 
 #include <dirent.h>
+#include <fcntl.h>
+#include <sys/file.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -72,6 +74,26 @@ void remove_tree(const std::string& dir) {
   rmdir(dir.c_str());
 }
 
+// Exclusive advisory lock on <db>/db_metadata.lock for a read-modify-write of the catalogue: several
+// processes (one rank per GPU) may share a database directory; the reference serialises these updates
+// in its single master process.
+class MetaLock {
+ public:
+  explicit MetaLock(const std::string& root) {
+    fd_ = ::open((root + "db_metadata.lock").c_str(), O_CREAT | O_RDWR, 0644);
+    if (fd_ >= 0) flock(fd_, LOCK_EX);
+  }
+  ~MetaLock() {
+    if (fd_ >= 0) {
+      flock(fd_, LOCK_UN);
+      ::close(fd_);
+    }
+  }
+
+ private:
+  int fd_ = -1;
+};
+
 i64 now_seconds() {
   return std::chrono::duration_cast<std::chrono::seconds>(std::chrono::system_clock::now().time_since_epoch())
       .count();
@@ -110,6 +132,12 @@ Result Database::load_meta() {
   return r;
 }
 
+void Database::refresh_meta() {
+  std::string bytes;
+  tables::DatabaseDescriptor fresh;
+  if (read_file(root_ + "db_metadata.bin", bytes) && fresh.ParseFromString(bytes)) meta_ = fresh;
+}
+
 Result Database::save_meta() const {
   Result r = ok();
   const std::string s = meta_.SerializeAsString();
@@ -120,6 +148,7 @@ Result Database::save_meta() const {
 
 std::vector<std::string> Database::table_names() const {
   std::lock_guard<std::mutex> g(mu_);
+  const_cast<Database*>(this)->refresh_meta();
   std::vector<std::string> out;
   for (const auto& t : meta_.tables())
     if (t.committed()) out.push_back(t.name());
@@ -128,6 +157,7 @@ std::vector<std::string> Database::table_names() const {
 
 i32 Database::table_id(const std::string& name) const {
   std::lock_guard<std::mutex> g(mu_);
+  const_cast<Database*>(this)->refresh_meta();
   for (const auto& t : meta_.tables())
     if (t.committed() && t.name() == name) return t.id();
   return -1;
@@ -146,6 +176,8 @@ Result Database::delete_table(const std::string& name) {
   i32 id = -1;
   {
     std::lock_guard<std::mutex> g(mu_);
+    MetaLock file_lock(root_);
+    refresh_meta();
     auto* ts = meta_.mutable_tables();
     for (size_t i = 0; i < ts->size(); ++i)
       if ((*ts)[i].name() == name) {
@@ -167,6 +199,8 @@ Result Database::new_table(const std::string& name, const std::vector<ColumnSpec
                            i32& table_id) {
   Result r = ok();
   std::lock_guard<std::mutex> g(mu_);
+  MetaLock file_lock(root_);
+  refresh_meta();
   for (const auto& t : meta_.tables())
     if (t.name() == name) {
       RESULT_ERROR(&r, "table %s already exists", name.c_str());
@@ -288,10 +322,14 @@ Result Database::commit_table(i32 table_id, const std::vector<i64>& end_rows) {
     RESULT_ERROR(&r, "cannot write the descriptor of table %d: %s", table_id, strerror(errno));
     return r;
   }
-  for (auto& t : *meta_.mutable_tables())
-    if (t.id() == table_id) t.set_committed(true);
-  pending_.erase(it);
-  return save_meta();
+  {
+    MetaLock file_lock(root_);
+    refresh_meta();
+    for (auto& t : *meta_.mutable_tables())
+      if (t.id() == table_id) t.set_committed(true);
+    pending_.erase(it);
+    return save_meta();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

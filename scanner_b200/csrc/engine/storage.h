@@ -77,6 +77,7 @@ class Database {
  private:
   Database() = default;
   Result load_meta();
+  void refresh_meta();  // re-read db_metadata.bin (another process may have changed it)
   Result save_meta() const;
   std::string item_base(i32 table_id, i32 column_id, i32 item_id) const;
 

@@ -325,3 +325,30 @@ def test_ffmpeg_decodes_the_synthetic_streams_to_the_source_luma(tmp_path, mode,
         src = i if mode == "pcm" else i // gop
         assert (y == yuv[src, :h * w].reshape(h, w)).all(), i
     assert not cap.read()[0]
+
+
+def _ingest_many(args):
+    root, prefix, stream = args
+    db = E.Database(root)
+    for i in range(6):
+        db.ingest_h264(f"{prefix}_{i}", stream)
+    names = db.tables()
+    db.close()
+    return len(names)
+
+
+def test_processes_sharing_one_database_do_not_lose_tables(tmp_path):
+    """One rank per GPU may write into the same database directory: catalogue updates are
+    read-modify-write under a file lock (the reference serialises them in its master)."""
+    import multiprocessing as mp
+    stream, _ = make_stream(12, 4, 48, 64, 2)
+    root = str(tmp_path / "db")
+    E.Database(root).close()
+    with mp.get_context("spawn").Pool(3) as pool:
+        pool.map(_ingest_many, [(root, p, stream) for p in ("a", "b", "c")])
+    db = E.Database(root)
+    names = db.tables()
+    assert len(names) == 18 and len({db.table_info(n)["id"] for n in names}) == 18
+    meta = parse_ref("DatabaseDescriptor", os.path.join(root, "db_metadata.bin"))
+    assert meta.next_table_id == 18 and all(t.committed for t in meta.tables)
+    db.close()

@@ -30,6 +30,10 @@ def clip(seed, w, h, frames, gop=30):
     return E.h264_synth(yuv, w, h, gop=gop, non_key="skip", frames=frames)
 
 
+def gpu_list(args):
+    return [args.gpu] if args.ngpus <= 1 else list(range(args.ngpus))
+
+
 def timed(fn, steps, warmup=2):
     for _ in range(warmup):
         fn()
@@ -72,8 +76,8 @@ def config2(args):
     torch.cuda.synchronize()
     prof = {k: v["ms"] / v["launches"] for k, v in cabi.prof_report().items()}
     L.scn_prof_enable(0)
-    clips, frames = 4, 60
-    eng = E.Engine(gpus=[args.gpu], instances_per_gpu=args.instances)
+    clips, frames = 4 * args.ngpus, 60
+    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
     data = [clip(300 + k, w, h, frames) for k in range(2)]
     sids = [eng.add_h264(data[k % 2]) for k in range(clips)]
     graph = E.Graph()
@@ -93,7 +97,7 @@ def config2(args):
     return {"config": "configs[2]: 4K H.264 decode + Blur(3) + Histogram", "kernel_stage": {
         "frames_per_s": n / (ms * 1e-3), "ms_per_16_frames": ms, "alg_bytes_per_frame": alg // n,
         "achieved_GBs": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / PEAK,
-        "kernels_ms": prof}, "e2e": {"frames_per_s": clips * frames / sec, "clips": clips, "frames_per_clip": frames,
+        "kernels_ms": prof}, "e2e": {"frames_per_s": clips * frames / sec, "clips": clips, "frames_per_clip": frames, "n_gpus": args.ngpus,
                                      "bound": "NVDEC (4K: ~4x the pixels of 1080p per picture)"}}
 
 
@@ -104,8 +108,8 @@ def config3(args):
     a = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
     b = torch.roll(a, shifts=(1, 2), dims=(1, 2)).contiguous()
     ms = timed(lambda: kernels.optical_flow(a, b), 5) / n
-    clips, frames = 2, 60
-    eng = E.Engine(gpus=[args.gpu], instances_per_gpu=args.instances)
+    clips, frames = 2 * args.ngpus, 60
+    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
     sids = [eng.add_h264(clip(400 + k, w, h, frames)) for k in range(clips)]
     graph = E.Graph()
     src = graph.add_source(True)
@@ -132,8 +136,8 @@ def config3(args):
 def config4(args):
     """Stride(30) over many 1080p clips, GOP 30: only IDR pictures are needed -- decode-bound."""
     w, h = 1920, 1080
-    clips, frames = 56, 300
-    eng = E.Engine(gpus=[args.gpu], instances_per_gpu=args.instances)
+    clips, frames = 56 * args.ngpus, 300
+    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
     data = [clip(500 + k, w, h, frames) for k in range(2)]
     sids = [eng.add_h264(data[k % 2]) for k in range(clips)]
     graph = E.Graph()
@@ -154,7 +158,7 @@ def config4(args):
     used = clips * (frames // 30)
     return {"config": "configs[4]: Stride(30) Histogram over 1080p clips (GOP 30)", "e2e": {
         "frames_used_per_s": used / sec, "source_frames_covered_per_s": clips * frames / sec, "clips": clips,
-        "frames_per_clip": frames, "frames_decoded_last_run": c["frames_decoded"], "frames_used_last_run": c["frames_used"],
+        "frames_per_clip": frames, "n_gpus": args.ngpus, "frames_decoded_last_run": c["frames_decoded"], "frames_used_last_run": c["frames_used"],
         "bound": "NVDEC: one ~3 MB I_PCM IDR picture per used frame; nothing else of a GOP is fed"}}
 
 
@@ -164,6 +168,7 @@ def main():
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--instances", type=int, default=14)
     ap.add_argument("--only", default="")
+    ap.add_argument("--ngpus", type=int, default=1, help="GPUs driven by ONE engine (tasks sharded over all of them)")
     args = ap.parse_args()
     E.load_stdlib()
     torch.cuda.set_device(args.gpu)
