@@ -76,7 +76,7 @@ def config2(args):
     torch.cuda.synchronize()
     prof = {k: v["ms"] / v["launches"] for k, v in cabi.prof_report().items()}
     L.scn_prof_enable(0)
-    clips, frames = 4 * args.ngpus, 60
+    clips, frames = 4 * args.ngpus * args.clip_mult, 60
     eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
     data = [clip(300 + k, w, h, frames) for k in range(2)]
     sids = [eng.add_h264(data[k % 2]) for k in range(clips)]
@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--gpu", type=int, default=0)
     ap.add_argument("--instances", type=int, default=14)
     ap.add_argument("--only", default="")
+    ap.add_argument("--clip-mult", type=int, default=1, help="multiply the number of clips of the e2e legs")
     ap.add_argument("--ngpus", type=int, default=1, help="GPUs driven by ONE engine (tasks sharded over all of them)")
     args = ap.parse_args()
     E.load_stdlib()
