@@ -312,9 +312,12 @@ def main():
     std = protolite.parse_proto(open(os.path.join(ROOT, "scanner_b200", "csrc", "ops", "stdlib_args.proto")).read())
     e2e_clips, e2e_frames = args.e2e_clips, args.e2e_frames
     if args.instances <= 0:
-        # every instance is a host thread that spends most of its time blocked in the NVDEC driver;
-        # 14 per GPU saturate the 7 engines, but the ranks of one box share the host's CPU quota
-        args.instances = max(2, min(14, 2 * usable_cores() // world))
+        # one decode session per NVDEC engine (7 on a B200) is the measured optimum -- 7: 8.3-8.8 K
+        # frames/s, 8: 6.3 K, 14: 7.5-8.0 K, 21-42: 6.1-7.0 K (profiles/r01_e2e_engine_scaling.md): an
+        # extra session shares an engine and the slowest pair sets the wall time -- but never more
+        # threads than the rank's share of the host cores can keep fed
+        engines = E.nvdec_caps(local_rank).get("engines", 7) or 7
+        args.instances = max(2, min(engines, 2 * usable_cores() // world))
     eng = E.Engine(gpus=[local_rank], instances_per_gpu=args.instances)
     uniq = [make_clip_bytes(2000 + 16 * rank + i, e2e_frames) for i in range(min(e2e_clips, 4))]
     sids = [eng.add_h264(uniq[i % len(uniq)]) for i in range(e2e_clips)]

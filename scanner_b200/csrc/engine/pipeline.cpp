@@ -736,9 +736,16 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   std::vector<std::unique_ptr<Instance>> instances;
   i32 node = 0;
   if (!gpu_ids_.empty()) {
-    const i32 per = instances_per_gpu_ > 0 ? instances_per_gpu_ : 4;
-    for (i32 g : gpu_ids_)
+    for (i32 g : gpu_ids_) {
+      // default: one pipeline instance (= one decode session) per NVDEC engine of the GPU -- more
+      // sessions than engines share an engine and the slowest pair sets the wall time
+      i32 per = instances_per_gpu_;
+      if (per <= 0) {
+        const NvdecCaps& caps = nvdec_caps(g);
+        per = caps.available && caps.num_engines > 0 ? caps.num_engines : 4;
+      }
       for (i32 i = 0; i < per; ++i) instances.emplace_back(new Instance{this, g, node++, {}});
+    }
   } else {
     const i32 n = cpu_instances_ > 0 ? cpu_instances_ : 1;
     for (i32 i = 0; i < n; ++i) instances.emplace_back(new Instance{this, -1, node++, {}});

@@ -30,6 +30,13 @@ def clip(seed, w, h, frames, gop=30):
     return E.h264_synth(yuv, w, h, gop=gop, non_key="skip", frames=frames)
 
 
+def inst(args, tuned):
+    """pipeline instances per GPU: --instances, else the value tuned for the config (the reference's
+    pipeline_instances_per_node knob): P_Skip-heavy 1080p decode is best at one session per NVDEC
+    engine (7), IDR-heavy or 4K decode at two (14); see profiles/r01_configs.md."""
+    return args.instances if args.instances > 0 else tuned
+
+
 def gpu_list(args):
     return [args.gpu] if args.ngpus <= 1 else list(range(args.ngpus))
 
@@ -77,7 +84,7 @@ def config2(args):
     prof = {k: v["ms"] / v["launches"] for k, v in cabi.prof_report().items()}
     L.scn_prof_enable(0)
     clips, frames = 4 * args.ngpus * args.clip_mult, 60
-    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
+    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=inst(args, 14))
     data = [clip(300 + k, w, h, frames) for k in range(2)]
     sids = [eng.add_h264(data[k % 2]) for k in range(clips)]
     graph = E.Graph()
@@ -109,7 +116,7 @@ def config3(args):
     b = torch.roll(a, shifts=(1, 2), dims=(1, 2)).contiguous()
     ms = timed(lambda: kernels.optical_flow(a, b), 5) / n
     clips, frames = 2 * args.ngpus, 60
-    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
+    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=inst(args, 7))
     sids = [eng.add_h264(clip(400 + k, w, h, frames)) for k in range(clips)]
     graph = E.Graph()
     src = graph.add_source(True)
@@ -137,7 +144,7 @@ def config4(args):
     """Stride(30) over many 1080p clips, GOP 30: only IDR pictures are needed -- decode-bound."""
     w, h = 1920, 1080
     clips, frames = 56 * args.ngpus, 300
-    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=args.instances)
+    eng = E.Engine(gpus=gpu_list(args), instances_per_gpu=inst(args, 14))
     data = [clip(500 + k, w, h, frames) for k in range(2)]
     sids = [eng.add_h264(data[k % 2]) for k in range(clips)]
     graph = E.Graph()
@@ -166,7 +173,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--gpu", type=int, default=0)
-    ap.add_argument("--instances", type=int, default=14)
+    ap.add_argument("--instances", type=int, default=0, help="pipeline instances per GPU (0: one per NVDEC engine)")
     ap.add_argument("--only", default="")
     ap.add_argument("--clip-mult", type=int, default=1, help="multiply the number of clips of the e2e legs")
     ap.add_argument("--ngpus", type=int, default=1, help="GPUs driven by ONE engine (tasks sharded over all of them)")
