@@ -230,7 +230,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=256,
+                    help="surfaces per step (kernels take 64 per launch: a step of 256 is 4 launches per kernel)")
     ap.add_argument("--e2e-clips", type=int, default=28)
     ap.add_argument("--e2e-frames", type=int, default=120)
     ap.add_argument("--instances", type=int, default=0,
@@ -363,12 +364,13 @@ def main():
         roof = None
         if kname:
             per_launch_s = prof[kname]["ms"] * 1e-3 / prof[kname]["launches"]
-            alg = (B_ALG_HIST_NV12 if kname.startswith("nv12_hist") else B_ALG_FUSED) * B
+            per_launch = min(B, 64)  # SCN_MAX_PTRS surfaces per launch
+            alg = (B_ALG_HIST_NV12 if kname.startswith("nv12_hist") else B_ALG_FUSED) * per_launch
             ach = alg / per_launch_s / 1e9
             roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "peak_kind": peak_kind + " (burst copy, MEASURED_PEAKS.json)",
                     "alg_bytes_per_launch": alg, "ms_per_launch": per_launch_s * 1e3,
-                    "traffic": NCU_DRAM_BYTES.get(kname) if B == 64 else None,
+                    "traffic": NCU_DRAM_BYTES.get(kname) if B % 64 == 0 else None,
                     "traffic_source": "dram__bytes_read+write of one ncu --set full capture of this launch "
                                       "shape (profiles/r01_nv12_hist_csa_v3.md)",
                     "launch_mode": "kernels timed one at a time; in the value leg Resize overlaps Histogram "
