@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256,
                     help="surfaces per step (kernels take 64 per launch: a step of 256 is 4 launches per kernel)")
-    ap.add_argument("--e2e-clips", type=int, default=28)
+    ap.add_argument("--e2e-clips", type=int, default=56)
     ap.add_argument("--e2e-frames", type=int, default=120)
     ap.add_argument("--instances", type=int, default=0,
                     help="pipeline instances per GPU for the e2e leg (0 = 14 capped by 2 x usable host cores / ranks)")
