@@ -352,3 +352,82 @@ def test_processes_sharing_one_database_do_not_lose_tables(tmp_path):
     meta = parse_ref("DatabaseDescriptor", os.path.join(root, "db_metadata.bin"))
     assert meta.next_table_id == 18 and all(t.committed for t in meta.tables)
     db.close()
+
+
+# ---- re-layout of an .mp4 in Python: the shapes other muxers produce (several chunks, 64-bit chunk
+# offsets, moov in front of mdat = "faststart"), to exercise the demuxer's table walking
+def _boxes(buf, start, end):
+    out, off = [], start
+    while off + 8 <= end:
+        size = struct.unpack(">I", buf[off:off + 4])[0]
+        hdr = 8
+        if size == 1:
+            size, hdr = struct.unpack(">Q", buf[off + 8:off + 16])[0], 16
+        if size < hdr or off + size > end:
+            break
+        out.append((buf[off + 4:off + 8], off, hdr, size))
+        off += size
+    return out
+
+
+def _box(kind, payload):
+    return struct.pack(">I", len(payload) + 8) + kind + payload
+
+
+def _relayout(mp4, chunk_sizes, use_co64, faststart):
+    """-> new file bytes with the samples grouped into chunks of chunk_sizes samples."""
+    top = {k: (o, h, s) for k, o, h, s in _boxes(mp4, 0, len(mp4))}
+    ftyp = mp4[top[b"ftyp"][0]:top[b"ftyp"][0] + top[b"ftyp"][2]]
+    mo, mh, ms = top[b"mdat"]
+    mdat_payload = mp4[mo + mh:mo + ms]
+    moov_o, moov_h, moov_s = top[b"moov"]
+    i = mp4.find(b"stsz", moov_o)
+    n = struct.unpack(">I", mp4[i + 12:i + 16])[0]
+    sizes = struct.unpack(f">{n}I", mp4[i + 16:i + 16 + 4 * n])
+    assert sum(chunk_sizes) == n
+
+    def table(offsets):
+        return _box(b"co64" if use_co64 else b"stco", struct.pack(">II", 0, len(offsets)) +
+                    b"".join(struct.pack(">Q" if use_co64 else ">I", o) for o in offsets))
+
+    def rebuild(off, hdr, size, chunk_table):
+        kind = mp4[off + 4:off + 8]
+        if kind in (b"moov", b"trak", b"mdia", b"minf", b"stbl"):
+            return _box(kind, b"".join(rebuild(o, h, sz, chunk_table) for _, o, h, sz in _boxes(mp4, off + hdr, off + size)))
+        if kind == b"stsc":
+            runs, prev = [], None
+            for c, cnt in enumerate(chunk_sizes):
+                if cnt != prev:
+                    runs.append((c + 1, cnt, 1))
+                    prev = cnt
+            return _box(b"stsc", struct.pack(">II", 0, len(runs)) + b"".join(struct.pack(">III", *r) for r in runs))
+        if kind in (b"stco", b"co64"):
+            return chunk_table
+        return mp4[off:off + size]
+
+    moov_len = len(rebuild(moov_o, moov_h, moov_s, table([0] * len(chunk_sizes))))
+    pos, s, offs = len(ftyp) + (moov_len if faststart else 0) + 8, 0, []
+    for c in chunk_sizes:
+        offs.append(pos)
+        pos += sum(sizes[s:s + c])
+        s += c
+    moov = rebuild(moov_o, moov_h, moov_s, table(offs))
+    assert len(moov) == moov_len
+    mdat = struct.pack(">I", len(mdat_payload) + 8) + b"mdat" + mdat_payload
+    return ftyp + (moov + mdat if faststart else mdat + moov)
+
+
+@pytest.mark.parametrize("chunks,co64,faststart", [([5, 5, 2], False, False), ([1] * 12, True, False),
+                                                   ([4, 4, 4], False, True), ([7, 3, 1, 1], True, True)])
+def test_demuxer_walks_the_chunk_tables_other_muxers_write(tmp_path, chunks, co64, faststart):
+    stream, _ = make_stream(13, 12, 48, 64, 4)
+    variant = _relayout(E.mp4_mux(stream, 25, 1), chunks, co64, faststart)
+    back, info = E.mp4_demux(variant)
+    assert info["samples"] == 12 and info["sync_samples"] == 3 and back == stream
+    path = str(tmp_path / "v.mp4")
+    open(path, "wb").write(variant)
+    frames = cv2_frames(path)                      # FFmpeg agrees that the re-laid-out file is valid
+    raw = str(tmp_path / "v.h264")
+    open(raw, "wb").write(stream)
+    want = cv2_frames(raw)
+    assert len(frames) == 12 and all((a == b).all() for a, b in zip(frames, want))
