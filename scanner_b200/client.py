@@ -249,6 +249,7 @@ class NamedVideoStream:
 
     def __init__(self, sc, name, path=None, data=None, frames=None, inplace=False):
         self._sc, self._name = sc, name
+        self._job, self._sink, self._type, self._sid = None, None, None, None  # output role (see NamedStream)
         db = sc._db
         if name in sc._streams and path is None and data is None and frames is None:
             self._sid = sc._streams[name]
@@ -258,7 +259,7 @@ class NamedVideoStream:
         elif db is not None:
             if not db.has_table(name):
                 if path is None and data is None:
-                    raise ScannerException(f"video table {name} does not exist and no path was given")
+                    return  # not stored yet: usable as the target of an Output (frames are stored RAW)
                 try:
                     if path is not None:
                         db.ingest_video(name, path)
@@ -271,7 +272,7 @@ class NamedVideoStream:
         else:
             if data is None:
                 if path is None:
-                    raise ScannerException(f"stream {name} is not known to this client")
+                    return  # target of an Output
                 with open(path, "rb") as f:
                     data = f.read()
             try:
@@ -285,17 +286,41 @@ class NamedVideoStream:
     def name(self):
         return self._name
 
+    def _stored(self):
+        db = self._sc._db
+        return db is not None and db.has_table(self._name)
+
+    def _bind(self):
+        """stream id for use as an input; a video written by an earlier job binds lazily"""
+        if self._sid is None:
+            db = self._sc._db
+            if db is not None and db.has_table(self._name) and db.table_info(self._name)["keyframes"] >= 0:
+                self._sid = db.add_video_stream(self._sc._engine, self._name)
+                self._sc._streams[self._name] = self._sid
+            else:
+                raise ScannerException(f"video stream {self._name} does not exist (no table, no path, not written yet)")
+        return self._sid
+
     def len(self):
-        return self._sc._engine.stream_rows(self._sid)
+        if self._sid is None and (self._job is not None or self._stored()):
+            return NamedStream.len(self)
+        return self._sc._engine.stream_rows(self._bind())
 
     def info(self):
-        return self._sc._engine.stream_info(self._sid)
+        return self._sc._engine.stream_info(self._bind())
 
     def exists(self):
-        return True
+        return self._sid is not None or self._job is not None or self._stored()
 
-    def committed(self):
-        return True
+    committed = exists
+
+    def load(self, ty=None, rows=None):
+        """Frames of a video written by a job (stored uncompressed); an ingested H.264 table is decoded
+        through a job, not loaded."""
+        return NamedStream.load(self, ty, rows)
+
+    def delete(self, sc=None):
+        NamedStream.delete(self, sc)
 
     def save_mp4(self, output_name, fps=None):
         """Write the stored video as `<output_name>.mp4` (reference storage.py NamedVideoStream.save_mp4)."""
@@ -592,7 +617,8 @@ class Client:
             job = E.Job()
             for node in order:
                 if node.kind == "input":
-                    job.bind_source(index[id(node)], node.streams[j]._sid)
+                    st = node.streams[j]
+                    job.bind_source(index[id(node)], st._bind() if isinstance(st, NamedVideoStream) else st._sid)
                 elif node.kind in ("sample", "space"):
                     args = node.per_stream[j if len(node.per_stream) > 1 else 0]
                     if isinstance(args, SliceList):

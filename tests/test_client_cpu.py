@@ -162,8 +162,10 @@ def test_ingest_videos_from_mp4_and_h264_files(tmp_path):
     cap = cv2.VideoCapture(out)
     assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n and abs(cap.get(cv2.CAP_PROP_FPS) - 25) < 1e-6
     assert E.mp4_demux(open(out, "rb").read())[0] == stream
+    missing = sp.NamedVideoStream(c2, "zzz")      # allowed: it may become the target of an Output
+    assert not missing.exists()
     with pytest.raises(sp.ScannerException, match="does not exist"):
-        sp.NamedVideoStream(c2, "zzz")
+        missing.len()
     c2.stop()
 
 
@@ -249,3 +251,24 @@ def test_slice_errors(sc):
     with pytest.raises(sp.ScannerException, match="3 samplers but there are 2 slice groups"):
         bad = sc.streams.Range(sliced, ranges=[sp.SliceList([{"start": 0, "end": 2}] * 3)])
         sc.run(sc.io.Output(sc.streams.Unslice(bad), [sp.NamedStream(sc, "e4")]), sp.PerfParams.manual(2, 2))
+
+
+def test_frame_outputs_into_a_named_video_stream(sc, tmp_path):
+    """An Output may target a NamedVideoStream (reference storage.py): frames are stored (uncompressed --
+    there is no encoder here) and load() yields them, in memory and from the database."""
+    frames = np.stack([synth.rand_frame(400 + i, 24, 32) for i in range(7)])
+    for client in (sc, _db_client(tmp_path / "db")):
+        if "TestResizeOracle" not in client._op_protos:
+            from scanner_b200 import protolite
+            msgs = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
+            client._op_protos["TestResizeOracle"] = {"stream": msgs["TestSizeArgs"]}
+        vin = sp.NamedVideoStream(client, "vs_in", frames=frames)
+        small = client.ops.TestResizeOracle(frame=client.io.Input([vin]), width=[16], height=[12])
+        vout = sp.NamedVideoStream(client, "vs_out")
+        assert not vout.exists()
+        client.run(client.io.Output(small, [vout]), sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)
+        assert vout.exists() and vout.len() == 7
+        for i, f in enumerate(vout.load()):
+            assert (f == oracle.resize(frames[i], 16, 12)).all()
+        if client is not sc:
+            client.stop()
