@@ -756,6 +756,43 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
 
   rs.profiler.keep_records(trace_);
   for (size_t i = 0; i < instances.size(); ++i) instances[i]->index = (i32)i;
+
+  // Decode sessions that do not exist yet are created here, one after the other and before any
+  // instance decodes, by pushing the first IDR of the job's first video through them: the driver
+  // places a session on an NVDEC engine when its decoder is created, and sessions created by the
+  // instance threads while others already decode sometimes end up two to an engine (one engine
+  // idle, end-to-end 6.7 K instead of 8.6 K frames/s).  SCN_NVDEC_PRIME=0 disables it.
+  {
+    const char* pe = getenv("SCN_NVDEC_PRIME");
+    const bool prime = !(pe && pe[0] == '0');
+    for (size_t i = 0; prime && i < instances.size() && !jobs.empty(); ++i) {
+      Instance& in = *instances[i];
+      if (in.gpu_id < 0 || !cuda_available()) continue;
+      Slot& slot = *slots_[(size_t)in.node_id];
+      ScopedDevice sd(in.gpu_id);
+      if (slot.gpu_id != in.gpu_id || !slot.stream) {
+        slot.sessions.clear();
+        if (slot.stream) cudaStreamDestroy(slot.stream);
+        slot.stream = nullptr;
+        if (cudaStreamCreateWithFlags(&slot.stream, cudaStreamNonBlocking) != cudaSuccess) break;
+        slot.gpu_id = in.gpu_id;
+      }
+      for (auto& kv : jobs[0]->source_streams) {
+        InputStream* st = stream(kv.second);
+        if (!st || st->kind != InputStream::H264 || st->index.frames() == 0 || slot.sessions.count(kv.first)) continue;
+        std::unique_ptr<NvdecSession> sess(new NvdecSession(in.gpu_id, slot.stream));
+        if (!sess->init().success()) continue;
+        const std::vector<u64> offs(st->index.sample_offsets.begin(), st->index.sample_offsets.begin() + 1);
+        const std::vector<u64> szs(st->index.sample_sizes.begin(), st->index.sample_sizes.begin() + 1);
+        Result pr = sess->begin_interval(st->encoded.data(), offs, szs, st->index.metadata_packets, {0}, 0,
+                                         [](i64, const Nv12Surface&) {});
+        if (pr.success()) pr = sess->advance(1);
+        if (pr.success()) pr = sess->end_interval();
+        sess->drain();
+        if (pr.success()) slot.sessions[kv.first] = std::move(sess);
+      }
+    }
+  }
   const auto t0 = std::chrono::steady_clock::now();
   for (auto& inst : instances) inst->th = std::thread([this, p = inst.get()] { instance_main(p); });
   for (auto& inst : instances) inst->th.join();
