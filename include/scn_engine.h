@@ -63,6 +63,10 @@ SCN_ENGINE_API int64_t scn_stream_add_bytes(scn_engine* e, const uint8_t* data, 
 SCN_ENGINE_API int64_t scn_stream_rows(scn_engine* e, int64_t stream);
 /* info[0..5] = is_video, width, height, channels, keyframes, encoded_bytes */
 SCN_ENGINE_API int scn_stream_info(scn_engine* e, int64_t stream, int64_t info[6]);
+/* 1 if the H.264 stream's SPS allows display order to differ from coding order (B pictures): the
+ * decode stage then feeds a GOP past the last wanted picture until that picture is displayed.
+ * 0 for POC type 2 streams, for a VUI with max_num_reorder_frames == 0, and for non-H.264. */
+SCN_ENGINE_API int scn_stream_may_reorder(scn_engine* e, int64_t stream);
 SCN_ENGINE_API int scn_stream_remove(scn_engine* e, int64_t stream);
 
 /* The decode stage on its own: `n` ascending frame indices of an H.264 stream -> dense RGB24 frames
@@ -148,7 +152,10 @@ SCN_ENGINE_API int scn_engine_stats_json(scn_engine* e, char* host_buf, size_t c
 /* Encodes `frames` I420 pictures (planes at yuv + f*(w*h*3/2): Y, U, V) as an Annex-B stream of
  * I_PCM macroblocks, IDR every `gop` frames; non_key_mode 0 = P slices of I_PCM macroblocks
  * (yuv holds `frames` pictures), 1 = P_Skip pictures that repeat the last key picture (yuv holds
- * only the ceil(frames/gop) key pictures, consecutively).  Returns the stream size, or the required size if cap is too
+ * only the ceil(frames/gop) key pictures, consecutively), 2 = Main profile with B pictures: the odd
+ * positions of a GOP that have a later anchor in it are non-reference B_Skip pictures, coded after
+ * that anchor and decoding to (anchor_before + anchor_after + 1) >> 1; yuv holds `frames` pictures
+ * of which only the anchors are read.  Returns the stream size, or the required size if cap is too
  * small (nothing written then). */
 SCN_ENGINE_API int64_t scn_h264_synth(const uint8_t* yuv, int width, int height, int64_t frames, int gop,
                                       int non_key_mode, uint8_t* out, size_t cap);

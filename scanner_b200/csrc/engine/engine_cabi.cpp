@@ -143,6 +143,11 @@ int scn_stream_info(scn_engine* e, int64_t id, int64_t info[6]) {
   }
   return 0;
 }
+int scn_stream_may_reorder(scn_engine* e, int64_t id) {
+  InputStream* s = e ? e->impl->stream(id) : nullptr;
+  if (!s) return fail("unknown stream");
+  return s->kind == InputStream::H264 && s->index.may_reorder ? 1 : 0;
+}
 int scn_stream_remove(scn_engine* e, int64_t id) { return e && e->impl->remove_stream(id) ? 0 : fail("unknown stream"); }
 
 int scn_engine_decode_to_device(scn_engine* e, int64_t stream, const int64_t* rows, int64_t n, int gpu_id,
@@ -374,7 +379,8 @@ int64_t scn_h264_synth(const uint8_t* yuv, int width, int height, int64_t frames
   const size_t ysz = (size_t)width * height, csz = ysz / 4, fsz = ysz + 2 * csz;
   std::vector<u8> stream;
   stream.reserve((size_t)frames * (fsz + fsz / 64 + 4096));
-  write_ipcm_stream(width, height, frames, gop, non_key_mode == 1 ? SynthNonKey::Skip : SynthNonKey::Pcm,
+  if (non_key_mode < 0 || non_key_mode > 2) return fail("non_key_mode must be 0 (pcm), 1 (skip) or 2 (bidir)");
+  write_ipcm_stream(width, height, frames, gop, (SynthNonKey)non_key_mode,
                     [&](i64 f, u8* y, u8* u, u8* v) {
                       // skip mode: only key pictures carry content, yuv holds one per GOP
                       const u8* src = yuv + (size_t)(non_key_mode == 1 ? f / (gop < 1 ? 1 : gop) : f) * fsz;

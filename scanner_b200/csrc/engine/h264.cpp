@@ -87,6 +87,70 @@ void skip_scaling_list(BitReader& br, int n) {
   }
 }
 
+void skip_hrd(BitReader& br) {
+  const u32 cpb = br.ue() + 1;
+  br.u(4);
+  br.u(4);
+  for (u32 i = 0; i < cpb && br.ok(); ++i) {
+    br.ue();
+    br.ue();
+    br.u(1);
+  }
+  br.u(5);
+  br.u(5);
+  br.u(5);
+  br.u(5);
+}
+
+// VUI (E.1.1) up to bitstream_restriction; reorder = max_num_reorder_frames, or -1 if not coded.
+bool parse_vui_reorder(BitReader& br, i64& reorder) {
+  reorder = -1;
+  if (br.u(1)) {                          // aspect_ratio_info_present_flag
+    if (br.u(8) == 255) {                 // Extended_SAR
+      br.u(16);
+      br.u(16);
+    }
+  }
+  if (br.u(1)) br.u(1);                   // overscan
+  if (br.u(1)) {                          // video_signal_type
+    br.u(3);
+    br.u(1);
+    if (br.u(1)) {
+      br.u(8);
+      br.u(8);
+      br.u(8);
+    }
+  }
+  if (br.u(1)) {                          // chroma_loc_info
+    br.ue();
+    br.ue();
+  }
+  if (br.u(1)) {                          // timing_info
+    br.u(32);
+    br.u(32);
+    br.u(1);
+  }
+  const u32 nal_hrd = br.u(1);
+  if (nal_hrd) skip_hrd(br);
+  const u32 vcl_hrd = br.u(1);
+  if (vcl_hrd) skip_hrd(br);
+  if (nal_hrd || vcl_hrd) br.u(1);        // low_delay_hrd_flag
+  br.u(1);                                // pic_struct_present_flag
+  if (!br.ok()) return false;
+  if (br.u(1)) {                          // bitstream_restriction_flag
+    br.u(1);
+    br.ue();
+    br.ue();
+    br.ue();
+    br.ue();
+    const u32 r = br.ue();                // max_num_reorder_frames
+    br.ue();                              // max_dec_frame_buffering
+    if (!br.ok()) return false;
+    reorder = r;
+  }
+  return br.ok();
+}
+
 bool parse_sps(const u8* d, size_t n, H264Index& out) {
   BitReader br(d, n);
   const u32 profile = br.u(8);
@@ -133,6 +197,14 @@ bool parse_sps(const u8* d, size_t n, H264Index& out) {
     cb = br.ue();
   }
   if (!br.ok()) return false;
+  // Can pictures leave the decoder in another order than they enter it?  Not with POC type 2
+  // (output order == decoding order, 8.2.1.3); otherwise only a VUI bitstream_restriction with
+  // max_num_reorder_frames == 0 rules it out.
+  out.may_reorder = poc_type != 2;
+  if (br.u(1) && out.may_reorder) {  // vui_parameters_present_flag
+    i64 reorder = -1;
+    if (parse_vui_reorder(br, reorder) && reorder == 0) out.may_reorder = false;
+  }
   out.coded_width = (i32)(w_mbs * 16);
   out.coded_height = (i32)((2 - frame_mbs_only) * h_units * 16);
   const u32 sub_w = (chroma_format_idc == 1 || chroma_format_idc == 2) ? 2 : 1;
@@ -296,17 +368,24 @@ void write_ipcm_stream(i32 width, i32 height, i64 frames, i32 gop, SynthNonKey n
   const i32 wmb = (width + 15) / 16, hmb = (height + 15) / 16;
   const i32 cw = wmb * 16, ch = hmb * 16;
   if (gop < 1) gop = 1;
+  const bool bidir = non_key == SynthNonKey::Bidir;
 
   std::vector<u8> sps, pps;
   {
     BitWriter b;
-    b.u(8, 66);    // profile_idc: Baseline
-    b.u(8, 0xC0);  // constraint_set0/1
+    b.u(8, bidir ? 77 : 66);      // profile_idc: Baseline, or Main when there are B pictures
+    b.u(8, bidir ? 0x40 : 0xC0);  // constraint_set0/1
     b.u(8, 51);    // level_idc 5.1 (I_PCM bitrates are far above the level limits anyway)
     b.ue(0);       // seq_parameter_set_id
     b.ue(0);       // log2_max_frame_num_minus4 -> MaxFrameNum 16
-    b.ue(2);       // pic_order_cnt_type 2: output order == decode order
-    b.ue(1);       // max_num_ref_frames
+    if (bidir) {
+      b.ue(0);     // pic_order_cnt_type 0: POC lsb in every slice header
+      b.ue(4);     // log2_max_pic_order_cnt_lsb_minus4 -> 8 bits
+      b.ue(2);     // max_num_ref_frames: the two anchors around a B picture
+    } else {
+      b.ue(2);     // pic_order_cnt_type 2: output order == decode order
+      b.ue(1);     // max_num_ref_frames
+    }
     b.u(1, 0);     // gaps_in_frame_num_value_allowed_flag
     b.ue(wmb - 1);
     b.ue(hmb - 1);
@@ -348,34 +427,62 @@ void write_ipcm_stream(i32 width, i32 height, i64 frames, i32 gop, SynthNonKey n
   std::vector<u8> y((size_t)cw * ch), u((size_t)(cw / 2) * (ch / 2)), v(u.size());
   std::vector<u8> ysrc((size_t)width * height), usrc((size_t)(width / 2) * (height / 2)), vsrc(usrc.size());
   u32 idr_id = 0;
-  for (i64 f = 0; f < frames; ++f) {
+  // Coding order.  Bidir: inside a GOP of L pictures the odd display positions that have a later
+  // anchor in the same GOP are non-reference B pictures, coded after that anchor (I0 P2 B1 P4 B3 ..).
+  std::vector<i64> order;
+  order.reserve((size_t)frames);
+  for (i64 g0 = 0; g0 < frames; g0 += gop) {
+    const i64 len = std::min<i64>(gop, frames - g0);
+    if (!bidir) {
+      for (i64 k = 0; k < len; ++k) order.push_back(g0 + k);
+      continue;
+    }
+    order.push_back(g0);
+    for (i64 k = 1; k < len; k += 2) {
+      if (k + 1 < len) order.push_back(g0 + k + 1);
+      order.push_back(g0 + k);
+    }
+  }
+  u32 refs_in_gop = 0;  // reference pictures coded so far in this GOP (frame_num)
+  for (i64 f : order) {
     const bool key = (f % gop) == 0;
     const i64 in_gop = f % gop;
+    const i64 gop_len = std::min<i64>(gop, frames - (f - in_gop));
+    const bool bpic = bidir && (in_gop & 1) && in_gop + 1 < gop_len;
     if (key) {
       emit_nal(out, 3, 7, sps);
       emit_nal(out, 3, 8, pps);
+      refs_in_gop = 0;
     }
-    const bool skip = !key && non_key == SynthNonKey::Skip;
+    const bool skip = (!key && non_key == SynthNonKey::Skip) || bpic;
     BitWriter b;
     b.ue(0);                         // first_mb_in_slice
-    b.ue(key ? 7 : 5);               // slice_type: I (7) / P (5), "all slices of this type"
+    b.ue(key ? 7 : (bpic ? 6 : 5));  // slice_type: I (7) / B (6) / P (5), "all slices of this type"
     b.ue(0);                         // pic_parameter_set_id
-    b.u(4, (u32)(in_gop % 16));      // frame_num
+    // frame_num: reference pictures count up; a non-reference picture carries PrevRefFrameNum + 1
+    b.u(4, (bidir ? refs_in_gop : (u32)in_gop) % 16);
+    if (!bpic) ++refs_in_gop;
     if (key) b.ue(idr_id++ & 0xFFFF);  // idr_pic_id
+    if (bidir) b.u(8, (u32)(2 * in_gop) & 0xFF);  // pic_order_cnt_lsb
+    if (bpic) b.u(1, 1);  // direct_spatial_mv_pred_flag
     if (!key) {
       b.u(1, 0);  // num_ref_idx_active_override_flag
       b.u(1, 0);  // ref_pic_list_modification_flag_l0
+      if (bpic) b.u(1, 0);  // ref_pic_list_modification_flag_l1
     }
     if (key) {
       b.u(1, 0);  // no_output_of_prior_pics_flag
       b.u(1, 0);  // long_term_reference_flag
-    } else {
-      b.u(1, 0);  // adaptive_ref_pic_marking_mode_flag
+    } else if (!bpic) {
+      b.u(1, 0);  // adaptive_ref_pic_marking_mode_flag (sliding window)
     }
     b.se(0);  // slice_qp_delta
     b.ue(1);  // disable_deblocking_filter_idc = 1 (off)
     if (skip) {
-      b.ue((u32)(wmb * hmb));  // mb_skip_run covering the whole picture
+      // mb_skip_run covering the whole picture.  P_Skip copies the previous picture; B_Skip with
+      // spatial direct prediction (no coded neighbours, intra co-located picture) is bi-predicted
+      // with zero motion: (anchor_before + anchor_after + 1) >> 1 per sample.
+      b.ue((u32)(wmb * hmb));
     } else {
       fill(f, ysrc.data(), usrc.data(), vsrc.data());
       // pad the display planes to the coded size by edge replication
@@ -412,7 +519,7 @@ void write_ipcm_stream(i32 width, i32 height, i64 frames, i32 gop, SynthNonKey n
         }
     }
     b.trailing();
-    emit_nal(out, key ? 3 : 2, key ? 5 : 1, b.data());
+    emit_nal(out, key ? 3 : (bpic ? 0 : 2), key ? 5 : 1, b.data());
   }
 }
 

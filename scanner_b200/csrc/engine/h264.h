@@ -7,7 +7,10 @@
 //    NVENC is available offline): Baseline profile, one slice per picture, every macroblock
 //    I_PCM (lossless; decoders reproduce the source planes bit-exactly), IDR + SPS + PPS at each
 //    GOP start, the other pictures either P slices of I_PCM macroblocks ("pcm") or a single
-//    mb_skip_run ("skip").  Used by tests and bench.py to make the H.264 of BASELINE.json's
+//    mb_skip_run ("skip"), or -- "bidir", Main profile with POC type 0 -- I_PCM anchors at the
+//    even GOP positions and non-reference B pictures (one B_Skip run, spatial direct: the rounded
+//    mean of the two anchors) at the odd ones, coded AFTER their later anchor so that decode
+//    order differs from display order.  Used by tests and bench.py to make the H.264 of BASELINE.json's
 //    configs.
 #pragma once
 #include <functional>
@@ -26,6 +29,10 @@ struct H264Index {
   std::vector<u64> sample_sizes;
   std::vector<i64> keyframe_indices;      // frame indices of IDR pictures
   std::vector<u8> metadata_packets;       // first SPS + PPS, with start codes
+  // false when the SPS rules picture reordering out (pic_order_cnt_type 2, or a VUI with
+  // max_num_reorder_frames == 0): display position k of a GOP is then its k-th sample and the
+  // decoder need not be fed past the last wanted picture.
+  bool may_reorder = false;
   i64 frames() const { return (i64)sample_offsets.size(); }
 };
 
@@ -35,7 +42,7 @@ struct H264Index {
 // packets) and fill the picture geometry without requiring any picture.
 Result index_bytestream(const u8* data, size_t size, H264Index& out, bool parameter_sets_only = false);
 
-enum class SynthNonKey { Pcm = 0, Skip = 1 };
+enum class SynthNonKey { Pcm = 0, Skip = 1, Bidir = 2 };
 
 // fill(frame_index, y, u, v): writes the 4:2:0 planes of one frame (y: w*h, u/v: (w/2)*(h/2)).
 using PlaneFiller = std::function<void(i64, u8*, u8*, u8*)>;

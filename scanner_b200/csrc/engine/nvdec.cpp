@@ -220,6 +220,7 @@ struct NvdecSession::Impl {
 
   // per-interval state
   std::vector<i64> wanted_store;
+  bool may_reorder = false;
   const std::vector<i64>* wanted = nullptr;
   size_t wanted_pos = 0;
   i64 display_pos = 0;
@@ -449,7 +450,8 @@ void nvdec_host_ns(long long out[6]) {
 
 Result NvdecSession::begin_interval(const u8* data, const std::vector<u64>& offsets,
                                     const std::vector<u64>& sizes, const std::vector<u8>& prefix,
-                                    const std::vector<i64>& wanted, i64 out_base, Consumer consumer) {
+                                    bool may_reorder, const std::vector<i64>& wanted, i64 out_base,
+                                    Consumer consumer) {
   Result r;
   Impl& s = *impl_;
   if (s.active) {
@@ -472,6 +474,7 @@ Result NvdecSession::begin_interval(const u8* data, const std::vector<u64>& offs
   s.offsets = offsets;
   s.sizes = sizes;
   s.next_sample = 0;
+  s.may_reorder = may_reorder;
   s.first_packet = true;
   s.flushed = false;
   s.active = true;
@@ -498,10 +501,14 @@ Result NvdecSession::advance(size_t count) {
   }
   ScopedDevice sd(s.gpu);
   if (count > s.wanted_store.size()) count = s.wanted_store.size();
-  const size_t last_needed = s.wanted_store.empty() ? 0 : (size_t)s.wanted_store.back() + 1;
+  // Without reordering, display position k is sample k: samples after the last wanted picture are
+  // never fed and the end-of-stream flush below releases whatever the display delay still holds
+  // back.  With B pictures a later sample can display earlier, so feeding continues until the
+  // wanted pictures have come out or the interval (= up to the next IDR) is exhausted.
+  const size_t last_needed = s.wanted_store.empty() ? 0
+                             : s.may_reorder        ? s.offsets.size()
+                                                    : (size_t)s.wanted_store.back() + 1;
   while (s.wanted_pos < count) {
-    // samples after the last wanted picture are never fed: the end-of-stream flush below
-    // releases whatever the display delay still holds back
     if (s.next_sample < s.offsets.size() && s.next_sample < last_needed) {
       const size_t i = s.next_sample++;
       const int rc = send_packet(s.parser, s.data + s.offsets[i], s.sizes[i],

@@ -62,11 +62,15 @@ class NvdecSession {
   //   data/offsets/sizes: the encoded samples of the interval, the first one an IDR (copied
   //   by reference: must stay valid until end_interval);
   //   prefix: SPS/PPS bytes sent before the first sample (may be empty);
+  //   may_reorder: the stream may display pictures in another order than it codes them (B
+  //   pictures; H264Index::may_reorder).  Display position k can then depend on samples after the
+  //   k-th, so samples are fed until the wanted pictures have come out (at most to the end of the
+  //   interval) instead of stopping at the last wanted position;
   //   wanted: ascending 0-based positions (display order, relative to the first sample) of the
   //   pictures to deliver; delivered picture k is passed to `consumer` as index out_base + k.
   Result begin_interval(const u8* data, const std::vector<u64>& offsets, const std::vector<u64>& sizes,
-                        const std::vector<u8>& prefix, const std::vector<i64>& wanted, i64 out_base,
-                        Consumer consumer);
+                        const std::vector<u8>& prefix, bool may_reorder, const std::vector<i64>& wanted,
+                        i64 out_base, Consumer consumer);
   // Feed samples until at least `count` of the wanted pictures have been delivered (the decoder
   // may deliver more); flushes at the end of the interval.
   Result advance(size_t count);

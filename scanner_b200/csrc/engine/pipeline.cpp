@@ -353,7 +353,7 @@ void Engine::instance_main(Instance* inst) {
                                      st.index.sample_sizes.begin() + iv.kf_end);
                 const size_t w = (size_t)st.index.width, h = (size_t)st.index.height;
                 r = sess.begin_interval(
-                    st.encoded.data(), offs, szs, st.index.metadata_packets, iv.wanted, iv.out_base,
+                    st.encoded.data(), offs, szs, st.index.metadata_packets, st.index.may_reorder, iv.wanted, iv.out_base,
                     [cur = &c, rsp = &rs, stream, w, h](i64 out_index, const Nv12Surface& s) {
                       const u8* lp = s.luma;
                       const u8* cp = s.chroma;
@@ -631,7 +631,8 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
       if (!r.success()) break;
       std::vector<u64> offs(st->index.sample_offsets.begin() + iv.kf_start, st->index.sample_offsets.begin() + iv.kf_end);
       std::vector<u64> szs(st->index.sample_sizes.begin() + iv.kf_start, st->index.sample_sizes.begin() + iv.kf_end);
-      r = sess.begin_interval(st->encoded.data(), offs, szs, st->index.metadata_packets, iv.wanted, iv.out_base,
+      r = sess.begin_interval(st->encoded.data(), offs, szs, st->index.metadata_packets, st->index.may_reorder, iv.wanted,
+                              iv.out_base,
                               [&, w, h, fb](i64 out_index, const Nv12Surface& s) {
                                 const u8* lp = s.luma;
                                 const u8* cp = s.chroma;
@@ -784,7 +785,7 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
         if (!sess->init().success()) continue;
         const std::vector<u64> offs(st->index.sample_offsets.begin(), st->index.sample_offsets.begin() + 1);
         const std::vector<u64> szs(st->index.sample_sizes.begin(), st->index.sample_sizes.begin() + 1);
-        Result pr = sess->begin_interval(st->encoded.data(), offs, szs, st->index.metadata_packets, {0}, 0,
+        Result pr = sess->begin_interval(st->encoded.data(), offs, szs, st->index.metadata_packets, false, {0}, 0,
                                          [](i64, const Nv12Surface&) {});
         if (pr.success()) pr = sess->advance(1);
         if (pr.success()) pr = sess->end_interval();

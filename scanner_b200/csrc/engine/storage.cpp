@@ -564,6 +564,7 @@ Result index_from_descriptor(const tables::VideoDescriptor& vd, H264Index& out) 
   out.height = vd.height();
   out.coded_width = meta.coded_width;
   out.coded_height = meta.coded_height;
+  out.may_reorder = meta.may_reorder;
   out.sample_offsets = vd.sample_offsets();
   out.sample_sizes = vd.sample_sizes();
   for (u64 k : vd.keyframe_indices()) out.keyframe_indices.push_back((i64)k);

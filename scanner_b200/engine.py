@@ -27,6 +27,7 @@ SIGNATURES = {
     "scn_stream_add_raw_frames": (_I64, [_VP, _VP, _I64, _I, _I, _I, _I]),
     "scn_stream_add_bytes": (_I64, [_VP, _VP, _VP, _I64]),
     "scn_stream_rows": (_I64, [_VP, _I64]),
+    "scn_stream_may_reorder": (_I, [_VP, _I64]),
     "scn_stream_info": (_I, [_VP, _I64, _c.POINTER(_I64)]),
     "scn_stream_remove": (_I, [_VP, _I64]),
     "scn_engine_decode_to_device": (_I, [_VP, _I64, _c.POINTER(_I64), _I64, _I, _VP]),
@@ -146,10 +147,13 @@ def h264_synth(yuv_frames, width, height, gop=30, non_key="pcm", frames=None):
     """yuv_frames: uint8 I420 pictures, flat (k, w*h*3/2) (Y plane, then U, then V).
     non_key="pcm": k = number of frames, every picture is coded (P slices of I_PCM macroblocks
     between IDRs).  non_key="skip": k = number of GOPs, `frames` total pictures are emitted, the
-    non-key ones as P_Skip repeats.  Returns the Annex-B stream as bytes."""
+    non-key ones as P_Skip repeats.  non_key="bidir": k = number of frames; odd GOP positions with a
+    later anchor in the GOP become B pictures coded after that anchor (decode order != display
+    order), decoding to the rounded mean of the two anchors -- see bidir_expected().
+    Returns the Annex-B stream as bytes."""
     arr = np.ascontiguousarray(yuv_frames, dtype=np.uint8).reshape(len(yuv_frames), -1)
     assert arr.shape[1] == width * height * 3 // 2
-    mode = {"pcm": 0, "skip": 1}[non_key]
+    mode = {"pcm": 0, "skip": 1, "bidir": 2}[non_key]
     if mode == 1:
         n = frames if frames is not None else arr.shape[0] * gop
         assert arr.shape[0] >= (n + gop - 1) // gop
@@ -161,6 +165,18 @@ def h264_synth(yuv_frames, width, height, gop=30, non_key="pcm", frames=None):
     got = lib().scn_h264_synth(arr.ctypes.data, width, height, n, gop, mode, out.ctypes.data, out.size)
     assert got == need
     return out.tobytes()
+
+
+def bidir_expected(yuv_frames, gop):
+    """What a decoder shows, in display order, for h264_synth(yuv_frames, ..., non_key="bidir")."""
+    src = np.asarray(yuv_frames, dtype=np.uint8)
+    out = src.copy()
+    n = len(src)
+    for g0 in range(0, n, gop):
+        ln = min(gop, n - g0)
+        for k in range(1, ln - 1, 2):
+            out[g0 + k] = ((src[g0 + k - 1].astype(np.uint16) + src[g0 + k + 1] + 1) >> 1).astype(np.uint8)
+    return out
 
 
 def mp4_mux(annexb, fps_num=25, fps_den=1):
@@ -339,6 +355,9 @@ class Engine:
         info = (ctypes.c_int64 * 6)()
         check(lib().scn_stream_info(self._h, sid, info), "stream_info")
         return dict(zip(["is_video", "width", "height", "channels", "keyframes", "bytes"], list(info)))
+
+    def stream_may_reorder(self, sid):
+        return bool(check(lib().scn_stream_may_reorder(self._h, sid), "stream_may_reorder"))
 
     def decode_to_device(self, sid, rows, gpu=0):
         """Decode `rows` (ascending) of an H.264 stream into a (n,h,w,3) uint8 CUDA tensor."""

@@ -40,11 +40,19 @@ def make_clip(seed, n, h, w, gop, non_key="pcm"):
     yuv = np.concatenate([y.reshape(n, -1), u.reshape(n, -1), v.reshape(n, -1)], axis=1)
     if non_key == "skip":
         data = E.h264_synth(yuv[::gop], w, h, gop=gop, non_key="skip", frames=n)
+    elif non_key == "bidir":
+        # odd GOP positions are B pictures coded after their later anchor; what is displayed there
+        # is the rounded mean of the two anchors (validated against FFmpeg in test_storage_cpu.py)
+        data = E.h264_synth(yuv, w, h, gop=gop, non_key="bidir")
+        shown = E.bidir_expected(yuv, gop)
+        y = shown[:, :h * w].reshape(n, h, w)
+        u = shown[:, h * w:h * w + h * w // 4].reshape(n, h // 2, w // 2)
+        v = shown[:, h * w + h * w // 4:].reshape(n, h // 2, w // 2)
     else:
         data = E.h264_synth(yuv, w, h, gop=gop)
     rgb = []
     for i in range(n):
-        src = i if non_key == "pcm" else (i // gop) * gop  # P_Skip repeats the last key picture
+        src = (i // gop) * gop if non_key == "skip" else i  # P_Skip repeats the last key picture
         chroma = np.empty((h // 2, w), np.uint8)
         chroma[:, 0::2], chroma[:, 1::2] = u[src], v[src]
         rgb.append(oracle.nv12_to_rgb(y[src], chroma))
@@ -57,7 +65,8 @@ def test_nvdec_is_present():
 
 
 @pytest.mark.parametrize("h,w,n,gop,mode", [(96, 128, 11, 4, "pcm"), (480, 640, 9, 5, "pcm"), (1080, 1920, 7, 3, "pcm"),
-                                            (112, 200, 8, 8, "pcm"), (96, 128, 10, 5, "skip")])
+                                            (112, 200, 8, 8, "pcm"), (96, 128, 10, 5, "skip"),
+                                            (96, 128, 13, 6, "bidir"), (480, 640, 9, 9, "bidir")])
 def test_decode_all_frames_bit_exact(eng, h, w, n, gop, mode):
     data, want = make_clip(11, n, h, w, gop, mode)
     sid = eng.add_h264(data)
@@ -98,6 +107,32 @@ def test_gather_decodes_only_needed_gops(eng):
     assert c["frames_used"] == 4
     # rows 3,4 need frames 0..4 of GOP 0; 17 needs 16..17; 39 needs 32..39: 5 + 2 + 8 decoded
     assert c["frames_decoded"] == 15
+
+
+def test_b_pictures_rows_are_display_order_and_sparse_rows_feed_past_the_target(eng):
+    """A stream whose coding order differs from its display order (I0 P2 B1 P4 B3 ...): table rows are
+    display positions, and a wanted B picture needs the anchor coded AFTER it -- the decode stage must
+    not stop feeding at the wanted position (it does for streams whose SPS rules reordering out)."""
+    n, gop = 24, 8
+    data, want = make_clip(21, n, 96, 128, gop, "bidir")
+    sid = eng.add_h264(data)
+    assert eng.stream_may_reorder(sid)
+    plain, _ = make_clip(21, 4, 96, 128, 2)
+    assert not eng.stream_may_reorder(eng.add_h264(plain))
+    g = E.Graph()
+    src = g.add_source(True)
+    s = g.add_sample((src, "frame"))
+    sink = g.add_sink((s, "frame"))
+    for rows in ([1], [3, 4, 9, 17, 23], [5, 6, 7], list(range(0, n, 3))):
+        j = E.Job()
+        j.bind_source(src, sid)
+        j.set_sampler(s, "Gather", protolite.encode(protolite.SAMPLER_ARGS["GatherSamplerArgs"], {"rows": rows}))
+        eng.run(g, [j], 2, 4)
+        assert j.output_rows(sink) == len(rows)
+        for k, r in enumerate(rows):
+            assert (j.output_row(sink, k) == want[r]).all(), (rows, r)
+    got = eng.decode_to_device(sid, [1, 2, 15, 16, 21]).cpu().numpy()
+    assert (got == want[[1, 2, 15, 16, 21]]).all()
 
 
 def test_stride_30_only_keyframes(eng):

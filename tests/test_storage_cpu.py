@@ -124,6 +124,125 @@ def test_mp4_written_here_is_read_by_ffmpeg_and_demuxes_back(tmp_path, h, w, n, 
     assert back == stream
 
 
+@pytest.mark.parametrize("n,gop", [(11, 6), (9, 9), (8, 4), (2, 2)])
+def test_b_picture_stream_is_what_ffmpeg_displays(tmp_path, n, gop):
+    """non_key="bidir": B pictures coded after their later anchor.  FFmpeg must show the pictures in
+    display order with the B pictures equal to the rounded mean of their anchors -- that pins
+    bidir_expected(), which the NVDEC parity tests compare against.  Through .mp4 as well: the
+    sample table is in coding order there."""
+    import cv2
+    h, w = 48, 64
+    rng = np.random.default_rng(7)
+    yuv = rng.integers(0, 256, (n, h * w * 3 // 2), dtype=np.uint8)
+    stream = E.h264_synth(yuv, w, h, gop=gop, non_key="bidir")
+    shown = E.bidir_expected(yuv, gop)
+    if n > 2 and gop > 2:
+        assert not (shown[1] == yuv[1]).all()
+    paths = [str(tmp_path / "b.h264"), str(tmp_path / "b.mp4")]
+    open(paths[0], "wb").write(stream)
+    open(paths[1], "wb").write(E.mp4_mux(stream, 30, 1))
+    for path in paths:
+        cap = cv2.VideoCapture(path)
+        cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)  # the raw luma plane
+        for i in range(n):
+            ok, f = cap.read()
+            assert ok, (path, i)
+            assert (np.asarray(f).reshape(-1)[:h * w] == shown[i][:h * w]).all(), (path, i)
+        assert not cap.read()[0]
+
+
+def test_ingested_b_picture_stream_keeps_its_reordering_flag(tmp_path):
+    """The flag is re-derived from the SPS stored in the VideoDescriptor (no field for it in the
+    reference's descriptor); the sample table of an .mp4 with B pictures is in coding order."""
+    h, w = 48, 64
+    rng = np.random.default_rng(5)
+    yuv = rng.integers(0, 256, (7, h * w * 3 // 2), dtype=np.uint8)
+    path = str(tmp_path / "b.mp4")
+    open(path, "wb").write(E.mp4_mux(E.h264_synth(yuv, w, h, gop=4, non_key="bidir")))
+    db = E.Database(str(tmp_path / "db"))
+    db.ingest_video("bclip", path)
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    sid = db.add_video_stream(eng, "bclip")
+    assert eng.stream_may_reorder(sid) and eng.stream_rows(sid) == 7
+    assert eng.stream_info(sid)["keyframes"] == 2
+    eng.close()
+    db.close()
+
+
+class _Bits:
+    def __init__(self):
+        self.b = []
+
+    def u(self, n, v):
+        self.b += [(v >> i) & 1 for i in range(n - 1, -1, -1)]
+
+    def ue(self, v):
+        k = v + 1
+        n = k.bit_length() - 1
+        self.u(n, 0)
+        self.u(n + 1, k)
+
+    def rbsp(self):
+        bits = self.b + [1]
+        bits += [0] * (-len(bits) % 8)
+        raw = bytes(int("".join(map(str, bits[i:i + 8])), 2) for i in range(0, len(bits), 8))
+        out, zeros = bytearray(), 0
+        for c in raw:  # emulation prevention
+            if zeros >= 2 and c <= 3:
+                out.append(3)
+                zeros = 0
+            out.append(c)
+            zeros = zeros + 1 if c == 0 else 0
+        return bytes(out)
+
+
+@pytest.mark.parametrize("reorder,hrd", [(0, False), (0, True), (1, False), (None, True)])
+def test_sps_vui_bitstream_restriction_decides_reordering(tmp_path, reorder, hrd):
+    """What encoders such as x264 write: POC type 0 plus a VUI whose bitstream_restriction says
+    max_num_reorder_frames.  0 -> display order is coding order and sparse decodes may stop at the
+    wanted picture; anything else (or no restriction coded) -> they may not.  The hand-built SPS is
+    swapped into a synthetic stream; FFmpeg decoding it unchanged shows the VUI is well-formed."""
+    h, w, n = 48, 64, 2
+    rng = np.random.default_rng(9)
+    yuv = rng.integers(0, 256, (n, h * w * 3 // 2), dtype=np.uint8)
+    stream = E.h264_synth(yuv, w, h, gop=2, non_key="bidir")  # I P: no B picture fits in 2 frames
+    b = _Bits()
+    b.u(8, 77), b.u(8, 0x40), b.u(8, 51), b.ue(0)
+    b.ue(0), b.ue(0), b.ue(4), b.ue(2), b.u(1, 0)         # frame_num, POC type 0 + lsb bits, refs, gaps
+    b.ue(w // 16 - 1), b.ue(h // 16 - 1), b.u(1, 1), b.u(1, 1), b.u(1, 0)
+    b.u(1, 1)                                             # vui_parameters_present_flag
+    b.u(1, 1), b.u(8, 255), b.u(16, 4), b.u(16, 3)        # Extended_SAR 4:3
+    b.u(1, 0)                                             # overscan
+    b.u(1, 1), b.u(3, 5), b.u(1, 0), b.u(1, 1), b.u(8, 1), b.u(8, 1), b.u(8, 1)   # video_signal_type
+    b.u(1, 1), b.ue(0), b.ue(0)                           # chroma_loc
+    b.u(1, 1), b.u(32, 1001), b.u(32, 60000), b.u(1, 1)   # timing_info
+    for present in (hrd, False):                          # nal_hrd, vcl_hrd
+        b.u(1, int(present))
+        if present:
+            b.ue(1), b.u(4, 4), b.u(4, 6)
+            for _ in range(2):
+                b.ue(999), b.ue(1999), b.u(1, 0)
+            b.u(5, 23), b.u(5, 23), b.u(5, 23), b.u(5, 24)
+    if hrd:
+        b.u(1, 0)                                         # low_delay_hrd_flag
+    b.u(1, 0)                                             # pic_struct_present_flag
+    b.u(1, int(reorder is not None))                      # bitstream_restriction_flag
+    if reorder is not None:
+        b.u(1, 1), b.ue(0), b.ue(0), b.ue(10), b.ue(10), b.ue(reorder), b.ue(2)
+    sc = b"\x00\x00\x00\x01"
+    assert stream.startswith(sc + b"\x67")
+    stream = sc + b"\x67" + b.rbsp() + stream[stream.index(sc, 4):]
+    path = str(tmp_path / "v.h264")
+    open(path, "wb").write(stream)
+    got = cv2_frames(path)
+    assert len(got) == n
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    sid = eng.add_h264(stream)
+    assert eng.stream_rows(sid) == n and eng.stream_info(sid)["width"] == w
+    assert eng.stream_may_reorder(sid) == (reorder != 0)
+    eng.close()
+
+
 def test_mp4_errors_are_reported():
     stream, _ = make_stream(4, 4, 48, 64, 2)
     mp4 = E.mp4_mux(stream)
@@ -188,6 +307,7 @@ def test_ingest_mp4_writes_the_reference_table_layout(tmp_path):
     sid = db.add_video_stream(eng, "clip")
     si = eng.stream_info(sid)
     assert (si["is_video"], si["width"], si["height"], si["keyframes"]) == (1, w, h, 2) and eng.stream_rows(sid) == n
+    assert not eng.stream_may_reorder(sid)  # POC type 2: display order is coding order
     eng.close()
     db.close()
 
