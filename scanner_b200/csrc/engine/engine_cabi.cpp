@@ -494,9 +494,8 @@ int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const char* table) {
   const size_t got = n ? fread(s->encoded.data(), 1, (size_t)n, f) : 0;
   fclose(f);
   if (got != (size_t)n) return fail("short read of " + file);
-  if (!s->index.sample_offsets.empty() &&
-      s->index.sample_offsets.back() + s->index.sample_sizes.back() > (u64)n)
-    return fail("video descriptor of table " + std::string(table) + " points past the end of " + file);
+  r = check_index(s->index, (size_t)n);
+  if (!r.success()) return fail("video descriptor of table " + std::string(table) + " does not match " + file + ": " + r.msg());
   return e->impl->add_stream(std::move(s));
 }
 

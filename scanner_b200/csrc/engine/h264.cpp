@@ -363,6 +363,42 @@ Result index_bytestream(const u8* data, size_t size, H264Index& out, bool parame
   return r;
 }
 
+Result check_index(const H264Index& index, size_t stream_size) {
+  Result r;
+  if (index.sample_offsets.size() != index.sample_sizes.size()) {
+    RESULT_ERROR(&r, "video index: %zu sample offsets but %zu sizes", index.sample_offsets.size(),
+                 index.sample_sizes.size());
+    return r;
+  }
+  for (size_t i = 0; i < index.sample_offsets.size(); ++i) {
+    const u64 off = index.sample_offsets[i], sz = index.sample_sizes[i];
+    if (off > stream_size || sz > stream_size - off) {
+      RESULT_ERROR(&r, "video index: sample %zu (offset %llu, %llu bytes) lies outside the %zu-byte stream", i,
+                   (unsigned long long)off, (unsigned long long)sz, stream_size);
+      return r;
+    }
+  }
+  i64 prev = -1;
+  for (i64 k : index.keyframe_indices) {
+    if (k <= prev || k >= index.frames()) {
+      RESULT_ERROR(&r, "video index: keyframe list is not ascending inside [0, %ld)", (long)index.frames());
+      return r;
+    }
+    prev = k;
+  }
+  if (index.frames() > 0 && (index.keyframe_indices.empty() || index.keyframe_indices[0] != 0)) {
+    RESULT_ERROR(&r, "video index: the first frame is not a keyframe");
+    return r;
+  }
+  if (index.width <= 0 || index.height <= 0 || index.width > index.coded_width || index.height > index.coded_height) {
+    RESULT_ERROR(&r, "video index: picture size %dx%d does not fit the coded size %dx%d", index.width, index.height,
+                 index.coded_width, index.coded_height);
+    return r;
+  }
+  r.set_success(true);
+  return r;
+}
+
 void write_ipcm_stream(i32 width, i32 height, i64 frames, i32 gop, SynthNonKey non_key,
                        const PlaneFiller& fill, std::vector<u8>& out) {
   const i32 wmb = (width + 15) / 16, hmb = (height + 15) / 16;

@@ -42,6 +42,11 @@ struct H264Index {
 // packets) and fill the picture geometry without requiring any picture.
 Result index_bytestream(const u8* data, size_t size, H264Index& out, bool parameter_sets_only = false);
 
+// An index that did not come from index_bytestream (a stored VideoDescriptor) against the byte
+// stream it describes: every sample inside [0, stream_size), keyframes ascending, inside the frame
+// range and starting at frame 0.
+Result check_index(const H264Index& index, size_t stream_size);
+
 enum class SynthNonKey { Pcm = 0, Skip = 1, Bidir = 2 };
 
 // fill(frame_index, y, u, v): writes the 4:2:0 planes of one frame (y: w*h, u/v: (w/2)*(h/2)).

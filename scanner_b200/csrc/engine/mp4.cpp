@@ -226,7 +226,11 @@ Result demux_mp4(const u8* data, size_t size, Mp4Track& out) {
     bool avc = false;
     std::string codec;
     for_each_box(entry_area, [&](u32 et, const View& e) {
-      codec.assign({(char)(et >> 24), (char)(et >> 16), (char)(et >> 8), (char)et});
+      codec.clear();
+      for (int sh = 24; sh >= 0; sh -= 8) {  // printable form of the fourcc for the error message
+        const u8 ch = (u8)(et >> sh);
+        codec.push_back(ch >= 0x20 && ch < 0x7F ? (char)ch : '?');
+      }
       if ((et == fourcc("avc1") || et == fourcc("avc3")) && e.n >= 78) {
         out.width = (i32)e.be16(24);
         out.height = (i32)e.be16(26);

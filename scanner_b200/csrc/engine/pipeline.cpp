@@ -358,6 +358,13 @@ void Engine::instance_main(Instance* inst) {
                       const u8* lp = s.luma;
                       const u8* cp = s.chroma;
                       u8* dst = cur->slot(out_index);
+                      // the element slots are sized from the index; a stream whose own SPS says
+                      // otherwise (resolution change mid-stream, foreign descriptor) must not be copied
+                      if ((size_t)s.width != w || (size_t)s.height != h) {
+                        rsp->fail("decoded picture is " + std::to_string(s.width) + "x" + std::to_string(s.height) +
+                                  " but the stream index says " + std::to_string(w) + "x" + std::to_string(h));
+                        return;
+                      }
                       if (cur->nv12) {
                         const int rc = scn_nv12_pack(&lp, &cp, s.pitch, 1, (int)w, (int)h, &dst, stream);
                         if (rc != 0) rsp->fail("scn_nv12_pack failed: " + std::to_string(rc));
@@ -637,6 +644,11 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
                                 const u8* lp = s.luma;
                                 const u8* cp = s.chroma;
                                 u8* d = dst + (size_t)out_index * fb;
+                                if ((size_t)s.width != w || (size_t)s.height != h) {
+                                  kerr = "decoded picture is " + std::to_string(s.width) + "x" + std::to_string(s.height) +
+                                         " but the stream index says " + std::to_string(w) + "x" + std::to_string(h);
+                                  return;
+                                }
                                 const int rc = scn_nv12_to_rgb24(&lp, &cp, s.pitch, 1, (int)w, (int)h, &d, w * 3, cs);
                                 if (rc != 0) kerr = "scn_nv12_to_rgb24 failed: " + std::to_string(rc);
                               });

@@ -102,9 +102,13 @@ def lib():
     return _lib
 
 
+def last_error():
+    return lib().scn_last_error().decode("utf-8", "replace")
+
+
 def check(rc, what):
     if rc is None or rc < 0:
-        raise EngineError(f"{what}: {lib().scn_last_error().decode()}")
+        raise EngineError(f"{what}: {last_error()}")
     return rc
 
 
@@ -139,7 +143,7 @@ def nvdec_caps(gpu=0):
     keys = ["available", "h264", "engines", "max_w", "max_h", "min_w"]
     d = dict(zip(keys, list(info)))
     if not d["available"]:
-        d["error"] = lib().scn_last_error().decode()
+        d["error"] = last_error()
     return d
 
 
@@ -205,7 +209,7 @@ class Database:
     def __init__(self, path):
         self._h = lib().scn_db_open(os.path.abspath(path).encode())
         if not self._h:
-            raise EngineError(f"scn_db_open({path}): {lib().scn_last_error().decode()}")
+            raise EngineError(f"scn_db_open({path}): {last_error()}")
         self.path = os.path.abspath(path)
 
     def close(self):
@@ -282,7 +286,7 @@ class Database:
         arr = (ctypes.c_int64 * max(1, len(rows)))(*rows)
         h = lib().scn_db_read_rows(self._h, table.encode(), column.encode(), arr, len(rows))
         if not h:
-            raise EngineError(f"read_rows({table}.{column}): {lib().scn_last_error().decode()}")
+            raise EngineError(f"read_rows({table}.{column}): {last_error()}")
         try:
             out = []
             for i in range(lib().scn_rows_count(h)):

@@ -243,6 +243,64 @@ def test_sps_vui_bitstream_restriction_decides_reordering(tmp_path, reorder, hrd
     eng.close()
 
 
+@pytest.mark.parametrize("what,match", [("offset", "lies outside"), ("size", "lies outside"),
+                                        ("keyframes", "keyframe"), ("first", "first frame"),
+                                        ("width", "does not fit"), ("count", "inconsistent")])
+def test_corrupt_video_descriptor_is_rejected_when_bound(tmp_path, what, match):
+    """The sample table of a stored descriptor becomes pointers handed to the hardware decoder:
+    every entry is checked against the data file when the table is bound to an engine."""
+    stream, _ = make_stream(8, 9, 48, 64, 3)
+    db = E.Database(str(tmp_path / "db"))
+    db.ingest_h264("clip", stream)
+    path = str(tmp_path / "db/tables/0/1_0_video_metadata.bin")
+    vd = parse_ref("VideoDescriptor", path)
+    if what == "offset":
+        vd.sample_offsets[4] = len(stream) + 5
+    elif what == "size":
+        vd.sample_sizes[2] = 2 ** 63
+    elif what == "keyframes":
+        vd.keyframe_indices[1] = 40
+    elif what == "first":
+        vd.keyframe_indices[0] = 1
+        vd.keyframe_indices[1] = 3
+    elif what == "width":
+        vd.width = 4096
+    elif what == "count":
+        vd.frames = 7
+    open(path, "wb").write(vd.SerializeToString())
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    with pytest.raises(E.EngineError, match=match):
+        db.add_video_stream(eng, "clip")
+    eng.close()
+    db.close()
+
+
+def test_parsers_survive_mutated_files_under_asan(tmp_path):
+    """Mutation fuzzing (byte flips, truncation, field smashing) of the Annex-B indexer, the mp4
+    demuxer/muxer and the descriptor readers, compiled with AddressSanitizer + UBSan: any
+    out-of-bounds access, overflow or leak fails the run."""
+    exe = os.path.join(ROOT, "build", "tests", "fuzz_parsers")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), exe], stdout=subprocess.DEVNULL)
+    seeds = []
+    for mode in ("pcm", "bidir", "skip"):
+        n = 6
+        stream, _ = make_stream(10, n, 48, 64, 3, mode) if mode != "bidir" else (
+            E.h264_synth(np.random.default_rng(10).integers(0, 256, (n, 48 * 64 * 3 // 2), dtype=np.uint8), 64, 48,
+                         gop=3, non_key="bidir"), None)
+        for ext, blob in ((".h264", stream), (".mp4", E.mp4_mux(stream, 30, 1))):
+            seeds.append(str(tmp_path / (mode + ext)))
+            open(seeds[-1], "wb").write(blob)
+    db = E.Database(str(tmp_path / "db"))
+    db.ingest_video("a", seeds[1])
+    db.close()
+    seeds += [str(tmp_path / "db" / f) for f in ("db_metadata.bin", "tables/0/descriptor.bin",
+                                                 "tables/0/1_0_video_metadata.bin")]
+    out = subprocess.run([exe, "1", "400"] + seeds, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    accepted, rejected = (int(x) for x in out.stdout.split()[1::2])
+    assert accepted > 100 and rejected > 100  # both outcomes exercised
+
+
 def test_mp4_errors_are_reported():
     stream, _ = make_stream(4, 4, 48, 64, 2)
     mp4 = E.mp4_mux(stream)
