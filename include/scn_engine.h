@@ -148,6 +148,60 @@ SCN_ENGINE_API int scn_engine_set_trace(scn_engine* e, int on);
 SCN_ENGINE_API int scn_engine_write_trace(scn_engine* e, const char* path);
 SCN_ENGINE_API int scn_engine_stats_json(scn_engine* e, char* host_buf, size_t cap);
 
+/* ---- kernels written in the host language ---------------------------------------------------
+ * The reference's `@scannerpy.register_python_op` (python/scannerpy/op.py:317-620, kernel.py:17-81,
+ * scanner/engine/python_kernel.cpp:49-361): an op whose kernel is a callable of the embedding
+ * process.  One callback per op receives every kernel event; `instance` identifies the kernel object
+ * (one per pipeline instance and graph node, constructed and called by that instance's evaluate
+ * thread only -- different instances call concurrently).  EXECUTE passes the input elements as
+ * elems[(col * n_rows + row) * n_stencil + s] (host memory, valid during the call; frames dense HWC)
+ * and expects exactly n_rows elements per output column through scn_cb_emit_*, which copy.
+ * The callback returns 0, or non-zero after writing a message to err: the run then fails with that
+ * message (CONSTRUCT / FETCH_RESOURCES / SETUP_WITH_RESOURCES failures are validation errors). */
+enum { SCN_CB_CONSTRUCT = 0, SCN_CB_DESTROY = 1, SCN_CB_NEW_STREAM = 2, SCN_CB_RESET = 3, SCN_CB_EXECUTE = 4,
+       SCN_CB_FETCH_RESOURCES = 5, SCN_CB_SETUP_WITH_RESOURCES = 6 };
+typedef struct scn_cb_elem {
+  const uint8_t* data; /* NULL: null row */
+  uint64_t size;
+  int32_t shape[3];    /* frames: height, width, channels */
+  int32_t frame_type;  /* frames: 0 U8, 1 F32, 2 F64, 3 U16; -1 for byte elements */
+  int64_t index;       /* row id in the op's input domain */
+} scn_cb_elem;
+typedef struct scn_cb_call {
+  int32_t event;
+  int32_t node_id;
+  int64_t instance;
+  int32_t device_type, device_id;
+  const uint8_t* args; /* CONSTRUCT: the op's kernel args; NEW_STREAM: the job's stream args */
+  uint64_t args_size;
+  int32_t n_cols, n_rows, n_stencil; /* EXECUTE */
+  int32_t reserved;
+  const scn_cb_elem* elems;
+  void* out;           /* EXECUTE: handle for scn_cb_emit_* */
+} scn_cb_call;
+typedef int (*scn_kernel_callback)(void* user, const scn_cb_call* call, char* err, size_t err_cap);
+typedef struct scn_cb_op_desc {
+  const char* name;
+  int32_t n_inputs;                 /* ignored when variadic_inputs */
+  const char* const* input_names;
+  const int32_t* input_is_frame;
+  int32_t variadic_inputs;
+  int32_t n_outputs;
+  const char* const* output_names;
+  const int32_t* output_is_frame;
+  const char* const* output_type_names; /* may be NULL; stored as the column's type name */
+  const int32_t* stencil;           /* n_stencil == 0: the op cannot stencil */
+  int32_t n_stencil;
+  int32_t bounded_state;            /* warmup rows, -1: none */
+  int32_t unbounded_state;
+  int32_t batch;                    /* >= 1; > 1: the kernel batches */
+  int32_t also_gpu;                 /* also register for DeviceType GPU (columns stay in host memory) */
+} scn_cb_op_desc;
+SCN_ENGINE_API int scn_register_callback_op(const scn_cb_op_desc* desc, scn_kernel_callback cb, void* user);
+SCN_ENGINE_API int scn_cb_emit_bytes(void* out, int col, const uint8_t* data, size_t size); /* size 0: null row */
+SCN_ENGINE_API int scn_cb_emit_frame(void* out, int col, const uint8_t* data, int height, int width, int channels,
+                                     int frame_type);
+
 /* ---- synthetic H.264 (tests / bench input generation; no encoder exists offline) ----------- */
 /* Encodes `frames` I420 pictures (planes at yuv + f*(w*h*3/2): Y, U, V) as an Annex-B stream of
  * I_PCM macroblocks, IDR every `gop` frames; non_key_mode 0 = P slices of I_PCM macroblocks

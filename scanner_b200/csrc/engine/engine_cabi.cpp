@@ -45,6 +45,12 @@ int copy_out(const std::string& s, char* buf, size_t cap) {
 }
 }  // namespace
 
+namespace scanner {
+namespace internal {
+Result register_callback_op(const scn_cb_op_desc& d, scn_kernel_callback cb, void* user);  // callback_op.cpp
+}
+}  // namespace scanner
+
 extern "C" {
 
 const char* scn_last_error(void) { return t_error.c_str(); }
@@ -53,6 +59,12 @@ int scn_load_op_library(const char* so_path) {
   if (!so_path) return fail("null path");
   return from_result(load_op_library(so_path));
 }
+int scn_register_callback_op(const scn_cb_op_desc* desc, scn_kernel_callback cb, void* user) {
+  if (!desc) return fail("null op description");
+  Result r = scanner::internal::register_callback_op(*desc, cb, user);
+  return r.success() ? 0 : fail(r.msg());
+}
+
 int scn_op_registered(const char* name) { return name && get_op_registry()->has_op(name) ? 1 : 0; }
 int scn_kernel_registered(const char* name, int device_type) {
   return name && get_kernel_registry()->has_kernel(name, device_type == 1 ? proto::GPU : proto::CPU) ? 1 : 0;

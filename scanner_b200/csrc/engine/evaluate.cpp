@@ -196,6 +196,11 @@ Result EvaluateWorker::new_task(const JobParams& job, const std::vector<i64>& ro
       st.kernel->reset();
       auto it = job.stream_args.find((i32)i);
       st.kernel->new_stream(it == job.stream_args.end() ? std::vector<u8>() : it->second);
+      std::string kerr;
+      if (take_kernel_error(&kerr)) {
+        RESULT_ERROR(&r, "Op %s failed in reset / new_stream: %s", op.name.c_str(), kerr.c_str());
+        return r;
+      }
     }
   }
   return ok();
@@ -376,6 +381,12 @@ Result EvaluateWorker::feed(std::map<i32, ColumnBatch>& source_columns,
         const timepoint_t t0 = now();
         st.kernel->execute_kernel(in, out);
         if (profiler_) profiler_->add_interval("evaluate:" + op.name, t0, now());
+        std::string kerr;
+        if (take_kernel_error(&kerr)) {  // a host-language kernel failed: the run fails, the process lives
+          for (size_t c = 0; c < n_out; ++c) delete_elements(st.out_dev[c], out[c]);
+          RESULT_ERROR(&r, "Op %s failed: %s", op.name.c_str(), kerr.c_str());
+          return r;
+        }
         for (size_t c = 0; c < n_out; ++c) {
           if (out[c].size() != nb) {
             RESULT_ERROR(&r, "Op %s produced %zu output elements for column %zu. Expected %zu outputs.",

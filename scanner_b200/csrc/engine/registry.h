@@ -83,5 +83,11 @@ KernelRegistry* get_kernel_registry();
 // (reference worker.cpp:732-744).  Returns an error Result if the library cannot be loaded.
 Result load_op_library(const std::string& so_path);
 
+// A kernel's way to fail the run without aborting the process (used by host-language kernels,
+// callback_op.cpp): the message is parked in a slot of the calling thread and collected by the
+// evaluate loop right after the kernel call returns.
+void raise_kernel_error(const std::string& msg);
+bool take_kernel_error(std::string* msg);
+
 }  // namespace internal
 }  // namespace scanner
