@@ -7,8 +7,8 @@ streams.py `sc.streams.Stride/Range/Gather/...`, storage.py:250-372 `NamedVideoS
 handed to libscn_engine.so through its C ABI.  With `Client(db_path=...)` named streams live in a
 database directory in the reference's on-disk layout (engine.Database): videos are ingested from
 .mp4 / .h264 files once and re-bound from their stored index afterwards, outputs are committed as
-tables and can be loaded by a later session.  Not reproduced: Slice/Unslice, Python kernels,
-multi-node master.
+tables and can be loaded by a later session.  Python kernels (`@register_python_op`, pyops.py) run
+inside the engine's evaluate threads.  Not reproduced: the multi-node master.
 
     sc = Client(gpus=[0])
     video = NamedVideoStream(sc, 'clip', path='clip.h264')         # Annex-B elementary stream
@@ -20,11 +20,14 @@ multi-node master.
 """
 import enum
 import os
+import pickle
 
 import numpy as np
 
 from . import engine as E
 from . import protolite
+from . import pyops
+from . import types as sctypes
 
 
 class DeviceType(enum.IntEnum):
@@ -91,9 +94,17 @@ class OpGenerator:
         if name not in ops:
             raise ScannerException(f"Op {name} is not registered (load_op first?)")
 
-        def make(device=DeviceType.CPU, batch=-1, stencil=(), bounded_state=None, **kwargs):
+        def make(*varargs, device=DeviceType.CPU, batch=-1, stencil=(), bounded_state=None, **kwargs):
             cols = [(k, v) for k, v in kwargs.items() if isinstance(v, OpColumn)]
             rest = {k: v for k, v in kwargs.items() if not isinstance(v, OpColumn)}
+            if varargs:  # variadic inputs are positional (op.py:196-205)
+                if cols or not all(isinstance(v, OpColumn) for v in varargs):
+                    raise ScannerException(f"Op {name}: positional arguments are variadic input columns and "
+                                           f"cannot be mixed with named inputs")
+                cols = [(f"arg{i}", v) for i, v in enumerate(varargs)]
+            pyop = pyops.PYTHON_OP_REGISTRY.get(name)
+            if pyop is not None:
+                return self._make_python(pyop, cols, rest, device, batch, stencil, bounded_state)
             protos = self._sc._op_protos.get(name, {})
             init_fields, stream_fields = protos.get("init"), protos.get("stream")
             init_vals, stream_vals = {}, {}
@@ -129,6 +140,50 @@ class OpGenerator:
             return res[0] if len(res) == 1 else tuple(res)
 
         return make
+
+
+    def _make_python(self, pyop, cols, rest, device, batch, stencil, bounded_state):
+        """A Python op: init arguments and per-stream arguments travel pickled (op.py:296-298,
+        kernel.py:12 `pickle.loads(config.args())`), list-valued kwargs named like a parameter of
+        `new_stream` are per-stream arguments."""
+        if not pyop.variadic:
+            declared = [c.name for c in pyop.inputs]
+            given = dict(cols)
+            if sorted(given) != sorted(declared):
+                raise ScannerException(f"Op {pyop.name} takes inputs {declared}, got {sorted(given)}")
+            cols = [(n, given[n]) for n in declared]  # the engine binds inputs by position
+        init_vals, stream_vals = {}, {}
+        for k, v in rest.items():
+            if k in pyop.stream_params:
+                if not isinstance(v, (list, tuple)):
+                    raise ScannerException(f"Op {pyop.name}: stream argument {k!r} takes a list (one value per stream)")
+                stream_vals[k] = list(v)
+            elif k in pyop.kernel_params:
+                init_vals[k] = v
+            else:
+                raise ScannerException(f"Op {pyop.name} does not take argument {k!r}")
+        per_stream = None
+        if stream_vals:
+            n = len(next(iter(stream_vals.values())))
+            if any(len(v) != n for v in stream_vals.values()):
+                raise ScannerException(f"Op {pyop.name}: stream arguments must all list one value per stream")
+            per_stream = []
+            for i in range(n):
+                vals = {k: v[i] for k, v in stream_vals.items()}
+                sliced = [v for v in vals.values() if isinstance(v, SliceList)]
+                if sliced:
+                    groups = max(len(v) for v in sliced)
+                    per_stream.append(SliceList(
+                        pickle.dumps({k: (v[g if len(v) > 1 else 0] if isinstance(v, SliceList) else v)
+                                      for k, v in vals.items()}) for g in range(groups)))
+                else:
+                    per_stream.append(pickle.dumps(vals))
+        node = _Node("op", pyop.name, [c for _, c in cols], DeviceType(device), pickle.dumps(init_vals), batch,
+                     stencil, -1 if bounded_state is None else bounded_state, per_stream)
+        node.input_names = [k for k, _ in cols]
+        node.type_names = {c.name: ("" if c.is_frame else c.info.cpp_name) for c in pyop.outputs}
+        res = [OpColumn(node, c.name, c.is_frame) for c in pyop.outputs]
+        return res[0] if len(res) == 1 else tuple(res)
 
 
 class StreamsGenerator:
@@ -338,6 +393,35 @@ def _is_mp4(data):
     return len(data) >= 12 and bytes(data[4:8]) in (b"ftyp", b"moov", b"mdat", b"free", b"skip", b"wide", b"styp")
 
 
+def _column_type_name(col):
+    """Type name stored with an output column: what the producing op declared (the reference keeps
+    it in ColumnDescriptor.type_name), through row-sampling nodes."""
+    node = col._op
+    while node is not None and node.kind in ("sample", "space", "slice", "unslice") and node.inputs:
+        col = node.inputs[0]
+        node = col._op
+    names = getattr(node, "type_names", None)
+    if names and col._col in names:
+        return names[col._col]
+    return "Histogram" if col._col == "histogram" else ""
+
+
+def _typed(row, ty):
+    """Deserialise a stored byte row by its column type name (scannerpy.types registry)."""
+    if row is None or isinstance(row, np.ndarray) or not ty:
+        return row
+    if isinstance(ty, str):
+        if ty in ("Bytes", "bytes"):
+            return row
+        try:
+            info = sctypes.get_type_info_cpp(ty)
+        except sctypes.ScannerTypeError:
+            return row  # a type this process has not registered: the raw bytes
+    else:
+        info = sctypes.get_type_info(ty)
+    return info.deserialize(bytes(row))
+
+
 class NamedStream:
     """An output column (or a byte-row input when created with rows=[...]).  With a database it is
     the table `name` with one data column, readable by later sessions."""
@@ -372,7 +456,9 @@ class NamedStream:
 
     def load(self, ty=None, rows=None):
         """Generator over rows, deserialised like scannerpy.types (types.py:91-132): frame columns
-        as ndarrays, `Histogram` as a list of three int32 arrays, anything else as bytes."""
+        as ndarrays, byte columns through the serializer registered for the column's type name
+        (`Histogram`: a list of three int32 arrays; unknown or empty type name: bytes).  `ty` may
+        be a type name or a registered Python type."""
         if self._job is not None:
             ty = ty or self._type
             idx = range(self.len()) if rows is None else rows
@@ -385,13 +471,7 @@ class NamedStream:
         else:
             raise ScannerException(f"stream {self._name} has not been written by a job")
         for r in fetched:
-            if r is None or isinstance(r, np.ndarray):
-                yield r
-            elif ty == "Histogram":
-                a = np.frombuffer(r, np.int32)
-                yield [a[0:16], a[16:32], a[32:48]]
-            else:
-                yield r
+            yield _typed(r, ty)
 
     def delete(self, sc=None):
         self._job = None
@@ -414,11 +494,7 @@ class Column:
     def load(self, ty=None, rows=None):
         ty = ty or self._desc["type_name"] or None
         for r in self._table._db.read_rows(self._table._name, self._desc["name"], rows):
-            if ty == "Histogram" and isinstance(r, (bytes, bytearray)):
-                a = np.frombuffer(r, np.int32)
-                yield [a[0:16], a[16:32], a[32:48]]
-            else:
-                yield r
+            yield _typed(r, ty)
 
 
 class Table:
@@ -646,7 +722,7 @@ class Client:
             try:
                 for node in out_nodes:
                     src_col = node.inputs[0]
-                    type_name = "Histogram" if src_col._col == "histogram" else ""
+                    type_name = _column_type_name(src_col)
                     for j, s in enumerate(node.streams):
                         if j in skip:
                             continue
@@ -672,7 +748,7 @@ class Client:
             raise ScannerException(str(e)) from e
         for node in out_nodes:
             src_col = node.inputs[0]
-            type_name = "Histogram" if src_col._col == "histogram" else ""
+            type_name = _column_type_name(src_col)
             for j, s in enumerate(node.streams):
                 if j in skip or self._db is not None:
                     s._job = None  # served from the stored table

@@ -116,7 +116,7 @@ class CallbackKernel : public BaseKernel {
             d.shape[0] = f->shape[0];
             d.shape[1] = f->shape[1];
             d.shape[2] = f->shape[2];
-            d.frame_type = (int32_t)f->type;
+            d.frame_type = (int32_t)(proto::FrameType)f->type;
           } else {
             d.data = e.buffer;
             d.size = e.size;
@@ -143,7 +143,7 @@ class CallbackKernel : public BaseKernel {
     memset(&c, 0, sizeof(c));
     c.event = event;
     c.instance = instance_;
-    c.device_type = (int)device_.type;
+    c.device_type = (int)(proto::DeviceType)device_.type;
     c.device_id = device_.id;
     c.node_id = node_id_;
     return c;
@@ -229,11 +229,11 @@ int scn_cb_emit_frame(void* out, int col, const uint8_t* data, int height, int w
     ctx->error = "output column " + std::to_string(col) + " is a bytes column: emit bytes";
     return -1;
   }
-  if (!data || height <= 0 || width <= 0 || channels <= 0 || frame_type < 0 || frame_type > (int)FrameType::U16) {
+  if (!data || height <= 0 || width <= 0 || channels <= 0 || frame_type < 0 || frame_type > (int)proto::U16) {
     ctx->error = "bad frame emitted for output column " + std::to_string(col);
     return -1;
   }
-  Frame* f = new_frame(CPU_DEVICE, FrameInfo(height, width, channels, (FrameType)frame_type));
+  Frame* f = new_frame(CPU_DEVICE, FrameInfo(height, width, channels, FrameType((proto::FrameType)frame_type)));
   memcpy(f->data, data, f->size());
   insert_frame((*ctx->out)[col], f);
   return 0;

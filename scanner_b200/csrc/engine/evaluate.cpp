@@ -81,8 +81,8 @@ Elements copy_or_ref_elements(DeviceHandle src, DeviceHandle dst, const Elements
 }
 
 EvaluateWorker::EvaluateWorker(const Graph& graph, const GraphAnalysis& analysis, i32 gpu_id,
-                               i32 node_id, Profiler* profiler)
-  : graph_(graph), an_(analysis), gpu_id_(gpu_id), node_id_(node_id), profiler_(profiler) {
+                               i32 node_id, Profiler* profiler, ResourceGate* gate)
+  : graph_(graph), an_(analysis), gpu_id_(gpu_id), node_id_(node_id), profiler_(profiler), gate_(gate) {
   state_.resize(graph_.ops.size());
 }
 
@@ -144,10 +144,33 @@ Result EvaluateWorker::init() {
       RESULT_ERROR(&r, "Op %s failed validation: %s", op.name.c_str(), v.msg().c_str());
       return r;
     }
-    st.kernel->fetch_resources(&v);
-    if (!v.success()) {
-      RESULT_ERROR(&r, "Op %s failed to fetch resources: %s", op.name.c_str(), v.msg().c_str());
-      return r;
+    bool fetch_here = true;
+    if (gate_) {
+      std::unique_lock<std::mutex> lk(gate_->mu);
+      int& s = gate_->state[(i32)i];
+      if (s == 0) {
+        s = 1;
+      } else {
+        fetch_here = false;
+        gate_->cv.wait(lk, [&] { return gate_->state[(i32)i] >= 2; });
+        if (gate_->state[(i32)i] == 3) {
+          RESULT_ERROR(&r, "Op %s failed to fetch resources: %s", op.name.c_str(), gate_->error[(i32)i].c_str());
+          return r;
+        }
+      }
+    }
+    if (fetch_here) {
+      st.kernel->fetch_resources(&v);
+      if (gate_) {
+        std::lock_guard<std::mutex> lk(gate_->mu);
+        gate_->state[(i32)i] = v.success() ? 2 : 3;
+        if (!v.success()) gate_->error[(i32)i] = v.msg();
+        gate_->cv.notify_all();
+      }
+      if (!v.success()) {
+        RESULT_ERROR(&r, "Op %s failed to fetch resources: %s", op.name.c_str(), v.msg().c_str());
+        return r;
+      }
     }
     st.kernel->setup_with_resources(&v);
     if (!v.success()) {

@@ -2,9 +2,11 @@
 // (reference scanner/engine/evaluate_worker.cpp:408-1327 EvaluateWorker, runtime.cpp:141-189
 // copy_or_ref_elements).  One instance per pipeline instance; single-threaded by contract.
 #pragma once
+#include <condition_variable>
 #include <deque>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "graph.h"
@@ -25,11 +27,23 @@ struct ColumnBatch {
 Elements copy_or_ref_elements(DeviceHandle src_device, DeviceHandle dst_device, const Elements& in);
 void delete_elements(DeviceHandle device, Elements& elements);
 
+// Shared by the pipeline instances of one run: fetch_resources() of an op runs on exactly one of
+// its kernel instances, every instance's setup_with_resources() runs after it has returned
+// (reference evaluate_worker.cpp:493-550: worker instance 0 fetches, the others wait on a
+// condition variable).
+struct ResourceGate {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::map<i32, int> state;  // op index -> 0 untouched, 1 fetching, 2 fetched, 3 failed
+  std::map<i32, std::string> error;
+};
+
 class EvaluateWorker {
  public:
   // gpu_id: the GPU this pipeline instance owns (-1 = none; GPU kernels are then an error).
+  // gate: shared by the instances of the run (nullptr: this worker fetches for itself).
   EvaluateWorker(const Graph& graph, const GraphAnalysis& analysis, i32 gpu_id, i32 node_id,
-                 Profiler* profiler);
+                 Profiler* profiler, ResourceGate* gate = nullptr);
   ~EvaluateWorker();
 
   // Instantiate every kernel: validate(), fetch_resources(), setup_with_resources()
@@ -72,6 +86,7 @@ class EvaluateWorker {
   i32 gpu_id_;
   i32 node_id_;
   Profiler* profiler_;
+  ResourceGate* gate_;
   std::vector<OpState> state_;
 };
 

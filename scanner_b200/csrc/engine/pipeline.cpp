@@ -80,6 +80,7 @@ struct Engine::RunState {
   std::mutex err_mu;
   std::string error;
   Profiler profiler;
+  ResourceGate resource_gate;  // fetch_resources once per op and run
   std::unique_ptr<Database> db;  // open when a job saves sinks into tables of out_dir
   std::atomic<i64> frames_decoded{0}, frames_used{0}, frames_native{0};
 
@@ -233,7 +234,7 @@ void Engine::instance_main(Instance* inst) {
   Profiler::thread_worker() = inst->index;
   const DeviceHandle gpu_dev(DeviceType::GPU, gpu);
   {
-    EvaluateWorker ew(*rs.graph, rs.an, gpu, inst->node_id, &rs.profiler);
+    EvaluateWorker ew(*rs.graph, rs.an, gpu, inst->node_id, &rs.profiler, &rs.resource_gate);
     Result r = ew.init();
     if (!r.success()) {
       rs.fail(r.msg());

@@ -28,6 +28,10 @@ SIGNATURES = {
     "scn_stream_add_bytes": (_I64, [_VP, _VP, _VP, _I64]),
     "scn_stream_rows": (_I64, [_VP, _I64]),
     "scn_stream_may_reorder": (_I, [_VP, _I64]),
+    # host-language kernels: pyops.py binds the struct / callback types over these
+    "scn_register_callback_op": (_I, [_VP, _VP, _VP]),
+    "scn_cb_emit_bytes": (_I, [_VP, _I, _VP, _SZ]),
+    "scn_cb_emit_frame": (_I, [_VP, _I, _VP, _I, _I, _I, _I]),
     "scn_stream_info": (_I, [_VP, _I64, _c.POINTER(_I64)]),
     "scn_stream_remove": (_I, [_VP, _I64]),
     "scn_engine_decode_to_device": (_I, [_VP, _I64, _c.POINTER(_I64), _I64, _I, _VP]),
