@@ -147,21 +147,32 @@ class OpGenerator:
         kernel.py:12 `pickle.loads(config.args())`), list-valued kwargs named like a parameter of
         `new_stream` are per-stream arguments."""
         if not pyop.variadic:
-            declared = [c.name for c in pyop.inputs]
             given = dict(cols)
-            if sorted(given) != sorted(declared):
-                raise ScannerException(f"Op {pyop.name} takes inputs {declared}, got {sorted(given)}")
-            cols = [(n, given[n]) for n in declared]  # the engine binds inputs by position
+            for c in pyop.inputs:
+                if c.name not in given:
+                    raise ScannerException(f"Op {pyop.name} required sequence {c.name} as input")
+            extra = sorted(set(given) - {c.name for c in pyop.inputs})
+            if extra:
+                raise ScannerException(f"Op {pyop.name} has no input named {extra[0]!r}")
+            cols = [(c.name, given[c.name]) for c in pyop.inputs]  # the engine binds inputs by position
+        # every other keyword is an init argument (function kernels read them from config.args,
+        # class kernels receive them in __init__), except the parameters of new_stream (op.py:189-222)
+        rest = dict(rest)
+        explicit = rest.pop("args", None)
+        rest.pop("extra", None)
         init_vals, stream_vals = {}, {}
         for k, v in rest.items():
             if k in pyop.stream_params:
                 if not isinstance(v, (list, tuple)):
-                    raise ScannerException(f"Op {pyop.name}: stream argument {k!r} takes a list (one value per stream)")
+                    raise ScannerException(f"The argument `{k}` to op `{pyop.name}` is a stream config argument "
+                                           f"and must be a list.")
                 stream_vals[k] = list(v)
-            elif k in pyop.kernel_params:
-                init_vals[k] = v
             else:
-                raise ScannerException(f"Op {pyop.name} does not take argument {k!r}")
+                init_vals[k] = v
+        if explicit is not None:
+            init_vals = explicit
+        if pyop.stream_params and not stream_vals:
+            raise ScannerException(f"No arguments provided to op `{pyop.name}` for stream parameters.")
         per_stream = None
         if stream_vals:
             n = len(next(iter(stream_vals.values())))
@@ -378,15 +389,59 @@ class NamedVideoStream:
         NamedStream.delete(self, sc)
 
     def save_mp4(self, output_name, fps=None):
-        """Write the stored video as `<output_name>.mp4` (reference storage.py NamedVideoStream.save_mp4)."""
-        if self._sc._db is None or not self._sc._db.has_table(self._name):
-            raise ScannerException("save_mp4 needs a database-backed video stream")
+        """Write the video as `<output_name>.mp4` (reference storage.py NamedVideoStream.save_mp4).
+        An ingested H.264 table is re-wrapped sample for sample.  Frames written by a job are stored
+        uncompressed here (there is no encoder on the box): they are converted to BT.601 4:2:0 and
+        written as intra-PCM H.264 -- every player opens it, the file is as large as the raw video."""
         path = output_name if output_name.endswith(".mp4") else output_name + ".mp4"
-        try:
-            self._sc._db.export_mp4(self._name, path, int(fps) if fps else 0, 1 if fps else 0)
-        except E.EngineError as e:
-            raise ScannerException(str(e)) from e
+        db = self._sc._db
+        if db is not None and db.has_table(self._name) and self._job is None:
+            info = db.table_info(self._name)
+            if info.get("keyframes", 0) > 0:  # compressed column: container work only
+                try:
+                    db.export_mp4(self._name, path, int(fps) if fps else 0, 1 if fps else 0)
+                except E.EngineError as e:
+                    raise ScannerException(str(e)) from e
+                return path
+        if not self.exists():
+            raise ScannerException(f"stream {self._name} does not exist")
+        planes, size = [], None
+        for f in self.load():
+            if f is None:
+                continue
+            if f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] not in (1, 3):
+                raise ScannerException("save_mp4 writes uint8 frames with 1 or 3 channels")
+            if size is None:
+                size = f.shape[:2]
+            elif f.shape[:2] != size:
+                raise ScannerException("save_mp4 needs frames of one size")
+            planes.append(_rgb_to_i420(f))
+        if not planes:
+            raise ScannerException(f"stream {self._name} has no frames")
+        h, w = size[0] + (size[0] & 1), size[1] + (size[1] & 1)
+        stream = E.h264_synth(np.stack(planes), w, h, gop=1)
+        with open(path, "wb") as out:
+            out.write(E.mp4_mux(stream, int(fps) if fps else 25, 1))
         return path
+
+
+def _rgb_to_i420(frame):
+    """uint8 (H, W, 3|1) -> flat I420 planes (BT.601 studio range, 2x2 box chroma), odd sizes padded
+    by edge replication."""
+    h, w = frame.shape[:2]
+    if (h & 1) or (w & 1):
+        frame = np.pad(frame, ((0, h & 1), (0, w & 1), (0, 0)), mode="edge")
+        h, w = frame.shape[:2]
+    f = frame.astype(np.float32)
+    if f.shape[2] == 1:
+        f = np.repeat(f, 3, axis=2)
+    r, g, b = f[..., 0], f[..., 1], f[..., 2]
+    y = 16.0 + 0.257 * r + 0.504 * g + 0.098 * b
+    cb = 128.0 - 0.148 * r - 0.291 * g + 0.439 * b
+    cr = 128.0 + 0.439 * r - 0.368 * g - 0.071 * b
+    sub = lambda p: p.reshape(h // 2, 2, w // 2, 2).mean(axis=(1, 3))  # noqa: E731
+    q = lambda p: np.clip(np.rint(p), 0, 255).astype(np.uint8).reshape(-1)  # noqa: E731
+    return np.concatenate([q(y), q(sub(cb)), q(sub(cr))])
 
 
 def _is_mp4(data):

@@ -111,7 +111,7 @@ class PyFail(Kernel):
 
 @register_python_op(name="CacheTest")
 def cache_test(config, n: Any) -> Any:
-    return n + 1
+    return n + (config.args or {}).get("step", 1)
 
 
 @register_python_op()
@@ -170,10 +170,15 @@ def test_python_kernel_init_and_stream_args(sc):
     # the wrong init argument fails the constructor: a validation error, not a crash
     with pytest.raises(sp.ScannerException, match="failed validation"):
         run(sc, sc.ops.TestPy(frame=rng, kernel_arg=2, x=[0], y=[0]), "test_hist2")
-    with pytest.raises(sp.ScannerException, match="does not take argument"):
-        sc.ops.TestPy(frame=rng, kernel_arg=1, z=[3])
-    with pytest.raises(sp.ScannerException, match="takes a list"):
+    # an unknown keyword is an init argument the constructor does not take
+    with pytest.raises(sp.ScannerException, match=r"(?s)failed validation.*unexpected keyword argument 'z'"):
+        run(sc, sc.ops.TestPy(frame=rng, kernel_arg=1, z=3, x=[0], y=[0]), "test_hist3")
+    with pytest.raises(sp.ScannerException, match="must be a list"):
         sc.ops.TestPy(frame=rng, kernel_arg=1, x=0, y=[0])
+    with pytest.raises(sp.ScannerException, match="for stream parameters"):
+        sc.ops.TestPy(frame=rng, kernel_arg=1)
+    with pytest.raises(sp.ScannerException, match="required sequence frame as input"):
+        sc.ops.TestPy(kernel_arg=1, x=[0], y=[0])
 
 
 def test_fetch_resources_runs_once_per_op_and_before_every_setup(sc, tmp_path):
@@ -226,6 +231,9 @@ def test_function_op_over_a_byte_stream(sc):
     col = sc.io.Input([src])
     out = run(sc, sc.ops.CacheTest(n=sc.ops.CacheTest(n=col)), "plus2", ios=2, wps=1)
     assert list(out.load()) == [i + 2 for i in range(7)]
+    # function kernels read their init arguments from config.args (tutorial 01_defining_python_ops.py)
+    out = run(sc, sc.ops.CacheTest(n=col, step=10), "plus10", ios=2, wps=1)
+    assert list(out.load()) == [i + 10 for i in range(7)]
 
 
 # ------------------------------------------------------------------ beyond the reference's tests
@@ -351,3 +359,35 @@ def test_types_registry_round_trips():
     assert T.get_type_info(Any).deserialize(T.get_type_info(Any).serialize({"a": 1})) == {"a": 1}
     with pytest.raises(T.ScannerTypeError):
         T.get_type_info_cpp("NoSuchType")
+
+
+@register_python_op()
+def Negative(config, frame: FrameType) -> FrameType:
+    return 255 - frame
+
+
+@pytest.mark.parametrize("with_db", [False, True])
+def test_frames_written_by_a_python_op_save_as_mp4(tmp_path, with_db):
+    """Tutorials 01/02 end with `stream.save_mp4(...)` on a job's frame output.  Such frames are
+    stored uncompressed here; save_mp4 writes them as intra-PCM H.264, which FFmpeg plays back to
+    within colour-conversion rounding plus the 2x2 chroma averaging of a gradient."""
+    import cv2
+    h, w, n = 37, 50, 5  # odd height: padded to 38 in the file
+    yy, xx = np.mgrid[0:h, 0:w]
+    src = np.stack([np.stack([xx * 4 + i, yy * 5, 200 - xx * 2 + 0 * yy], axis=2).clip(0, 255).astype(np.uint8)
+                    for i in range(n)])
+    sc = sp.Client(gpus=[], cpu_instances=2, db_path=str(tmp_path / "db") if with_db else None)
+    frame = sc.io.Input([sp.NamedVideoStream(sc, "src", frames=src)])
+    out = sp.NamedVideoStream(sc, "neg")
+    sc.run(sc.io.Output(sc.ops.Negative(frame=frame), [out]), sp.PerfParams.manual(2, 4))
+    path = out.save_mp4(str(tmp_path / "neg"), fps=30)
+    cap = cv2.VideoCapture(path)
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == n and abs(cap.get(cv2.CAP_PROP_FPS) - 30) < 1e-6
+    for i in range(n):
+        ok, bgr = cap.read()
+        assert ok and bgr.shape == (h + 1, w, 3)
+        err = np.abs(bgr[:h, :, ::-1].astype(np.int32) - (255 - src[i]).astype(np.int32))
+        assert err.max() <= 8 and err.mean() < 2.5, (i, err.max(), err.mean())
+    if with_db:
+        out.delete()
+    sc.stop()
