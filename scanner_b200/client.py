@@ -64,8 +64,37 @@ class PerfParams:
 
 # ------------------------------------------------------------------------------------------------
 class OpColumn:
-    def __init__(self, op, column, is_frame):
+    """An edge of the graph: output column `column` of node `op` (reference scannerpy/op.py:26-119)."""
+
+    def __init__(self, op, column, is_frame, encode_options=None):
         self._op, self._col, self._is_frame = op, column, is_frame
+        self._encode_options = encode_options
+
+    # How a frame column is stored when it reaches an Output (op.py:57-98).  There is no video encoder
+    # on the box (no NVENC library, no x264): every choice is recorded and the frames are stored
+    # uncompressed, i.e. `lossless()` is exact and `compress_video()` keeps more than it asked for.
+    def _stored_as(self, options):
+        if not self._is_frame:
+            raise ScannerException(f'Compression only supported for sequences of type "video". Sequence '
+                                   f'{self._col} type is Bytes.')
+        return OpColumn(self._op, self._col, self._is_frame, options)
+
+    def compress(self, codec="video", **kwargs):
+        codecs = {"video": self.compress_video, "default": self.compress_default, "raw": self.lossless}
+        if codec not in codecs:
+            raise ScannerException(f"Compression codec {codec} not currently supported. Available codecs are: "
+                                   f"{' '.join(codecs)}.")
+        return codecs[codec](**kwargs)
+
+    def compress_video(self, quality=-1, bitrate=-1, keyframe_distance=-1):
+        return self._stored_as({"codec": "h264", "quality": quality, "bitrate": bitrate,
+                                "keyframe_distance": keyframe_distance})
+
+    def lossless(self):
+        return self._stored_as({"codec": "raw"})
+
+    def compress_default(self):
+        return self._stored_as({"codec": "default"})
 
 
 class SliceList(list):
@@ -380,10 +409,13 @@ class NamedVideoStream:
 
     committed = exists
 
-    def load(self, ty=None, rows=None):
+    def load_bytes(self, rows=None):
+        return NamedStream.load_bytes(self, rows)
+
+    def load(self, ty=None, fn=None, rows=None):
         """Frames of a video written by a job (stored uncompressed); an ingested H.264 table is decoded
         through a job, not loaded."""
-        return NamedStream.load(self, ty, rows)
+        return NamedStream.load(self, ty, fn, rows)
 
     def delete(self, sc=None):
         NamedStream.delete(self, sc)
@@ -509,11 +541,16 @@ class NamedStream:
             return self._sc._db.table_info(self._name)["rows"]
         raise ScannerException(f"stream {self._name} does not exist")
 
-    def load(self, ty=None, rows=None):
+    def load_bytes(self, rows=None):
+        """Rows as stored: bytes (frame columns: ndarrays), no deserialisation (storage.py:88-100)."""
+        return self.load(ty="Bytes", rows=rows)
+
+    def load(self, ty=None, fn=None, rows=None):
         """Generator over rows, deserialised like scannerpy.types (types.py:91-132): frame columns
         as ndarrays, byte columns through the serializer registered for the column's type name
         (`Histogram`: a list of three int32 arrays; unknown or empty type name: bytes).  `ty` may
-        be a type name or a registered Python type."""
+        be a type name or a registered Python type; `fn` is a custom bytes -> value function that
+        takes precedence (storage.py:135-173)."""
         if self._job is not None:
             ty = ty or self._type
             idx = range(self.len()) if rows is None else rows
@@ -526,7 +563,10 @@ class NamedStream:
         else:
             raise ScannerException(f"stream {self._name} has not been written by a job")
         for r in fetched:
-            yield _typed(r, ty)
+            if fn is not None and r is not None and not isinstance(r, np.ndarray):
+                yield fn(bytes(r))
+            else:
+                yield _typed(r, ty)
 
     def delete(self, sc=None):
         self._job = None
@@ -546,10 +586,13 @@ class Column:
     def type(self):
         return self._desc["type"]
 
-    def load(self, ty=None, rows=None):
+    def load(self, ty=None, fn=None, rows=None):
         ty = ty or self._desc["type_name"] or None
         for r in self._table._db.read_rows(self._table._name, self._desc["name"], rows):
-            yield _typed(r, ty)
+            if fn is not None and r is not None and not isinstance(r, np.ndarray):
+                yield fn(bytes(r))
+            else:
+                yield _typed(r, ty)
 
 
 class Table:

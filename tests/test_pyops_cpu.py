@@ -267,6 +267,25 @@ def test_typed_columns_survive_the_database(tmp_path):
     sc.stop()
 
 
+def test_storage_hints_and_custom_loaders(sc):
+    """`.lossless()` / `.compress_video()` on a frame column (tutorial 06) and `load(fn=...)`,
+    `load_bytes()` of the reference's StoredStream."""
+    frame = sc.io.Input([video(sc, n=6)])
+    neg = sc.ops.Negative(frame=frame)
+    for name, col in (("raw", neg.lossless()), ("h264", neg.compress_video(quality=35)),
+                      ("dflt", neg.compress("default"))):
+        got = list(run(sc, col, name, video_out=True).load())
+        assert len(got) == 6 and all((g == 255 - i).all() for i, g in enumerate(got))  # stored exactly
+    with pytest.raises(sp.ScannerException, match="not currently supported"):
+        neg.compress("av1")
+    meta = sc.ops.TestPy(frame=frame, kernel_arg=1, x=[1], y=[2])
+    with pytest.raises(sp.ScannerException, match='only supported for sequences of type "video"'):
+        meta.lossless()
+    out = run(sc, meta, "meta")
+    assert list(out.load(fn=lambda b: len(pickle.loads(b))))[:2] == [3, 3]
+    assert list(out.load_bytes())[1] == pickle.dumps({"x": 1, "y": 2, "v": 1})
+
+
 def test_unbounded_state_sees_every_row_of_its_task_after_a_reset(sc):
     frame = sc.io.Input([video(sc)])
     strided = sc.streams.Stride(sc.ops.RunningCount(frame=frame), [5])
