@@ -123,7 +123,13 @@ class OpGenerator:
         if name not in ops:
             raise ScannerException(f"Op {name} is not registered (load_op first?)")
 
-        def make(*varargs, device=DeviceType.CPU, batch=-1, stencil=(), bounded_state=None, **kwargs):
+        def make(*varargs, device=None, batch=-1, stencil=(), bounded_state=None, **kwargs):
+            if device is None:
+                # the reference defaults to DeviceType.CPU (op.py:184); the stdlib pixel ops here have
+                # GPU kernels only, so an op without a CPU kernel defaults to the GPU instead of failing
+                has_cpu = E.lib().scn_kernel_registered(name.encode(), int(DeviceType.CPU)) == 1
+                has_gpu = E.lib().scn_kernel_registered(name.encode(), int(DeviceType.GPU)) == 1
+                device = DeviceType.GPU if (has_gpu and not has_cpu) else DeviceType.CPU
             cols = [(k, v) for k, v in kwargs.items() if isinstance(v, OpColumn)]
             rest = {k: v for k, v in kwargs.items() if not isinstance(v, OpColumn)}
             if varargs:  # variadic inputs are positional (op.py:196-205)
@@ -633,7 +639,7 @@ class Profile:
 
     def write_trace(self, path):
         if not self._sc._profiling:
-            raise ScannerException("create the Client with profiling=True to record a trace")
+            raise ScannerException("this Client was created with profiling=False: no trace was recorded")
         self._sc._engine.write_trace(path)
 
 
@@ -647,7 +653,10 @@ class Client:
         if gpus is None:
             gpus = list(range(torch.cuda.device_count())) if torch.cuda.is_available() else []
         self._engine = E.Engine(gpus, instances_per_gpu, cpu_instances)
-        self._profiling = bool(_ignored.get("profiling", False))
+        self._gpus = list(gpus)
+        # the reference always records a profile (get_profile after any job); interval records are a
+        # few dozen bytes per task and kernel call, so it is on unless profiling=False is passed
+        self._profiling = bool(_ignored.get("profiling", True))
         if self._profiling:
             self._engine.set_trace(True)
         self._db = E.Database(db_path) if db_path else None
@@ -858,6 +867,10 @@ class Client:
 
     def stats(self):
         return self._engine.stats()
+
+    def has_gpu(self):
+        """True if this client's engine drives at least one GPU (reference Client.has_gpu)."""
+        return bool(self._gpus)
 
     def get_profile(self, job_id=None):
         """Like scannerpy's `sc.get_profile(job_id)` for the last run: `.statistics()` and, if the
