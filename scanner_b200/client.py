@@ -419,9 +419,46 @@ class NamedVideoStream:
         return NamedStream.load_bytes(self, rows)
 
     def load(self, ty=None, fn=None, rows=None):
-        """Frames of a video written by a job (stored uncompressed); an ingested H.264 table is decoded
-        through a job, not loaded."""
+        """Generator over frames (ndarrays).  Frames written by a job are stored uncompressed and
+        read back as they are; an ingested H.264 video is decoded for the asked rows (the reference
+        runs a Gather + ImageEncoder job for this, column.py:227-240; here the decode stage is
+        called directly, which needs a GPU)."""
+        if self._job is None and self._sid is not None and self._is_compressed():
+            return self._decode(rows)
         return NamedStream.load(self, ty, fn, rows)
+
+    def _is_compressed(self):
+        try:
+            return self._sc._engine.stream_info(self._sid)["keyframes"] > 0
+        except E.EngineError:
+            return False
+
+    def _decode(self, rows, chunk=32):
+        if not self._sc._gpus:
+            raise ScannerException(f"loading frames of the compressed video {self._name} needs a GPU (NVDEC)")
+        n = self._sc._engine.stream_rows(self._sid)
+        rows = list(range(n)) if rows is None else [int(r) for r in rows]
+        order = sorted(set(rows))
+        if order and (order[0] < 0 or order[-1] >= n):
+            raise ScannerException(f"rows must be inside [0, {n})")
+        def chunks():
+            for i in range(0, len(order), chunk):
+                part = order[i:i + chunk]
+                try:
+                    frames = self._sc._engine.decode_to_device(self._sid, part, gpu=self._sc._gpus[0]).cpu().numpy()
+                except E.EngineError as e:
+                    raise ScannerException(str(e)) from e
+                yield part, frames
+
+        if rows == order:  # ascending: stream chunk by chunk
+            for _, frames in chunks():
+                yield from frames
+            return
+        decoded = {}
+        for part, frames in chunks():
+            decoded.update(zip(part, frames))
+        for r in rows:
+            yield decoded[r]
 
     def delete(self, sc=None):
         NamedStream.delete(self, sc)
@@ -867,6 +904,13 @@ class Client:
 
     def stats(self):
         return self._engine.stats()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.stop()
+        return False
 
     def has_gpu(self):
         """True if this client's engine drives at least one GPU (reference Client.has_gpu)."""

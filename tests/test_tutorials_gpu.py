@@ -81,6 +81,11 @@ def test_00_basic(sc, example):
         num_rows += 1
     assert num_rows == video_stream1.len() == FRAMES
     assert named_stream2.len() == FRAMES
+    # py_test.py test_load_video_column / test_gather_video_column: frames of an ingested video
+    assert (next(video_stream1.load()) == shown[0]).all()
+    rows = [0, 10, 100, 57]
+    frames = list(video_stream2.load(rows=rows))
+    assert len(frames) == len(rows) and all((f == shown[r]).all() for f, r in zip(frames, rows))
     for stream in [video_stream1, video_stream2, named_stream1, named_stream2]:
         stream.delete(sc)
 
