@@ -253,6 +253,12 @@ SCN_ENGINE_API int scn_db_save_job(scn_db* db, scn_job* j, const char* table, co
 SCN_ENGINE_API int scn_db_new_table(scn_db* db, const char* table, const char* column_name, int is_video,
                                     const char* type_name, int job_id); /* -> table id */
 SCN_ENGINE_API int scn_job_set_sink_table(scn_job* j, int sink, int table_id, int keep_rows);
+/* A table of byte columns written from host rows in one call (reference Client.new_table ->
+ * master.cpp NewTable: one item holding every row): element (row r, column c) is the
+ * sizes[r * n_cols + c] bytes at data[r * n_cols + c] (size 0: null).  -> table id */
+SCN_ENGINE_API int scn_db_new_table_from_rows(scn_db* db, const char* table, int n_cols,
+                                              const char* const* column_names, int64_t n_rows,
+                                              const uint8_t* const* data, const uint64_t* sizes);
 SCN_ENGINE_API int scn_db_commit_job_table(scn_db* db, int table_id, scn_job* j);
 SCN_ENGINE_API scn_rows* scn_db_read_rows(scn_db* db, const char* table, const char* column, const int64_t* rows,
                                           int64_t n);

@@ -732,6 +732,22 @@ class Client:
                 failed.append((path, str(e)))
         return done, failed
 
+    def new_table(self, name, columns, rows, fns=None, force=False):
+        """A table of byte columns from Python rows (reference Client.new_table, client.py:1068-1121):
+        `rows` is a list of rows, each a list with one serialized element per column."""
+        db = self._need_db()
+        if db.has_table(name):
+            if not force:
+                raise ScannerException(f"Attempted to create table with existing name {name}")
+            db.delete_table(name)
+        if fns is not None:
+            rows = [[fn(col, None) for fn, col in zip(fns, row)] for row in rows]
+        try:
+            db.new_table_from_rows(name, list(columns), [list(r) for r in rows])
+        except E.EngineError as e:
+            raise ScannerException(str(e)) from e
+        return self.table(name)
+
     def has_table(self, name):
         return self._need_db().has_table(name)
 

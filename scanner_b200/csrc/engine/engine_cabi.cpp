@@ -530,6 +530,42 @@ int scn_db_new_table(scn_db* db, const char* table, const char* column_name, int
   return r.success() ? id : fail(r.msg());
 }
 
+int scn_db_new_table_from_rows(scn_db* db, const char* table, int n_cols, const char* const* column_names,
+                               int64_t n_rows, const uint8_t* const* data, const uint64_t* sizes) {
+  if (!db || !table || n_cols <= 0 || !column_names || n_rows < 0 || (n_rows > 0 && (!data || !sizes)))
+    return fail("bad arguments");
+  std::vector<ColumnSpec> specs((size_t)n_cols);
+  for (int c = 0; c < n_cols; ++c) {
+    if (!column_names[c] || !column_names[c][0]) return fail("empty column name");
+    specs[(size_t)c].name = column_names[c];
+    specs[(size_t)c].type = proto::Bytes;
+  }
+  i32 id = -1;
+  Result r = db->impl->new_table(table, specs, -1, id);
+  if (!r.success()) return fail(r.msg());
+  r = db->impl->write_index_item(id, 0, 0, n_rows);
+  for (int c = 0; c < n_cols && r.success(); ++c) {
+    std::vector<u8> bytes;
+    std::vector<u64> row_sizes((size_t)n_rows);
+    for (int64_t row = 0; row < n_rows; ++row) {
+      const size_t k = (size_t)row * (size_t)n_cols + (size_t)c;
+      row_sizes[(size_t)row] = data[k] ? sizes[k] : 0;
+      if (row_sizes[(size_t)row]) bytes.insert(bytes.end(), data[k], data[k] + sizes[k]);
+    }
+    ItemColumn ic;
+    ic.data = bytes.data();
+    ic.bytes = bytes.size();
+    ic.sizes = &row_sizes;
+    r = db->impl->write_item(id, c + 1, 0, ic, false);  // column 0 is the index column
+  }
+  if (r.success()) r = db->impl->commit_table(id, {n_rows});
+  if (!r.success()) {
+    db->impl->delete_table(table);
+    return fail(r.msg());
+  }
+  return id;
+}
+
 int scn_db_commit_job_table(scn_db* db, int table_id, scn_job* j) {
   if (!db || !j || j->j.task_starts.size() < 1) return fail("bad arguments");
   std::vector<i64> end_rows(j->j.task_starts.begin() + 1, j->j.task_starts.end());

@@ -28,6 +28,7 @@ SIGNATURES = {
     "scn_stream_add_bytes": (_I64, [_VP, _VP, _VP, _I64]),
     "scn_stream_rows": (_I64, [_VP, _I64]),
     "scn_stream_may_reorder": (_I, [_VP, _I64]),
+    "scn_db_new_table_from_rows": (_I, [_VP, _CP, _I, _VP, _I64, _VP, _VP]),
     # host-language kernels: pyops.py binds the struct / callback types over these
     "scn_register_callback_op": (_I, [_VP, _VP, _VP]),
     "scn_cb_emit_bytes": (_I, [_VP, _I, _VP, _SZ]),
@@ -264,6 +265,19 @@ class Database:
 
     def add_video_stream(self, engine, table):
         return check(lib().scn_db_add_video_stream(self._h, engine._h, table.encode()), f"add_video_stream({table})")
+
+    def new_table_from_rows(self, table, columns, rows):
+        """rows: list of rows, each a list of bytes (or None) per column -> table id"""
+        n_cols, n_rows = len(columns), len(rows)
+        names = (ctypes.c_char_p * n_cols)(*[c.encode() for c in columns])
+        cells = [None if v is None else bytes(v) for row in rows for v in row]
+        if len(cells) != n_cols * n_rows:
+            raise EngineError(f"new_table_from_rows({table}): every row must have {n_cols} elements")
+        keep = [ctypes.create_string_buffer(v, len(v)) if v else None for v in cells]
+        ptrs = (ctypes.c_void_p * max(1, len(cells)))(*[ctypes.addressof(b) if b is not None else None for b in keep])
+        sizes = (ctypes.c_uint64 * max(1, len(cells)))(*[len(v) if v else 0 for v in cells])
+        return check(lib().scn_db_new_table_from_rows(self._h, table.encode(), n_cols, names, n_rows, ptrs, sizes),
+                     f"new_table_from_rows({table})")
 
     def new_table(self, table, column, is_video=False, type_name="", job_id=-1):
         """Reserve a one-column table a job will save into while it runs -> table id."""

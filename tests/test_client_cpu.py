@@ -272,3 +272,27 @@ def test_frame_outputs_into_a_named_video_stream(sc, tmp_path):
             assert (f == oracle.resize(frames[i], 16, 12)).all()
         if client is not sc:
             client.stop()
+
+
+def test_new_table_from_python_rows(tmp_path):
+    """Reference tests/py_test.py:209-217 (test_new_table) plus nulls, force and the catalogue."""
+    c = sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False)
+    t = c.new_table("test", ["col1", "col2"], [[b"r00", b"r01"], [b"r10", b"r11"], [b"", None]])
+    assert t.num_rows() == 3 and t.column_names() == ["index", "col1", "col2"]
+    assert next(t.column("col2").load()) == b"r01"
+    assert list(t.column("col1").load()) == [b"r00", b"r10", None]
+    assert list(t.column("col2").load(rows=[1, 2])) == [b"r11", None]
+    assert [struct.unpack("<q", r)[0] for r in t.column("index").load()] == [0, 1, 2]
+    with pytest.raises(sp.ScannerException, match="existing name"):
+        c.new_table("test", ["a"], [[b"x"]])
+    t = c.new_table("test", ["a"], [[b"x"]], force=True)
+    assert t.column_names() == ["index", "a"] and t.num_rows() == 1
+    with pytest.raises(sp.ScannerException, match="every row must have 2 elements"):
+        c.new_table("bad", ["a", "b"], [[b"x"]])
+    assert not c.has_table("bad")
+    # the table is a normal stored stream: a job can read its column
+    src = sp.NamedStream(c, "test")
+    assert src.exists() and list(src.load()) == [b"x"]
+    with sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False) as c2:
+        assert c2.table("test").num_rows() == 1
+    c.stop()
