@@ -395,11 +395,18 @@ class NamedVideoStream:
         """stream id for use as an input; a video written by an earlier job binds lazily"""
         if self._sid is None:
             db = self._sc._db
-            if db is not None and db.has_table(self._name) and db.table_info(self._name)["keyframes"] >= 0:
-                self._sid = db.add_video_stream(self._sc._engine, self._name)
-                self._sc._streams[self._name] = self._sid
+            if self._job is None and db is not None and db.has_table(self._name) and \
+                    db.table_info(self._name)["keyframes"] > 0:
+                self._sid = db.add_video_stream(self._sc._engine, self._name)  # ingested H.264
+            elif self._job is not None or self._stored():
+                # frames written by an earlier job (stored uncompressed): the next job's input
+                frames = list(NamedStream.load(self))
+                if not frames or any(f is None for f in frames):
+                    raise ScannerException(f"video stream {self._name} has null or no frames: it cannot be an input")
+                self._sid = self._sc._engine.add_raw_frames(np.stack(frames))
             else:
                 raise ScannerException(f"video stream {self._name} does not exist (no table, no path, not written yet)")
+            self._sc._streams[self._name] = self._sid
         return self._sid
 
     def len(self):
@@ -569,6 +576,19 @@ class NamedStream:
     def _stored(self):
         db = self._sc._db
         return db is not None and db.has_table(self._name)
+
+    def _bind(self):
+        """stream id for use as an input: the rows an earlier job wrote (in memory or in the
+        database) become a byte stream of the engine"""
+        if self._sid is None:
+            if self._job is None and not self._stored():
+                raise ScannerException(f"stream {self._name} does not exist (not written yet)")
+            rows = list(self.load_bytes())
+            if any(isinstance(r, np.ndarray) for r in rows):
+                raise ScannerException(f"stream {self._name} holds frames: bind it as a NamedVideoStream")
+            self._sid = self._sc._engine.add_bytes([b"" if r is None else bytes(r) for r in rows])
+            self._sc._streams[self._name] = self._sid
+        return self._sid
 
     def exists(self):
         return self._job is not None or self._sid is not None or self._stored()
@@ -854,7 +874,7 @@ class Client:
             for node in order:
                 if node.kind == "input":
                     st = node.streams[j]
-                    job.bind_source(index[id(node)], st._bind() if isinstance(st, NamedVideoStream) else st._sid)
+                    job.bind_source(index[id(node)], st._bind())
                 elif node.kind in ("sample", "space"):
                     args = node.per_stream[j if len(node.per_stream) > 1 else 0]
                     if isinstance(args, SliceList):
@@ -910,6 +930,9 @@ class Client:
             src_col = node.inputs[0]
             type_name = _column_type_name(src_col)
             for j, s in enumerate(node.streams):
+                if j not in skip:  # freshly written: an input binding made from older rows is stale
+                    s._sid = None
+                    self._streams.pop(s.name(), None)
                 if j in skip or self._db is not None:
                     s._job = None  # served from the stored table
                     continue

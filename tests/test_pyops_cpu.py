@@ -410,3 +410,36 @@ def test_frames_written_by_a_python_op_save_as_mp4(tmp_path, with_db):
     if with_db:
         out.delete()
     sc.stop()
+
+
+@register_python_op()
+def FrameSum(config, frame: FrameType) -> Any:
+    return int(frame.sum())
+
+
+@pytest.mark.parametrize("with_db", [False, True])
+def test_outputs_of_one_job_are_inputs_of_the_next(tmp_path, with_db):
+    """Tables written by a job (byte rows and frames) feed later jobs, in memory or through the
+    database, and a re-written stream is re-read rather than served from a stale binding."""
+    sc = sp.Client(gpus=[], cpu_instances=2, db_path=str(tmp_path / "db") if with_db else None)
+    v = sp.NamedVideoStream(sc, "v", frames=frames(9))
+    sums, inv = sp.NamedStream(sc, "sums"), sp.NamedVideoStream(sc, "inv")
+    frame = sc.io.Input([v])
+    sc.run([sc.io.Output(sc.ops.FrameSum(frame=frame), [sums]), sc.io.Output(sc.ops.Negative(frame=frame), [inv])],
+           sp.PerfParams.manual(2, 4))
+    out2, out3 = sp.NamedStream(sc, "sums_plus"), sp.NamedStream(sc, "inv_sums")
+    sc.run([sc.io.Output(sc.ops.CacheTest(n=sc.io.Input([sums])), [out2]),
+            sc.io.Output(sc.ops.FrameSum(frame=sc.io.Input([inv])), [out3])], sp.PerfParams.manual(2, 4))
+    px = H * W * 3
+    assert list(out2.load()) == [i * px + 1 for i in range(9)]
+    assert list(out3.load()) == [(255 - i) * px for i in range(9)]
+    # overwrite `sums` with other values and consume it again
+    sc.run(sc.io.Output(sc.ops.CacheTest(n=sc.io.Input([out2]), step=100), [sums]), sp.PerfParams.manual(2, 4),
+           cache_mode=sp.CacheMode.Overwrite)
+    sc.run(sc.io.Output(sc.ops.CacheTest(n=sc.io.Input([sums])), [out2]), sp.PerfParams.manual(2, 4),
+           cache_mode=sp.CacheMode.Overwrite)
+    assert list(out2.load()) == [i * px + 102 for i in range(9)]
+    with pytest.raises(sp.ScannerException, match="does not exist"):
+        sc.run(sc.io.Output(sc.ops.CacheTest(n=sc.io.Input([sp.NamedStream(sc, "nope")])), [out3]),
+               sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)
+    sc.stop()
