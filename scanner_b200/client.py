@@ -41,6 +41,27 @@ class CacheMode(enum.Enum):
     Overwrite = 3
 
 
+class NullElement:
+    """A null row of a loaded stream (reference storage.py:8-16): what RepeatNull spacing or a kernel
+    returning None leaves behind.  Falsy and equal to None, so `if row:` and `row == None` both work."""
+
+    def __repr__(self):
+        return "NullElement()"
+
+    def __bool__(self):
+        return False
+
+    def __eq__(self, other):
+        return other is None or isinstance(other, NullElement)
+
+    def __hash__(self):
+        return hash(None)
+
+
+def _is_null(row):
+    return row is None or isinstance(row, NullElement)
+
+
 class ScannerException(Exception):
     pass
 
@@ -255,6 +276,21 @@ class StreamsGenerator:
     def _pair(r):
         return (r["start"], r["end"]) if isinstance(r, dict) else (r[0], r[1])
 
+    @staticmethod
+    def _fields(e, names):
+        """One per-stream sampler argument as the reference accepts it (op.py extra/arg_builder:
+        a dict is keyword arguments, a tuple positional ones, anything else the single argument)."""
+        if isinstance(e, dict):
+            missing = [n for n in names if n not in e]
+            if missing:
+                raise ScannerException(f"sampler argument {e!r} lacks {missing[0]!r}")
+            return tuple(e[n] for n in names)
+        if isinstance(e, tuple) or (isinstance(e, list) and len(names) > 1):
+            if len(e) != len(names):
+                raise ScannerException(f"sampler argument {e!r} must have {len(names)} entries {names}")
+            return tuple(e)
+        return (e,)
+
     def Slice(self, input, partitions):
         """partitions: one partitioner per stream (sc.partitioner.all / strided / ranges / ...)."""
         node = _Node("slice", "Slice", [input], per_stream=list(partitions))
@@ -268,7 +304,8 @@ class StreamsGenerator:
         return self._sample(input, "All", None, [{}])
 
     def Stride(self, input, strides):
-        return self._sample(input, "Strided", "StridedSamplerArgs", [self._map(s, lambda e: {"stride": e}) for s in strides])
+        return self._sample(input, "Strided", "StridedSamplerArgs",
+                            [self._map(s, lambda e: {"stride": self._fields(e, ["stride"])[0]}) for s in strides])
 
     def Range(self, input, ranges):
         ds = [self._map(r, lambda e: {"stride": 1, "starts": [self._pair(e)[0]], "ends": [self._pair(e)[1]]})
@@ -279,23 +316,29 @@ class StreamsGenerator:
         return self.StridedRanges(input, intervals, [1] * len(intervals))
 
     def StridedRange(self, input, ranges):
-        return self.StridedRanges(input, [[(s, e)] for s, e, _ in ranges], [st for _, _, st in ranges])
+        triples = [self._fields(r, ["start", "end", "stride"]) for r in ranges]
+        return self.StridedRanges(input, [[(s, e)] for s, e, _ in triples], [st for _, _, st in triples])
 
-    def StridedRanges(self, input, intervals, strides):
+    def StridedRanges(self, input, intervals, strides=None, stride=None):
+        if strides is None:
+            strides = 1 if stride is None else stride  # the reference's single `stride` for every stream
         strides = strides if isinstance(strides, (list, tuple)) else [strides] * len(intervals)
         return self._sample(input, "StridedRanges", "StridedRangeSamplerArgs",
                             [{"stride": st, "starts": [self._pair(p)[0] for p in iv],
                               "ends": [self._pair(p)[1] for p in iv]} for iv, st in zip(intervals, strides)])
 
     def Gather(self, input, indices):
-        return self._sample(input, "Gather", "GatherSamplerArgs", [self._map(r, lambda e: {"rows": list(e)}) for r in indices])
+        return self._sample(input, "Gather", "GatherSamplerArgs",
+                            [self._map(r, lambda e: {"rows": list(e["rows"] if isinstance(e, dict) else e)})
+                             for r in indices])
 
     def RepeatNull(self, input, spacings):
-        return self._sample(input, "SpaceNull", "SpaceNullSamplerArgs", [{"spacing": s} for s in spacings], "space")
+        return self._sample(input, "SpaceNull", "SpaceNullSamplerArgs",
+                            [{"spacing": self._fields(s, ["spacing"])[0]} for s in spacings], "space")
 
     def Repeat(self, input, spacings):
-        return self._sample(input, "SpaceRepeat", "SpaceRepeatSamplerArgs", [{"spacing": s} for s in spacings],
-                            "space")
+        return self._sample(input, "SpaceRepeat", "SpaceRepeatSamplerArgs",
+                            [{"spacing": self._fields(s, ["spacing"])[0]} for s in spacings], "space")
 
 
 class Partitioner:
@@ -401,7 +444,7 @@ class NamedVideoStream:
             elif self._job is not None or self._stored():
                 # frames written by an earlier job (stored uncompressed): the next job's input
                 frames = list(NamedStream.load(self))
-                if not frames or any(f is None for f in frames):
+                if not frames or any(_is_null(f) for f in frames):
                     raise ScannerException(f"video stream {self._name} has null or no frames: it cannot be an input")
                 self._sid = self._sc._engine.add_raw_frames(np.stack(frames))
             else:
@@ -489,7 +532,7 @@ class NamedVideoStream:
             raise ScannerException(f"stream {self._name} does not exist")
         planes, size = [], None
         for f in self.load():
-            if f is None:
+            if _is_null(f):
                 continue
             if f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] not in (1, 3):
                 raise ScannerException("save_mp4 writes uint8 frames with 1 or 3 channels")
@@ -545,7 +588,9 @@ def _column_type_name(col):
 
 def _typed(row, ty):
     """Deserialise a stored byte row by its column type name (scannerpy.types registry)."""
-    if row is None or isinstance(row, np.ndarray) or not ty:
+    if row is None:
+        return NullElement()
+    if isinstance(row, np.ndarray) or not ty:
         return row
     if isinstance(ty, str):
         if ty in ("Bytes", "bytes"):
@@ -586,7 +631,7 @@ class NamedStream:
             rows = list(self.load_bytes())
             if any(isinstance(r, np.ndarray) for r in rows):
                 raise ScannerException(f"stream {self._name} holds frames: bind it as a NamedVideoStream")
-            self._sid = self._sc._engine.add_bytes([b"" if r is None else bytes(r) for r in rows])
+            self._sid = self._sc._engine.add_bytes([b"" if _is_null(r) else bytes(r) for r in rows])
             self._sc._streams[self._name] = self._sid
         return self._sid
 

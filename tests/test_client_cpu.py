@@ -280,8 +280,9 @@ def test_new_table_from_python_rows(tmp_path):
     t = c.new_table("test", ["col1", "col2"], [[b"r00", b"r01"], [b"r10", b"r11"], [b"", None]])
     assert t.num_rows() == 3 and t.column_names() == ["index", "col1", "col2"]
     assert next(t.column("col2").load()) == b"r01"
-    assert list(t.column("col1").load()) == [b"r00", b"r10", None]
-    assert list(t.column("col2").load(rows=[1, 2])) == [b"r11", None]
+    assert list(t.column("col1").load()) == [b"r00", b"r10", None]  # NullElement() == None
+    got = list(t.column("col2").load(rows=[1, 2]))
+    assert got[0] == b"r11" and isinstance(got[1], sp.NullElement)
     assert [struct.unpack("<q", r)[0] for r in t.column("index").load()] == [0, 1, 2]
     with pytest.raises(sp.ScannerException, match="existing name"):
         c.new_table("test", ["a"], [[b"x"]])
@@ -296,3 +297,39 @@ def test_new_table_from_python_rows(tmp_path):
     with sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False) as c2:
         assert c2.table("test").num_rows() == 1
     c.stop()
+
+
+def test_sampler_arguments_in_every_form_the_reference_accepts(sc):
+    """py_test.py:274-336 test_sample / test_space call the samplers with keyword `input=` and with
+    dict arguments ({'stride': 8}, {'start': 0, 'end': 30}, {'start':, 'end':, 'stride':}); the
+    tutorials use plain numbers and tuples.  Both must select the same rows."""
+    src = _ints(sc, "samp_in", 60)
+
+    def rows(make):
+        out = sp.NamedStream(sc, "samp_out")
+        sc.run(sc.io.Output(make(sc.io.Input([src])), [out]), sp.PerfParams.manual(4, 8),
+               cache_mode=sp.CacheMode.Overwrite)
+        return list(out.load())
+
+    def ints(make):
+        return [struct.unpack("<q", r)[0] for r in rows(make)]
+
+    assert ints(lambda c: sc.streams.Stride(input=c, strides=[{"stride": 8}])) == list(range(0, 60, 8)) \
+        == ints(lambda c: sc.streams.Stride(c, [8]))
+    assert ints(lambda c: sc.streams.Range(input=c, ranges=[{"start": 0, "end": 30}])) == list(range(30)) \
+        == ints(lambda c: sc.streams.Range(c, [(0, 30)]))
+    assert ints(lambda c: sc.streams.StridedRange(input=c, ranges=[{"start": 0, "end": 50, "stride": 10}])) \
+        == [0, 10, 20, 30, 40] == ints(lambda c: sc.streams.StridedRange(c, [(0, 50, 10)]))
+    assert ints(lambda c: sc.streams.StridedRanges(c, [[(0, 10), (30, 40)]], stride=5)) == [0, 5, 30, 35]
+    assert ints(lambda c: sc.streams.Gather(input=c, indices=[[0, 15, 37, 50]])) == [0, 15, 37, 50]
+    rep = ints(lambda c: sc.streams.Repeat(input=sc.streams.Range(c, [(0, 3)]), spacings=[4]))
+    assert rep == [0] * 4 + [1] * 4 + [2] * 4
+    nulls = rows(lambda c: sc.streams.RepeatNull(input=sc.streams.Range(c, [(0, 3)]), spacings=[{"spacing": 4}]))
+    assert len(nulls) == 12
+    for i, r in enumerate(nulls):
+        if i % 4 == 0:
+            assert not isinstance(r, sp.NullElement) and struct.unpack("<q", r)[0] == i // 4
+        else:
+            assert isinstance(r, sp.NullElement)
+    with pytest.raises(sp.ScannerException, match="lacks 'end'"):
+        sc.streams.StridedRange(sc.io.Input([src]), [{"start": 0, "stride": 2}])

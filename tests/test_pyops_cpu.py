@@ -245,8 +245,8 @@ def test_null_rows_and_two_typed_outputs(sc):
     v, im = list(o1.load()), list(o2.load())
     for i in range(9):
         if i % 3 == 0:
-            assert v[i] is None or len(v[i]) == 0
-            assert im[i] is None
+            assert isinstance(v[i], sp.NullElement) and isinstance(im[i], sp.NullElement)
+            assert not v[i] and v[i] == None  # noqa: E711  (falsy, equal to None)
         else:
             assert v[i].dtype == np.float32 and v[i].tolist() == [i, 2 * i]
             assert im[i].dtype == np.float32 and im[i].shape == (4, 5, 1) and (im[i] == i / 2).all()
