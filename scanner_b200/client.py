@@ -695,6 +695,13 @@ class Column:
         return self._desc["type"]
 
     def load(self, ty=None, fn=None, rows=None):
+        """Rows of the column (reference column.py:200-260): byte columns through their type's
+        deserializer, stored frames as ndarrays, a compressed (ingested) video column decoded."""
+        if self._desc["type"] == "Video" and self._table._info.get("keyframes", 0) > 0:
+            if self._table._sc is None:
+                raise ScannerException("loading a compressed video column needs the table from Client.table()")
+            yield from NamedVideoStream(self._table._sc, self._table._name).load(rows=rows)
+            return
         ty = ty or self._desc["type_name"] or None
         for r in self._table._db.read_rows(self._table._name, self._desc["name"], rows):
             if fn is not None and r is not None and not isinstance(r, np.ndarray):
@@ -706,8 +713,8 @@ class Column:
 class Table:
     """A stored table (reference scannerpy/table.py): id, name, rows, columns."""
 
-    def __init__(self, db, name):
-        self._db, self._name = db, name
+    def __init__(self, db, name, sc=None):
+        self._db, self._name, self._sc = db, name, sc
         self._info = db.table_info(name)
 
     def id(self):
@@ -819,7 +826,7 @@ class Client:
     def table(self, name):
         if not self._need_db().has_table(name):
             raise ScannerException(f"table {name} does not exist")
-        return Table(self._db, name)
+        return Table(self._db, name, self)
 
     def summarize(self):
         """Text table of the catalogue (reference client.py summarize): name, id, rows, columns."""

@@ -86,6 +86,9 @@ def test_00_basic(sc, example):
     rows = [0, 10, 100, 57]
     frames = list(video_stream2.load(rows=rows))
     assert len(frames) == len(rows) and all((f == shown[r]).all() for f, r in zip(frames, rows))
+    table = sc.table("example1")  # py_test.py test_table_properties
+    assert table.num_rows() == FRAMES and table.column_names() == ["index", "frame"]
+    assert (next(table.column("frame").load(rows=[33])) == shown[33]).all()
     for stream in [video_stream1, video_stream2, named_stream1, named_stream2]:
         stream.delete(sc)
 
