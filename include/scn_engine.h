@@ -37,7 +37,8 @@ SCN_ENGINE_API const char* scn_last_error(void);
 SCN_ENGINE_API int scn_load_op_library(const char* so_path);
 SCN_ENGINE_API int scn_op_registered(const char* op_name);                    /* 1 / 0 */
 SCN_ENGINE_API int scn_kernel_registered(const char* op_name, int device_type); /* 1 / 0 */
-/* Writes "name:n_inputs:n_outputs:can_stencil:bounded:unbounded:warmup\n" per registered op. */
+/* Writes "name:n_inputs:n_outputs:can_stencil:bounded:unbounded:warmup:protobuf_name:stream_protobuf_name\n"
+ * per registered op (the last two: the op's argument message names, empty if it declared none). */
 SCN_ENGINE_API int scn_list_ops(char* host_buf, size_t cap);
 
 /* ---- engine ------------------------------------------------------------------------------- */

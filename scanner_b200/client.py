@@ -849,6 +849,18 @@ class Client:
         E.load_op_library(so_path)
         if proto_path:
             msgs = protolite.parse_proto(open(proto_path).read())
+            # the message names an op registered with (.protobuf_name / .stream_protobuf_name) are looked
+            # up in the proto file, as the reference does with the compiled module (op.py:299-307)
+            for op, info in E.list_ops().items():
+                if op in self._op_protos:
+                    continue
+                found = {}
+                if info["protobuf_name"] in msgs:
+                    found["init"] = msgs[info["protobuf_name"]]
+                if info["stream_protobuf_name"] in msgs:
+                    found["stream"] = msgs[info["stream_protobuf_name"]]
+                if found:
+                    self._op_protos[op] = found
             for op, d in (protos or {}).items():
                 self._op_protos[op] = {k: msgs[v] for k, v in d.items()}
 

@@ -74,7 +74,8 @@ int scn_list_ops(char* buf, size_t cap) {
   for (const std::string& n : get_op_registry()->names()) {
     const OpInfo* i = get_op_registry()->get_op_info(n);
     ss << n << ":" << i->input_columns.size() << ":" << i->output_columns.size() << ":" << i->can_stencil << ":"
-       << i->has_bounded_state << ":" << i->has_unbounded_state << ":" << i->warmup << "\n";
+       << i->has_bounded_state << ":" << i->has_unbounded_state << ":" << i->warmup << ":" << i->protobuf_name << ":"
+       << i->stream_protobuf_name << "\n";
   }
   return copy_out(ss.str(), buf, cap);
 }

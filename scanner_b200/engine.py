@@ -136,9 +136,10 @@ def list_ops():
     check(lib().scn_list_ops(buf, len(buf)), "scn_list_ops")
     out = {}
     for line in buf.value.decode().splitlines():
-        n, ni, no, st, b, ub, w = line.split(":")
+        n, ni, no, st, b, ub, w, *names = line.split(":")
         out[n] = dict(inputs=int(ni), outputs=int(no), can_stencil=bool(int(st)), bounded=bool(int(b)),
-                      unbounded=bool(int(ub)), warmup=int(w))
+                      unbounded=bool(int(ub)), warmup=int(w), protobuf_name=names[0] if names else "",
+                      stream_protobuf_name=names[1] if len(names) > 1 else "")
     return out
 
 

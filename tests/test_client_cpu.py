@@ -21,12 +21,10 @@ def sc():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
     c = sp.Client(gpus=[], cpu_instances=2)
     so = os.path.join(ROOT, "build", "tests", "libtest_plugin_ops.so")
-    if "TestWindow" not in E.list_ops():
-        c.load_op(so)
-    from scanner_b200 import protolite
-    msgs = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
-    c._op_protos["TestAffine"] = {"init": msgs["TestScaleArgs"], "stream": msgs["TestOffsetArgs"]}
-    c._op_protos["TestResizeOracle"] = {"stream": msgs["TestSizeArgs"]}
+    # Client.load_op(so_path, proto_path) (reference client.py:514-537): the argument messages of the
+    # ops are the ones they registered with (.protobuf_name / .stream_protobuf_name), found in the file
+    c.load_op(so, os.path.join(ROOT, "tests", "cpp", "test_args.proto"))
+    assert sorted(c._op_protos["TestAffine"]) == ["init", "stream"] and list(c._op_protos["TestResizeOracle"]) == ["stream"]
     yield c
     c.stop()
 
@@ -89,9 +87,8 @@ def test_errors_are_scanner_exceptions(sc):
 # ------------------------------------------------------------------------------------------------
 def _db_client(path):
     c = sp.Client(gpus=[], cpu_instances=2, db_path=str(path))
-    from scanner_b200 import protolite
-    msgs = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
-    c._op_protos["TestAffine"] = {"init": msgs["TestScaleArgs"], "stream": msgs["TestOffsetArgs"]}
+    c.load_op(os.path.join(ROOT, "build", "tests", "libtest_plugin_ops.so"),
+              os.path.join(ROOT, "tests", "cpp", "test_args.proto"))
     return c
 
 
@@ -258,10 +255,6 @@ def test_frame_outputs_into_a_named_video_stream(sc, tmp_path):
     there is no encoder here) and load() yields them, in memory and from the database."""
     frames = np.stack([synth.rand_frame(400 + i, 24, 32) for i in range(7)])
     for client in (sc, _db_client(tmp_path / "db")):
-        if "TestResizeOracle" not in client._op_protos:
-            from scanner_b200 import protolite
-            msgs = protolite.parse_proto(open(os.path.join(ROOT, "tests", "cpp", "test_args.proto")).read())
-            client._op_protos["TestResizeOracle"] = {"stream": msgs["TestSizeArgs"]}
         vin = sp.NamedVideoStream(client, "vs_in", frames=frames)
         small = client.ops.TestResizeOracle(frame=client.io.Input([vin]), width=[16], height=[12])
         vout = sp.NamedVideoStream(client, "vs_out")
