@@ -7,7 +7,12 @@
 //   ImageDecoder  PNG bytes -> frame (the op pipelines pair with it: examples/tutorials/
 //                 05_sources_sinks.py:41-47; upstream it lives in scannertools and calls
 //                 cv::imdecode).  Non-interlaced PNG of colour types 0, 2, 4, 6 with 8 or 16 bits.
-// Both are CPU kernels like the reference's: the pipeline moves frame elements between devices.
+//                 The GPU kernel of the op also takes JPEG: decoded by nvJPEG (a CUDA toolkit
+//                 library, as SURVEY 8f rank 3 names it) straight into a device frame, RGB order;
+//                 PNG elements reaching the GPU kernel are inflated on the host and copied up.
+// The CPU kernels are like the reference's: the pipeline moves frame elements between devices.
+#include <cuda_runtime.h>
+#include <nvjpeg.h>
 #include <zlib.h>
 
 #include <cstring>
@@ -245,6 +250,82 @@ class ImageDecoderKernel : public BatchedKernel {
 
 REGISTER_OP(ImageDecoder).input("img").frame_output("frame");
 REGISTER_KERNEL(ImageDecoder, ImageDecoderKernel).device(DeviceType::CPU).batch(8).num_devices(1);
+
+// ---- GPU kernel: JPEG through nvJPEG, output frames in device memory ---------------------------
+class ImageDecoderKernelGPU : public BatchedKernel {
+ public:
+  ImageDecoderKernelGPU(const KernelConfig& config) : BatchedKernel(config), device_(config.devices[0]) {
+    if (cudaSetDevice(device_.id) != cudaSuccess) {
+      RESULT_ERROR(&valid_, "ImageDecoder: cannot select GPU %d", device_.id);
+      return;
+    }
+    nvjpegStatus_t st = nvjpegCreateSimple(&handle_);
+    if (st == NVJPEG_STATUS_SUCCESS) st = nvjpegJpegStateCreate(handle_, &state_);
+    if (st != NVJPEG_STATUS_SUCCESS) {
+      RESULT_ERROR(&valid_, "ImageDecoder: nvJPEG initialisation failed (status %d)", (int)st);
+      return;
+    }
+    valid_.set_success(true);
+  }
+  ~ImageDecoderKernelGPU() override {
+    if (state_) nvjpegJpegStateDestroy(state_);
+    if (handle_) nvjpegDestroy(handle_);
+  }
+  void validate(Result* result) override { result->CopyFrom(valid_); }
+
+  void execute(const BatchedElements& in, BatchedElements& out) override {
+    if (cudaSetDevice(device_.id) != cudaSuccess) LOG(FATAL) << "ImageDecoder: cannot select GPU " << device_.id;
+    cudaStream_t stream = (cudaStream_t)device_stream(device_);
+    for (const Element& e : in[0]) {
+      if (e.is_null()) {
+        out[0].push_back(Element());
+        continue;
+      }
+      if (e.size >= 8 && memcmp(e.buffer, kPngSig, 8) == 0) {
+        Frame* host = nullptr;
+        const std::string err = decode_png(e.buffer, e.size, host);
+        if (!err.empty()) LOG(FATAL) << err;
+        Frame* dev = new_frame(device_, host->as_frame_info());
+        if (cudaMemcpyAsync(dev->data, host->data, host->size(), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess)
+          LOG(FATAL) << "ImageDecoder: copying a decoded PNG to GPU " << device_.id << " failed";
+        delete_buffer(CPU_DEVICE, host->data);
+        delete host;
+        insert_frame(out[0], dev);
+        continue;
+      }
+      int components = 0, widths[NVJPEG_MAX_COMPONENT] = {0}, heights[NVJPEG_MAX_COMPONENT] = {0};
+      nvjpegChromaSubsampling_t subsampling;
+      nvjpegStatus_t st = nvjpegGetImageInfo(handle_, e.buffer, e.size, &components, &subsampling, widths, heights);
+      if (st != NVJPEG_STATUS_SUCCESS || widths[0] <= 0 || heights[0] <= 0)
+        LOG(FATAL) << "ImageDecoder: element " << e.index << " is neither PNG nor a JPEG nvJPEG can parse (status "
+                   << (int)st << ")";
+      Frame* f = new_frame(device_, FrameInfo(heights[0], widths[0], 3, FrameType::U8));
+      nvjpegImage_t img;
+      memset(&img, 0, sizeof(img));
+      img.channel[0] = f->data;
+      img.pitch[0] = (size_t)widths[0] * 3;
+      st = nvjpegDecode(handle_, state_, e.buffer, e.size, NVJPEG_OUTPUT_RGBI, &img, stream);
+      if (st != NVJPEG_STATUS_SUCCESS)
+        LOG(FATAL) << "ImageDecoder: nvjpegDecode failed on element " << e.index << " (status " << (int)st << ")";
+      insert_frame(out[0], f);
+    }
+    // the encoded bytes are borrowed from the engine: nothing of this batch may still be reading them
+    if (cudaStreamSynchronize(stream) != cudaSuccess) LOG(FATAL) << "ImageDecoder: stream synchronisation failed";
+  }
+
+ private:
+  DeviceHandle device_;
+  nvjpegHandle_t handle_ = nullptr;
+  nvjpegJpegState_t state_ = nullptr;
+  Result valid_;
+};
+
+REGISTER_KERNEL(ImageDecoder, ImageDecoderKernelGPU)
+    .device(DeviceType::GPU)
+    .batch(8)
+    .num_devices(1)
+    .input_device("img", DeviceType::CPU);
 
 }  // namespace
 }  // namespace scanner
