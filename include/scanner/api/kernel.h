@@ -162,6 +162,14 @@ class Kernel : public BaseKernel {
 
 // Mix-in for kernels that consume frame columns: check_frame() fires new_frame_info() when the
 // shape/type differs from the cached one (reference kernel.cpp:97-109).
+// Fails the running job with `message` without taking the process down.  The reference's only
+// runtime error path is LOG(FATAL) (a worker failure the master recovers from); here the engine
+// lives inside the user's process, so kernels facing bad DATA (an undecodable image, a raising
+// host-language kernel) report it and return normally -- still producing one element per row, null
+// where they have nothing -- and the evaluate loop ends the run with the message.  Call it from the
+// thread that runs execute() / new_stream() / reset().
+void report_kernel_error(const std::string& message);
+
 class VideoKernel {
  protected:
   void check_frame(const DeviceHandle& device, const Element& element);

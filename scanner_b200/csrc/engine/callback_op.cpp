@@ -39,6 +39,12 @@ bool take_kernel_error(std::string* msg) {
   return true;
 }
 
+}  // namespace internal
+
+void report_kernel_error(const std::string& message) { internal::raise_kernel_error(message); }
+
+namespace internal {
+
 namespace {
 
 struct CallbackOp {

@@ -220,8 +220,12 @@ class ImageEncoderKernel : public BatchedKernel {
   void execute(const BatchedElements& in, BatchedElements& out) override {
     for (const Element& e : in[0]) {
       std::vector<u8> png;
-      const std::string err = encode_png(e.as_const_frame(), png);
-      if (!err.empty()) LOG(FATAL) << err;
+      const std::string err = e.is_null() ? std::string("null frame") : encode_png(e.as_const_frame(), png);
+      if (!err.empty()) {
+        report_kernel_error("ImageEncoder, row " + std::to_string(e.index) + ": " + err);
+        out[0].push_back(Element());
+        continue;
+      }
       u8* buf = new_buffer(CPU_DEVICE, png.size());
       memcpy(buf, png.data(), png.size());
       insert_element(out[0], buf, png.size());
@@ -241,8 +245,12 @@ class ImageDecoderKernel : public BatchedKernel {
   void execute(const BatchedElements& in, BatchedElements& out) override {
     for (const Element& e : in[0]) {
       Frame* f = nullptr;
-      const std::string err = decode_png(e.buffer, e.size, f);
-      if (!err.empty()) LOG(FATAL) << err;
+      const std::string err = e.is_null() ? std::string("ImageDecoder: null element") : decode_png(e.buffer, e.size, f);
+      if (!err.empty()) {
+        report_kernel_error(err + " (row " + std::to_string(e.index) + ")");
+        out[0].push_back(Element());
+        continue;
+      }
       insert_frame(out[0], f);
     }
   }
@@ -276,15 +284,22 @@ class ImageDecoderKernelGPU : public BatchedKernel {
   void execute(const BatchedElements& in, BatchedElements& out) override {
     if (cudaSetDevice(device_.id) != cudaSuccess) LOG(FATAL) << "ImageDecoder: cannot select GPU " << device_.id;
     cudaStream_t stream = (cudaStream_t)device_stream(device_);
+    auto bad = [&](const Element& e, const std::string& why) {
+      report_kernel_error("ImageDecoder, row " + std::to_string(e.index) + ": " + why);
+      out[0].push_back(Element());
+    };
     for (const Element& e : in[0]) {
       if (e.is_null()) {
-        out[0].push_back(Element());
+        bad(e, "null element");
         continue;
       }
       if (e.size >= 8 && memcmp(e.buffer, kPngSig, 8) == 0) {
         Frame* host = nullptr;
         const std::string err = decode_png(e.buffer, e.size, host);
-        if (!err.empty()) LOG(FATAL) << err;
+        if (!err.empty()) {
+          bad(e, err);
+          continue;
+        }
         Frame* dev = new_frame(device_, host->as_frame_info());
         if (cudaMemcpyAsync(dev->data, host->data, host->size(), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
             cudaStreamSynchronize(stream) != cudaSuccess)
@@ -297,17 +312,22 @@ class ImageDecoderKernelGPU : public BatchedKernel {
       int components = 0, widths[NVJPEG_MAX_COMPONENT] = {0}, heights[NVJPEG_MAX_COMPONENT] = {0};
       nvjpegChromaSubsampling_t subsampling;
       nvjpegStatus_t st = nvjpegGetImageInfo(handle_, e.buffer, e.size, &components, &subsampling, widths, heights);
-      if (st != NVJPEG_STATUS_SUCCESS || widths[0] <= 0 || heights[0] <= 0)
-        LOG(FATAL) << "ImageDecoder: element " << e.index << " is neither PNG nor a JPEG nvJPEG can parse (status "
-                   << (int)st << ")";
+      if (st != NVJPEG_STATUS_SUCCESS || widths[0] <= 0 || heights[0] <= 0) {
+        bad(e, "neither PNG nor a JPEG that nvJPEG can parse (status " + std::to_string((int)st) + ")");
+        continue;
+      }
       Frame* f = new_frame(device_, FrameInfo(heights[0], widths[0], 3, FrameType::U8));
       nvjpegImage_t img;
       memset(&img, 0, sizeof(img));
       img.channel[0] = f->data;
       img.pitch[0] = (size_t)widths[0] * 3;
       st = nvjpegDecode(handle_, state_, e.buffer, e.size, NVJPEG_OUTPUT_RGBI, &img, stream);
-      if (st != NVJPEG_STATUS_SUCCESS)
-        LOG(FATAL) << "ImageDecoder: nvjpegDecode failed on element " << e.index << " (status " << (int)st << ")";
+      if (st != NVJPEG_STATUS_SUCCESS) {
+        Element dead(f);
+        delete_element(device_, dead);
+        bad(e, "nvjpegDecode failed (status " + std::to_string((int)st) + ")");
+        continue;
+      }
       insert_frame(out[0], f);
     }
     // the encoded bytes are borrowed from the engine: nothing of this batch may still be reading them

@@ -81,3 +81,17 @@ def test_encoder_validates_its_format_argument():
     with pytest.raises(E.EngineError, match="Valid types are: png"):
         run_encoder(np.zeros((1, 4, 4, 3), np.uint8), "jpg")
     assert run_encoder(np.zeros((1, 4, 4, 3), np.uint8))[0][:4] == b"\x89PNG"   # default format
+
+
+def test_undecodable_image_fails_the_run_not_the_process():
+    """Bad DATA is reported through scanner::report_kernel_error: the run ends with the reason and
+    the row, the engine (and the interpreter it lives in) stays up.  The reference aborts the worker."""
+    good = run_encoder(np.full((1, 6, 5, 3), 7, np.uint8))[0]
+    broken = bytearray(good)
+    broken[40] ^= 0xFF  # inside the IDAT chunk: CRC mismatch
+    with pytest.raises(E.EngineError, match=r"CRC mismatch \(row 1\)"):
+        run_decoder([good, bytes(broken), good])
+    with pytest.raises(E.EngineError, match="not a PNG stream"):
+        run_decoder([b"\xff\xd8\xff\xe0 this is a JPEG header, the CPU kernel reads PNG only"])
+    out = run_decoder([good, good])  # still working
+    assert len(out) == 2 and (out[1] == 7).all()
