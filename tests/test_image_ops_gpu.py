@@ -15,7 +15,7 @@ def _smooth(h, w, seed):
     rng = np.random.default_rng(seed)
     a, b, c = rng.uniform(0.5, 2.0, 3)
     img = np.stack([128 + 100 * np.sin(xx / (9 * a) + seed), 128 + 100 * np.cos(yy / (7 * b)),
-                    (xx * c + yy * 2) % 256 * 0.5 + 60], axis=2)
+                    128 + 90 * np.sin((xx * c + yy) / 40)], axis=2)
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
@@ -23,8 +23,11 @@ def test_image_decoder_gpu_jpeg_and_png():
     rgb = [_smooth(48, 64, 1), _smooth(77, 123, 2), _smooth(240, 320, 3)]
     gray = _smooth(40, 56, 4)[..., 0]
     blobs, want = [], []
-    for im in rgb:
-        ok, enc = cv2.imencode(".jpg", im[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, 95])
+    full = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    for k, im in enumerate(rgb):
+        # 4:4:4 for the first two (odd size included): only IDCT rounding can differ between decoders;
+        # the third is 4:2:0, where chroma upsampling filters differ too (looser bound below)
+        ok, enc = cv2.imencode(".jpg", im[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, 95] + (full if k < 2 else []))
         assert ok
         blobs.append(enc.tobytes())
         want.append(cv2.imdecode(enc, cv2.IMREAD_COLOR)[..., ::-1])
@@ -49,5 +52,7 @@ def test_image_decoder_gpu_jpeg_and_png():
         err = np.abs(g.astype(np.int32) - w.astype(np.int32))
         if i == 4:
             assert err.max() == 0  # PNG is lossless
+        elif i == 2:
+            assert err.mean() < 2.5 and np.percentile(err, 99) <= 10, (i, err.mean(), err.max())
         else:
-            assert err.mean() < 2.0 and np.percentile(err, 99) <= 8, (i, err.mean(), err.max())
+            assert err.mean() < 1.0 and err.max() <= 4, (i, err.mean(), err.max())
