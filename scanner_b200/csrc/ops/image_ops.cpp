@@ -75,7 +75,6 @@ std::string encode_png(const Frame* f, std::vector<u8>& out) {
     }
     // minimum sum of absolute differences over the five filters (what libpng / lodepng default to)
     long best = -1;
-    int best_t = 0;
     u8* dst = raw.data() + (size_t)y * (row + 1);
     for (int t = 0; t < 5; ++t) {
       long sum = 0;
@@ -94,12 +93,10 @@ std::string encode_png(const Frame* f, std::vector<u8>& out) {
       }
       if (best < 0 || sum < best) {
         best = sum;
-        best_t = t;
         dst[0] = (u8)t;
         memcpy(dst + 1, cand.data(), row);
       }
     }
-    (void)best_t;
     prev.swap(cur);
   }
   uLongf zn = compressBound((uLong)raw.size());
