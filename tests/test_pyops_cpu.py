@@ -443,3 +443,35 @@ def test_outputs_of_one_job_are_inputs_of_the_next(tmp_path, with_db):
         sc.run(sc.io.Output(sc.ops.CacheTest(n=sc.io.Input([sp.NamedStream(sc, "nope")])), [out3]),
                sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)
     sc.stop()
+
+
+@register_python_op()
+class Fragile(Kernel):
+    def __init__(self, config, fail_in=""):
+        self.fail_in = fail_in
+
+    def fetch_resources(self):
+        if self.fail_in == "fetch":
+            raise RuntimeError("no network here")
+
+    def setup_with_resources(self):
+        if self.fail_in == "setup":
+            raise RuntimeError("model file is missing")
+
+    def new_stream(self, mode="ok"):
+        if mode == "bad":
+            raise ValueError("unknown mode")
+
+    def execute(self, frame: FrameType) -> bytes:
+        return b"x"
+
+
+def test_failures_outside_execute_are_reported_too(sc):
+    frame = sc.io.Input([video(sc, n=6)])
+    with pytest.raises(sp.ScannerException, match=r"(?s)failed to fetch resources.*no network here"):
+        run(sc, sc.ops.Fragile(frame=frame, fail_in="fetch", mode=["ok"]), "f1")
+    with pytest.raises(sp.ScannerException, match=r"(?s)failed setup.*model file is missing"):
+        run(sc, sc.ops.Fragile(frame=frame, fail_in="setup", mode=["ok"]), "f2")
+    with pytest.raises(sp.ScannerException, match=r"(?s)failed in reset / new_stream.*unknown mode"):
+        run(sc, sc.ops.Fragile(frame=frame, mode=["bad"]), "f3")
+    assert run(sc, sc.ops.Fragile(frame=frame, mode=["ok"]), "f4").len() == 6
