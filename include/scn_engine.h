@@ -235,6 +235,10 @@ typedef struct scn_rows scn_rows;
 SCN_ENGINE_API scn_db* scn_db_open(const char* path);
 SCN_ENGINE_API void scn_db_close(scn_db* db);
 SCN_ENGINE_API int scn_db_ingest_video(scn_db* db, const char* table, const char* video_path);
+/* As above without copying the bitstream into the database (reference ingest `inplace`): the table
+ * records the absolute path; binding or exporting it reads (and, for .mp4, demuxes) that file again
+ * and fails if it no longer yields the ingested stream. */
+SCN_ENGINE_API int scn_db_ingest_video_inplace(scn_db* db, const char* table, const char* video_path);
 SCN_ENGINE_API int scn_db_ingest_h264(scn_db* db, const char* table, const uint8_t* bytes, size_t size, int fps_num,
                                       int fps_den);
 SCN_ENGINE_API int scn_db_has_table(scn_db* db, const char* table);

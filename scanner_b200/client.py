@@ -406,7 +406,7 @@ class NamedVideoStream:
                     return  # not stored yet: usable as the target of an Output (frames are stored RAW)
                 try:
                     if path is not None:
-                        db.ingest_video(name, path)
+                        db.ingest_video(name, path, inplace=inplace)
                     else:
                         stream = E.mp4_demux(data)[0] if _is_mp4(data) else data
                         db.ingest_h264(name, stream)
@@ -798,7 +798,7 @@ class Client:
                         raise ScannerException(f"table {name} already exists")
                     db.delete_table(name)
                     self._streams.pop(name, None)
-                db.ingest_video(name, path)
+                db.ingest_video(name, path, inplace=inplace)
                 done.append(NamedVideoStream(self, name))
             except (E.EngineError, ScannerException) as e:
                 failed.append((path, str(e)))

@@ -442,6 +442,10 @@ int scn_db_ingest_video(scn_db* db, const char* table, const char* video_path) {
   if (!db || !table || !video_path) return fail("bad arguments");
   return from_result(db->impl->ingest_video(table, video_path));
 }
+int scn_db_ingest_video_inplace(scn_db* db, const char* table, const char* video_path) {
+  if (!db || !table || !video_path) return fail("bad arguments");
+  return from_result(db->impl->ingest_video(table, video_path, true));
+}
 int scn_db_ingest_h264(scn_db* db, const char* table, const uint8_t* bytes, size_t size, int fps_num, int fps_den) {
   if (!db || !table || !bytes || !size) return fail("bad arguments");
   return from_result(db->impl->ingest_h264(table, bytes, size, fps_den > 0 ? fps_den : 1, fps_num > 0 ? fps_num : 25));
@@ -491,24 +495,15 @@ int scn_db_table_info(scn_db* db, const char* table, int64_t info[8], char* colu
 int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const char* table) {
   if (!db || !e || !table) return fail("bad arguments");
   tables::VideoDescriptor vd;
-  std::string file;
-  Result r = db->impl->read_video(table, vd, file);
-  if (!r.success()) return fail(r.msg());
   std::unique_ptr<InputStream> s(new InputStream());
   s->kind = InputStream::H264;
+  Result r = db->impl->load_video(table, vd, s->encoded);
+  if (!r.success()) return fail(r.msg());
   r = index_from_descriptor(vd, s->index);
   if (!r.success()) return fail(r.msg());
-  FILE* f = fopen(file.c_str(), "rb");
-  if (!f) return fail("cannot open " + file);
-  fseek(f, 0, SEEK_END);
-  const long n = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  s->encoded.resize((size_t)n);
-  const size_t got = n ? fread(s->encoded.data(), 1, (size_t)n, f) : 0;
-  fclose(f);
-  if (got != (size_t)n) return fail("short read of " + file);
-  r = check_index(s->index, (size_t)n);
-  if (!r.success()) return fail("video descriptor of table " + std::string(table) + " does not match " + file + ": " + r.msg());
+  r = check_index(s->index, s->encoded.size());
+  if (!r.success())
+    return fail("video descriptor of table " + std::string(table) + " does not match its data: " + r.msg());
   return e->impl->add_stream(std::move(s));
 }
 
@@ -669,21 +664,12 @@ void scn_rows_free(scn_rows* r) { delete r; }
 int scn_db_export_mp4(scn_db* db, const char* table, const char* out_path, int fps_num, int fps_den) {
   if (!db || !table || !out_path) return fail("bad arguments");
   tables::VideoDescriptor vd;
-  std::string file;
-  Result r = db->impl->read_video(table, vd, file);
+  std::vector<u8> stream;
+  Result r = db->impl->load_video(table, vd, stream);
   if (!r.success()) return fail(r.msg());
   H264Index idx;
   r = index_from_descriptor(vd, idx);
   if (!r.success()) return fail(r.msg());
-  FILE* f = fopen(file.c_str(), "rb");
-  if (!f) return fail("cannot open " + file);
-  fseek(f, 0, SEEK_END);
-  const long n = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<u8> stream((size_t)n);
-  const size_t got = n ? fread(stream.data(), 1, (size_t)n, f) : 0;
-  fclose(f);
-  if (got != (size_t)n) return fail("short read of " + file);
   if (fps_num <= 0 || fps_den <= 0) {  // default: the stored time base (ticks per second / ticks per frame 1)
     fps_num = vd.time_base_denom() > 0 ? vd.time_base_denom() : 25;
     fps_den = vd.time_base_num() > 0 ? vd.time_base_num() : 1;

@@ -333,8 +333,18 @@ Result Database::commit_table(i32 table_id, const std::vector<i64>& end_rows) {
 }
 
 // ---------------------------------------------------------------------------------------------
-Result Database::ingest_video(const std::string& table, const std::string& video_path) {
+Result Database::ingest_video(const std::string& table, const std::string& video_path, bool inplace) {
   Result r = ok();
+  std::string keep;
+  if (inplace) {
+    char* abs = realpath(video_path.c_str(), nullptr);
+    if (!abs) {
+      RESULT_ERROR(&r, "cannot read %s: %s", video_path.c_str(), strerror(errno));
+      return r;
+    }
+    keep = abs;
+    free(abs);
+  }
   std::string bytes;
   if (!read_file(video_path, bytes)) {
     RESULT_ERROR(&r, "cannot read %s: %s", video_path.c_str(), strerror(errno));
@@ -346,12 +356,13 @@ Result Database::ingest_video(const std::string& table, const std::string& video
     r = demux_mp4(p, bytes.size(), trk);
     if (!r.success()) return r;
     // time base of one tick (reference stores the codec context's time_base, ingest.cpp:303-304)
-    return ingest_h264(table, trk.annexb.data(), trk.annexb.size(), 1, (i32)trk.timescale);
+    return ingest_h264(table, trk.annexb.data(), trk.annexb.size(), 1, (i32)trk.timescale, keep);
   }
-  return ingest_h264(table, p, bytes.size(), 1, 25);
+  return ingest_h264(table, p, bytes.size(), 1, 25, keep);
 }
 
-Result Database::ingest_h264(const std::string& table, const u8* annexb, size_t size, i32 tb_num, i32 tb_den) {
+Result Database::ingest_h264(const std::string& table, const u8* annexb, size_t size, i32 tb_num, i32 tb_den,
+                             const std::string& inplace_path) {
   H264Index idx;
   Result r = index_bytestream(annexb, size, idx);
   if (!r.success()) return r;
@@ -363,7 +374,7 @@ Result Database::ingest_h264(const std::string& table, const u8* annexb, size_t 
   r = new_table(table, {ColumnSpec{"frame", proto::Video, ""}}, -1, id);
   if (!r.success()) return r;
   const std::string base = item_base(id, 1, 0);
-  {
+  if (inplace_path.empty()) {
     std::ofstream f(base + ".bin", std::ios::binary | std::ios::trunc);
     f.write((const char*)annexb, (std::streamsize)size);
     if (!f) {
@@ -392,8 +403,8 @@ Result Database::ingest_h264(const std::string& table, const u8* annexb, size_t 
   for (u64 v : idx.sample_sizes) vd.add_sample_sizes(v);
   for (i64 v : idx.keyframe_indices) vd.add_keyframe_indices((u64)v);
   vd.mutable_metadata_packets()->assign((const char*)idx.metadata_packets.data(), idx.metadata_packets.size());
-  vd.set_data_path(base + ".bin");
-  vd.set_inplace(false);
+  vd.set_data_path(inplace_path.empty() ? base + ".bin" : inplace_path);
+  vd.set_inplace(!inplace_path.empty());
   const std::string s = vd.SerializeAsString();
   if (!write_file_atomic(base + "_video_metadata.bin", s.data(), s.size())) {
     RESULT_ERROR(&r, "cannot write %s_video_metadata.bin: %s", base.c_str(), strerror(errno));
@@ -442,6 +453,34 @@ Result Database::read_video(const std::string& table, tables::VideoDescriptor& o
   // the stored data_path is absolute for the writer's mount point; the file next to the
   // descriptor is authoritative (a database directory can be moved)
   data_file = base + ".bin";
+  return r;
+}
+
+Result Database::load_video(const std::string& table, tables::VideoDescriptor& vd, std::vector<u8>& annexb) const {
+  std::string file;
+  Result r = read_video(table, vd, file);
+  if (!r.success()) return r;
+  if (vd.inplace()) file = vd.data_path();
+  std::string bytes;
+  if (!read_file(file, bytes)) {
+    RESULT_ERROR(&r, "cannot read %s (video data of table %s%s): %s", file.c_str(), table.c_str(),
+                 vd.inplace() ? ", ingested in place" : "", strerror(errno));
+    return r;
+  }
+  const u8* p = (const u8*)bytes.data();
+  if (vd.inplace() && looks_like_mp4(p, bytes.size())) {
+    Mp4Track trk;
+    r = demux_mp4(p, bytes.size(), trk);
+    if (!r.success()) return r;
+    annexb.swap(trk.annexb);
+  } else {
+    annexb.assign(p, p + bytes.size());
+  }
+  if (vd.inplace() && vd.size_per_video_size() > 0 && (i64)annexb.size() != vd.size_per_video(0)) {
+    RESULT_ERROR(&r, "%s changed since table %s was ingested in place (%zu stream bytes now, %ld then)", file.c_str(),
+                 table.c_str(), annexb.size(), (long)vd.size_per_video(0));
+    return r;
+  }
   return r;
 }
 

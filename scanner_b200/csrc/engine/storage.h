@@ -52,9 +52,14 @@ class Database {
   Result delete_table(const std::string& name);
 
   // ---- ingest: `video_path` is an .mp4/.mov (demuxed here) or a raw H.264 Annex-B file
-  Result ingest_video(const std::string& table, const std::string& video_path);
+  // inplace (reference ingest.cpp:175-215 `inplace`): the bitstream is not copied into the database;
+  // the descriptor records the absolute path and the sample table of the Annex-B view of that file
+  // (what demuxing it yields), and binding the table demuxes the file again.
+  Result ingest_video(const std::string& table, const std::string& video_path, bool inplace = false);
   Result ingest_h264(const std::string& table, const u8* annexb, size_t size, i32 time_base_num,
-                     i32 time_base_denom);
+                     i32 time_base_denom, const std::string& inplace_path = "");
+  // descriptor + the Annex-B bytes of a compressed video column, wherever they live
+  Result load_video(const std::string& table, tables::VideoDescriptor& vd, std::vector<u8>& annexb) const;
 
   // ---- read side
   Result read_table(const std::string& table, tables::TableDescriptor& out) const;

@@ -28,6 +28,7 @@ SIGNATURES = {
     "scn_stream_add_bytes": (_I64, [_VP, _VP, _VP, _I64]),
     "scn_stream_rows": (_I64, [_VP, _I64]),
     "scn_stream_may_reorder": (_I, [_VP, _I64]),
+    "scn_db_ingest_video_inplace": (_I, [_VP, _CP, _CP]),
     "scn_db_new_table_from_rows": (_I, [_VP, _CP, _I, _VP, _I64, _VP, _VP]),
     # host-language kernels: pyops.py binds the struct / callback types over these
     "scn_register_callback_op": (_I, [_VP, _VP, _VP]),
@@ -229,9 +230,10 @@ class Database:
         except Exception:
             pass
 
-    def ingest_video(self, table, video_path):
-        check(lib().scn_db_ingest_video(self._h, table.encode(), os.path.abspath(video_path).encode()),
-              f"ingest_video({video_path})")
+    def ingest_video(self, table, video_path, inplace=False):
+        """inplace: keep the bitstream where it is (the table records the path) instead of copying it"""
+        fn = lib().scn_db_ingest_video_inplace if inplace else lib().scn_db_ingest_video
+        check(fn(self._h, table.encode(), os.path.abspath(video_path).encode()), f"ingest_video({video_path})")
 
     def ingest_h264(self, table, data, fps_num=25, fps_den=1):
         buf = np.frombuffer(bytes(data), np.uint8)

@@ -148,6 +148,13 @@ def test_ingest_videos_from_mp4_and_h264_files(tmp_path):
     assert "already exists" in failed[0][1]
     done, failed = c.ingest_videos([("a", str(raw))], force=True)
     assert not failed and done[0].len() == n
+    # inplace=True: the table points at the file instead of holding a copy (py_test.py 'test1_inplace')
+    done, failed = c.ingest_videos([("a_inplace", str(mp4))], inplace=True)
+    assert not failed and done[0].len() == n and done[0].info()["keyframes"] == 2
+    assert not os.path.exists(os.path.join(str(tmp_path / "db"), "tables", str(c.table("a_inplace").id()), "1_0.bin"))
+    assert sp.NamedVideoStream(c, "v_inplace", path=str(raw), inplace=True).len() == n
+    for name in ("a_inplace", "v_inplace"):
+        c.delete_table(name)
     c.stop()
     c2 = sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False)
     assert sorted(c2.table_names()) == ["a", "b"]

@@ -135,6 +135,46 @@ def test_b_pictures_rows_are_display_order_and_sparse_rows_feed_past_the_target(
     assert (got == want[[1, 2, 15, 16, 21]]).all()
 
 
+def strip_repeated_parameter_sets(stream):
+    """Drop the SPS / PPS NAL units of every GOP but the first: what encoders write unless asked to
+    repeat headers (x264 without --repeat-headers, most .mp4 -> Annex-B conversions of one avcC)."""
+    sc = b"\x00\x00\x00\x01"
+    parts = stream.split(sc)[1:]
+    out, seen = [], set()
+    for nal in parts:
+        t = nal[0] & 0x1F
+        if t in (7, 8):
+            if t in seen:
+                continue
+            seen.add(t)
+        out.append(sc + nal)
+    return b"".join(out)
+
+
+def test_seeking_into_a_stream_whose_parameter_sets_appear_once(eng):
+    """A decode that starts at a later IDR gets SPS / PPS from the index's metadata packets (the
+    reference replays them the same way after a seek, decoder_automata.cpp:299-318)."""
+    n, gop = 24, 6
+    data, want = make_clip(31, n, 96, 128, gop)
+    lean = strip_repeated_parameter_sets(data)
+    assert len(lean) < len(data) and lean.count(b"\x00\x00\x00\x01\x67") == 1
+    sid = eng.add_h264(lean)
+    assert eng.stream_rows(sid) == n and eng.stream_info(sid)["keyframes"] == n // gop
+    got = eng.decode_to_device(sid, [20, 21]).cpu().numpy()
+    assert (got == want[[20, 21]]).all()
+    g = E.Graph()
+    src = g.add_source(True)
+    s = g.add_sample((src, "frame"))
+    sink = g.add_sink((s, "frame"))
+    rows = [7, 13, 14, 23]
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_sampler(s, "Gather", protolite.encode(protolite.SAMPLER_ARGS["GatherSamplerArgs"], {"rows": rows}))
+    eng.run(g, [j], 2, 4)
+    for k, r in enumerate(rows):
+        assert (j.output_row(sink, k) == want[r]).all(), r
+
+
 def test_stride_30_only_keyframes(eng):
     """configs[4] shape: Stride(gop) touches exactly the IDR of every GOP."""
     n, gop = 60, 6

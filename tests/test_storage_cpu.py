@@ -609,3 +609,42 @@ def test_demuxer_walks_the_chunk_tables_other_muxers_write(tmp_path, chunks, co6
     open(raw, "wb").write(stream)
     want = cv2_frames(raw)
     assert len(frames) == 12 and all((a == b).all() for a, b in zip(frames, want))
+
+
+@pytest.mark.parametrize("container", ["mp4", "h264"])
+def test_inplace_ingest_keeps_the_bitstream_where_it_is(tmp_path, container):
+    """Reference ingest `inplace` (ingest.cpp:175-215, test tables 'test1_inplace'): no copy of the
+    bitstream in the database; the table binds by reading the original file again, notices when that
+    file changed, and deleting the table leaves the file alone."""
+    stream, _ = make_stream(12, 10, 48, 64, 5)
+    path = str(tmp_path / ("clip." + container))
+    open(path, "wb").write(E.mp4_mux(stream, 30, 1) if container == "mp4" else stream)
+    root = str(tmp_path / "db")
+    db = E.Database(root)
+    db.ingest_video("copied", path)
+    db.ingest_video("inplace", path, inplace=True)
+    assert os.path.exists(os.path.join(root, "tables/0/1_0.bin"))
+    assert not os.path.exists(os.path.join(root, "tables/1/1_0.bin"))
+    a = parse_ref("VideoDescriptor", os.path.join(root, "tables/0/1_0_video_metadata.bin"))
+    b = parse_ref("VideoDescriptor", os.path.join(root, "tables/1/1_0_video_metadata.bin"))
+    assert b.inplace and not a.inplace and b.data_path == os.path.realpath(path)
+    assert list(a.sample_offsets) == list(b.sample_offsets) and list(a.keyframe_indices) == list(b.keyframe_indices)
+    assert db.table_info("inplace")["rows"] == 10 and db.table_info("inplace")["keyframes"] == 2
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    sid = db.add_video_stream(eng, "inplace")
+    assert eng.stream_rows(sid) == 10 and eng.stream_info(sid)["bytes"] == len(stream)
+    out = str(tmp_path / "back.mp4")
+    db.export_mp4("inplace", out, 30, 1)
+    assert E.mp4_demux(open(out, "rb").read())[0] == stream
+    # the file changes under the table
+    other, _ = make_stream(13, 8, 48, 64, 4)
+    open(path, "wb").write(E.mp4_mux(other, 30, 1) if container == "mp4" else other)
+    with pytest.raises(E.EngineError, match="changed since table inplace was ingested in place"):
+        db.add_video_stream(eng, "inplace")
+    os.remove(path)
+    with pytest.raises(E.EngineError, match="ingested in place"):
+        db.add_video_stream(eng, "inplace")
+    db.delete_table("inplace")
+    assert db.tables() == ["copied"] and eng.stream_rows(db.add_video_stream(eng, "copied")) == 10
+    eng.close()
+    db.close()
