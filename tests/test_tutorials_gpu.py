@@ -66,7 +66,7 @@ def test_00_basic(sc, example):
     sc.run(output_op, sp.PerfParams.estimate())
 
     named_stream1.delete(sc)
-    video_stream2 = sp.NamedVideoStream(sc, "example2", path=path)
+    video_stream2 = sp.NamedVideoStream(sc, "example2", path=path, inplace=True)  # py_test.py 'test1_inplace'
     frames = sc.io.Input([video_stream1, video_stream2])
     hists = sc.ops.Histogram(frame=frames)
     named_stream2 = sp.NamedStream(sc, "example2_hist")
