@@ -153,19 +153,20 @@ def test_02_op_attributes(sc, example):
     sc.run(sc.io.Output(resized_frame, [stream]), sp.PerfParams.estimate())
     assert all((f == cv2.resize(shown[i], (64, 48))).all() for i, f in enumerate(stream.load()))
 
+    # the tutorial's two flow ops (dense Farneback on the stencil pair, then an HSV rendering of the
+    # field), written out here rather than copied
     @sp.register_python_op(stencil=[0, 1])
     def optical_flow(config, frame: Sequence[sp.FrameType]) -> sp.FrameType:
-        gray1 = cv2.cvtColor(frame[0], cv2.COLOR_BGR2GRAY)
-        gray2 = cv2.cvtColor(frame[1], cv2.COLOR_BGR2GRAY)
-        return cv2.calcOpticalFlowFarneback(gray1, gray2, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+        prev, nxt = (cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in frame)
+        return cv2.calcOpticalFlowFarneback(prev, nxt, None, pyr_scale=0.5, levels=3, winsize=15, iterations=3,
+                                            poly_n=5, poly_sigma=1.2, flags=0)
 
     @sp.register_python_op()
     def visualize_flow(config, flow: sp.FrameType) -> sp.FrameType:
-        hsv = np.zeros(shape=(flow.shape[0], flow.shape[1], 3), dtype=np.uint8)
-        hsv[..., 1] = 255
-        mag, ang = cv2.cartToPolar(flow[..., 0], flow[..., 1])
-        hsv[..., 0] = ang * 180 / np.pi / 2
-        hsv[..., 2] = cv2.normalize(mag, None, 0, 255, cv2.NORM_MINMAX).reshape(mag.shape)
+        magnitude, angle = cv2.cartToPolar(flow[..., 0], flow[..., 1])
+        hue = (angle * (90.0 / np.pi)).astype(np.uint8)                      # 0..2pi -> 0..180
+        value = cv2.normalize(magnitude, None, 0, 255, cv2.NORM_MINMAX).reshape(magnitude.shape).astype(np.uint8)
+        hsv = np.dstack([hue, np.full_like(hue, 255), value])
         return cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR)
 
     frames = sc.io.Input([video_stream])
@@ -186,24 +187,24 @@ def _background_subtraction():
 
     @sp.register_python_op(bounded_state=60)
     class BackgroundSubtraction(sp.Kernel):
+        """Tutorial 02/04's stateful op: an exponential running mean of the frames is the background;
+        pixels within `threshold` of it (in any channel) are blanked.  State restarts at reset()."""
+
         def __init__(self, config, alpha, threshold):
-            self.config = config
-            self.alpha = alpha
-            self.thresh = threshold
+            self.alpha, self.limit = alpha, 255 * threshold
+            self.background = None
 
         def reset(self):
-            self.average_image = None
+            self.background = None
 
         def execute(self, frame: sp.FrameType) -> sp.FrameType:
-            if self.average_image is None:
-                self.average_image = frame
-            mask = np.abs(frame - self.average_image) < 255 * self.thresh
-            mask = np.any(mask, axis=2)
-            masked_image = np.copy(frame)
-            wmask = np.where(mask)
-            masked_image[wmask[0], wmask[1], :] = 0
-            self.average_image = (self.average_image * (1.0 - self.alpha) + frame * self.alpha)
-            return masked_image
+            if self.background is None:
+                self.background = frame
+            near = (np.abs(frame - self.background) < self.limit).any(axis=2)
+            out = frame.copy()
+            out[near] = 0
+            self.background = self.background * (1.0 - self.alpha) + frame * self.alpha
+            return out
 
 
 def test_03_sampling(sc, example):
