@@ -56,31 +56,10 @@ inline void insert_frame(Element& element, Frame* frame) { element = Element{fra
 
 // A second handle on the same payload: bumps the block refcount; frame elements get their own
 // Frame header (headers are not refcounted).
-inline Element add_element_ref(DeviceHandle device, Element& element) {
-  if (element.is_null()) return Element();
-  Element ele;
-  if (element.is_frame) {
-    Frame* frame = element.as_frame();
-    add_buffer_ref(device, frame->data);
-    ele = Element{new Frame(frame->as_frame_info(), frame->data)};
-  } else {
-    add_buffer_ref(device, element.buffer);
-    ele = element;
-  }
-  ele.index = element.index;
-  return ele;
-}
-
-inline void delete_element(DeviceHandle device, Element& element) {
-  if (element.is_null()) return;
-  if (element.is_frame) {
-    Frame* frame = element.as_frame();
-    delete_buffer(device, frame->data);
-    delete frame;
-  } else {
-    delete_buffer(device, element.buffer);
-  }
-}
+// A second owner of the same payload (the block's reference count goes up; frame elements get
+// their own Frame header), and giving an element up.  Null elements pass through.  (api.cpp)
+Element add_element_ref(DeviceHandle device, Element& element);
+void delete_element(DeviceHandle device, Element& element);
 
 struct KernelConfig {
   std::vector<DeviceHandle> devices;  // non-empty; devices[0] is where the kernel runs
@@ -180,68 +159,75 @@ class VideoKernel {
   FrameInfo frame_info_{};
 };
 
+// What REGISTER_KERNEL(...) accumulates: one implementation of an op for one device type.
+using KernelConstructor = std::function<BaseKernel*(const KernelConfig& config)>;
+struct KernelDeclaration {
+  std::string op_name;
+  KernelConstructor make;
+  DeviceType device = DeviceType::CPU;
+  i32 max_devices = 1;
+  bool batches = false;           // .batch() was called
+  i32 batch_size = 1;             // preferred rows per execute() when the graph does not say
+  // columns that live on another device type than the kernel (e.g. encoded bytes for a GPU decoder)
+  std::map<std::string, DeviceType> input_devices, output_devices;
+  // frame columns the kernel also accepts in a non-HWC layout (B200 addition: decoder-native NV12)
+  std::map<std::string, FrameLayout> input_layouts;
+};
+
 namespace internal {
 
-class KernelBuilder;
-using KernelConstructor = std::function<BaseKernel*(const KernelConfig& config)>;
-
-class KernelRegistration {
- public:
-  KernelRegistration(const KernelBuilder& builder);
-};
+using ::scanner::KernelConstructor;
 
 class KernelBuilder {
  public:
-  friend class KernelRegistration;
-  KernelBuilder(const std::string& name, KernelConstructor constructor)
-    : name_(name), constructor_(constructor) {}
-
-  KernelBuilder& device(DeviceType device_type) {
-    device_type_ = device_type;
+  KernelBuilder(const std::string& op_name, KernelConstructor make) {
+    decl_.op_name = op_name;
+    decl_.make = std::move(make);
+  }
+  KernelBuilder& device(DeviceType type) {
+    decl_.device = type;
     return *this;
   }
-  KernelBuilder& num_devices(i32 devices) {
-    num_devices_ = devices;
-    return *this;
-  }
-  KernelBuilder& input_device(const std::string& input_name, DeviceType device_type) {
-    input_devices_[input_name] = device_type;
-    return *this;
-  }
-  KernelBuilder& output_device(const std::string& output_name, DeviceType device_type) {
-    output_devices_[output_name] = device_type;
-    return *this;
-  }
-  // scanner-b200 extension: this kernel also accepts `input_name` as a decoder-native surface
-  // (see FrameLayout in frame.h); without it the column always arrives as dense RGB24.
-  KernelBuilder& input_layout(const std::string& input_name, FrameLayout layout) {
-    input_layouts_[input_name] = layout;
+  KernelBuilder& num_devices(i32 n) {
+    decl_.max_devices = n;
     return *this;
   }
   KernelBuilder& batch(i32 preferred_batch_size = 1) {
-    can_batch_ = true;
-    preferred_batch_size_ = preferred_batch_size;
+    decl_.batches = true;
+    decl_.batch_size = preferred_batch_size;
     return *this;
   }
+  KernelBuilder& input_device(const std::string& column, DeviceType type) {
+    decl_.input_devices[column] = type;
+    return *this;
+  }
+  KernelBuilder& output_device(const std::string& column, DeviceType type) {
+    decl_.output_devices[column] = type;
+    return *this;
+  }
+  KernelBuilder& input_layout(const std::string& column, FrameLayout layout) {
+    decl_.input_layouts[column] = layout;
+    return *this;
+  }
+  const KernelDeclaration& declaration() const { return decl_; }
 
  private:
-  std::string name_;
-  KernelConstructor constructor_;
-  DeviceType device_type_ = DeviceType::CPU;
-  i32 num_devices_ = 1;
-  std::map<std::string, DeviceType> input_devices_;
-  std::map<std::string, DeviceType> output_devices_;
-  std::map<std::string, FrameLayout> input_layouts_;
-  bool can_batch_ = false;
-  i32 preferred_batch_size_ = 1;
+  KernelDeclaration decl_;
 };
+
+// Constructing one files the kernel with the registry under (op name, device type) (registry.cpp).
+struct KernelRegistration {
+  KernelRegistration(const KernelBuilder& builder);
+};
+
 }  // namespace internal
 
-#define REGISTER_KERNEL(name__, kernel__) REGISTER_KERNEL_HELPER(__COUNTER__, name__, kernel__)
-#define REGISTER_KERNEL_HELPER(uid__, name__, kernel__) REGISTER_KERNEL_UID(uid__, name__, kernel__)
-#define REGISTER_KERNEL_UID(uid__, name__, kernel__)                                          \
-  static ::scanner::internal::KernelRegistration kernel_registration_##uid__                  \
-      __attribute__((unused)) = ::scanner::internal::KernelBuilder(                           \
-          #name__, [](const ::scanner::KernelConfig& config) { return new kernel__(config); })
+#define SCN_KERNEL_PASTE2(a__, b__) a__##b__
+#define SCN_KERNEL_PASTE(a__, b__) SCN_KERNEL_PASTE2(a__, b__)
+// REGISTER_KERNEL(Op, Class).device(...).batch(...): Class must be constructible from a KernelConfig.
+#define REGISTER_KERNEL(op__, class__)                                                                        \
+  static const ::scanner::internal::KernelRegistration SCN_KERNEL_PASTE(scn_registered_kernel_, __COUNTER__) \
+      __attribute__((unused)) = ::scanner::internal::KernelBuilder(                                           \
+          #op__, [](const ::scanner::KernelConfig& config) -> ::scanner::BaseKernel* { return new class__(config); })
 
 }  // namespace scanner

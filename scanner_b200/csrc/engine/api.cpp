@@ -48,6 +48,33 @@ std::vector<Frame*> new_frames(DeviceHandle device, FrameInfo info, i32 num) {
   return frames;
 }
 
+// ---- element ownership -------------------------------------------------------------------------
+Element add_element_ref(DeviceHandle device, Element& element) {
+  Element second;
+  if (element.is_null()) return second;
+  if (element.is_frame) {
+    Frame* frame = element.as_frame();
+    add_buffer_ref(device, frame->data);
+    second = Element(new Frame(frame->as_frame_info(), frame->data));
+  } else {
+    add_buffer_ref(device, element.buffer);
+    second = element;
+  }
+  second.index = element.index;
+  return second;
+}
+
+void delete_element(DeviceHandle device, Element& element) {
+  if (element.is_null()) return;
+  if (!element.is_frame) {
+    delete_buffer(device, element.buffer);
+    return;
+  }
+  Frame* frame = element.as_frame();
+  delete_buffer(device, frame->data);
+  delete frame;
+}
+
 // ---- calling-convention adapters: the engine always hands column -> batch -> stencil ---------
 void StenciledBatchedKernel::execute_kernel(const StenciledBatchedElements& in,
                                             BatchedElements& out) {

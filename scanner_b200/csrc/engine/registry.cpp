@@ -85,37 +85,37 @@ Result load_op_library(const std::string& so_path) {
 }
 
 // ---- registration objects constructed by REGISTER_OP / REGISTER_KERNEL ---------------------
-OpRegistration::OpRegistration(const OpBuilder& b) {
+OpRegistration::OpRegistration(const OpBuilder& builder) {
+  const OpDeclaration& d = builder.declaration();
   OpInfo info;
-  info.name = b.name_;
-  info.variadic_inputs = b.variadic_inputs_;
-  for (auto& c : b.input_columns_)
-    info.input_columns.push_back({std::get<0>(c), (proto::ColumnType)std::get<1>(c), ""});
-  for (auto& c : b.output_columns_)
-    info.output_columns.push_back({std::get<0>(c), (proto::ColumnType)std::get<1>(c), std::get<2>(c)});
-  info.can_stencil = b.can_stencil_;
-  info.preferred_stencil = b.preferred_stencil_;
-  info.has_bounded_state = b.has_bounded_state_;
-  info.warmup = b.warmup_;
-  info.has_unbounded_state = b.has_unbounded_state_;
-  info.protobuf_name = b.protobuf_name_;
-  info.stream_protobuf_name = b.stream_protobuf_name_;
-  Result r = get_op_registry()->add_op(b.name_, info);
-  LOG_IF(FATAL, !r.success()) << "Failed to register op " << b.name_ << ": " << r.msg();
+  info.name = d.name;
+  info.variadic_inputs = d.variadic;
+  for (const auto& c : d.inputs) info.input_columns.push_back({c.name, (proto::ColumnType)c.type, ""});
+  for (const auto& c : d.outputs) info.output_columns.push_back({c.name, (proto::ColumnType)c.type, c.type_name});
+  info.can_stencil = d.stencils;
+  info.preferred_stencil = d.default_stencil;
+  info.has_bounded_state = d.warmup >= 0;
+  info.warmup = d.warmup >= 0 ? d.warmup : 0;
+  info.has_unbounded_state = d.unbounded;
+  info.protobuf_name = d.args_message;
+  info.stream_protobuf_name = d.stream_args_message;
+  Result r = get_op_registry()->add_op(d.name, info);
+  LOG_IF(FATAL, !r.success()) << "Failed to register op " << d.name << ": " << r.msg();
 }
 
-KernelRegistration::KernelRegistration(const KernelBuilder& b) {
+KernelRegistration::KernelRegistration(const KernelBuilder& builder) {
+  const KernelDeclaration& d = builder.declaration();
   KernelFactory f;
-  f.op_name = b.name_;
-  f.device_type = (proto::DeviceType)b.device_type_;
-  f.max_devices = b.num_devices_;
-  for (auto& kv : b.input_devices_) f.input_devices[kv.first] = (proto::DeviceType)kv.second;
-  for (auto& kv : b.output_devices_) f.output_devices[kv.first] = (proto::DeviceType)kv.second;
-  f.input_layouts = b.input_layouts_;
-  f.can_batch = b.can_batch_;
-  f.preferred_batch_size = b.preferred_batch_size_;
-  f.constructor = b.constructor_;
-  get_kernel_registry()->add_kernel(b.name_, std::move(f));
+  f.op_name = d.op_name;
+  f.device_type = (proto::DeviceType)d.device;
+  f.max_devices = d.max_devices;
+  for (const auto& kv : d.input_devices) f.input_devices[kv.first] = (proto::DeviceType)kv.second;
+  for (const auto& kv : d.output_devices) f.output_devices[kv.first] = (proto::DeviceType)kv.second;
+  f.input_layouts = d.input_layouts;
+  f.can_batch = d.batches;
+  f.preferred_batch_size = d.batch_size;
+  f.constructor = d.make;
+  get_kernel_registry()->add_kernel(d.op_name, std::move(f));
 }
 
 }  // namespace internal
