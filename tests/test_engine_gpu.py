@@ -3,7 +3,6 @@ the stdlib GPU ops behind REGISTER_KERNEL, results brought back through the save
 Every comparison is bit-exact: I_PCM decodes to the source planes, so the expected RGB is the
 oracle's NV12->RGB of the planes the stream was made from."""
 import os
-import struct
 
 import numpy as np
 import pytest
@@ -414,7 +413,6 @@ def test_mp4_ingest_to_stored_histograms_through_the_database(tmp_path):
 
 
 def test_decode_to_device_matches_engine_path(eng):
-    import torch
     data, want = make_clip(31, 20, 96, 128, 6)
     sid = eng.add_h264(data)
     rows = [0, 1, 5, 6, 7, 13, 19]
@@ -428,8 +426,7 @@ def test_decode_to_device_matches_engine_path(eng):
 
 def test_single_rank_sharded_flow_equals_direct():
     """halo.sharded_optical_flow with world size 1 == decode + optical_flow with the edge repeated."""
-    import torch
-    from scanner_b200 import halo, kernels
+    from scanner_b200 import halo
     data, want = make_clip(32, 6, 96, 128, 3)
     e = E.Engine(gpus=[0])
     sid = e.add_h264(data)

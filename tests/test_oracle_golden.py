@@ -7,7 +7,6 @@ independent numpy restatement in oracle/make_golden.py.  CPU only.
 import os
 
 import numpy as np
-import pytest
 
 import oracle
 from oracle import synth

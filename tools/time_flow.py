@@ -2,7 +2,6 @@
 """Per-kernel CUDA-event timing of the Farneback OpticalFlow path on 1080p pairs."""
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, ".")
