@@ -135,6 +135,34 @@ class TestAffineKernel : public Kernel {
 REGISTER_OP(TestAffine).input("col").output("out").protobuf_name("TestScaleArgs").stream_protobuf_name("TestOffsetArgs");
 REGISTER_KERNEL(TestAffine, TestAffineKernel).device(DeviceType::CPU).num_devices(1);
 
+// ---- a C++ kernel that meets bad data: scanner::report_kernel_error instead of LOG(FATAL)
+class TestRefuseValueKernel : public Kernel {
+ public:
+  TestRefuseValueKernel(const KernelConfig& config) : Kernel(config) {
+    TestScaleArgs a;  // the value that cannot be processed travels in the `scale` field
+    a.ParseFromArray(config.args.data(), (int)config.args.size());
+    refused_ = a.scale();
+  }
+  void execute(const Elements& in, Elements& out) override {
+    i64 v;
+    memcpy(&v, in[0].buffer, 8);
+    if (v == refused_) {
+      report_kernel_error("TestRefuseValue cannot process the value " + std::to_string(v) + " (row " +
+                          std::to_string(in[0].index) + ")");
+      out[0] = Element();  // still one element per row: null
+      return;
+    }
+    u8* b = new_buffer(CPU_DEVICE, 8);
+    memcpy(b, &v, 8);
+    insert_element(out[0], b, 8);
+  }
+
+ private:
+  i64 refused_ = -1;
+};
+REGISTER_OP(TestRefuseValue).input("col").output("out").protobuf_name("TestScaleArgs");
+REGISTER_KERNEL(TestRefuseValue, TestRefuseValueKernel).device(DeviceType::CPU).num_devices(1);
+
 // ---- frame ops on the CPU through the ORACLE (plumbing tests only)
 class TestHistogramOracleKernel : public BatchedKernel {
  public:

@@ -333,3 +333,16 @@ def test_sampler_arguments_in_every_form_the_reference_accepts(sc):
             assert isinstance(r, sp.NullElement)
     with pytest.raises(sp.ScannerException, match="lacks 'end'"):
         sc.streams.StridedRange(sc.io.Input([src]), [{"start": 0, "stride": 2}])
+
+
+def test_cpp_kernel_reports_bad_data_without_aborting(sc):
+    """scanner::report_kernel_error (scanner/api/kernel.h) from a C++ plugin kernel: the run fails
+    with the kernel's message; the same client then runs the next job."""
+    src = _ints(sc, "refuse_in", 20)
+    col = sc.io.Input([src])
+    out = sp.NamedStream(sc, "refuse_out")
+    with pytest.raises(sp.ScannerException, match=r"Op TestRefuseValue failed: .*cannot process the value 13 \(row 13\)"):
+        sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=13), [out]), sp.PerfParams.manual(2, 4))
+    sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=99), [out]), sp.PerfParams.manual(2, 4),
+           cache_mode=sp.CacheMode.Overwrite)
+    assert _load_ints(out) == list(range(20))
