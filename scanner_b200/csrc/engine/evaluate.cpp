@@ -248,6 +248,24 @@ Result EvaluateWorker::feed(std::map<i32, ColumnBatch>& source_columns,
     have[i].assign(cols[i].size(), false);
   }
 
+  // Whatever this packet still owns when the function is left -- columns whose consumers all ran
+  // on the normal path; on an error path also the rows handed in and the sink rows not handed out
+  // yet -- is released exactly once, here.
+  bool failed = true;
+  struct AtExit {
+    std::function<void()> fn;
+    ~AtExit() { fn(); }
+  } at_exit{[&] {
+    for (size_t p = 0; p < n; ++p)
+      for (size_t c = 0; c < cols[p].size(); ++c)
+        if (have[p][c]) delete_elements(cols[p][c].device, cols[p][c].elements);
+    if (!failed) return;
+    for (auto& kv : source_columns) delete_elements(kv.second.device, kv.second.elements);
+    source_columns.clear();
+    for (auto& kv : sink_columns) delete_elements(kv.second.device, kv.second.elements);
+    sink_columns.clear();
+  }};
+
   auto release_dead = [&](size_t k) {
     // drop every column whose last reader is op k (liveness, reference :1225-1238)
     for (size_t p = 0; p < n; ++p)
@@ -342,6 +360,12 @@ Result EvaluateWorker::feed(std::map<i32, ColumnBatch>& source_columns,
 
     const size_t n_out = std::max<size_t>(1, op.output_columns.size());
     std::vector<ColumnBatch> produced(op.kind == OpKind::Sink ? 1 : n_out);
+    // rows produced by earlier batches of this op in this packet, until step 4 hands them on
+    bool produced_owned = true;
+    AtExit drop_produced{[&] {
+      if (!produced_owned) return;
+      for (ColumnBatch& pc : produced) delete_elements(pc.device, pc.elements);
+    }};
 
     // ---- 3. produce
     if (op.kind == OpKind::Sample || op.kind == OpKind::Space) {
@@ -430,6 +454,7 @@ Result EvaluateWorker::feed(std::map<i32, ColumnBatch>& source_columns,
     st.next_compute = row_end;
 
     // ---- 4. keep only rows that are valid outputs of this op for this task (:1146-1188)
+    produced_owned = false;  // from here every element of `produced` is either handed on or deleted
     if (op.kind == OpKind::Sink) {
       ColumnBatch& dst = sink_columns[(i32)k];
       dst.device = produced[0].device;
@@ -486,10 +511,7 @@ Result EvaluateWorker::feed(std::map<i32, ColumnBatch>& source_columns,
     release_dead(k);
     if (profiler_) profiler_->add_interval("op:" + op.name, op_start, now());
   }
-  // anything still held (e.g. a column whose consumers all ran) is released here
-  for (size_t p = 0; p < n; ++p)
-    for (size_t c = 0; c < cols[p].size(); ++c)
-      if (have[p][c]) delete_elements(cols[p][c].device, cols[p][c].elements);
+  failed = false;
   return ok();
 }
 

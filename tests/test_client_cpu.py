@@ -341,8 +341,13 @@ def test_cpp_kernel_reports_bad_data_without_aborting(sc):
     src = _ints(sc, "refuse_in", 20)
     col = sc.io.Input([src])
     out = sp.NamedStream(sc, "refuse_out")
+    sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=99), [out]), sp.PerfParams.manual(2, 4))
+    live = sc.stats()["counters"]["cpu_bytes_live"]
     with pytest.raises(sp.ScannerException, match=r"Op TestRefuseValue failed: .*cannot process the value 13 \(row 13\)"):
-        sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=13), [out]), sp.PerfParams.manual(2, 4))
+        sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=13), [out]), sp.PerfParams.manual(2, 4),
+               cache_mode=sp.CacheMode.Overwrite)
+    # the failed packet released what it owned (rows handed in, rows of earlier batches, sink rows)
+    assert sc.stats()["counters"]["cpu_bytes_live"] == live
     sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=99), [out]), sp.PerfParams.manual(2, 4),
            cache_mode=sp.CacheMode.Overwrite)
     assert _load_ints(out) == list(range(20))
