@@ -843,6 +843,26 @@ class Client:
         self._need_db().delete_table(name)
         self._streams.pop(name, None)
 
+    def delete_tables(self, names):
+        """Reference Client.delete_tables (client.py:1044-1056)."""
+        for name in names:
+            self.delete_table(name)
+
+    def sequence(self, name):
+        """The data column of a table (reference client.py:1158-1164): `frame` of a video table,
+        else the single column a job wrote."""
+        t = self.table(name)
+        cols = [c for c in t.column_names() if c != "index"]
+        return t.column("frame" if "frame" in cols else cols[0])
+
+    def get_active_jobs(self):
+        """run() returns when the job is done: there is never a job in flight to report."""
+        return []
+
+    def wait_on_job(self, bulk_job_id=None, show_progress=True):
+        """Jobs run synchronously inside run(); kept so scripts that wait explicitly still work."""
+        return None
+
     def load_op(self, so_path, proto_path=None, protos=None):
         """Load an op library (reference Client.load_op, client.py:514-537).  `protos` maps op name to
         {"init": MessageName, "stream": MessageName} inside `proto_path`."""

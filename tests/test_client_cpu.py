@@ -296,6 +296,10 @@ def test_new_table_from_python_rows(tmp_path):
     assert src.exists() and list(src.load()) == [b"x"]
     with sp.Client(gpus=[], cpu_instances=1, db_path=str(tmp_path / "db"), load_stdlib=False) as c2:
         assert c2.table("test").num_rows() == 1
+        assert list(c2.sequence("test").load()) == [b"x"] and c2.get_active_jobs() == []
+        c2.new_table("other", ["v"], [[b"1"]])
+        c2.delete_tables(["test", "other"])
+        assert c2.table_names() == []
     c.stop()
 
 
