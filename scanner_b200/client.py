@@ -35,6 +35,28 @@ class DeviceType(enum.IntEnum):
     GPU = 1
 
 
+class ColumnType(enum.Enum):
+    """What a column holds (reference common.py:57-69)."""
+    Blob = 0
+    Video = 1
+
+
+class DeviceHandle:
+    """(device type, device id), as KernelConfig.devices lists them (reference common.py:51-54)."""
+
+    def __init__(self, device, device_id):
+        self.device, self.device_id = device, device_id
+
+    def __iter__(self):  # unpacks like the (type, id) pair it replaces
+        return iter((self.device, self.device_id))
+
+    def __getitem__(self, i):
+        return (self.device, self.device_id)[i]
+
+    def __repr__(self):
+        return f"DeviceHandle({self.device!r}, {self.device_id})"
+
+
 class CacheMode(enum.Enum):
     Error = 1
     Ignore = 2

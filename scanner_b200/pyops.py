@@ -227,7 +227,9 @@ class _PythonOp:
         if ev == EV_CONSTRUCT:
             blob = ctypes.string_at(call.args, int(call.args_size)) if call.args_size else b""
             args = pickle.loads(blob) if blob else {}
-            config = KernelConfig([(call.device_type, call.device_id)], [c.name for c in self.inputs],
+            from .client import DeviceHandle, DeviceType  # client imports this module
+            config = KernelConfig([DeviceHandle(DeviceType(call.device_type), call.device_id)],
+                                  [c.name for c in self.inputs],
                                   ["Video" if c.is_frame else "Bytes" for c in self.inputs],
                                   [c.name for c in self.outputs],
                                   ["Video" if c.is_frame else "Bytes" for c in self.outputs], args, call.node_id)
