@@ -62,6 +62,21 @@ def register_type(cls):
     return cls
 
 
+def ProtobufType(name, proto):
+    """A column type whose elements are messages of the protobuf class `proto` (types.py:57-67):
+    anything with SerializeToString / ParseFromString, e.g. a google.protobuf generated class."""
+
+    def serialize(message):
+        return message.SerializeToString()
+
+    def deserialize(buf):
+        message = proto()
+        message.ParseFromString(bytes(buf))
+        return message
+
+    return register_type(type(name, (), dict(serialize=staticmethod(serialize), deserialize=staticmethod(deserialize))))
+
+
 def VariableList(name, typ):
     """u64 count, then per element u64 size + bytes (types.py:70-93)."""
 

@@ -378,6 +378,14 @@ def test_types_registry_round_trips():
     assert T.get_type_info(Any).deserialize(T.get_type_info(Any).serialize({"a": 1})) == {"a": 1}
     with pytest.raises(T.ScannerTypeError):
         T.get_type_info_cpp("NoSuchType")
+    # a protobuf-backed type and a list of them (the reference's Bbox / BboxList pattern)
+    from google.protobuf import descriptor_pb2
+    field = T.ProtobufType("FieldProto", descriptor_pb2.FieldDescriptorProto)
+    fields = T.VariableList("FieldProtoList", field)
+    msgs = [descriptor_pb2.FieldDescriptorProto(name="x", number=1), descriptor_pb2.FieldDescriptorProto(name="y", number=2)]
+    back = fields.deserialize(fields.serialize(msgs))
+    assert [(m.name, m.number) for m in back] == [("x", 1), ("y", 2)]
+    assert T.get_type_info_cpp("FieldProtoList").type is fields
 
 
 @register_python_op()
