@@ -483,3 +483,14 @@ def test_failures_outside_execute_are_reported_too(sc):
     with pytest.raises(sp.ScannerException, match=r"(?s)failed in reset / new_stream.*unknown mode"):
         run(sc, sc.ops.Fragile(frame=frame, mode=["bad"]), "f3")
     assert run(sc, sc.ops.Fragile(frame=frame, mode=["ok"]), "f4").len() == 6
+
+
+def test_the_cpu_example_runs():
+    """examples/python_ops_cpu.py (own process: it registers ops by global name)."""
+    import subprocess
+    import sys
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    out = subprocess.run([sys.executable, __import__("os").path.join(root, "examples", "python_ops_cpu.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "smoothed brightness of every third frame: [32.0, 36.0, 42.0" in out.stdout and "tinted.mp4" in out.stdout
