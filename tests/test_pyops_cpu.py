@@ -5,8 +5,11 @@ The cases follow the reference's own tests of the feature (tests/py_test.py:557-
 TestPyFail, CacheTest) plus what they leave out: typed columns stored in a database, null rows,
 state handling, registration errors.
 """
+import os
 import pickle
 import struct
+import subprocess
+import sys
 from typing import Any, Sequence, Tuple
 
 import numpy as np
@@ -487,10 +490,8 @@ def test_failures_outside_execute_are_reported_too(sc):
 
 def test_the_cpu_example_runs():
     """examples/python_ops_cpu.py (own process: it registers ops by global name)."""
-    import subprocess
-    import sys
-    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
-    out = subprocess.run([sys.executable, __import__("os").path.join(root, "examples", "python_ops_cpu.py")],
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "python_ops_cpu.py")],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "smoothed brightness of every third frame: [32.0, 36.0, 42.0" in out.stdout and "tinted.mp4" in out.stdout
