@@ -11,10 +11,10 @@ missing or no device is present.
 """
 from . import cabi  # noqa: F401
 from . import types  # noqa: F401
-from .client import (CacheMode, Client, ColumnType, DeviceHandle, DeviceType, NamedStream,  # noqa: F401
+from .client import (CacheMode, Client, ColumnType, DeviceHandle, DeviceType, FilesStream, NamedStream,  # noqa: F401
                      NamedVideoStream, NullElement, PerfParams, ScannerException, SliceList)
 from .pyops import Kernel, KernelConfig, register_python_op  # noqa: F401
 from .types import BlobType, FrameType  # noqa: F401
 
 __all__ = ["cabi", "Client", "DeviceType", "PerfParams", "NamedStream", "NamedVideoStream", "CacheMode",
-           "ScannerException", "SliceList", "NullElement", "ColumnType", "DeviceHandle", "BlobType", "register_python_op", "Kernel", "KernelConfig", "FrameType", "types"]
+           "ScannerException", "SliceList", "NullElement", "FilesStream", "ColumnType", "DeviceHandle", "BlobType", "register_python_op", "Kernel", "KernelConfig", "FrameType", "types"]

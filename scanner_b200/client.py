@@ -398,12 +398,19 @@ class IOGenerator:
     def __init__(self, sc):
         self._sc = sc
 
+    def _attach(self, streams):
+        for st in streams:
+            if hasattr(st, "_attach"):
+                st._attach(self._sc)
+
     def Input(self, streams):
+        self._attach(streams)
         is_video = isinstance(streams[0], NamedVideoStream) or getattr(streams[0], "_is_frame", False)
         node = _Node("input", "Input", streams=list(streams))
         return OpColumn(node, "frame" if is_video else "column", is_video)
 
     def Output(self, op, streams):
+        self._attach(streams)
         return _Node("output", "Output", [op], streams=list(streams))
 
 
@@ -702,6 +709,70 @@ class NamedStream:
         self._job = None
         if self._stored():
             self._sc._db.delete_table(self._name)
+
+
+class FilesStream(NamedStream):
+    """One row per file (scannertools.storage.files.FilesStream, used by the reference's tutorial
+    05_sources_sinks.py): as an Input the rows are the files' bytes, as an Output every row is
+    written to its path when the job finishes (null rows leave no file)."""
+
+    _counter = 0
+
+    def __init__(self, sc_or_paths, paths=None):
+        # the scannertools class takes only `paths`; the client is picked up when the stream is used
+        sc, paths = (None, sc_or_paths) if paths is None else (sc_or_paths, paths)
+        FilesStream._counter += 1
+        self._paths = [str(p) for p in paths]
+        self._sc, self._name = sc, f"__files_{FilesStream._counter}"
+        self._job, self._sink, self._type, self._sid = None, None, None, None
+
+    def _attach(self, sc):
+        if self._sc is None:
+            self._sc = sc
+
+    def len(self):
+        return len(self._paths)
+
+    def exists(self):
+        return all(os.path.exists(p) for p in self._paths)
+
+    committed = exists
+
+    def _bind(self):
+        if self._sid is None:
+            rows = []
+            for p in self._paths:
+                with open(p, "rb") as f:
+                    rows.append(f.read())
+            self._sid = self._sc._engine.add_bytes(rows)
+        return self._sid
+
+    def _after_run(self):
+        rows = list(NamedStream.load(self, ty="Bytes"))
+        if len(rows) != len(self._paths):
+            raise ScannerException(f"FilesStream lists {len(self._paths)} paths but the job wrote {len(rows)} rows")
+        for p, r in zip(self._paths, rows):
+            if _is_null(r):
+                continue
+            if isinstance(r, np.ndarray):
+                raise ScannerException("FilesStream stores byte rows; encode frames first (ImageEncoder)")
+            with open(p, "wb") as f:
+                f.write(bytes(r))
+        if self._stored():  # the rows went through a scratch table
+            self._sc._db.delete_table(self._name)
+        self._job = None
+
+    def load(self, ty=None, fn=None, rows=None):
+        idx = range(len(self._paths)) if rows is None else rows
+        for i in idx:
+            with open(self._paths[i], "rb") as f:
+                blob = f.read()
+            yield fn(blob) if fn is not None else _typed(blob, ty)
+
+    def delete(self, sc=None):
+        for p in self._paths:
+            if os.path.exists(p):
+                os.remove(p)
 
 
 class Column:
@@ -1044,6 +1115,10 @@ class Client:
                     continue
                 s._job, s._sink = jobs[job_of[j]], index[id(node)]
                 s._type = type_name or None
+        for node in out_nodes:
+            for j, s in enumerate(node.streams):
+                if j not in skip and hasattr(s, "_after_run"):
+                    s._after_run()
         self._last_graph = g
         return len(jobs)
 

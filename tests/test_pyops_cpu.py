@@ -495,3 +495,29 @@ def test_the_cpu_example_runs():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "smoothed brightness of every third frame: [32.0, 36.0, 42.0" in out.stdout and "tinted.mp4" in out.stdout
+
+
+@pytest.mark.parametrize("with_db", [False, True])
+def test_files_in_files_out(tmp_path, with_db):
+    """The reference's tutorial 05_sources_sinks.py shape: image files -> ImageDecoder -> an op ->
+    ImageEncoder -> image files, through FilesStream (png: the in-tree encoder's only format)."""
+    import cv2
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (20 + i, 30, 3), dtype=np.uint8) for i in range(3)]
+    src_paths = [str(tmp_path / f"sample-frame-{i + 1}.png") for i in range(3)]
+    for p, im in zip(src_paths, imgs):
+        cv2.imwrite(p, im[..., ::-1])
+    dst_paths = [str(tmp_path / f"negative-{i + 1}.png") for i in range(3)]
+    with sp.Client(gpus=[], cpu_instances=2, db_path=str(tmp_path / "db") if with_db else None) as sc:
+        image_stream = sp.FilesStream(src_paths)
+        frames = sc.ops.ImageDecoder(img=sc.io.Input([image_stream]))
+        encoded = sc.ops.ImageEncoder(frame=sc.ops.Negative(frame=frames), format="png")
+        out_stream = sp.FilesStream(dst_paths)
+        assert not out_stream.exists()
+        sc.run(sc.io.Output(encoded, [out_stream]), sp.PerfParams.estimate(), cache_mode=sp.CacheMode.Overwrite)
+        assert out_stream.exists() and (not with_db or sc.table_names() == [])
+    for p, im in zip(dst_paths, imgs):
+        assert (cv2.imread(p)[..., ::-1] == 255 - im).all()
+    assert [len(b) for b in out_stream.load()] == [os.path.getsize(p) for p in dst_paths]
+    out_stream.delete()
+    assert not out_stream.exists()
