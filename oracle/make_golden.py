@@ -67,10 +67,11 @@ def np_nv12_to_rgb(luma, chroma, width):
     l = (luma[:, :width].astype(np.uint32) << 2).astype(np.float32)
     fcb = ((cb << 2) - 512).astype(np.float32)
     fcr = ((cr << 2) - 512).astype(np.float32)
-    ly = (l * np.float32(1.1644)).astype(np.float32)
-    r = _fma32(fcr, np.float32(1.596), _fma32(fcb, np.float32(0.0), ly))
-    g = _fma32(fcr, np.float32(-0.813), _fma32(fcb, np.float32(-0.3918), ly))
-    b = _fma32(fcr, np.float32(0.0), _fma32(fcb, np.float32(2.0172), ly))
+    # nvcc's contraction of image.cu:81-90 (SASS of oracle/_ref): fma(cr,k2, fma(y,k0, fl(cb*k1)))
+    k0 = np.float32(1.1644)
+    r = _fma32(fcr, np.float32(1.596), _fma32(l, k0, (fcb * np.float32(0.0)).astype(np.float32)))
+    g = _fma32(fcr, np.float32(-0.813), _fma32(l, k0, (fcb * np.float32(-0.3918)).astype(np.float32)))
+    b = _fma32(fcr, np.float32(0.0), _fma32(l, k0, (fcb * np.float32(2.0172)).astype(np.float32)))
     out = np.stack([r, g, b], -1)
     out = np.minimum(np.maximum(out, np.float32(0)), np.float32(1023))
     return (out.astype(np.uint32) >> 2).astype(np.uint8)

@@ -201,10 +201,14 @@ ORC_API void orc_blur_u8c3(const uint8_t* src, int width, int height,
  *   G = Y'*1.1644 + Cb'*-.3918 + Cr'*-.813
  *   B = Y'*1.1644 + Cb'*2.0172 + Cr'*0
  *   clamp to [0,1023], truncate to uint, >>2   (:92-102)
- * The reference is CUDA source compiled by nvcc with its default -fmad=true,
- * under which `a*b + c*d + e*f` contracts to fma(e,f, fma(c,d, a*b)); that
- * contraction is written out explicitly here so the CPU and GPU agree bit for
- * bit.  (There is no -16 luma offset in the reference, :74.) */
+ * The reference is CUDA source compiled by nvcc with its default -fmad=true.
+ * oracle/_ref builds that source UNMODIFIED (oracle/Makefile, nvcc 12.9, sm_100a);
+ * its SASS evaluates `a*b + c*d + e*f` as  fma(e,f, fma(a,b, fl(c*d)))  -- the
+ * MIDDLE product is the one rounded on its own (FMUL cb*k1; FFMA luma,k0; FFMA
+ * cr,k2).  That order is written out explicitly here, and
+ * tests/test_ref_pin_gpu.py runs the compiled reference kernel on B200 over all
+ * 2^24 (Y,Cb,Cr) triples and asserts equality with this function.
+ * (There is no -16 luma offset in the reference, :74.) */
 static inline uint8_t orc_pack10(float v) {
   v = fminf(fmaxf(v, 0.0f), 1023.f);
   return (uint8_t)(((uint32_t)v) >> 2);
@@ -226,9 +230,9 @@ ORC_API void orc_nv12_to_rgb24(const uint8_t* luma, const uint8_t* chroma,
       float l = (float)((uint32_t)luma[(size_t)y * pitch + x] << 2);
       float fcb = (float)((int)(cb << 2) - 512);
       float fcr = (float)((int)(cr << 2) - 512);
-      float r = fmaf(fcr, 1.596f, fmaf(fcb, 0.0f, l * 1.1644f));
-      float g = fmaf(fcr, -0.813f, fmaf(fcb, -0.3918f, l * 1.1644f));
-      float b = fmaf(fcr, 0.0f, fmaf(fcb, 2.0172f, l * 1.1644f));
+      float r = fmaf(fcr, 1.596f, fmaf(l, 1.1644f, fcb * 0.0f));
+      float g = fmaf(fcr, -0.813f, fmaf(l, 1.1644f, fcb * -0.3918f));
+      float b = fmaf(fcr, 0.0f, fmaf(l, 1.1644f, fcb * 2.0172f));
       uint8_t* o = rgb + (size_t)y * rgb_pitch + (size_t)x * 3;
       o[0] = orc_pack10(r);
       o[1] = orc_pack10(g);

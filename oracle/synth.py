@@ -52,3 +52,24 @@ def flow_pair(seed, h, w, kind="shift"):
         return np.clip(out, 0, 255).astype(np.uint8)
 
     return tex(xx, yy), tex(xx - dx, yy - dy)
+
+
+# ---- exhaustive NV12 -> RGB input (oracle/_ref pin) -------------------------------------------
+EXH_FRAMES, EXH_W, EXH_H = 64, 512, 2048
+
+
+def nv12_exhaustive(f):
+    """Frame f (0..63) of a 64 x (512 x 2048) set that presents every (Y, Cb, Cr) triple on an EVEN
+    luma row (co-sited chroma, image.cu:153-170): chroma row j of frame f carries the constant pair
+    (Cb, Cr) = divmod(f * 1024 + j, 256) and the even luma row above it every Y twice.  Odd rows
+    exercise the rounded chroma average (:133-151) with a scrambled Y, and each frame's last odd row
+    the no-average case (:138)."""
+    j = np.arange(EXH_H // 2, dtype=np.int64) + f * (EXH_H // 2)
+    chroma = np.empty((EXH_H // 2, EXH_W), np.uint8)
+    chroma[:, 0::2] = (j >> 8)[:, None]
+    chroma[:, 1::2] = (j & 255)[:, None]
+    x = np.arange(EXH_W, dtype=np.int64)
+    luma = np.empty((EXH_H, EXH_W), np.uint8)
+    luma[0::2] = (x & 255)[None, :]
+    luma[1::2] = ((x[None, :] * 5 + j[:, None] * 3) & 255)
+    return luma, chroma

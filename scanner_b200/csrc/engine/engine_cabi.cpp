@@ -580,10 +580,10 @@ int scn_db_save_job(scn_db* db, scn_job* j, const char* table, const int* sinks,
     outs.push_back(&it->second);
     if (c == 0) n_tasks = it->second.size();
     else if (it->second.size() != n_tasks) return fail("sinks of one job must have the same number of tasks");
-    bool is_frame = false;
-    for (const TaskOutput& t : it->second)
-      for (size_t i = 0; i < t.sizes.size(); ++i)
-        if (t.shapes[4 * i + 3] >= 0) is_frame = true;
+    // declared type of the sink's column, recorded by the run (not inferred from the rows: a column
+    // of null rows is still a frame column)
+    auto sf = j->j.sink_is_frame.find(sinks[c]);
+    const bool is_frame = sf != j->j.sink_is_frame.end() && sf->second;
     ColumnSpec cs;
     cs.name = column_names[c];
     cs.type = is_frame ? proto::Video : proto::Bytes;

@@ -13,6 +13,8 @@ void set_thread_stream(int gpu_id, void* stream);
 // API without copying it: add_buffer_ref / delete_buffer work on it, the memory is never freed.
 void adopt_block(DeviceHandle device, u8* base, size_t size);
 void disown_block(DeviceHandle device, u8* base);
+// true when `buffer` lies in adopted memory (its lifetime is the input stream's, not the block's refcount)
+bool block_is_external(DeviceHandle device, const u8* buffer);
 
 struct ScopedDevice {
   explicit ScopedDevice(int id);

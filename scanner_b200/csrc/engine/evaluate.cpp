@@ -50,9 +50,15 @@ Elements copy_or_ref_elements(DeviceHandle src, DeviceHandle dst, const Elements
   std::vector<size_t> sizes;
   std::vector<u8*> srcs;
   size_t total = 0;
+  // an element without payload bytes crosses as a null element (stored rows cannot tell the two
+  // apart: null = size 0, column_sink.cpp:181-195); giving it the address one past the block would
+  // make delete_element reject it
+  auto payload = [](const Element& e) -> size_t {
+    return e.is_null() ? 0 : (e.is_frame ? e.as_const_frame()->size() : e.size);
+  };
   for (const Element& e : in) {
-    if (e.is_null()) continue;
-    const size_t s = e.is_frame ? e.as_const_frame()->size() : e.size;
+    const size_t s = payload(e);
+    if (s == 0) continue;
     sizes.push_back(s);
     srcs.push_back(e.is_frame ? e.as_const_frame()->data : e.buffer);
     total += s;
@@ -68,7 +74,7 @@ Elements copy_or_ref_elements(DeviceHandle src, DeviceHandle dst, const Elements
   size_t k = 0;
   for (const Element& e : in) {
     Element c;
-    if (!e.is_null()) {
+    if (payload(e) != 0) {
       if (e.is_frame) c = Element(new Frame(e.as_const_frame()->as_frame_info(), dsts[k]));
       else c = Element(dsts[k], e.size);
       ++k;

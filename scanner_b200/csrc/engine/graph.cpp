@@ -169,8 +169,19 @@ class GatherSampler : public DomainSampler {
       RESULT_ERROR(&valid_, "Gather sampler provided with invalid protobuf args");
       return;
     }
-    i64 off = 0;
-    for (i64 r : args_.rows()) index_[r] = off++;
+    // the evaluate stage walks output rows with an ascending cursor and `index_` maps an upstream
+    // row to ONE downstream row: rows must be strictly ascending (what the Gather partitioner also
+    // demands); say so here instead of failing later with "Not enough rows in argument 0"
+    i64 off = 0, prev = -1;
+    for (i64 r : args_.rows()) {
+      if (r < 0 || r <= prev) {
+        RESULT_ERROR(&valid_, "Gather sampler rows must be non-negative and strictly ascending (row %ld follows %ld "
+                              "at position %ld)", (long)r, (long)prev, (long)off);
+        return;
+      }
+      prev = r;
+      index_[r] = off++;
+    }
   }
   Result validate() const override { return valid_; }
   Result get_upstream_rows(const std::vector<i64>& d, std::vector<i64>& u) const override {
@@ -396,6 +407,24 @@ Result make_domain_sampler(const std::string& name, const std::vector<u8>& args,
 }
 
 // ---------------------------------------------------------------------------------------------
+proto::ColumnType Graph::column_type_of(i32 op_index, const std::string& column) const {
+  for (size_t hops = 0; hops <= ops.size(); ++hops) {
+    if (op_index < 0 || (size_t)op_index >= ops.size()) return proto::Bytes;
+    const GraphOp& op = ops[(size_t)op_index];
+    if (op.kind == OpKind::Source) return op.column_type;
+    if (op.kind == OpKind::Kernel) {
+      const OpInfo* info = get_op_registry()->get_op_info(op.name);
+      if (info)
+        for (const ColumnDesc& c : info->output_columns)
+          if (c.name == column) return c.type;
+      return proto::Bytes;
+    }
+    if (op.inputs.empty()) return proto::Bytes;
+    op_index = op.inputs[0].op_index;  // Sample / Space / Sink: one input, same column
+  }
+  return proto::Bytes;
+}
+
 Result Graph::analyze(GraphAnalysis& an) {
   Result r;
   const size_t n = ops.size();

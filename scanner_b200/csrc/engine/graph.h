@@ -140,6 +140,11 @@ class Graph {
 
   std::vector<i32> slice_level;  // filled by analyze(): 0 outside, 1 between Slice and Unslice
 
+  // Declared type of output column `column` of op `op_index` (Source: its column_type; Kernel: the
+  // op's registration; Sample / Space / Slice ops pass their input's type through).  What the save
+  // stage stores a sink as is decided by this, never by the rows that happen to arrive.
+  proto::ColumnType column_type_of(i32 op_index, const std::string& column) const;
+
   // Back-propagate `output_rows` (rows of every sink for this task) to every op
   // (derive_stencil_requirements).  task_streams[i] corresponds to ops[i]; for Source ops
   // valid_output_rows are the rows to load.

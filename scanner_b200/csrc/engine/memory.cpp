@@ -249,7 +249,7 @@ void delete_buffer(DeviceHandle device, u8* buffer) {
     if (--it->second.refs > 0) return;
     b = it->second;
     base = it->first;
-    t.current -= b.size;
+    if (!b.external) t.current -= b.size;  // adopted memory was never counted
     t.blocks.erase(it);
   }
   if (b.external) return;
@@ -271,7 +271,18 @@ void adopt_block(DeviceHandle device, u8* base, size_t size) {
 void disown_block(DeviceHandle device, u8* base) {
   DeviceTable& t = table_for(device);
   std::lock_guard<std::mutex> g(t.mu);
-  t.blocks.erase((uintptr_t)base);
+  auto it = t.blocks.find((uintptr_t)base);
+  if (it == t.blocks.end()) return;
+  // drop the owner's reference; an entry somebody still references stays (orphaned, external: never
+  // freed here) so that their delete_buffer finds it and erases it on the last reference
+  if (--it->second.refs <= 0) t.blocks.erase(it);
+}
+bool block_is_external(DeviceHandle device, const u8* buffer) {
+  if (!buffer) return false;
+  DeviceTable& t = table_for(device);
+  std::lock_guard<std::mutex> g(t.mu);
+  auto it = find_block(t, buffer);
+  return it != t.blocks.end() && it->second.external;
 }
 }  // namespace internal
 

@@ -455,7 +455,10 @@ void Engine::instance_main(Instance* inst) {
             to.offsets.push_back(to.data.size());
             to.sizes.push_back(n);
             to.shapes.insert(to.shapes.end(), shape, shape + 4);
-            if (n >= TaskOutput::kLargeRow) {
+            // rows that pass an input stream through unchanged still point into the stream's adopted
+            // storage, which goes away with the stream (remove_stream / ~Engine), possibly before the
+            // job's outputs do: those are copied, only engine-allocated blocks are held by reference
+            if (n >= TaskOutput::kLargeRow && !block_is_external(CPU_DEVICE, src)) {
               to.ext.resize(to.sizes.size(), nullptr);
               to.ext.back() = src;
               to.held.push_back(e);  // the reference this element holds on its block moves to the task
@@ -498,8 +501,9 @@ void Engine::instance_main(Instance* inst) {
           auto st = job.sink_tables.find(kv.first);
           if (st == job.sink_tables.end()) continue;
           TaskOutput& to = *kv.second;
-          bool video = false;
-          for (size_t i = 0; i < to.sizes.size(); ++i) video = video || to.shapes[4 * i + 3] >= 0;
+          // Video or Bytes item: from the declared type of the column (a task whose rows are all null
+          // has no frame to look at and must still be a video item of a Video table)
+          const bool video = job.sink_is_frame.count(kv.first) && job.sink_is_frame.at(kv.first);
           std::vector<u8> flat;
           ItemColumn ic;
           if (to.held.empty()) {
@@ -736,8 +740,13 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
     }
     const i64 n_tasks = (i64)job.task_starts.size();
     job.task_starts.push_back(job.total_rows);
+    job.sink_is_frame.clear();
     for (size_t k = 0; k < graph.ops.size(); ++k)
-      if (graph.ops[k].kind == OpKind::Sink) job.outputs[(i32)k].resize((size_t)n_tasks);
+      if (graph.ops[k].kind == OpKind::Sink) {
+        job.outputs[(i32)k].resize((size_t)n_tasks);
+        const OpInput& in = graph.ops[k].inputs.at(0);
+        job.sink_is_frame[(i32)k] = graph.column_type_of(in.op_index, in.column) == proto::Video;
+      }
     for (i64 t = 0; t < n_tasks; ++t) {
       i64 end = job.task_starts[(size_t)t + 1];
       if (groups_of_task[(size_t)t] >= 0) end = std::min(end, job.slices.out_base[(size_t)groups_of_task[(size_t)t] + 1]);

@@ -116,6 +116,7 @@ struct Job {
   std::vector<i64> task_starts;  // first output row of every task, then total_rows (tasks never
                                  // span slice groups, so they are not all io_packet long)
   std::map<i32, std::vector<TaskOutput>> outputs;  // sink op -> per task
+  std::map<i32, bool> sink_is_frame;               // sink op -> its column is declared a frame (Video) column
   // save stage to disk (reference SaveWorker / ColumnSink, one item per task): sink op -> id of a
   // table reserved with Database::new_table in the database rooted at the run's out_dir.  With
   // keep_rows == false the rows of such sinks are dropped from memory once their item is written.

@@ -287,12 +287,22 @@ Result Database::write_item(i32 table_id, i32 column_id, i32 item_id, const Item
     vd.add_sample_offsets(off);
     vd.add_sample_sizes(sizes[i]);
     off += sizes[i];
-    if (!have_shape && sizes[i] && col.shapes && col.shapes->size() >= 4 * (i + 1)) {
-      vd.set_height((*col.shapes)[4 * i + 0]);
-      vd.set_width((*col.shapes)[4 * i + 1]);
-      vd.set_channels((*col.shapes)[4 * i + 2]);
-      vd.set_frame_type((*col.shapes)[4 * i + 3]);
-      have_shape = true;
+    if (sizes[i] && col.shapes && col.shapes->size() >= 4 * (i + 1)) {
+      const i32* sh = col.shapes->data() + 4 * i;
+      if (!have_shape) {
+        vd.set_height(sh[0]);
+        vd.set_width(sh[1]);
+        vd.set_channels(sh[2]);
+        vd.set_frame_type(sh[3]);
+        have_shape = true;
+      } else if (sh[0] != vd.height() || sh[1] != vd.width() || sh[2] != vd.channels() || sh[3] != vd.frame_type()) {
+        // a VideoDescriptor carries ONE frame shape per item (metadata.proto:63-128); rows of another
+        // shape could be stored but never read back
+        RESULT_ERROR(&r, "frame column %d of table %d: row %zu of item %d is %dx%dx%d, earlier rows are %dx%dx%d "
+                         "(frames of one stored item must share a shape)",
+                     column_id, table_id, i, item_id, sh[0], sh[1], sh[2], vd.height(), vd.width(), vd.channels());
+        return r;
+      }
     }
   }
   vd.set_num_encoded_videos(1);
@@ -534,6 +544,11 @@ Result Database::read_rows(const std::string& table, const std::string& column, 
         }
         I.offs = vd.sample_offsets();
         I.sizes = vd.sample_sizes();
+        if (I.offs.size() != I.sizes.size()) {
+          RESULT_ERROR(&r, "%s_video_metadata.bin: %zu sample offsets for %zu sizes", base.c_str(), I.offs.size(),
+                       I.sizes.size());
+          return r;
+        }
         I.shape[0] = vd.height();
         I.shape[1] = vd.width();
         I.shape[2] = vd.channels();
@@ -545,7 +560,7 @@ Result Database::read_rows(const std::string& table, const std::string& column, 
         }
         u64 n;
         memcpy(&n, bytes.data(), 8);
-        if (bytes.size() < 8 + 8 * n) {
+        if (n > (bytes.size() - 8) / 8) {  // (not 8 + 8 * n: n comes from the file and may overflow)
           RESULT_ERROR(&r, "%s_metadata.bin is truncated", base.c_str());
           return r;
         }

@@ -37,12 +37,14 @@ __device__ __forceinline__ uint32_t to_u8_bits(float x) {  // 0x4B0000vv
 struct RgbBits {
   uint32_t r, g, b;
 };
+// image.cu's `y*k0 + cb*k1 + cr*k2` as nvcc contracts it (see nv12_math.cuh): fma(cr,k2, fma(y,k0, fl(cb*k1)))
 __device__ __forceinline__ RgbBits convert(float ym, float cb, float cr) {  // ym = 2^23 + Y, cb/cr centred
-  const float ly = __fmaf_rn(ym, kCY, -kMagic * kCY);
+  const float yf = ym - kMagic;                          // exact
+  const float ly = __fmaf_rn(ym, kCY, -kMagic * kCY);    // == fl(yf * kCY): R's middle product is +-0
   RgbBits o;
   o.r = to_u8_bits(fma_sat(cr, kKR, ly));
-  o.g = to_u8_bits(fma_sat(cr, kKG2, __fmaf_rn(cb, kKG1, ly)));
-  o.b = to_u8_bits(fma_sat(cb, kKB, ly));
+  o.g = to_u8_bits(fma_sat(cr, kKG2, __fmaf_rn(yf, kCY, __fmul_rn(cb, kKG1))));
+  o.b = to_u8_bits(fma_sat(yf, kCY, __fmul_rn(cb, kKB)));
   return o;
 }
 __device__ __forceinline__ uint32_t avg4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >> 1

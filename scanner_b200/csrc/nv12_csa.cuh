@@ -99,17 +99,32 @@ struct S3 {
   f2 r, g, b;  // (word A, word B) accumulators per channel
 };
 
+struct Chroma2 {   // per (Cb,Cr) sample pair of words A and B: Cr, and the two products image.cu rounds on their own
+  f2 tg, tb;       // fl(cb * kKG1), fl(cb * kKB)   (A, B)
+  float crA, crB;
+};
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 template <int J>  // J = pixel index inside the 4-pixel words
-__device__ __forceinline__ void pixel_pair(S3& s, float yA, float yB, float cbA, float crA, float cbB, float crB) {
+__device__ __forceinline__ void pixel_pair(S3& s, float yA, float yB, const Chroma2& c) {
   constexpr float w = (float)(16 << (4 * J));  // 16^(J+1)
-  const f2 ly = fma2(pack2(yA, yB), splat(kCY), splat(-kMagic * kCY));
-  const f2 gi = fma2(pack2(cbA, cbB), splat(kKG1), ly);
-  float lyA, lyB, giA, giB;
+  // image.cu's  y*k0 + cb*k1 + cr*k2  as nvcc contracts it:  fma(cr,k2, fma(y,k0, fl(cb*k1)))  (nv12_math.cuh)
+  const f2 ym = pack2(yA, yB);
+  const f2 yf = add2(ym, splat(-kMagic));                     // exact
+  const f2 ly = fma2(ym, splat(kCY), splat(-kMagic * kCY));   // == fl(yf * kCY)  (R: the middle product is +-0)
+  const f2 gi = fma2(yf, splat(kCY), c.tg);
+  const f2 bi = fma2(yf, splat(kCY), c.tb);                   // B before the clamp
+  float lyA, lyB, giA, giB, biA, biB;
   unpack2(ly, lyA, lyB);
   unpack2(gi, giA, giB);
-  const f2 r = pack2(fma_sat(crA, kKR, lyA), fma_sat(crB, kKR, lyB));
-  const f2 g = pack2(fma_sat(crA, kKG2, giA), fma_sat(crB, kKG2, giB));
-  const f2 b = pack2(fma_sat(cbA, kKB, lyA), fma_sat(cbB, kKB, lyB));
+  unpack2(bi, biA, biB);
+  const f2 r = pack2(fma_sat(c.crA, kKR, lyA), fma_sat(c.crB, kKR, lyB));
+  const f2 g = pack2(fma_sat(c.crA, kKG2, giA), fma_sat(c.crB, kKG2, giB));
+  const f2 b = pack2(fma_sat(biA, 1.0f, 0.0f), fma_sat(biB, 1.0f, 0.0f));
   const f2 k32 = splat(32.0f), mg = splat(kMagic);
   float ra, rb, ga, gb, ba, bb;
   unpack2(fma2_rm(r, k32, mg), ra, rb);
@@ -144,10 +159,13 @@ __device__ __forceinline__ void eight(Acc (&A)[3], Acc (&B)[3], uint32_t (&cyA)[
   unpack2(add2(pack2(byte_magic(cA, 0x7442u), byte_magic(cB, 0x7442u)), bias), cb1A, cb1B);
   unpack2(add2(pack2(byte_magic(cA, 0x7443u), byte_magic(cB, 0x7443u)), bias), cr1A, cr1B);
   S3 s{splat(kSInit), splat(kSInit), splat(kSInit)};
-  pixel_pair<0>(s, byte_magic(yA, 0x7440u), byte_magic(yB, 0x7440u), cb0A, cr0A, cb0B, cr0B);
-  pixel_pair<1>(s, byte_magic(yA, 0x7441u), byte_magic(yB, 0x7441u), cb0A, cr0A, cb0B, cr0B);
-  pixel_pair<2>(s, byte_magic(yA, 0x7442u), byte_magic(yB, 0x7442u), cb1A, cr1A, cb1B, cr1B);
-  pixel_pair<3>(s, byte_magic(yA, 0x7443u), byte_magic(yB, 0x7443u), cb1A, cr1A, cb1B, cr1B);
+  const f2 cb0 = pack2(cb0A, cb0B), cb1 = pack2(cb1A, cb1B);
+  const Chroma2 c0{mul2(cb0, splat(kKG1)), mul2(cb0, splat(kKB)), cr0A, cr0B};
+  const Chroma2 c1{mul2(cb1, splat(kKG1)), mul2(cb1, splat(kKB)), cr1A, cr1B};
+  pixel_pair<0>(s, byte_magic(yA, 0x7440u), byte_magic(yB, 0x7440u), c0);
+  pixel_pair<1>(s, byte_magic(yA, 0x7441u), byte_magic(yB, 0x7441u), c0);
+  pixel_pair<2>(s, byte_magic(yA, 0x7442u), byte_magic(yB, 0x7442u), c1);
+  pixel_pair<3>(s, byte_magic(yA, 0x7443u), byte_magic(yB, 0x7443u), c1);
   float lo, hi;
   unpack2(s.r, lo, hi);
   count4<K>(A[0], B[0], __float_as_uint(lo), cyA[0], cyB[0], lut_lo);

@@ -3,8 +3,12 @@
 //   Y' = Y<<2, C' = (C<<2)-512 (10-bit widen), float matrix {1.1644,0,1.596; 1.1644,-.3918,
 //   -.813; 1.1644,2.0172,0}, clamp [0,1023], truncate, >>2.  On odd luma rows (except the last
 //   chroma row) chroma is the rounded average of the two neighbouring chroma rows (:133-151).
-// The products are contracted the way nvcc's default -fmad contracts the reference source:
-// fma(cr,k2, fma(cb,k1, y*k0)); terms with a zero coefficient are dropped (x + (+-0) == x).
+// The products are contracted the way nvcc (12.9, default -fmad, sm_100a) contracts the reference
+// source `y*k0 + cb*k1 + cr*k2` -- read off the SASS of the unmodified image.cu (oracle/_ref):
+//     fma(cr, k2, fma(y, k0, fl(cb * k1)))          the MIDDLE product is rounded on its own.
+// Terms with a zero coefficient are dropped (x + (+-0) == x, and fl(y*k0 + (+-0)) == fl(y*k0)).
+// tests/test_ref_pin_gpu.py holds every kernel built on this to the reference kernel's own output
+// over all 2^24 (Y,Cb,Cr) triples.
 #pragma once
 #include <stdint.h>
 
@@ -25,11 +29,10 @@ __device__ __forceinline__ Rgb8 yuv_to_rgb_plain(uint32_t y, uint32_t cb, uint32
   const float l = (float)(y << 2);
   const float fcb = (float)((int)(cb << 2) - 512);
   const float fcr = (float)((int)(cr << 2) - 512);
-  const float ly = __fmul_rn(l, 1.1644f);
   Rgb8 o;
-  o.r = pack10(__fmaf_rn(fcr, 1.596f, ly));
-  o.g = pack10(__fmaf_rn(fcr, -0.813f, __fmaf_rn(fcb, -0.3918f, ly)));
-  o.b = pack10(__fmaf_rn(fcb, 2.0172f, ly));
+  o.r = pack10(__fmaf_rn(fcr, 1.596f, __fmul_rn(l, 1.1644f)));
+  o.g = pack10(__fmaf_rn(fcr, -0.813f, __fmaf_rn(l, 1.1644f, __fmul_rn(fcb, -0.3918f))));
+  o.b = pack10(__fmaf_rn(l, 1.1644f, __fmul_rn(fcb, 2.0172f)));
   return o;
 }
 
@@ -42,14 +45,13 @@ __device__ __forceinline__ Rgb8 yuv_to_rgb(uint32_t y, uint32_t cb, uint32_t cr)
   constexpr float s = 1.0f / 2048.0f, magic = 8388608.0f, top = 1023.0f * s;
   constexpr float cy = 4.0f * 1.1644f * s, kr = 4.0f * 1.596f * s, kg1 = 4.0f * -0.3918f * s;
   constexpr float kg2 = 4.0f * -0.813f * s, kb = 4.0f * 2.0172f * s;
-  const float ym = __uint_as_float(0x4B000000u | y);
+  const float yf = __uint_as_float(0x4B000000u | y) - magic;
   const float fcb = __uint_as_float(0x4B000000u | cb) - (magic + 128.0f);
   const float fcr = __uint_as_float(0x4B000000u | cr) - (magic + 128.0f);
-  const float ly = __fmaf_rn(ym, cy, -magic * cy);
   float r, g, b;
-  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fcr), "f"(kr), "f"(ly));
-  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(g) : "f"(fcr), "f"(kg2), "f"(__fmaf_rn(fcb, kg1, ly)));
-  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(fcb), "f"(kb), "f"(ly));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(fcr), "f"(kr), "f"(__fmul_rn(yf, cy)));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(g) : "f"(fcr), "f"(kg2), "f"(__fmaf_rn(yf, cy, __fmul_rn(fcb, kg1))));
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(yf), "f"(cy), "f"(__fmul_rn(fcb, kb)));
   auto u8bits = [&](float x) {
     float q;
     asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(q) : "f"(fminf(x, top)), "f"(512.0f), "f"(magic));

@@ -355,3 +355,51 @@ def test_cpp_kernel_reports_bad_data_without_aborting(sc):
     sc.run(sc.io.Output(sc.ops.TestRefuseValue(col=col, scale=99), [out]), sp.PerfParams.manual(2, 4),
            cache_mode=sp.CacheMode.Overwrite)
     assert _load_ints(out) == list(range(20))
+
+
+# ---- regressions for the round-1 advisor findings -------------------------------------------------
+def test_null_only_tasks_of_a_video_table_stay_video_items(tmp_path):
+    """A task whose rows are all null (RepeatNull spacing) must still be written as a video item of a
+    Video column: the item kind comes from the declared column type, not from the rows."""
+    c = _db_client(tmp_path / "db")
+    frames = np.stack([synth.rand_frame(900 + i, 16, 24) for i in range(3)])
+    vin = sp.NamedVideoStream(c, "nul_in", frames=frames)
+    spaced = c.streams.RepeatNull(c.io.Input([vin]), [8])
+    vout = sp.NamedVideoStream(c, "nul_out")
+    c.run(c.io.Output(spaced, [vout]), sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)
+    got = list(vout.load())
+    assert len(got) == 24
+    for i, f in enumerate(got):
+        if i % 8 == 0:
+            assert (f == frames[i // 8]).all()
+        else:
+            assert isinstance(f, sp.NullElement)
+    c.stop()
+
+
+def test_large_pass_through_rows_survive_engine_teardown():
+    """Sink rows >= 64 KB that pass an input stream through unchanged pointed into the stream's adopted
+    storage; destroying the engine before the job's outputs aborted the process ("not a live buffer")."""
+    import gc
+    c = sp.Client(gpus=[], cpu_instances=1)
+    frames = np.stack([synth.rand_frame(950 + i, 200, 200) for i in range(6)])
+    vin = sp.NamedVideoStream(c, "big_in", frames=frames)
+    strided = c.streams.Stride(c.io.Input([vin]), [2])
+    vout = sp.NamedVideoStream(c, "big_out")
+    c.run(c.io.Output(strided, [vout]), sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)
+    got = [np.array(f) for f in vout.load()]
+    c.stop()
+    del c, vin, vout, strided
+    gc.collect()
+    assert len(got) == 3 and all((got[i] == frames[2 * i]).all() for i in range(3))
+
+
+def test_gather_rows_must_ascend(sc):
+    rows = [struct.pack("<q", i) for i in range(20)]
+    a = sp.NamedStream(sc, "ints_g", rows=rows)
+    g = sc.streams.Gather(sc.io.Input([a]), indices=[[5, 3, 10]])
+    with pytest.raises((sp.ScannerException, E.EngineError), match="strictly ascending"):
+        sc.run(sc.io.Output(g, [sp.NamedStream(sc, "g_out")]), sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)
+    g2 = sc.streams.Gather(sc.io.Input([a]), indices=[[3, 3, 10]])
+    with pytest.raises((sp.ScannerException, E.EngineError), match="strictly ascending"):
+        sc.run(sc.io.Output(g2, [sp.NamedStream(sc, "g_out2")]), sp.PerfParams.manual(2, 4), cache_mode=sp.CacheMode.Overwrite)

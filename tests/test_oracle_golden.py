@@ -116,3 +116,21 @@ def test_flow_matches_cv2_golden(golden_dir):
         if kind == 0 and h >= 64:  # the pair moves by (+1.5, -0.75): direction and rough size come out
             inner = got[16:-16, 16:-16].reshape(-1, 2).mean(0)
             assert 0.5 < inner[0] < 2.0 and -1.2 < inner[1] < -0.2, inner
+
+
+def test_nv12_matches_the_reference_kernels_own_output(golden_dir):
+    """tests/golden/nv12_ref.npz holds what the reference's OWN kernel (scanner/util/image.cu compiled
+    unmodified, oracle/_ref) produced on a B200 (oracle/make_golden_ref.py): seeded surfaces, and the
+    SHA-256 of its output over an input set that presents every (Y,Cb,Cr) triple (synth.nv12_exhaustive).
+    The restatement must reproduce both -- this is what pins the oracle's FMA contraction order."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "nv12_ref.npz"))
+    for k in _cases(g):
+        seed, h, w, pitch = [int(x) for x in g[k + "_meta"]]
+        luma, chroma = synth.nv12_surface(seed, h, w, pitch)
+        assert (oracle.nv12_to_rgb(luma, chroma, w) == g[k + "_out"]).all(), (k, h, w, pitch)
+    sha = hashlib.sha256()
+    for f in range(synth.EXH_FRAMES):
+        luma, chroma = synth.nv12_exhaustive(f)
+        sha.update(oracle.nv12_to_rgb(luma, chroma, synth.EXH_W).tobytes())
+    assert sha.digest() == g["exhaustive_sha256"].tobytes()
