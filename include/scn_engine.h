@@ -119,6 +119,28 @@ SCN_ENGINE_API int scn_job_set_group_stream_args(scn_job* j, int op, int group, 
 
 SCN_ENGINE_API int scn_job_set_stream_args(scn_job* j, int op, const uint8_t* args, size_t args_size);
 
+/* ---- one clip across several ranks (BASELINE configs[3]; SURVEY 8e "stencil halo") -------------
+ * The reference hands every task the stencil rows beyond its interval by loading and decoding them
+ * again (derive_stencil_requirements, scanner/engine/dag_analysis.cpp:1634-1657; gathered at
+ * evaluate_worker.cpp:1068-1089).  Here a job may compute ONE contiguous interval of its output rows
+ * (scn_job_set_shard: bounds[0] = 0 <= ... <= bounds[n] = rows, interval q belongs to rank ranks[q],
+ * this job computes interval `index`); rows its stencil needs from a neighbouring interval arrive as
+ * decoded elements from the rank that owns them, exchanged inside scn_engine_run before the pipeline
+ * instances start -- ncclSend/ncclRecv between the ranks' GPUs (scn_engine_comm_init; every rank
+ * passes the 128 bytes rank 0 got from scn_engine_comm_unique_id, the call is collective), or a host
+ * callback moving n buffers (scn_engine_set_halo_callback; CPU runs, tests).  Every rank must list
+ * the same jobs in the same order.  Counters halo_bytes_sent / halo_bytes_received /
+ * halo_exchange_us appear in scn_engine_stats_json. */
+#define SCN_COMM_ID_BYTES 128
+typedef int (*scn_halo_exchange_fn)(void* user, int n, const int* peers, void* const* buffers,
+                                    const uint64_t* bytes, const int* is_send);
+SCN_ENGINE_API int scn_engine_comm_unique_id(uint8_t out[SCN_COMM_ID_BYTES]);
+SCN_ENGINE_API int scn_engine_comm_init(scn_engine* e, int gpu_id, int rank, int world,
+                                        const uint8_t id[SCN_COMM_ID_BYTES]);
+SCN_ENGINE_API int scn_engine_set_halo_callback(scn_engine* e, int rank, int world, scn_halo_exchange_fn fn,
+                                                void* user);
+SCN_ENGINE_API int scn_job_set_shard(scn_job* j, int index, int n, const int64_t* bounds, const int* ranks);
+
 /* ---- run ----------------------------------------------------------------------------------- */
 /* work_packet_size / io_packet_size: rows per evaluate packet / per task (reference
  * BulkJobParameters, rpc.proto:238-274; io must be a multiple of work).  out_dir: if non-NULL the

@@ -156,6 +156,17 @@ SCN_API int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const uint8
                                double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * FrameDigest: a 16-byte fingerprint of each of n equally sized buffers (`bytes` a multiple of 4):
+ *     out[2i]   = sum of the buffer's little-endian 32-bit words            (mod 2^64)
+ *     out[2i+1] = sum of word[k] * (k mod 65521 + 1)                         (mod 2^64)
+ * Exact integer arithmetic on the raw bytes: two runs agree iff (up to collisions) their buffers are
+ * byte-identical.  No counterpart in the reference; it exists so that frame-valued results too large to
+ * bring back (a 1080p flow field is 16.6 MB per row) can be compared between a run on one GPU and a run
+ * sharded over several (bench.py --config 3, SURVEY 8d configs[3] "must be identical").  `out` is fully
+ * overwritten. */
+SCN_API int scn_frame_digest(const uint8_t* const* host_ptrs, int n, size_t bytes, uint64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libscn_kernels.so")
+# SCN_KERNELS_LIB: developer switch used by tools/sweep_stream.py to time build variants of the library
+LIB_PATH = os.environ.get("SCN_KERNELS_LIB") or os.path.join(_HERE, "lib", "libscn_kernels.so")
 
 _c = ctypes
 _VP = _c.c_void_p
@@ -36,6 +37,7 @@ SIGNATURES = {
                                       _c.c_int, _c.c_int, _c.c_double, _VP, _c.c_size_t, _VP]),
     "scn_nv12_hist_resize": (_c.c_int, [_PP, _PP, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _VP, _PP,
                                         _c.c_int, _c.c_int, _VP, _VP]),
+    "scn_frame_digest": (_c.c_int, [_PP, _c.c_int, _c.c_size_t, _VP, _VP]),
 }
 
 _lib = None

@@ -507,6 +507,35 @@ int64_t scn_db_add_video_stream(scn_db* db, scn_engine* e, const char* table) {
   return e->impl->add_stream(std::move(s));
 }
 
+int scn_engine_comm_unique_id(uint8_t out[SCN_COMM_ID_BYTES]) {
+  if (!out) return fail("null buffer");
+  Result r = halo_nccl_unique_id(out);
+  return r.success() ? 0 : fail(r.msg());
+}
+
+int scn_engine_comm_init(scn_engine* e, int gpu_id, int rank, int world, const uint8_t id[SCN_COMM_ID_BYTES]) {
+  if (!e || !id || world < 1 || rank < 0 || rank >= world || gpu_id < 0) return fail("bad arguments");
+  std::unique_ptr<HaloTransport> t;
+  Result r = make_nccl_transport(gpu_id, rank, world, id, t);
+  if (!r.success()) return fail(r.msg());
+  e->impl->set_halo_transport(std::move(t));
+  return 0;
+}
+
+int scn_engine_set_halo_callback(scn_engine* e, int rank, int world, scn_halo_exchange_fn fn, void* user) {
+  if (!e || !fn || world < 1 || rank < 0 || rank >= world) return fail("bad arguments");
+  e->impl->set_halo_transport(make_callback_transport(rank, world, fn, user));
+  return 0;
+}
+
+int scn_job_set_shard(scn_job* j, int index, int n, const int64_t* bounds, const int* ranks) {
+  if (!j || n < 1 || index < 0 || index >= n || !bounds || !ranks) return fail("bad arguments");
+  j->j.shard_index = index;
+  j->j.shard_bounds.assign(bounds, bounds + n + 1);
+  j->j.shard_ranks.assign(ranks, ranks + n);
+  return 0;
+}
+
 int scn_job_set_sink_table(scn_job* j, int sink, int table_id, int keep_rows) {
   if (!j || table_id < 0) return fail("bad arguments");
   j->j.sink_tables[sink] = table_id;

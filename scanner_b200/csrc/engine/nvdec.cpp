@@ -508,6 +508,11 @@ Result NvdecSession::advance(size_t count) {
   const size_t last_needed = s.wanted_store.empty() ? 0
                              : s.may_reorder        ? s.offsets.size()
                                                     : (size_t)s.wanted_store.back() + 1;
+  struct Busy {
+    i64& acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~Busy() { acc += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+  } busy{busy_ns_};
   while (s.wanted_pos < count) {
     if (s.next_sample < s.offsets.size() && s.next_sample < last_needed) {
       const size_t i = s.next_sample++;

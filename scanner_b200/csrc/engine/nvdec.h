@@ -83,12 +83,15 @@ class NvdecSession {
 
   i64 frames_decoded() const { return frames_decoded_; }
   i64 frames_used() const { return frames_used_; }
+  // host nanoseconds this session has spent feeding samples (cuvidParseVideoData with its decode /
+  // map callbacks: waiting for the NVDEC engine); frames_decoded / busy = the session's picture rate
+  i64 busy_ns() const { return busy_ns_; }
 
   struct Impl;
 
  private:
   std::unique_ptr<Impl> impl_;
-  i64 frames_decoded_ = 0, frames_used_ = 0;
+  i64 frames_decoded_ = 0, frames_used_ = 0, busy_ns_ = 0;
 };
 
 }  // namespace internal

@@ -10,6 +10,8 @@
 #include <fstream>
 #include <thread>
 
+#include <sched.h>
+
 #include "engine_internal.h"
 #include "nvdec.h"
 #include "storage.h"
@@ -45,10 +47,15 @@ struct VideoInterval {
   i64 out_base;
 };
 
-std::vector<VideoInterval> slice_into_intervals(const H264Index& idx, const std::vector<i64>& rows) {
+// `skip` (optional, one flag per row): rows delivered by other means (halo elements received from a
+// neighbouring rank); they form a prefix and/or suffix of `rows`, so the decoded rows in between keep
+// consecutive indices.
+std::vector<VideoInterval> slice_into_intervals(const H264Index& idx, const std::vector<i64>& rows,
+                                                const std::vector<u8*>* skip = nullptr) {
   std::vector<VideoInterval> out;
   const std::vector<i64>& kf = idx.keyframe_indices;
   for (size_t i = 0; i < rows.size(); ++i) {
+    if (skip && (*skip)[i]) continue;
     const i64 r = rows[i];
     // keyframe interval containing r
     const size_t k = (size_t)(std::upper_bound(kf.begin(), kf.end(), r) - kf.begin()) - 1;
@@ -83,6 +90,10 @@ struct Engine::RunState {
   ResourceGate resource_gate;  // fetch_resources once per op and run
   std::unique_ptr<Database> db;  // open when a job saves sinks into tables of out_dir
   std::atomic<i64> frames_decoded{0}, frames_used{0}, frames_native{0};
+  // decoded elements received from neighbouring ranks: (input stream, source row) -> buffer on halo_dev
+  std::map<std::pair<const InputStream*, i64>, u8*> halo_rows;
+  DeviceHandle halo_dev = CPU_DEVICE;
+  i64 halo_bytes_sent = 0, halo_bytes_received = 0, halo_ns = 0;
 
   void fail(const std::string& msg) {
     std::lock_guard<std::mutex> g(err_mu);
@@ -96,6 +107,8 @@ struct Engine::Instance {
   i32 node_id;
   i32 index = 0;  // position in this run's instance list (trace tid)
   std::thread th;
+  // what this instance did in the run (per-session decode rate = frames_decoded / decode_busy_ns)
+  i64 frames_decoded = 0, decode_busy_ns = 0, wall_ns = 0, tasks_done = 0;
 };
 
 // What survives between runs for pipeline-instance slot `node_id`: its CUDA stream and its NVDEC
@@ -182,6 +195,7 @@ struct SourceCursor {
   size_t cur_interval = 0;
   bool interval_open = false;
   std::unique_ptr<NvdecSession> session;
+  std::vector<u8*> halo;      // per row: non-null = the element was received from another rank (not decoded here)
   std::map<i64, u8*> blocks;  // packet index -> frame block on the GPU (RGB24, or NV12 surfaces)
   size_t frame_bytes = 0;
   bool nv12 = false;          // deliver decoder-native surfaces (every consumer accepts them)
@@ -209,9 +223,49 @@ void TaskOutput::release() {
   ext.clear();
 }
 
+// Run the calling thread on the CPUs that are local to `gpu` (its PCIe root's NUMA node,
+// /sys/bus/pci/devices/<bdf>/local_cpulist) intersected with what the process may use.  A decode
+// thread spends its life in cuvidMapVideoFrame waiting for doorbells from that GPU; on the two-socket
+// hosts of the B200 boxes a thread on the far socket adds a cross-socket hop to every wake-up.
+// SCN_PIN_NUMA=0 disables.  Returns the number of CPUs in the mask (0: left alone).
+static int pin_thread_to_gpu_numa(i32 gpu) {
+  const char* e = getenv("SCN_PIN_NUMA");
+  if (e && e[0] == '0') return 0;
+  char bdf[32] = {0};
+  if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), gpu) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  for (char* c = bdf; *c; ++c) *c = (char)tolower(*c);
+  std::ifstream f(std::string("/sys/bus/pci/devices/") + bdf + "/local_cpulist");
+  std::string list;
+  if (!f || !std::getline(f, list) || list.empty()) return 0;
+  cpu_set_t allowed, want;
+  CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return 0;
+  size_t pos = 0;
+  while (pos < list.size()) {  // "0-31,64-95"
+    size_t end = list.find(',', pos);
+    if (end == std::string::npos) end = list.size();
+    const std::string part = list.substr(pos, end - pos);
+    const size_t dash = part.find('-');
+    const int a = atoi(part.c_str()), b = dash == std::string::npos ? a : atoi(part.c_str() + dash + 1);
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+      if (c >= 0 && CPU_ISSET(c, &allowed)) CPU_SET(c, &want);
+    pos = end + 1;
+  }
+  const int n = CPU_COUNT(&want);
+  if (n == 0 || n == CPU_COUNT(&allowed)) return 0;
+  return sched_setaffinity(0, sizeof(want), &want) == 0 ? n : 0;
+}
+
 void Engine::instance_main(Instance* inst) {
   RunState& rs = *run_;
   const i32 gpu = inst->gpu_id;
+  if (gpu >= 0 && cuda_available()) {
+    const int pinned = pin_thread_to_gpu_numa(gpu);
+    if (pinned && inst->index == 0) rs.profiler.increment("numa_pinned_cpus", pinned);
+  }
   Slot& slot = *slots_[(size_t)inst->node_id];
   if (gpu >= 0) {
     if (cudaSetDevice(gpu) != cudaSuccess) {
@@ -241,11 +295,13 @@ void Engine::instance_main(Instance* inst) {
       return;
     }
     std::map<i32, std::unique_ptr<NvdecSession>>& sessions = slot.sessions;
-    i64 decoded0 = 0, used0 = 0;
+    i64 decoded0 = 0, used0 = 0, busy0 = 0;
     for (auto& kv : sessions) {
       decoded0 += kv.second->frames_decoded();
       used0 += kv.second->frames_used();
+      busy0 += kv.second->busy_ns();
     }
+    const auto inst_t0 = std::chrono::steady_clock::now();
 
     while (!rs.failed.load()) {
       const size_t ti = rs.next.fetch_add(1);
@@ -293,6 +349,18 @@ void Engine::instance_main(Instance* inst) {
           break;
         }
         max_rows = std::max(max_rows, c.rows.size());
+        if (!rs.halo_rows.empty()) {
+          c.halo.assign(c.rows.size(), nullptr);
+          bool any = false;
+          for (size_t i = 0; i < c.rows.size(); ++i) {
+            auto hit = rs.halo_rows.find({c.stream, c.rows[i]});
+            if (hit != rs.halo_rows.end()) {
+              c.halo[i] = hit->second;
+              any = true;
+            }
+          }
+          if (!any) c.halo.clear();
+        }
         if (c.stream->kind == InputStream::H264) {
           if (gpu < 0) {
             RESULT_ERROR(&r, "H.264 sources need a GPU pipeline instance (NVDEC); there is no software decoder");
@@ -307,7 +375,7 @@ void Engine::instance_main(Instance* inst) {
               break;
             }
           }
-          c.intervals = slice_into_intervals(c.stream->index, c.rows);
+          c.intervals = slice_into_intervals(c.stream->index, c.rows, c.halo.empty() ? nullptr : &c.halo);
           // decoder-native delivery when every consumer kernel takes NV12 (frame.h FrameLayout);
           // SCN_DECODE_RGB=1 forces the reference's RGB24 elements
           const char* force_rgb = getenv("SCN_DECODE_RGB");
@@ -392,7 +460,14 @@ void Engine::instance_main(Instance* inst) {
             }
             if (!r.success()) break;
             for (size_t i = i0; i < i1; ++i) {
-              cb.elements.push_back(Element(new Frame(finfo, c.slot((i64)i))));
+              if (!c.halo.empty() && c.halo[i]) {  // received from the rank that owns the row
+                add_buffer_ref(gpu_dev, c.halo[i]);
+                cb.elements.push_back(Element(new Frame(finfo, c.halo[i])));
+                // the packet's block counts one reference per row: give back this row's unused slot
+                if (c.blocks.count((i64)i / c.wps)) delete_buffer(gpu_dev, c.slot((i64)i));
+              } else {
+                cb.elements.push_back(Element(new Frame(finfo, c.slot((i64)i))));
+              }
               cb.row_ids.push_back(c.rows[i]);
             }
             if (c.nv12) rs.frames_native += (i64)(i1 - i0);
@@ -407,7 +482,10 @@ void Engine::instance_main(Instance* inst) {
                 break;
               }
               u8* ptr = st.data.data() + st.offsets[row];
-              if (st.kind == InputStream::RawFrames) {
+              if (!c.halo.empty() && c.halo[i] && st.kind == InputStream::RawFrames) {
+                add_buffer_ref(CPU_DEVICE, c.halo[i]);
+                cb.elements.push_back(Element(new Frame(st.info, c.halo[i])));
+              } else if (st.kind == InputStream::RawFrames) {
                 add_buffer_ref(CPU_DEVICE, ptr);
                 cb.elements.push_back(Element(new Frame(st.info, ptr)));
               } else if (st.sizes[row] == 0) {
@@ -564,14 +642,21 @@ void Engine::instance_main(Instance* inst) {
         }
       }
       rs.profiler.add_interval("task", task_start, now());
+      ++inst->tasks_done;
     }
+    i64 busy1 = 0, decoded1 = 0;
     for (auto& kv : sessions) {
       kv.second->drain();
       rs.frames_decoded += kv.second->frames_decoded();
       rs.frames_used += kv.second->frames_used();
+      decoded1 += kv.second->frames_decoded();
+      busy1 += kv.second->busy_ns();
     }
     rs.frames_decoded -= decoded0;
     rs.frames_used -= used0;
+    inst->frames_decoded = decoded1 - decoded0;
+    inst->decode_busy_ns = busy1 - busy0;
+    inst->wall_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - inst_t0).count();
     if (gpu >= 0) cudaStreamSynchronize(stream);
   }  // kernels destroyed here, while the stream is alive
   if (gpu >= 0) {
@@ -618,6 +703,14 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
     RESULT_ERROR(&r, "stream %ld is not an H.264 stream", (long)stream_id);
     return r;
   }
+  return decode_rows(*st, rows, gpu_id, false, dst);
+}
+
+// rows (ascending) of an H.264 stream -> dense elements in device memory: packed NV12 surfaces
+// (w*h*3/2 bytes each) or RGB24 frames
+Result Engine::decode_rows(InputStream& stref, const std::vector<i64>& rows, i32 gpu_id, bool nv12, u8* dst) {
+  Result r;
+  InputStream* st = &stref;
   for (size_t i = 0; i < rows.size(); ++i)
     if (rows[i] < 0 || rows[i] >= st->rows() || (i && rows[i] <= rows[i - 1])) {
       RESULT_ERROR(&r, "rows must be ascending and inside [0, %ld)", (long)st->rows());
@@ -637,7 +730,7 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
   {
     NvdecSession sess(gpu_id, cs);
     r = sess.init();
-    const size_t w = (size_t)st->index.width, h = (size_t)st->index.height, fb = w * h * 3;
+    const size_t w = (size_t)st->index.width, h = (size_t)st->index.height, fb = nv12 ? w * h * 3 / 2 : w * h * 3;
     std::string kerr;
     for (const VideoInterval& iv : slice_into_intervals(st->index, rows)) {
       if (!r.success()) break;
@@ -654,8 +747,9 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
                                          " but the stream index says " + std::to_string(w) + "x" + std::to_string(h);
                                   return;
                                 }
-                                const int rc = scn_nv12_to_rgb24(&lp, &cp, s.pitch, 1, (int)w, (int)h, &d, w * 3, cs);
-                                if (rc != 0) kerr = "scn_nv12_to_rgb24 failed: " + std::to_string(rc);
+                                const int rc = nv12 ? scn_nv12_pack(&lp, &cp, s.pitch, 1, (int)w, (int)h, &d, cs)
+                                                    : scn_nv12_to_rgb24(&lp, &cp, s.pitch, 1, (int)w, (int)h, &d, w * 3, cs);
+                                if (rc != 0) kerr = "decode-stage kernel failed: " + std::to_string(rc);
                               });
       if (r.success()) r = sess.end_interval();
     }
@@ -664,6 +758,122 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
     if (r.success() && !kerr.empty()) RESULT_ERROR(&r, "%s", kerr.c_str());
   }
   cudaStreamDestroy(cs);
+  return r;
+}
+
+// ---- stencil halo exchange of sharded jobs (halo.h) ------------------------------------------------
+// For every job that computes one interval of a clip: which source rows do the OTHER intervals' tasks
+// need from mine (derive_task_streams over their output rows -- the same back-propagation the reference
+// uses to over-fetch, dag_analysis.cpp:1470-1718), which do mine need from theirs.  Mine are decoded
+// once here and sent; theirs are received into element buffers the decode stage then hands out instead
+// of decoding.  Every rank builds its transfer list in (job, source op, row) order, so the lists of a
+// pair of ranks match; all transfers of the run go out in one group.
+Result Engine::exchange_halos(Graph& graph, const std::vector<Job*>& jobs) {
+  Result r = ok();
+  RunState& rs = *run_;
+  bool any = false;
+  for (Job* jb : jobs) any = any || jb->shard_index >= 0;
+  if (!any) return r;
+  const auto t0 = std::chrono::steady_clock::now();
+  const i32 my_rank = halo_ ? halo_->rank() : 0;
+  struct Plan {
+    Job* job;
+    InputStream* st;
+    i32 peer;
+    std::vector<i64> rows;
+    bool send;
+    bool nv12;
+    size_t frame_bytes;
+    u8* staging = nullptr;  // sends: rows.size() dense elements
+  };
+  std::vector<Plan> plans;
+  for (Job* jb : jobs) {
+    if (jb->shard_index < 0) continue;
+    Job& job = *jb;
+    const size_t nsh = job.shard_ranks.size();
+    auto window_rows = [&](size_t q) {
+      std::vector<i64> rows;
+      for (i64 row = job.shard_bounds[q]; row < job.shard_bounds[q + 1]; ++row) rows.push_back(row);
+      return rows;
+    };
+    const i64 w0 = job.shard_bounds[(size_t)job.shard_index], w1 = job.shard_bounds[(size_t)job.shard_index + 1];
+    for (size_t k = 0; k < graph.ops.size(); ++k) {
+      if (graph.ops[k].kind != OpKind::Source) continue;
+      auto bit = job.source_streams.find((i32)k);
+      InputStream* st = bit == job.source_streams.end() ? nullptr : stream(bit->second);
+      if (!st || st->kind == InputStream::Bytes) continue;  // byte rows are read from the stream, never decoded
+      if (job.rows_per_op[k] != job.total_rows) {
+        RESULT_ERROR(&r, "a sharded job needs sources with one row per output row (source %zu has %ld rows, the job %ld)",
+                     k, (long)job.rows_per_op[k], (long)job.total_rows);
+        return r;
+      }
+      const bool nv12 = st->kind == InputStream::H264 && !(getenv("SCN_DECODE_RGB") && getenv("SCN_DECODE_RGB")[0] == '1') &&
+                        graph.consumers_accept_layout((i32)k, FrameLayout::NV12);
+      size_t fb;
+      if (st->kind == InputStream::H264) {
+        const size_t px = (size_t)st->index.width * st->index.height;
+        fb = nv12 ? px + px / 2 : px * 3;
+      } else {
+        fb = st->info.size();
+      }
+      for (size_t q = 0; q < nsh; ++q) {
+        if ((i32)q == job.shard_index || job.shard_ranks[q] == my_rank) continue;
+        // what shard q needs from my interval -> send; what I need from shard q's interval -> receive
+        std::vector<TaskStream> ts;
+        Result d = graph.derive_task_streams(rs.an, job.params, job.rows_per_op, window_rows(q), ts);
+        if (!d.success()) return d;
+        Plan snd{jb, st, job.shard_ranks[q], {}, true, nv12, fb};
+        for (i64 row : ts[k].valid_output_rows)
+          if (row >= w0 && row < w1) snd.rows.push_back(row);
+        d = graph.derive_task_streams(rs.an, job.params, job.rows_per_op, window_rows((size_t)job.shard_index), ts);
+        if (!d.success()) return d;
+        Plan rcv{jb, st, job.shard_ranks[q], {}, false, nv12, fb};
+        for (i64 row : ts[k].valid_output_rows)
+          if (row >= job.shard_bounds[q] && row < job.shard_bounds[q + 1]) rcv.rows.push_back(row);
+        if (!snd.rows.empty()) plans.push_back(std::move(snd));
+        if (!rcv.rows.empty()) plans.push_back(std::move(rcv));
+      }
+    }
+  }
+  if (plans.empty()) return r;
+  if (!halo_) {
+    RESULT_ERROR(&r, "a sharded job needs rows from another rank but the engine has no halo transport "
+                     "(scn_engine_comm_init / scn_engine_set_halo_callback)");
+    return r;
+  }
+  const bool on_device = halo_->device_buffers();
+  const DeviceHandle dev = on_device ? DeviceHandle(DeviceType::GPU, halo_->gpu_id()) : CPU_DEVICE;
+  rs.halo_dev = dev;
+  std::vector<HaloXfer> xfers;
+  for (Plan& p : plans) {
+    if ((p.st->kind == InputStream::H264) != on_device) {
+      RESULT_ERROR(&r, "halo exchange: H.264 sources travel over the NCCL transport, raw-frame sources over the host "
+                       "transport (stream kind %d, transport on %s)", (int)p.st->kind, on_device ? "device" : "host");
+      break;
+    }
+    if (p.send) {
+      if (on_device) {
+        p.staging = new_buffer(dev, p.rows.size() * p.frame_bytes);
+        r = decode_rows(*p.st, p.rows, dev.id, p.nv12, p.staging);
+        if (!r.success()) break;
+        for (size_t i = 0; i < p.rows.size(); ++i) xfers.push_back({p.peer, p.staging + i * p.frame_bytes, p.frame_bytes, true});
+      } else {
+        for (i64 row : p.rows) xfers.push_back({p.peer, p.st->data.data() + p.st->offsets[(size_t)row], p.frame_bytes, true});
+      }
+      rs.halo_bytes_sent += (i64)(p.rows.size() * p.frame_bytes);
+    } else {
+      for (i64 row : p.rows) {
+        u8* buf = new_buffer(dev, p.frame_bytes);
+        rs.halo_rows[{p.st, row}] = buf;
+        xfers.push_back({p.peer, buf, p.frame_bytes, false});
+      }
+      rs.halo_bytes_received += (i64)(p.rows.size() * p.frame_bytes);
+    }
+  }
+  if (r.success()) r = halo_->exchange(xfers);
+  for (Plan& p : plans)
+    if (p.staging) delete_buffer(dev, p.staging);
+  rs.halo_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
   return r;
 }
 
@@ -738,8 +948,28 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
         groups_of_task.push_back(-1);
       }
     }
+    i64 window_end = job.total_rows;
+    if (job.shard_index >= 0) {
+      // one interval of the clip: tasks cover [bounds[index], bounds[index + 1]) only
+      const size_t nsh = job.shard_ranks.size();
+      bool good = job.slices.groups == 0 && nsh >= 1 && job.shard_bounds.size() == nsh + 1 && (size_t)job.shard_index < nsh &&
+                  job.shard_bounds.front() == 0 && job.shard_bounds.back() == job.total_rows;
+      for (size_t q = 0; good && q < nsh; ++q) good = job.shard_bounds[q] <= job.shard_bounds[q + 1];
+      if (!good) {
+        RESULT_ERROR(&r, "job %zu: shard bounds must ascend from 0 to the job's %ld rows, one rank per interval, and the "
+                         "graph must not slice", j, (long)job.total_rows);
+        return r;
+      }
+      job.task_starts.clear();
+      groups_of_task.clear();
+      window_end = job.shard_bounds[(size_t)job.shard_index + 1];
+      for (i64 row = job.shard_bounds[(size_t)job.shard_index]; row < window_end; row += ios) {
+        job.task_starts.push_back(row);
+        groups_of_task.push_back(-1);
+      }
+    }
     const i64 n_tasks = (i64)job.task_starts.size();
-    job.task_starts.push_back(job.total_rows);
+    job.task_starts.push_back(window_end);
     job.sink_is_frame.clear();
     for (size_t k = 0; k < graph.ops.size(); ++k)
       if (graph.ops[k].kind == OpKind::Sink) {
@@ -817,8 +1047,16 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
     }
   }
   const auto t0 = std::chrono::steady_clock::now();
-  for (auto& inst : instances) inst->th = std::thread([this, p = inst.get()] { instance_main(p); });
-  for (auto& inst : instances) inst->th.join();
+  {
+    Result hr = exchange_halos(graph, jobs);
+    if (!hr.success()) rs.fail(hr.msg());
+  }
+  if (!rs.failed.load()) {
+    for (auto& inst : instances) inst->th = std::thread([this, p = inst.get()] { instance_main(p); });
+    for (auto& inst : instances) inst->th.join();
+  }
+  for (auto& kv : rs.halo_rows) delete_buffer(rs.halo_dev, kv.second);
+  rs.halo_rows.clear();
   stats_ = RunStats();
   stats_.wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   stats_.counters = rs.profiler.counters();
@@ -842,6 +1080,22 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   }
   stats_.counters["tasks"] = (i64)rs.tasks.size();
   stats_.counters["instances"] = (i64)instances.size();
+  stats_.counters["halo_bytes_sent"] = rs.halo_bytes_sent;
+  stats_.counters["halo_bytes_received"] = rs.halo_bytes_received;
+  stats_.counters["halo_exchange_us"] = rs.halo_ns / 1000;
+  // per pipeline instance (= per decode session): what it decoded and how long it waited on its NVDEC
+  // engine -- frames / busy is the session's picture rate, the evidence for where an end-to-end
+  // number below the expected one went (measured: all sessions of a run always share one rate, slow
+  // runs are slow for every session -- profiles/r02_e2e_variance.md)
+  for (size_t i = 0; i < instances.size(); ++i) {
+    const Instance& in = *instances[i];
+    const std::string k = "inst" + std::to_string(i) + "_";
+    stats_.counters[k + "gpu"] = in.gpu_id;
+    stats_.counters[k + "tasks"] = in.tasks_done;
+    stats_.counters[k + "frames_decoded"] = in.frames_decoded;
+    stats_.counters[k + "decode_busy_us"] = in.decode_busy_ns / 1000;
+    stats_.counters[k + "wall_us"] = in.wall_ns / 1000;
+  }
   stats_.interval_ns = rs.profiler.interval_totals_ns();
   stats_.interval_counts = rs.profiler.interval_counts();
   for (const Profiler::TaskRecord& rec : rs.profiler.records()) {

@@ -18,6 +18,7 @@
 
 #include "evaluate.h"
 #include "graph.h"
+#include "halo.h"
 #include "h264.h"
 #include "scanner/api/frame.h"
 
@@ -122,6 +123,13 @@ struct Job {
   // keep_rows == false the rows of such sinks are dropped from memory once their item is written.
   std::map<i32, i32> sink_tables;
   bool keep_rows = true;
+  // One clip split into contiguous output-row intervals across ranks (configs[3]): this job computes
+  // rows [shard_bounds[shard_index], shard_bounds[shard_index + 1]) only; shard q is computed by rank
+  // shard_ranks[q].  Source rows a stencil reaches into a neighbouring interval are not decoded here:
+  // the owning rank sends them as decoded elements before the run's instances start (halo.h).
+  std::vector<i64> shard_bounds;
+  std::vector<i32> shard_ranks;
+  i32 shard_index = -1;
 };
 
 struct TraceEvent {
@@ -163,6 +171,10 @@ class Engine {
   // pid = GPU id (-1: CPU instance), tid = pipeline instance.
   Result write_trace(const std::string& path) const;
   const std::vector<i32>& gpu_ids() const { return gpu_ids_; }
+  // Transport for the stencil halo exchange of sharded jobs (NCCL between the ranks' GPUs, or a host
+  // callback); the engine owns it.
+  void set_halo_transport(std::unique_ptr<HaloTransport> t) { halo_ = std::move(t); }
+  const HaloTransport* halo_transport() const { return halo_.get(); }
 
  private:
   struct Instance;
@@ -177,6 +189,10 @@ class Engine {
   i64 next_stream_id_ = 1;
   RunStats stats_;
   bool trace_ = false;
+
+  std::unique_ptr<HaloTransport> halo_;
+  Result exchange_halos(Graph& graph, const std::vector<Job*>& jobs);
+  Result decode_rows(InputStream& st, const std::vector<i64>& rows, i32 gpu_id, bool nv12, u8* dst);
 
   // state of the run in flight
   struct RunState;

@@ -4,7 +4,7 @@
 // read them back).  Here the surface (1.5 WH bytes) is the only large read: the histogram is
 // taken from RGB values converted in registers, and the resize converts just the 4 taps of each
 // destination pixel.  Results are bit-identical to the three-pass composition.
-#include "nv12_csa.cuh"
+#include "nv12_stream.cuh"
 #include "nv12_math.cuh"
 #include "scn_common.cuh"
 
@@ -189,6 +189,17 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
     if (e != cudaSuccess) return (int)e;
   }
   const int quads = (width + 3) / 4;
+  // Large aligned surfaces take the one-pass streaming kernel (nv12_stream.cuh): histogram and, when
+  // both are wanted, the Resize rows of every span right behind it.  Everything else (tiny, ragged or
+  // unaligned surfaces; Resize alone) runs the generic kernels below.
+  bool stream_ok = do_hist;
+  for (int i0 = 0; i0 < n && stream_ok; i0 += SCN_MAX_PTRS) {
+    const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
+    stream_ok = nvs::eligible(host_luma_ptrs + i0, host_chroma_ptrs + i0, cnt, pitch, width, height);
+  }
+  if (stream_ok)
+    return nvs::launch(host_luma_ptrs, host_chroma_ptrs, n, pitch, width, height, hist_out, do_resize ? host_dst_ptrs : nullptr,
+                       (do_resize && !area2x) ? (const uint8_t*)plan + kPlanHeaderBytes : nullptr, dst_w, dst_h, area2x ? 1 : 0, st);
   // fork: the resize kernels of this call go to the side stream (see SideStream)
   SideStream* side = (do_hist && do_resize) ? side_stream() : nullptr;
   cudaStream_t rst = st;
@@ -212,23 +223,17 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
       d.p[i] = do_resize ? host_dst_ptrs[i0 + i] : nullptr;
       if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i]) & 3) vec_ok = 0;
     }
-    // the histogram kernel goes first: its persistent CTAs take one slot per SM and the resize
-    // CTAs fill in around them (the other order makes the histogram wait for the resize grid)
     if (do_hist) {
-      if (nvcsa::eligible(l.p, c.p, cnt, pitch, width, height)) {
-        rc = nvcsa::launch(l.p, c.p, cnt, pitch, width, height, hist_out + (size_t)i0 * 48, st);
-      } else {
-        const int gx = (quads + HT - 1) / HT;
-        int gy = (sm_count() * 8 + gx * cnt - 1) / (gx * cnt);
-        if (gy < 1) gy = 1;
-        if (gy > height) gy = height;
-        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
-        {
-          LaunchScope ls("nv12_hist_kernel", st);
-          nv12_hist_kernel<<<grid, HT, 0, st>>>(l, c, pitch, width, height, quads, vec_ok, hist_out + (size_t)i0 * 48);
-        }
-        rc = launch_status();
+      const int gx = (quads + HT - 1) / HT;
+      int gy = (sm_count() * 8 + gx * cnt - 1) / (gx * cnt);
+      if (gy < 1) gy = 1;
+      if (gy > height) gy = height;
+      dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
+      {
+        LaunchScope ls("nv12_hist_kernel", st);
+        nv12_hist_kernel<<<grid, HT, 0, st>>>(l, c, pitch, width, height, quads, vec_ok, hist_out + (size_t)i0 * 48);
       }
+      rc = launch_status();
       if (rc) break;
     }
     if (do_resize) {

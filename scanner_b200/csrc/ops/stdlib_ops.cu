@@ -223,41 +223,109 @@ class OpticalFlowKernelGPU : public StenciledKernel, public VideoKernel {
   OpticalFlowKernelGPU(const KernelConfig& config) : StenciledKernel(config), device_(config.devices[0]) {}
   ~OpticalFlowKernelGPU() {
     if (workspace_) delete_buffer(device_, workspace_);
+    for (u8*& b : rgb_)
+      if (b) delete_buffer(device_, b);
   }
 
   void new_frame_info() override {
     if (workspace_) delete_buffer(device_, workspace_);
-    workspace_bytes_ = scn_farneback_workspace_bytes(frame_info_.width(), frame_info_.height());
+    const int w = pic_width_, h = pic_height_;
+    workspace_bytes_ = scn_farneback_workspace_bytes(w, h);
     workspace_ = new_buffer(device_, workspace_bytes_);
+    for (u8*& b : rgb_) {
+      if (b) delete_buffer(device_, b);
+      b = nullptr;
+    }
+    rgb_of_[0] = rgb_of_[1] = -1;
   }
+
+  void reset() override { rgb_of_[0] = rgb_of_[1] = -1; }  // row ids identify a frame within one task only
 
   void execute(const StenciledElements& input_columns, Elements& output_columns) override {
     const Elements& window = input_columns[0];
     CU_CHECK(cudaSetDevice(device_.id));
-    check_frame(device_, window[0]);
     const Frame* f0 = window[0].as_const_frame();
     const Frame* f1 = window[1].as_const_frame();
     require_rgb8(f0, "OpticalFlow");
+    pic_width_ = pic_width(f0);
+    pic_height_ = pic_height(f0);
+    check_frame(device_, window[0]);
     if (!(f0->as_frame_info() == f1->as_frame_info())) LOG(FATAL) << "OpticalFlow: frames of one window differ in size";
-    FrameInfo out_info(f0->height(), f0->width(), 2, FrameType::F32);
+    const int w = pic_width_, h = pic_height_;
+    FrameInfo out_info(h, w, 2, FrameType::F32);
     Frame* out = new_frame(device_, out_info);
-    const u8* prev = f0->data;
-    const u8* next = f1->data;
+    // decoder-native (packed NV12) elements are converted here with the reference's NV12 -> RGB
+    // arithmetic; the frame that was `next` of the previous row is `prev` of this one and is reused
+    const u8* prev = is_nv12(f0) ? rgb_of(f0, window[0].index, w, h) : f0->data;
+    const u8* next = is_nv12(f1) ? rgb_of(f1, window[1].index, w, h) : f1->data;
     float* flow = reinterpret_cast<float*>(out->data);
-    SCN_CHECK(scn_farneback_u8c3(&prev, &next, 1, f0->width(), f0->height(), &flow, 3, 0.5, 15, 3, 5, 1.2, workspace_,
-                                 workspace_bytes_, device_stream(device_)));
+    SCN_CHECK(scn_farneback_u8c3(&prev, &next, 1, w, h, &flow, 3, 0.5, 15, 3, 5, 1.2, workspace_, workspace_bytes_,
+                                 device_stream(device_)));
     insert_frame(output_columns[0], out);
   }
 
  private:
+  const u8* rgb_of(const Frame* f, i64 row, int w, int h) {
+    for (int k = 0; k < 2; ++k)
+      if (rgb_of_[k] == row && row >= 0 && rgb_[k]) {
+        last_used_ = k;
+        return rgb_[k];
+      }
+    const int k = 1 - last_used_;  // overwrite the copy not used by the other frame of this window
+    if (!rgb_[k]) rgb_[k] = new_buffer(device_, (size_t)w * h * 3);
+    const u8* lp = f->data;
+    const u8* cp = f->data + (size_t)w * h;
+    u8* dst = rgb_[k];
+    SCN_CHECK(scn_nv12_to_rgb24(&lp, &cp, (size_t)w, 1, w, h, &dst, (size_t)w * 3, device_stream(device_)));
+    rgb_of_[k] = row;
+    last_used_ = k;
+    return rgb_[k];
+  }
+
   DeviceHandle device_;
   u8* workspace_ = nullptr;
   size_t workspace_bytes_ = 0;
+  int pic_width_ = 0, pic_height_ = 0;
+  u8* rgb_[2] = {nullptr, nullptr};          // RGB24 copies of the window's NV12 elements
+  i64 rgb_of_[2] = {-1, -1};                 // input row (Element::index) each holds
+  int last_used_ = 1;
 };
 
 REGISTER_OP(OpticalFlow).frame_input("frame").frame_output("flow").stencil({0, 1});
 
-REGISTER_KERNEL(OpticalFlow, OpticalFlowKernelGPU).device(DeviceType::GPU).num_devices(1);
+REGISTER_KERNEL(OpticalFlow, OpticalFlowKernelGPU)
+    .device(DeviceType::GPU)
+    .num_devices(1)
+    .input_layout("frame", FrameLayout::NV12);
+
+// ---------------------------------------------------------------------------------------------
+// FrameDigest: frame -> 16 bytes (scn_frame_digest).  Lets frame-valued columns that are too large to
+// bring back (flow fields) be compared exactly between runs; not a reference op.
+class FrameDigestKernelGPU : public BatchedKernel {
+ public:
+  FrameDigestKernelGPU(const KernelConfig& config) : BatchedKernel(config), device_(config.devices[0]) {}
+
+  void execute(const BatchedElements& input_columns, BatchedElements& output_columns) override {
+    const Elements& frames = input_columns[0];
+    const i32 n = (i32)num_rows(frames);
+    if (n == 0) return;
+    CU_CHECK(cudaSetDevice(device_.id));
+    u8* block = new_block_buffer_size(device_, 16, n);
+    for_each_run(frames, [&](size_t i0, size_t i1, const Frame* f0) {
+      std::vector<const u8*> ptrs;
+      for (size_t i = i0; i < i1; ++i) ptrs.push_back(frames[i].as_const_frame()->data);
+      SCN_CHECK(scn_frame_digest(ptrs.data(), (int)ptrs.size(), f0->size(), (uint64_t*)(block + i0 * 16), device_stream(device_)));
+    });
+    for (i32 i = 0; i < n; ++i) insert_element(output_columns[0], block + (size_t)i * 16, 16);
+  }
+
+ private:
+  DeviceHandle device_;
+};
+
+REGISTER_OP(FrameDigest).frame_input("frame").output("digest");
+
+REGISTER_KERNEL(FrameDigest, FrameDigestKernelGPU).device(DeviceType::GPU).batch(8).num_devices(1);
 
 }  // namespace
 }  // namespace scanner

@@ -2,6 +2,7 @@
 import ctypes
 import json
 import os
+import sys
 
 import numpy as np
 
@@ -62,6 +63,10 @@ SIGNATURES = {
     "scn_job_set_partitioner": (_I, [_VP, _I, _CP, _VP, _SZ]),
     "scn_job_set_group_sampler": (_I, [_VP, _I, _I, _CP, _VP, _SZ]),
     "scn_job_set_group_stream_args": (_I, [_VP, _I, _I, _VP, _SZ]),
+    "scn_engine_comm_unique_id": (_I, [_VP]),
+    "scn_engine_comm_init": (_I, [_VP, _I, _I, _I, _VP]),
+    "scn_engine_set_halo_callback": (_I, [_VP, _I, _I, _VP, _VP]),
+    "scn_job_set_shard": (_I, [_VP, _I, _I, _c.POINTER(_I64), _IP]),
     "scn_engine_set_trace": (_I, [_VP, _I]),
     "scn_engine_write_trace": (_I, [_VP, _CP]),
     "scn_db_open": (_VP, [_CP]),
@@ -365,6 +370,47 @@ class Engine:
         data = np.frombuffer(b"".join(bytes(r) for r in rows) or b"\0", np.uint8)
         return check(lib().scn_stream_add_bytes(self._h, data.ctypes.data, sizes.ctypes.data, len(rows)), "add_bytes")
 
+    # ---- one clip across several ranks: stencil halo exchange (include/scn_engine.h) ----
+    def init_comm(self, gpu, group=None):
+        """NCCL transport between the ranks' GPUs for the halo exchange of sharded jobs.  Collective over
+        the torch.distributed group: rank 0's ncclUniqueId travels through broadcast_object_list."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            check(lib().scn_engine_comm_unique_id(ident), "comm_unique_id")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (ctypes.c_uint8 * 128).from_buffer_copy(box[0])
+        check(lib().scn_engine_comm_init(self._h, gpu, rank, world, ident), "comm_init")
+
+    def init_host_halo(self, group=None):
+        """Host transport for the halo exchange (CPU instances over raw-frame streams): the buffers are
+        moved with torch.distributed point-to-point operations of `group` (gloo)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+        def exchange(_user, n, peers, buffers, nbytes, is_send):
+            try:
+                ops = []
+                for i in range(n):
+                    arr = np.ctypeslib.as_array(ctypes.cast(buffers[i], ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes[i],))
+                    t = torch.from_numpy(arr)
+                    ops.append(dist.P2POp(dist.isend if is_send[i] else dist.irecv, t, peers[i], group))
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                return 0
+            except Exception as e:  # noqa: BLE001 -- reported through the C return code
+                sys.stderr.write(f"halo exchange failed: {e}\n")
+                return 1
+
+        proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                 ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int))
+        self._halo_cb = proto(exchange)  # keep the trampoline alive as long as the engine
+        check(lib().scn_engine_set_halo_callback(self._h, rank, world, ctypes.cast(self._halo_cb, ctypes.c_void_p), None),
+              "set_halo_callback")
+
     def set_trace(self, on=True):
         """Keep every profiler interval of the following runs (see write_trace)."""
         check(lib().scn_engine_set_trace(self._h, 1 if on else 0), "set_trace")
@@ -470,6 +516,15 @@ class Job:
         check(lib().scn_job_set_sampler(self._h, op, function.encode(), ctypes.cast(buf, ctypes.c_void_p) if buf else None,
                                         len(args)), f"set_sampler({function})")
 
+    def set_shard(self, index, bounds, ranks):
+        """This job computes output rows [bounds[index], bounds[index+1]) of its clip; interval q belongs to
+        rank ranks[q] (rows a stencil needs from a neighbouring interval come from that rank)."""
+        n = len(ranks)
+        assert len(bounds) == n + 1
+        b = (ctypes.c_int64 * (n + 1))(*[int(x) for x in bounds])
+        r = (ctypes.c_int * n)(*[int(x) for x in ranks])
+        check(lib().scn_job_set_shard(self._h, int(index), n, b, r), "set_shard")
+
     def set_partitioner(self, slice_op, name, args):
         buf = ctypes.create_string_buffer(args, len(args)) if args else None
         check(lib().scn_job_set_partitioner(self._h, slice_op, name.encode(),
@@ -512,9 +567,10 @@ class Job:
             return np.frombuffer(raw, dt).reshape(shape[0], shape[1], shape[2])
         return raw
 
-    def output_array(self, sink, row_bytes, dtype=np.uint8):
-        """All rows of equal size as one (n, row_bytes/itemsize) array."""
+    def output_array(self, sink, row_bytes, dtype=np.uint8, row0=0):
+        """All rows of equal size as one (n, row_bytes/itemsize) array.  row0: first row id the job computed
+        (a sharded job addresses its rows by their position in the whole clip)."""
         n = self.output_rows(sink)
         out = np.empty((n, row_bytes), np.uint8)
-        check(lib().scn_job_output_copy(self._h, sink, 0, n, out.ctypes.data, row_bytes), "output_copy")
+        check(lib().scn_job_output_copy(self._h, sink, row0, n, out.ctypes.data, row_bytes), "output_copy")
         return out.view(dtype)

@@ -172,3 +172,15 @@ def optical_flow(prev_frames, next_frames, num_levels=3, pyr_scale=0.5, win_size
                                        poly_sigma, workspace.data_ptr(), workspace.numel(), _stream())
     cabi.check(rc, "scn_farneback_u8c3")
     return out
+
+
+def frame_digest(frames):
+    """frames: (N, ...) contiguous CUDA tensor -> (N, 2) uint64-as-int64 fingerprints (scn_frame_digest)."""
+    _need_cuda(frames)
+    frames = frames.contiguous()
+    n = frames.shape[0]
+    nbytes = frames[0].numel() * frames.element_size()
+    out = torch.empty((n, 2), dtype=torch.int64, device=frames.device)
+    pp, keep = cabi.ptr_array([frames.data_ptr() + i * nbytes for i in range(n)])
+    cabi.check(cabi.lib().scn_frame_digest(pp, n, nbytes, out.data_ptr(), _stream()), "scn_frame_digest")
+    return out

@@ -230,3 +230,55 @@ def test_4k_blur_then_histogram_properties():
     got = blurred[0].cpu().numpy()
     assert (got[1:-1, 1:-1] == want[1:-1, 1:-1]).all() and (got[0] == 0).all() and (got[:, 0] == 0).all()
     assert (hist[0] == oracle.hist16(got)).all()
+
+
+def test_frame_digest_matches_numpy():
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for shape, dt in (((5, 37, 53, 2), torch.float32), ((3, 270, 480, 3), torch.uint8), ((70, 64, 4), torch.int32)):
+        if dt == torch.float32:
+            x = torch.randn(shape, device="cuda", generator=g)
+        else:
+            x = torch.randint(0, 200, shape, device="cuda", generator=g).to(dt)
+        if (x[0].numel() * x.element_size()) % 4:
+            continue
+        got = kernels.frame_digest(x).cpu().numpy().view(np.uint64)
+        for i in range(shape[0]):
+            w = np.frombuffer(x[i].cpu().numpy().tobytes(), "<u4").astype(np.uint64)
+            k = (np.arange(w.size, dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
+            with np.errstate(over="ignore"):
+                want = np.array([w.sum(dtype=np.uint64), (w * k).sum(dtype=np.uint64)], np.uint64)
+            assert (got[i] == want).all(), (shape, i)
+
+
+def test_sharded_job_windows_on_one_gpu_equal_the_whole_clip():
+    """scn_job_set_shard with every interval owned by this rank (no transport): each job computes its window,
+    decoding the stencil rows beyond it itself; the windows together equal the unsharded job.  (The NCCL
+    exchange between ranks is exercised by `bench.py --config 3 --gpus N` and, on the CPU, by the gloo test.)"""
+    from scanner_b200 import engine as E
+    E.load_stdlib()
+    w, h, n = 128, 96, 25
+    rng = np.random.default_rng(4)
+    yuv = rng.integers(0, 256, (n, h * w * 3 // 2), dtype=np.uint8)
+    eng = E.Engine(gpus=[0], instances_per_gpu=2)
+    sid = eng.add_h264(E.h264_synth(yuv, w, h, gop=6, non_key="pcm"))
+    g = E.Graph()
+    src = g.add_source(True)
+    fl = g.add_op("OpticalFlow", [(src, "frame")], device=1)
+    dg = g.add_op("FrameDigest", [(fl, "flow")], device=1)
+    sink = g.add_sink((dg, "digest"))
+    whole = E.Job()
+    whole.bind_source(src, sid)
+    eng.run(g, [whole], 4, 8)
+    full = whole.output_array(sink, 16, np.uint64)
+    assert full.shape == (n, 2)
+    bounds = [0, 7, 7, 19, n]  # one empty interval
+    parts = []
+    for q in range(4):
+        j = E.Job()
+        j.bind_source(src, sid)
+        j.set_shard(q, bounds, [0, 0, 0, 0])
+        eng.run(g, [j], 4, 8)
+        assert j.output_rows(sink) == bounds[q + 1] - bounds[q]
+        parts.append(j.output_array(sink, 16, np.uint64, row0=bounds[q]))
+    assert (np.concatenate(parts) == full).all()
+    eng.close()

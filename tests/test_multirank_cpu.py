@@ -124,3 +124,63 @@ def test_halo_exchange_gloo(tmp_path, world):
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
     assert f"HALO_OK {world}" in out.stdout, out.stdout[-3000:]
+
+
+ENGINE_HALO_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["SCN_ROOT"])
+from oracle import synth
+from scanner_b200 import engine as E, halo
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+E.load_op_library(os.path.join(os.environ["SCN_ROOT"], "build", "tests", "libtest_plugin_ops.so"))
+lengths = [23, 9, 40]                                   # three clips, each split over all ranks
+clips = [np.stack([synth.rand_frame(100 * c + k, 12, 16) for k in range(n)]) for c, n in enumerate(lengths)]
+eng = E.Engine(gpus=[], cpu_instances=2)
+eng.init_host_halo()
+g = E.Graph(); src = g.add_source(True)
+d = g.add_op("TestFrameDiff", [(src, "frame")]); sink = g.add_sink((d, "diff"))
+jobs, windows = [], []
+for c, n in enumerate(lengths):
+    bounds = [halo.interval_of(n, r, world)[0] for r in range(world)] + [n]
+    a, b = bounds[rank], bounds[rank + 1]
+    mine = clips[c].copy()
+    mine[:a] = 0; mine[b:] = 0                          # rows of other ranks are NOT available here:
+    j = E.Job(); j.bind_source(src, eng.add_raw_frames(mine))   # a correct result proves they arrived over the wire
+    j.set_shard(rank, bounds, list(range(world)))
+    jobs.append(j); windows.append((a, b))
+eng.run(g, jobs, 2, 4)
+st = eng.stats()["counters"]
+for c, n in enumerate(lengths):
+    a, b = windows[c]
+    assert jobs[c].output_rows(sink) == b - a
+    got = jobs[c].output_array(sink, 8, np.float64, row0=a).ravel()
+    nxt = clips[c][np.minimum(np.arange(a, b) + 1, n - 1)].astype(np.int64)
+    want = np.abs(nxt - clips[c][a:b].astype(np.int64)).reshape(b - a, -1).sum(1).astype(np.float64)
+    assert (got == want).all(), (rank, c, got, want)
+frame = 12 * 16 * 3
+expect_recv = sum(frame for c, n in enumerate(lengths) if windows[c][1] < n and windows[c][1] > windows[c][0])
+assert st["halo_bytes_received"] == expect_recv, (rank, st["halo_bytes_received"], expect_recv)
+dist.barrier()
+if rank == 0:
+    print("ENGINE_HALO_OK", world, st["halo_bytes_sent"], st["halo_bytes_received"])
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_engine_halo_exchange_for_sharded_clips_gloo(tmp_path, world):
+    """configs[3] on the CPU: every rank computes one interval of every clip through scn_engine_run; the frame
+    its stencil {0,1} needs from the next interval comes from the neighbouring rank (host transport over gloo),
+    never from the rank's own (zeroed) copy."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
+    script = tmp_path / "engine_halo_worker.py"
+    script.write_text(ENGINE_HALO_WORKER)
+    env = dict(os.environ, SCN_ROOT=ROOT, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29630 + world), str(script)]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert f"ENGINE_HALO_OK {world}" in out.stdout, out.stdout[-3000:]

@@ -648,3 +648,17 @@ def test_inplace_ingest_keeps_the_bitstream_where_it_is(tmp_path, container):
     assert db.tables() == ["copied"] and eng.stream_rows(db.add_video_stream(eng, "copied")) == 10
     eng.close()
     db.close()
+
+
+def test_product_stream_writer_equals_the_independent_numpy_writer():
+    """scn_h264_synth ("skip" shape: I_PCM IDR + P_Skip) against oracle/h264_writer.py, byte for byte --
+    including cropped sizes and payloads that need emulation-prevention bytes.  The benchmark's CPU
+    reference arm builds its clips with the numpy writer (it must not load product libraries)."""
+    from oracle import h264_writer
+    for (w, h, gop, frames, k) in [(64, 48, 4, 10, 3), (30, 22, 3, 7, 3), (128, 96, 1, 3, 3), (320, 240, 5, 11, 3)]:
+        rng = np.random.default_rng(w * 7 + h)
+        yuv = rng.integers(0, 256, (k, w * h * 3 // 2), dtype=np.uint8)
+        yuv[0, :300] = 0            # runs of zeros: 00 00 0x patterns
+        yuv[1, 100:140] = [0, 0, 3, 0] * 10
+        assert E.h264_synth(yuv, w, h, gop=gop, non_key="skip", frames=frames) == \
+            h264_writer.h264_synth_skip(yuv, w, h, gop=gop, frames=frames), (w, h, gop, frames)
