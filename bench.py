@@ -152,6 +152,13 @@ def make_clip_bytes(seed, frames, gop=30, w=W, h=H):
     return E.h264_synth(clip_yuv(seed, frames, gop, w, h), w, h, gop=gop, non_key="skip", frames=frames)
 
 
+def make_clip_cavlc(seed, frames, gop=30):
+    """A stream a real encoder could have produced (scanner_b200/synth_h264.py, pure numpy: Intra16x16 + CAVLC key
+    pictures, motion-compensated P pictures; ~35 KB per key picture, ~5 KB per P picture) -> (bytes, expected I420)."""
+    from scanner_b200 import synth_h264
+    return synth_h264.write(W, H, frames, gop=gop, seed=seed, mv=(2, -2))
+
+
 def make_clip_bytes_ref(seed, frames, gop=30):
     """The same stream (byte for byte, tests/test_storage_cpu.py) from the pure-numpy writer: the CPU
     reference arm must not load product libraries."""
@@ -222,14 +229,18 @@ def run_reference(args, rank, world):
     n_clips = max(2 * cores, 8)
     clips = [make_clip_bytes_ref(500 + i, frames_per_clip) for i in range(min(n_clips, 4))]
     fps, s_per_step, cores, sample = cpu_reference_fps(clips, n_clips, args.steps, max(1, min(args.warmup, 1)))
+    realistic = [make_clip_cavlc(500 + i, frames_per_clip)[0] for i in range(min(n_clips, 4))]
+    fps_cavlc = cpu_reference_fps(realistic, n_clips, max(1, min(args.steps, 3)), 1)[0]
     desc = (f"{n_clips} clips x {frames_per_clip} frames per step ({sample} frames), cv2.VideoCapture (FFmpeg) decode + "
             f"cv2.calcHist x3 + cv2.resize(224), one process per core; {cv2_note()}")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, sample),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                             "cavlc_stream": {"value": fps_cavlc, "unit": "frames/s"}},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e_cavlc_stream": {"value": fps_cavlc, "unit": "frames/s", "stream": "cavlc"},
             "not_implemented": CONFIG0_NOTE}
     emit(line)
     return 0
@@ -329,7 +340,7 @@ def session_rates(counters):
 
 
 # ------------------------------------------------------------------------------------------
-def e2e_config1(args, R, sampler):
+def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     """configs[1] end to end: one database of ingested clips shared by all ranks, the table list sharded
     over the ranks (scanner_b200/shard.py), sinks saved into output tables inside the timed region."""
     import numpy as np
@@ -340,6 +351,7 @@ def e2e_config1(args, R, sampler):
     E.load_stdlib()
     std = protolite.parse_proto(open(os.path.join(ROOT, "scanner_b200", "csrc", "ops", "stdlib_args.proto")).read())
     clips_per_rank, frames = args.e2e_clips, args.e2e_frames
+    steps = steps or args.steps
     total = clips_per_rank * world
     root = R.bcast(tempfile.mkdtemp(prefix="scn_bench_db_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
                    if rank == 0 else None)
@@ -352,7 +364,7 @@ def e2e_config1(args, R, sampler):
     for i in range(rank, total, world):
         s = uniq_seed(i)
         if s not in cache:
-            cache[s] = make_clip_bytes(s, frames)
+            cache[s] = make_clip_bytes(s, frames) if stream_kind == "pcm" else make_clip_cavlc(s, frames)[0]
         db.ingest_h264(f"clip_{i:05d}", cache[s])
     ingest_s = time.perf_counter() - t_ing
     R.barrier()
@@ -396,7 +408,7 @@ def e2e_config1(args, R, sampler):
         one_step(f"w{k}")  # warm-up: decoder creation, memory pools
         drop(f"w{k}")
     step_s, rates, video = [], [], []
-    for k in range(args.steps):
+    for k in range(steps):
         R.barrier()
         sampler.reset()
         t0 = time.perf_counter()
@@ -407,18 +419,18 @@ def e2e_config1(args, R, sampler):
         step_s.append(dt)
         rates.append(session_rates(eng.stats()["counters"]))
         video.append(sampler.video_result())
-        if k + 1 < args.steps:
+        if k + 1 < steps:
             drop(f"s{k}")  # untimed: the next step writes fresh tables
     stats = eng.stats()["counters"]
     # parity on what the save stage stored (last step): rows of one of this rank's clips against the oracle
-    last = f"s{args.steps - 1}"
+    last = f"s{steps - 1}"
     i0 = mine[0]
-    yuv = clip_yuv(uniq_seed(i0), frames)
+    yuv = clip_yuv(uniq_seed(i0), frames) if stream_kind == "pcm" else make_clip_cavlc(uniq_seed(i0), frames)[1]
     check_rows = sorted({0, 1, min(frames - 1, 31), frames - 1})
     got_h = db.read_rows(f"hist_{last}_{i0:05d}", "histogram", check_rows)
     got_r = db.read_rows(f"small_{last}_{i0:05d}", "frame", check_rows)
     for row, gh, gr in zip(check_rows, got_h, got_r):
-        src_pic = yuv[row // 30]
+        src_pic = yuv[row // 30] if stream_kind == "pcm" else yuv[row]
         y = src_pic[:H * W].reshape(H, W)
         chroma = np.empty((H // 2, W), np.uint8)
         chroma[:, 0::2] = src_pic[H * W:H * W * 5 // 4].reshape(H // 2, W // 2)
@@ -436,7 +448,7 @@ def e2e_config1(args, R, sampler):
     if rank == 0:
         shutil.rmtree(root, ignore_errors=True)
     frames_per_step_all = total * frames
-    return {"value": frames_per_step_all * args.steps / sum(step_max), "unit": "frames/s",
+    return {"value": frames_per_step_all * steps / sum(step_max), "unit": "frames/s", "stream": stream_kind, "steps": steps,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(mine) * frames * (192 + DH * DW * 3),
             "frames_per_step": frames_per_step_all, "clips": total, "frames_per_clip": frames,
             "pipeline_instances": instances, "frames_decoded_last_step": stats.get("frames_decoded"),
@@ -445,7 +457,7 @@ def e2e_config1(args, R, sampler):
                       "writing every task into them, commit}, max over ranks; the steps summed",
             "stored_rows_checked_against_oracle": len(check_rows) * 2,
             "step_fps": [frames_per_step_all / s for s in step_max],
-            "per_rank": [{"rank": p["rank"], "fps": p["frames_per_step"] * args.steps / sum(p["step_s"]),
+            "per_rank": [{"rank": p["rank"], "fps": p["frames_per_step"] * steps / sum(p["step_s"]),
                           "step_fps_min_median_max": _mmm([p["frames_per_step"] / s for s in p["step_s"]]),
                           "session_pictures_per_s_last_step": p["session_pictures_per_s"][-1],
                           "session_rate_spread_worst_step": max((max(r) - min(r)) / max(1, max(r)) for r in p["session_pictures_per_s"] if r),
@@ -510,6 +522,8 @@ def run_config1(args, R):
     torch.cuda.empty_cache()
 
     e2e = e2e_config1(args, R, ClockSampler(local_rank))
+    # the same leg on a stream with a real encoder's bitrate (CAVLC intra + motion-compensated pictures)
+    e2e_cavlc = e2e_config1(args, R, ClockSampler(local_rank), stream_kind="cavlc", steps=max(2, min(args.steps, 5)))
     ms = R.max([ms])[0]
 
     if rank == 0:
@@ -539,7 +553,7 @@ def run_config1(args, R):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": workload_config(args, B), "clocks": clocks, "e2e": e2e,
+                "config": workload_config(args, B), "clocks": clocks, "e2e": e2e, "e2e_cavlc_stream": e2e_cavlc,
                 "gpu_launches": int(launches), "roofline": roof,
                 "whole_step_roofline_frac": value / world * B_ALG_FUSED / 1e9 / peak,
                 "not_implemented": CONFIG0_NOTE}
@@ -555,9 +569,13 @@ def cpu_baseline(args):
     n_clips = max(2 * cores, 8)
     clips = [make_clip_bytes_ref(700 + i, 60) for i in range(min(n_clips, 4))]
     fps, s_per_step, cores, sample = cpu_reference_fps(clips, n_clips, 1, 1)
+    realistic = [make_clip_cavlc(700 + i, 60)[0] for i in range(min(n_clips, 4))]
+    fps2 = cpu_reference_fps(realistic, n_clips, 1, 1)[0]
     return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{sample} frames ({n_clips} clips x 60), cv2.VideoCapture (FFmpeg) decode + cv2.calcHist x3 + "
-                      f"cv2.resize(224), one process per core; {cv2_note()}"}
+                      f"cv2.resize(224), one process per core; {cv2_note()}",
+            "cavlc_stream": {"value": fps2, "unit": "frames/s",
+                             "sample": "the same sample on the Intra16x16/CAVLC + motion-compensated stream"}}
 
 
 # ------------------------------------------------------------------------------------------

@@ -197,11 +197,22 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
     const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
     stream_ok = nvs::eligible(host_luma_ptrs + i0, host_chroma_ptrs + i0, cnt, pitch, width, height);
   }
-  if (stream_ok)
+  // SCN_NV12_RESIZE=split (measurement switch): histogram by the streaming kernel, Resize by its own kernel
+  // behind it, instead of the Resize rows produced inside the streaming pass
+  static const bool split_resize = [] {
+    const char* e = getenv("SCN_NV12_RESIZE");
+    return e && e[0] == 's';
+  }();
+  if (stream_ok && !(do_resize && split_resize))
     return nvs::launch(host_luma_ptrs, host_chroma_ptrs, n, pitch, width, height, hist_out, do_resize ? host_dst_ptrs : nullptr,
                        (do_resize && !area2x) ? (const uint8_t*)plan + kPlanHeaderBytes : nullptr, dst_w, dst_h, area2x ? 1 : 0, st);
+  if (stream_ok) {
+    const int rc0 = nvs::launch(host_luma_ptrs, host_chroma_ptrs, n, pitch, width, height, hist_out, nullptr, nullptr, 0, 0, 0, st);
+    if (rc0) return rc0;
+  }
+  const bool hist_done = stream_ok;
   // fork: the resize kernels of this call go to the side stream (see SideStream)
-  SideStream* side = (do_hist && do_resize) ? side_stream() : nullptr;
+  SideStream* side = (do_hist && do_resize && !hist_done) ? side_stream() : nullptr;
   cudaStream_t rst = st;
   if (side) {
     if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
@@ -223,7 +234,7 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
       d.p[i] = do_resize ? host_dst_ptrs[i0 + i] : nullptr;
       if (((uintptr_t)l.p[i] | (uintptr_t)c.p[i]) & 3) vec_ok = 0;
     }
-    if (do_hist) {
+    if (do_hist && !hist_done) {
       const int gx = (quads + HT - 1) / HT;
       int gy = (sm_count() * 8 + gx * cnt - 1) / (gx * cnt);
       if (gy < 1) gy = 1;

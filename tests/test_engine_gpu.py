@@ -468,3 +468,50 @@ def test_random_gathers_across_gops_both_element_layouts(eng):
             for k, r in enumerate(rows):
                 assert (j.output_row(s_f, k) == want[r]).all(), (trial, r)
                 assert (hist[k] == oracle.hist16(want[r])).all(), (trial, r)
+
+
+@pytest.mark.parametrize("h,w,n,gop,mv", [(96, 128, 12, 5, (2, -2)), (1080, 1920, 9, 4, (-4, 6)), (270, 480, 10, 10, (0, 2))])
+def test_decode_cavlc_intra_and_motion_compensated_pictures_bit_exact(eng, h, w, n, gop, mv):
+    """Streams a real encoder could have produced (scanner_b200/synth_h264.py: Intra16x16 DC prediction +
+    CAVLC residuals, P_L0_16x16 macroblocks with a motion vector) through the indexer and NVDEC: every
+    picture equals the writer's integer model of the decoder -- the same model FFmpeg is held to on the CPU
+    (tests/test_storage_cpu.py).  Histogram / Gather rows on such a stream are checked too."""
+    from scanner_b200 import synth_h264
+    data, yuv = synth_h264.write(w, h, n, gop=gop, seed=h + w, mv=mv)
+    sid = eng.add_h264(data)
+    info = eng.stream_info(sid)
+    assert (info["width"], info["height"]) == (w, h) and eng.stream_rows(sid) == n
+    assert info["keyframes"] == (n + gop - 1) // gop
+    want = []
+    for i in range(n):
+        y = yuv[i, :h * w].reshape(h, w)
+        chroma = np.empty((h // 2, w), np.uint8)
+        chroma[:, 0::2] = yuv[i, h * w:h * w * 5 // 4].reshape(h // 2, w // 2)
+        chroma[:, 1::2] = yuv[i, h * w * 5 // 4:].reshape(h // 2, w // 2)
+        want.append(oracle.nv12_to_rgb(y, chroma))
+    g = E.Graph()
+    src = g.add_source(True)
+    sink = g.add_sink((src, "frame"))
+    hs = g.add_op("Histogram", [(src, "frame")], device=1)
+    sink_h = g.add_sink((hs, "histogram"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    for (wps, ios) in [(4, 8), (1, 1)]:
+        eng.run(g, [j], wps, ios)
+        assert j.output_rows(sink) == n
+        for i in range(n):
+            got = j.output_row(sink, i)
+            assert (got == want[i]).all(), (i, wps, ios, np.abs(got.astype(int) - want[i]).max())
+            assert (np.frombuffer(j.output_row(sink_h, i), np.int32).reshape(3, 16) == oracle.hist16(want[i])).all()
+    # seeking into the middle of a GOP decodes from its IDR through the motion-compensated pictures
+    g2 = E.Graph()
+    src2 = g2.add_source(True)
+    s2 = g2.add_sample((src2, "frame"))
+    sink2 = g2.add_sink((s2, "frame"))
+    rows = sorted({n - 1, gop + 1 if gop + 1 < n else 0})
+    j2 = E.Job()
+    j2.bind_source(src2, sid)
+    j2.set_sampler(s2, "Gather", protolite.encode(protolite.SAMPLER_ARGS["GatherSamplerArgs"], {"rows": rows}))
+    eng.run(g2, [j2], 2, 2)
+    for k, r in enumerate(rows):
+        assert (j2.output_row(sink2, k) == want[r]).all(), r

@@ -282,3 +282,27 @@ def test_sharded_job_windows_on_one_gpu_equal_the_whole_clip():
         parts.append(j.output_array(sink, 16, np.uint64, row0=bounds[q]))
     assert (np.concatenate(parts) == full).all()
     eng.close()
+
+
+@pytest.mark.parametrize("h,w,k,n", [(480, 640, 5, 2), (2160, 3840, 5, 1), (1080, 1920, 9, 2), (70, 3088, 7, 2), (40, 1040, 31, 1),
+                                     (129, 1024, 4, 1), (257, 2064, 6, 2), (131, 48, 2, 3), (31, 16, 31, 1), (200, 1920, 16, 1)])
+def test_blur_streaming_kernel_vs_oracle(h, w, k, n):
+    """box_stream_kernel (bulk-async row ring, sliding sums): 16-byte aligned rows, several strips / row ranges,
+    even and odd kernel sizes (fl != fr), windows as tall as the frame."""
+    assert w % 16 == 0
+    frames = np.stack([synth.rand_frame(60 + i, h, w) for i in range(n)])
+    l0 = cabi.lib().scn_launch_count()
+    got = kernels.blur(dev(frames), k).cpu().numpy()
+    assert cabi.lib().scn_launch_count() > l0
+    for i in range(n):
+        want = oracle.blur(frames[i], k)
+        assert (got[i] == want).all(), (i, np.argwhere(got[i] != want)[:4])
+
+
+def test_blur_division_by_multiply_shift_is_exact():
+    """box_stream_kernel divides a window sum by k*k with umulhi(v, floor(2^32 / k^2) + 1)."""
+    for k in range(2, 32):
+        d = k * k
+        v = np.arange(0, 255 * d + 1, dtype=np.uint64)
+        m = np.uint64((1 << 32) // d + 1)
+        assert (((v * m) >> np.uint64(32)) == v // np.uint64(d)).all(), k

@@ -662,3 +662,31 @@ def test_product_stream_writer_equals_the_independent_numpy_writer():
         yuv[1, 100:140] = [0, 0, 3, 0] * 10
         assert E.h264_synth(yuv, w, h, gop=gop, non_key="skip", frames=frames) == \
             h264_writer.h264_synth_skip(yuv, w, h, gop=gop, frames=frames), (w, h, gop, frames)
+
+
+@pytest.mark.parametrize("w,h,n,gop,mv", [(64, 48, 9, 4, (2, -2)), (128, 96, 10, 5, (-4, 6)), (1920, 1080, 4, 3, (2, -2)),
+                                          (30, 22, 5, 2, (0, 2))])
+def test_ffmpeg_decodes_the_cavlc_motion_streams_to_the_writers_model(tmp_path, w, h, n, gop, mv):
+    """Pin of scanner_b200/synth_h264.py (Intra16x16 + CAVLC key pictures, motion-compensated P pictures): an
+    independent decoder (FFmpeg through cv2, raw output = the luma plane) outputs exactly the pictures the
+    writer's integer model predicts; the index built from the stream has the right samples and keyframes."""
+    import cv2
+    from scanner_b200 import synth_h264
+    stream, expect = synth_h264.write(w, h, n, gop=gop, seed=w, mv=mv)
+    path = str(tmp_path / "s.h264")
+    open(path, "wb").write(stream)
+    cap = cv2.VideoCapture(path)
+    if not cap.set(cv2.CAP_PROP_CONVERT_RGB, 0):
+        pytest.skip("this OpenCV build cannot return undecorated decoder output")
+    for i in range(n):
+        ok, y = cap.read()
+        assert ok and y.shape == (h, w)
+        assert (y == expect[i, :h * w].reshape(h, w)).all(), i
+    assert not cap.read()[0]
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    sid = eng.add_h264(stream)
+    info = eng.stream_info(sid)
+    assert (info["width"], info["height"], info["keyframes"]) == (w, h, (n + gop - 1) // gop) and eng.stream_rows(sid) == n
+    eng.close()
+    # bitrate of a real encoder, not of PCM: well under a tenth of the raw size
+    assert len(stream) < n * w * h * 3 // 2 // 10
