@@ -9,7 +9,8 @@ A "step" is one pass of the hot path over one batch of `--batch` decoded 1080p s
 NVDEC layout, pitch 2048): surfaces -> RGB -> {Histogram 3x16 int32, Resize 224x224 RGB24}.
   value   frames/s over all ranks with the surfaces already resident in HBM (CUDA events, max
           over ranks); inputs rotate between two batches, each larger than the 126 MB L2.
-  e2e     same metric end to end through the public pipeline API as configs[1] states it: the clips are
+  e2e     same metric end to end through the public pipeline API as configs[1] states it, on a stream with a real
+          encoder's structure (scanner_b200/synth_h264.py; `e2e_ipcm_stream` repeats it on r01's lossless stream): the clips are
           TABLES of a database directory shared by all ranks (ingested H.264 + stored index); every step
           each rank binds its shard of the table list, runs scn_engine_run (host H.264 -> NVDEC ->
           Histogram + Resize(224) GPU ops -> host rows) with the save stage writing every finished task
@@ -227,20 +228,21 @@ def run_reference(args, rank, world):
     cores = usable_cores()
     frames_per_clip = 60
     n_clips = max(2 * cores, 8)
-    clips = [make_clip_bytes_ref(500 + i, frames_per_clip) for i in range(min(n_clips, 4))]
-    fps, s_per_step, cores, sample = cpu_reference_fps(clips, n_clips, args.steps, max(1, min(args.warmup, 1)))
     realistic = [make_clip_cavlc(500 + i, frames_per_clip)[0] for i in range(min(n_clips, 4))]
-    fps_cavlc = cpu_reference_fps(realistic, n_clips, max(1, min(args.steps, 3)), 1)[0]
-    desc = (f"{n_clips} clips x {frames_per_clip} frames per step ({sample} frames), cv2.VideoCapture (FFmpeg) decode + "
+    fps, s_per_step, cores, sample = cpu_reference_fps(realistic, n_clips, args.steps, max(1, min(args.warmup, 1)))
+    clips = [make_clip_bytes_ref(500 + i, frames_per_clip) for i in range(min(n_clips, 4))]
+    fps_ipcm = cpu_reference_fps(clips, n_clips, max(1, min(args.steps, 3)), 1)[0]
+    desc = (f"{n_clips} clips x {frames_per_clip} frames per step ({sample} frames, Intra16x16/CAVLC + motion-compensated "
+            f"stream), cv2.VideoCapture (FFmpeg) decode + "
             f"cv2.calcHist x3 + cv2.resize(224), one process per core; {cv2_note()}")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, sample),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
-                             "cavlc_stream": {"value": fps_cavlc, "unit": "frames/s"}},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "e2e_cavlc_stream": {"value": fps_cavlc, "unit": "frames/s", "stream": "cavlc"},
+                             "ipcm_stream": {"value": fps_ipcm, "unit": "frames/s"}},
+            "e2e": {"value": fps, "unit": "frames/s", "stream": "cavlc", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e_ipcm_stream": {"value": fps_ipcm, "unit": "frames/s", "stream": "pcm"},
             "not_implemented": CONFIG0_NOTE}
     emit(line)
     return 0
@@ -251,9 +253,9 @@ def workload_config(args, batch):
             "frame": [H, W], "pitch": PITCH, "resize": [DH, DW], "frames_per_step": batch,
             "value_leg": "decoded NV12 surfaces resident in HBM -> one streaming kernel (Histogram + Resize) "
                          "(two rotating input batches, each > the 126 MB L2)",
-            "e2e_leg": "clips are tables of one database directory shared by all ranks (H.264: I_PCM IDR / 30 + "
-                       "P_Skip, ~105 KB/frame) -> NVDEC -> GPU ops -> save stage into output tables, through "
-                       "scn_engine_run",
+            "e2e_leg": "clips are tables of one database directory shared by all ranks (H.264: Intra16x16 + CAVLC key picture "
+                       "every 30, motion-compensated P pictures, ~6 KB/frame; e2e_ipcm_stream: I_PCM IDR + P_Skip, ~105 KB/frame) "
+                       "-> NVDEC -> GPU ops -> save stage into output tables, through scn_engine_run",
             "goldens": "OpenCV 4.13.0 (the reference pins 4.2.0); NV12->RGB pinned to the reference's own image.cu"}
 
 
@@ -462,9 +464,9 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
                           "session_pictures_per_s_last_step": p["session_pictures_per_s"][-1],
                           "session_rate_spread_worst_step": max((max(r) - min(r)) / max(1, max(r)) for r in p["session_pictures_per_s"] if r),
                           "nvml_last_step": p["nvml"][-1], "numa_pinned_cpus": p["numa_pinned_cpus"]} for p in per_rank],
-            "bound": "NVDEC (7 engines/GPU, ~1.3 K pictures/s each on this stream); the pixel kernels take ~5 % of a step. "
-                     "All sessions of a rank run at the same rate within a step; slow steps are slow for every session "
-                     "(profiles/r02_e2e_variance.md)"}
+            "bound": "NVDEC (7 engines/GPU; ~2 K pictures/s per session on the CAVLC stream, ~1.3 K on I_PCM); the pixel kernels "
+                     "take ~5 % of a step. All sessions of a rank run at the same rate within a step; slow steps are slow for "
+                     "every session (profiles/r02_e2e_variance.md)"}
 
 
 def _mmm(v):
@@ -521,9 +523,10 @@ def run_config1(args, R):
     del batches
     torch.cuda.empty_cache()
 
-    e2e = e2e_config1(args, R, ClockSampler(local_rank))
-    # the same leg on a stream with a real encoder's bitrate (CAVLC intra + motion-compensated pictures)
-    e2e_cavlc = e2e_config1(args, R, ClockSampler(local_rank), stream_kind="cavlc", steps=max(2, min(args.steps, 5)))
+    # headline: a stream with a real encoder's structure and bitrate (CAVLC intra + motion-compensated pictures);
+    # the lossless I_PCM / P_Skip stream r01 reported (105 KB per frame, nothing an encoder would produce) beside it
+    e2e = e2e_config1(args, R, ClockSampler(local_rank), stream_kind="cavlc")
+    e2e_ipcm = e2e_config1(args, R, ClockSampler(local_rank), stream_kind="pcm", steps=max(2, min(args.steps, 5)))
     ms = R.max([ms])[0]
 
     if rank == 0:
@@ -553,7 +556,7 @@ def run_config1(args, R):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": workload_config(args, B), "clocks": clocks, "e2e": e2e, "e2e_cavlc_stream": e2e_cavlc,
+                "config": workload_config(args, B), "clocks": clocks, "e2e": e2e, "e2e_ipcm_stream": e2e_ipcm,
                 "gpu_launches": int(launches), "roofline": roof,
                 "whole_step_roofline_frac": value / world * B_ALG_FUSED / 1e9 / peak,
                 "not_implemented": CONFIG0_NOTE}
@@ -567,15 +570,14 @@ def cpu_baseline(args):
     """The reference's CPU path (FFmpeg decode + OpenCV ops) on a bounded sample, all host cores."""
     cores = usable_cores()
     n_clips = max(2 * cores, 8)
-    clips = [make_clip_bytes_ref(700 + i, 60) for i in range(min(n_clips, 4))]
-    fps, s_per_step, cores, sample = cpu_reference_fps(clips, n_clips, 1, 1)
     realistic = [make_clip_cavlc(700 + i, 60)[0] for i in range(min(n_clips, 4))]
-    fps2 = cpu_reference_fps(realistic, n_clips, 1, 1)[0]
+    fps, s_per_step, cores, sample = cpu_reference_fps(realistic, n_clips, 1, 1)
+    clips = [make_clip_bytes_ref(700 + i, 60) for i in range(min(n_clips, 4))]
+    fps2 = cpu_reference_fps(clips, n_clips, 1, 1)[0]
     return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{sample} frames ({n_clips} clips x 60), cv2.VideoCapture (FFmpeg) decode + cv2.calcHist x3 + "
-                      f"cv2.resize(224), one process per core; {cv2_note()}",
-            "cavlc_stream": {"value": fps2, "unit": "frames/s",
-                             "sample": "the same sample on the Intra16x16/CAVLC + motion-compensated stream"}}
+            "sample": f"{sample} frames ({n_clips} clips x 60, Intra16x16/CAVLC + motion-compensated stream), cv2.VideoCapture "
+                      f"(FFmpeg) decode + cv2.calcHist x3 + cv2.resize(224), one process per core; {cv2_note()}",
+            "ipcm_stream": {"value": fps2, "unit": "frames/s", "sample": "the same sample on the I_PCM / P_Skip stream"}}
 
 
 # ------------------------------------------------------------------------------------------

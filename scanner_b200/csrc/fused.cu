@@ -102,27 +102,14 @@ nv12_resize_kernel(PtrBatch lumas, PtrBatch chromas, size_t pitch, int width, in
     o[2] = (uint8_t)((a.b + b.b + c.b + d.b + 2) >> 2);
     return;
   }
-  const Tap* __restrict__ xt = reinterpret_cast<const Tap*>(plan + kPlanHeaderBytes);
-  const Tap* __restrict__ yt = xt + dw;
-  const int4 tx = __ldg(reinterpret_cast<const int4*>(xt + dx));
-  const int4 ty = __ldg(reinterpret_cast<const int4*>(yt + dy));
-  const Rgb8 p00 = nv12_pixel(luma, chroma, pitch, height, tx.x, ty.x);
-  const Rgb8 p01 = nv12_pixel(luma, chroma, pitch, height, tx.y, ty.x);
-  const Rgb8 p10 = nv12_pixel(luma, chroma, pitch, height, tx.x, ty.y);
-  const Rgb8 p11 = nv12_pixel(luma, chroma, pitch, height, tx.y, ty.y);
-  const int a0 = tx.z, a1 = tx.w, b0 = ty.z, b1 = ty.w;
-  {
-    const int h0 = (int)p00.r * a0 + (int)p01.r * a1, h1 = (int)p10.r * a0 + (int)p11.r * a1;
-    o[0] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
-  }
-  {
-    const int h0 = (int)p00.g * a0 + (int)p01.g * a1, h1 = (int)p10.g * a0 + (int)p11.g * a1;
-    o[1] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
-  }
-  {
-    const int h0 = (int)p00.b * a0 + (int)p01.b * a1, h1 = (int)p10.b * a0 + (int)p11.b * a1;
-    o[2] = (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
-  }
+  // the lean tap chain of the streaming kernel (nv12_stream.cuh): row state once, byte -> float on the XU pipe
+  nvs::ResizeArgs a{luma, chroma, dst.p[blockIdx.y], reinterpret_cast<const nvs::Tap*>(plan + kPlanHeaderBytes), pitch, height,
+                    dw, dh, 0u};
+  const int4 ty = __ldg(reinterpret_cast<const int4*>(a.xt + dw + dy));
+  const nvs::Rgb24 p = nvs::resize_pixel(a, nvs::tap_row(a, ty.x), nvs::tap_row(a, ty.y), ty.z, ty.w, dx);
+  o[0] = p.r;
+  o[1] = p.g;
+  o[2] = p.b;
 }
 
 // Histogram and Resize of the configs[1] DAG are independent readers of the same surfaces: the
@@ -203,7 +190,8 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
     const char* e = getenv("SCN_NV12_RESIZE");
     return e && e[0] == 's';
   }();
-  if (stream_ok && !(do_resize && split_resize))
+  // (the exact-2x Resize, an INTER_AREA average, is not produced inside the streaming pass)
+  if (stream_ok && !(do_resize && (split_resize || area2x)))
     return nvs::launch(host_luma_ptrs, host_chroma_ptrs, n, pitch, width, height, hist_out, do_resize ? host_dst_ptrs : nullptr,
                        (do_resize && !area2x) ? (const uint8_t*)plan + kPlanHeaderBytes : nullptr, dst_w, dst_h, area2x ? 1 : 0, st);
   if (stream_ok) {

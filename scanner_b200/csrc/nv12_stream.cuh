@@ -276,21 +276,35 @@ struct ResizeArgs {   // by value: a non-inlined function cannot address the ker
   uint8_t* dst;
   const Tap* xt;
   size_t pitch;
-  int height, dw, dh, area2x;
+  int height, dw, dh;
   uint32_t units_per_row;
 };
 
-// One tapped pixel -> 8-bit RGB, the exact chain (nv12_math.cuh) with byte -> float on the XU pipe.
-// Two byte loads for luma/chroma pair + one more pair on averaged (odd) rows.
-__device__ __forceinline__ Rgb8 tap_rgb(const ResizeArgs& a, int x, int y) {
+// Everything about one tapped source row that does not depend on the column: where its luma and chroma bytes
+// start and whether its chroma is the rounded average with the next chroma row (odd luma rows, image.cu:133-151)
+struct TapRow {
+  const uint8_t* luma;
+  const uint8_t* chroma;
+  size_t next;   // 0: no averaging, else the distance to the second chroma row
+};
+__device__ __forceinline__ TapRow tap_row(const ResizeArgs& a, int y) {
   const int yc = y >> 1;
-  const uint8_t* cp = a.chroma + (size_t)yc * a.pitch + (x & ~1);
+  TapRow r;
+  r.luma = a.luma + (size_t)y * a.pitch;
+  r.chroma = a.chroma + (size_t)yc * a.pitch;
+  r.next = ((y & 1) && yc < (a.height >> 1) - 1) ? a.pitch : 0;
+  return r;
+}
+
+// One tapped pixel -> 8-bit RGB, the exact chain (nv12_math.cuh) with byte -> float on the XU pipe.
+__device__ __forceinline__ Rgb8 tap_rgb(const TapRow& row, int x) {
+  const uint8_t* cp = row.chroma + (x & ~1);
   uint32_t c = __ldg(reinterpret_cast<const uint16_t*>(cp));                 // Cb | Cr << 8 (2-byte aligned)
-  if ((y & 1) && yc < (a.height >> 1) - 1) {
-    const uint32_t c2 = __ldg(reinterpret_cast<const uint16_t*>(cp + a.pitch));
+  if (row.next) {
+    const uint32_t c2 = __ldg(reinterpret_cast<const uint16_t*>(cp + row.next));
     c = (c | c2) - (((c ^ c2) & 0xFEFEu) >> 1);                              // per byte (a + b + 1) >> 1
   }
-  const float yf = (float)__ldg(a.luma + (size_t)y * a.pitch + x);
+  const float yf = (float)__ldg(row.luma + x);
   const float cbc = byte_f<0>(c) - 128.0f, crc = byte_f<1>(c) - 128.0f;
   constexpr float kKR = 4.0f * 1.596f * kS, kKB = 4.0f * 2.0172f * kS, kTop = 1023.0f * kS;
   const float r = fma_sat(crc, kKR, __fmul_rn(yf, kCY));
@@ -307,18 +321,13 @@ __device__ __forceinline__ Rgb8 tap_rgb(const ResizeArgs& a, int x, int y) {
 struct Rgb24 {
   uint8_t r, g, b;
 };
-// one destination pixel (the read-only loads of its four taps come first: callers interleave several)
-__device__ __forceinline__ Rgb24 resize_pixel(const ResizeArgs& a, int dx, int dy, const int4 ty) {
-  if (a.area2x) {
-    const Rgb8 p = tap_rgb(a, 2 * dx, 2 * dy), q = tap_rgb(a, 2 * dx + 1, 2 * dy);
-    const Rgb8 r = tap_rgb(a, 2 * dx, 2 * dy + 1), t = tap_rgb(a, 2 * dx + 1, 2 * dy + 1);
-    return Rgb24{(uint8_t)((p.r + q.r + r.r + t.r + 2) >> 2), (uint8_t)((p.g + q.g + r.g + t.g + 2) >> 2),
-                 (uint8_t)((p.b + q.b + r.b + t.b + 2) >> 2)};
-  }
+// one destination pixel of the row whose tap rows are r0 / r1 with weights b0 / b1 (the read-only loads of its
+// four taps come first: callers interleave several)
+__device__ __forceinline__ Rgb24 resize_pixel(const ResizeArgs& a, const TapRow& r0, const TapRow& r1, int b0, int b1, int dx) {
   const int4 tx = __ldg(reinterpret_cast<const int4*>(a.xt + dx));
-  const Rgb8 p00 = tap_rgb(a, tx.x, ty.x), p01 = tap_rgb(a, tx.y, ty.x);
-  const Rgb8 p10 = tap_rgb(a, tx.x, ty.y), p11 = tap_rgb(a, tx.y, ty.y);
-  const int a0 = tx.z, a1 = tx.w, b0 = ty.z, b1 = ty.w;
+  const Rgb8 p00 = tap_rgb(r0, tx.x), p01 = tap_rgb(r0, tx.y);
+  const Rgb8 p10 = tap_rgb(r1, tx.x), p11 = tap_rgb(r1, tx.y);
+  const int a0 = tx.z, a1 = tx.w;
   auto blend = [&](uint32_t v00, uint32_t v01, uint32_t v10, uint32_t v11) {
     const int h0 = (int)v00 * a0 + (int)v01 * a1, h1 = (int)v10 * a0 + (int)v11 * a1;
     return (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
@@ -326,34 +335,33 @@ __device__ __forceinline__ Rgb24 resize_pixel(const ResizeArgs& a, int dx, int d
   return Rgb24{blend(p00.r, p01.r, p10.r, p11.r), blend(p00.g, p01.g, p10.g, p11.g), blend(p00.b, p01.b, p10.b, p11.b)};
 }
 
-// first source row a destination row reads
-__device__ __forceinline__ int first_tap_row(const ResizeArgs& a, int dy) {
-  return a.area2x ? 2 * dy : __ldg(&a.xt[a.dw + dy].i0);
-}
-
 // Destination rows whose first tap row starts in units [u0, u1) of the frame (row-pair-major unit order).
 // Called every kResizeChunk steps from the streaming loop: the tapped rows were streamed moments ago (or
 // are about to be), so the gathers hit L1/L2 and the surface still crosses HBM once.  Not inlined: the
 // streaming loop keeps its registers (the call saves what it needs), this path runs once per chunk.
+// (The exact-2x case, OpenCV's INTER_AREA average, is left to nv12_resize_kernel: the launcher does not fuse it.)
 __device__ __noinline__ void resize_units(ResizeArgs a, uint32_t u0, uint32_t u1, int lane) {
   const uint32_t p0 = (u0 + a.units_per_row - 1) / a.units_per_row;  // first row pair starting in the range
   const uint32_t p1 = (u1 + a.units_per_row - 1) / a.units_per_row;  // first row pair starting after it
   const int r0 = (int)(2 * p0), r1 = (int)(2 * p1);
   if (r0 >= r1) return;
-  // the row taps ascend: binary search for the first dy with first_tap_row(dy) >= r0
+  const Tap* yt = a.xt + a.dw;
+  // the row taps ascend: binary search for the first dy whose first tap row is >= r0
   int lo = 0, hi = a.dh;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (first_tap_row(a, mid) < r0) lo = mid + 1;
+    if (__ldg(&yt[mid].i0) < r0) lo = mid + 1;
     else hi = mid;
   }
-  for (int dy = lo; dy < a.dh && first_tap_row(a, dy) < r1; ++dy) {
-    const int4 ty = a.area2x ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.xt + a.dw + dy));
+  for (int dy = lo; dy < a.dh; ++dy) {
+    const int4 ty = __ldg(reinterpret_cast<const int4*>(yt + dy));
+    if (ty.x >= r1) break;
+    const TapRow t0 = tap_row(a, ty.x), t1 = tap_row(a, ty.y);
     uint8_t* row = a.dst + (size_t)dy * a.dw * 3;
     // two destination pixels per iteration: the gathers of both are in flight together
     for (int dx = lane; dx < a.dw; dx += 64) {
       const int dx2 = dx + 32 < a.dw ? dx + 32 : dx;
-      const Rgb24 p = resize_pixel(a, dx, dy, ty), q = resize_pixel(a, dx2, dy, ty);
+      const Rgb24 p = resize_pixel(a, t0, t1, ty.z, ty.w, dx), q = resize_pixel(a, t0, t1, ty.z, ty.w, dx2);
       row[dx * 3 + 0] = p.r;
       row[dx * 3 + 1] = p.g;
       row[dx * 3 + 2] = p.b;
@@ -487,7 +495,7 @@ nv12_stream_kernel(const Params prm, int32_t* __restrict__ out) {
         if ((step & (kResizeChunk - 1)) == kResizeChunk - 1 || step + 1 == ns) {
           const uint32_t c0s = step & ~(uint32_t)(kResizeChunk - 1);
           const ResizeArgs ra{prm.luma.p[frame], prm.chroma.p[frame], prm.dst.p[frame], prm.xt, prm.pitch, prm.height,
-                              prm.dw, prm.dh, prm.area2x, prm.units_per_row};
+                              prm.dw, prm.dh, prm.units_per_row};
           resize_units(ra, (s0 + c0s) * 32u, min((s0 + step + 1) * 32u, prm.units_per_frame), lane);
         }
       }
