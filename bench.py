@@ -46,6 +46,7 @@ W, H, PITCH = 1920, 1080, 2048
 DW, DH = 224, 224
 SURF_ROWS = H * 3 // 2
 B_ALG_FUSED = W * H * 3 // 2 + DW * DH * 3 + 192      # 3,261,120 B / frame
+B_ALG_HIST_NV12 = W * H * 3 // 2 + 192                  # the histogram kernel alone
 METRIC = "frames/sec (1080p H.264 decode+resize+histogram)"
 CONFIG0_NOTE = ("configs[0] (H.264 on a CPU-only instance) is not implemented: no software H.264 decoder "
                 "(FFmpeg unavailable offline); CPU instances take raw-frame columns")
@@ -251,7 +252,7 @@ def run_reference(args, rank, world):
 def workload_config(args, batch):
     return {"workload": "configs[1]: 1080p H.264 decode + Resize(224x224) + Histogram",
             "frame": [H, W], "pitch": PITCH, "resize": [DH, DW], "frames_per_step": batch,
-            "value_leg": "decoded NV12 surfaces resident in HBM -> one streaming kernel (Histogram + Resize) "
+            "value_leg": "decoded NV12 surfaces resident in HBM -> streaming Histogram kernel + Resize kernel "
                          "(two rotating input batches, each > the 126 MB L2)",
             "e2e_leg": "clips are tables of one database directory shared by all ranks (H.264: Intra16x16 + CAVLC key picture "
                        "every 30, motion-compensated P pictures, ~6 KB/frame; e2e_ipcm_stream: I_PCM IDR + P_Skip, ~105 KB/frame) "
@@ -538,7 +539,10 @@ def run_config1(args, R):
         if kname:
             per_launch_s = prof[kname]["ms"] * 1e-3 / prof[kname]["launches"]
             per_launch = min(B, 64)  # SCN_MAX_PTRS surfaces per launch
-            alg = B_ALG_FUSED * per_launch
+            # the streaming kernel alone reads the surface and writes the histogram; when the Resize rows are produced
+            # in the same pass (SCN_NV12_RESIZE=fused) there is no separate Resize kernel and its output counts too
+            separate_resize = any(k.startswith("nv12_resize") for k in prof)
+            alg = (B_ALG_HIST_NV12 if separate_resize else B_ALG_FUSED) * per_launch
             ach = alg / per_launch_s / 1e9
             tr = NCU_TRAFFIC.get(kname, {})
             roof = {"bound": "issue", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -550,7 +554,10 @@ def run_config1(args, R):
                                       "(carry-save histogram), the FMA pipe (exact colour matrix) and the issue port all "
                                       "~70 % busy; measured pipe model in profiles/r02_pipe_ubench.md, ncu in "
                                       "profiles/r02_nv12_stream.md, budget argument in DESIGN.md section 4",
-                    "launch_mode": "one kernel per 64 surfaces does Histogram and Resize in one pass",
+                    "launch_mode": ("Histogram by the streaming kernel, Resize by nv12_resize_kernel on a forked stream next to it "
+                                    "(measured faster than producing the Resize rows inside the streaming pass: "
+                                    "profiles/r02_nv12_stream.md)") if separate_resize else
+                                   "one kernel per 64 surfaces does Histogram and Resize in one pass",
                     "kernel_share_of_step": prof[kname]["ms"] / sum(v["ms"] for v in prof.values()),
                     "all_kernels_ms": {k: v["ms"] / v["launches"] for k, v in prof.items()}}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -594,8 +601,8 @@ def run_config3(args, R):
     rank, world, local_rank = R.rank, R.world, R.local_rank
     E.load_stdlib()
     n_clips, frames = args.flow_clips, args.flow_frames
-    clips = [E.h264_synth(np.stack([_flow_picture(300 + c, k) for k in range(frames)]), W, H, gop=30, non_key="pcm")
-             for c in range(min(n_clips, 2))]
+    # realistic streams (CAVLC key pictures, motion-compensated P pictures): decode must not be what is measured
+    clips = [make_clip_cavlc(300 + c, frames)[0] for c in range(min(n_clips, 2))]
     eng = E.Engine(gpus=[local_rank], instances_per_gpu=default_instances(args, local_rank, world))
     if world > 1:
         eng.init_comm(local_rank)
@@ -657,21 +664,11 @@ def run_config3(args, R):
                         "d2h_bytes_per_step": n_clips * (b - a) * 16},
                 "halo": {"bytes_sent_rank0": st.get("halo_bytes_sent"), "bytes_received_rank0": st.get("halo_bytes_received"),
                          "exchange_us_rank0": st.get("halo_exchange_us"), "element": "packed NV12 surface (3.1 MB per 1080p frame)",
-                         "identical_to_single_gpu": identical}}
+                         "identical_to_single_gpu": identical,
+                         "note": "exchange_us covers decoding the boundary rows, the NCCL group and the wait for the slowest peer"},
+                "step_fps": [n_clips * frames / s_ for s_ in step_max]}
         emit(line)
     return 0
-
-
-def _flow_picture(seed, k):
-    """I420 picture k of a smooth moving texture (content for which flow is well conditioned)."""
-    import numpy as np
-    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
-    ph = 0.05 * k * (1 + seed % 3)
-    y = 128 + 60 * np.sin(0.02 * xx + ph) * np.cos(0.017 * yy - 0.5 * ph) + 20 * np.sin(0.11 * (xx + yy) + ph)
-    u = 128 + 40 * np.sin(0.01 * xx[::2, ::2] + ph)
-    v = 128 + 40 * np.cos(0.013 * yy[::2, ::2] - ph)
-    return np.concatenate([np.clip(y, 0, 255).astype(np.uint8).ravel(), np.clip(u, 0, 255).astype(np.uint8).ravel(),
-                           np.clip(v, 0, 255).astype(np.uint8).ravel()])
 
 
 def main():
@@ -686,7 +683,7 @@ def main():
                     help="surfaces per step (kernels take 64 per launch: a step of 256 is 4 launches)")
     ap.add_argument("--e2e-clips", type=int, default=56, help="clips (tables) per rank in the e2e leg; configs[1] as stated: 1000")
     ap.add_argument("--e2e-frames", type=int, default=120, help="frames per clip in the e2e leg; configs[1] as stated: 300")
-    ap.add_argument("--flow-clips", type=int, default=2, help="--config 3: clips; configs[3] as stated: 16")
+    ap.add_argument("--flow-clips", type=int, default=8, help="--config 3: clips; configs[3] as stated: 16")
     ap.add_argument("--flow-frames", type=int, default=96, help="--config 3: frames per clip; configs[3] as stated: 1200")
     ap.add_argument("--instances", type=int, default=0,
                     help="pipeline instances per GPU for the e2e leg (0 = one per NVDEC engine, capped by the host cores)")

@@ -6,6 +6,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
+#include <deque>
+#include <condition_variable>
 #include <cstring>
 #include <fstream>
 #include <thread>
@@ -70,6 +73,65 @@ std::vector<VideoInterval> slice_into_intervals(const H264Index& idx, const std:
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// Save workers (reference SaveWorker threads, worker.cpp:1718-1800: `save_workers_per_node`, default 4): finished
+// tasks are written to their table items by these threads while the pipeline instance that produced them goes on
+// decoding.  A bounded queue: a producer that finds it full writes its item itself.
+class SavePool {
+ public:
+  explicit SavePool(int threads) {
+    for (int i = 0; i < threads; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~SavePool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  // false: the queue is full (the caller runs the job itself)
+  bool submit(std::function<void()> job) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      if (queue_.size() >= kMaxPending) return false;
+      queue_.push_back(std::move(job));
+      ++pending_;
+    }
+    cv_.notify_one();
+    return true;
+  }
+  void wait_idle() {
+    std::unique_lock<std::mutex> g(mu_);
+    idle_.wait(g, [this] { return pending_ == 0; });
+  }
+
+ private:
+  static constexpr size_t kMaxPending = 32;
+  void loop() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return stop_ || !queue_.empty(); });
+        if (queue_.empty()) return;
+        job = std::move(queue_.front());
+        queue_.pop_front();
+      }
+      job();
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        if (--pending_ == 0) idle_.notify_all();
+      }
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, idle_;
+  std::deque<std::function<void()>> queue_;
+  std::vector<std::thread> workers_;
+  size_t pending_ = 0;
+  bool stop_ = false;
+};
+
 struct Engine::RunState {
   Graph* graph = nullptr;
   GraphAnalysis an;
@@ -89,6 +151,7 @@ struct Engine::RunState {
   Profiler profiler;
   ResourceGate resource_gate;  // fetch_resources once per op and run
   std::unique_ptr<Database> db;  // open when a job saves sinks into tables of out_dir
+  std::unique_ptr<SavePool> savers;  // with db: the threads that write finished tasks
   std::atomic<i64> frames_decoded{0}, frames_used{0}, frames_native{0};
   // decoded elements received from neighbouring ranks: (input stream, source row) -> buffer on halo_dev
   std::map<std::pair<const InputStream*, i64>, u8*> halo_rows;
@@ -129,6 +192,8 @@ Engine::Engine(std::vector<i32> gpu_ids, i32 instances_per_gpu, i32 cpu_instance
 }
 
 Engine::~Engine() {
+  halo_decoders_.clear();
+  halo_.reset();
   for (auto& sl : slots_) {
     if (sl->gpu_id >= 0 && cuda_available()) {
       cudaSetDevice(sl->gpu_id);
@@ -578,35 +643,43 @@ void Engine::instance_main(Instance* inst) {
         for (auto& kv : outs) {
           auto st = job.sink_tables.find(kv.first);
           if (st == job.sink_tables.end()) continue;
-          TaskOutput& to = *kv.second;
+          TaskOutput* to = kv.second;
           // Video or Bytes item: from the declared type of the column (a task whose rows are all null
           // has no frame to look at and must still be a video item of a Video table)
           const bool video = job.sink_is_frame.count(kv.first) && job.sink_is_frame.at(kv.first);
-          std::vector<u8> flat;
-          ItemColumn ic;
-          if (to.held.empty()) {
-            ic.data = to.data.data();
-            ic.bytes = to.data.size();
-          } else {
-            flat.reserve(to.total_bytes());
-            for (size_t i = 0; i < to.sizes.size(); ++i) flat.insert(flat.end(), to.row(i), to.row(i) + to.sizes[i]);
-            ic.data = flat.data();
-            ic.bytes = flat.size();
-          }
-          ic.sizes = &to.sizes;
-          ic.shapes = &to.shapes;
-          r = rs.db->write_index_item(st->second, t.task, t.row0, t.row1);
-          if (r.success()) r = rs.db->write_item(st->second, 1, t.task, ic, video);
-          if (!r.success()) {
-            rs.fail(r.msg());
-            break;
-          }
-          rs.profiler.increment("io_write", (i64)ic.bytes);
-          if (!job.keep_rows) {
-            to.release();
-            std::vector<u8>().swap(to.data);
-            to.dropped = true;
-          }
+          const i32 table = st->second, task_id = t.task;
+          const i64 row0 = t.row0, row1 = t.row1;
+          const bool keep = job.keep_rows;
+          RunState* rsp = &rs;
+          auto write = [rsp, to, video, table, task_id, row0, row1, keep] {
+            std::vector<u8> flat;
+            ItemColumn ic;
+            if (to->held.empty()) {
+              ic.data = to->data.data();
+              ic.bytes = to->data.size();
+            } else {
+              flat.reserve(to->total_bytes());
+              for (size_t i = 0; i < to->sizes.size(); ++i) flat.insert(flat.end(), to->row(i), to->row(i) + to->sizes[i]);
+              ic.data = flat.data();
+              ic.bytes = flat.size();
+            }
+            ic.sizes = &to->sizes;
+            ic.shapes = &to->shapes;
+            Result wr = rsp->db->write_index_item(table, task_id, row0, row1);
+            if (wr.success()) wr = rsp->db->write_item(table, 1, task_id, ic, video);
+            if (!wr.success()) {
+              rsp->fail(wr.msg());
+              return;
+            }
+            rsp->profiler.increment("io_write", (i64)ic.bytes);
+            if (!keep) {
+              to->release();
+              std::vector<u8>().swap(to->data);
+              to->dropped = true;
+            }
+          };
+          // the rows of a finished task are complete and nobody else touches them until the run ends
+          if (!rs.savers || !rs.savers->submit(write)) write();
         }
         if (rs.failed.load()) break;
       } else if (!rs.out_dir.empty()) {
@@ -708,7 +781,21 @@ Result Engine::decode_rows_to_device(i64 stream_id, const std::vector<i64>& rows
 
 // rows (ascending) of an H.264 stream -> dense elements in device memory: packed NV12 surfaces
 // (w*h*3/2 bytes each) or RGB24 frames
-Result Engine::decode_rows(InputStream& stref, const std::vector<i64>& rows, i32 gpu_id, bool nv12, u8* dst) {
+struct Engine::DecodeContext {
+  i32 gpu = -1;
+  cudaStream_t stream = nullptr;
+  std::unique_ptr<NvdecSession> session;
+  ~DecodeContext() {
+    if (gpu >= 0 && cuda_available()) {
+      ScopedDevice sd(gpu);
+      session.reset();
+      if (stream) cudaStreamDestroy(stream);
+    }
+  }
+};
+
+Result Engine::decode_rows(InputStream& stref, const std::vector<i64>& rows, i32 gpu_id, bool nv12, u8* dst,
+                           DecodeContext* reuse) {
   Result r;
   InputStream* st = &stref;
   for (size_t i = 0; i < rows.size(); ++i)
@@ -722,14 +809,28 @@ Result Engine::decode_rows(InputStream& stref, const std::vector<i64>& rows, i32
     return r;
   }
   ScopedDevice sd(gpu_id);
-  cudaStream_t cs = nullptr;
-  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
-    RESULT_ERROR(&r, "cannot create a stream on GPU %d", gpu_id);
-    return r;
+  DecodeContext local;
+  DecodeContext& ctx = reuse ? *reuse : local;
+  if (!ctx.stream) {
+    ctx.gpu = gpu_id;
+    if (cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      RESULT_ERROR(&r, "cannot create a stream on GPU %d", gpu_id);
+      return r;
+    }
+  }
+  cudaStream_t cs = ctx.stream;
+  if (!ctx.session) {
+    ctx.session.reset(new NvdecSession(gpu_id, cs));
+    r = ctx.session->init();
+    if (!r.success()) {
+      ctx.session.reset();
+      return r;
+    }
+  } else {
+    r.set_success(true);
   }
   {
-    NvdecSession sess(gpu_id, cs);
-    r = sess.init();
+    NvdecSession& sess = *ctx.session;
     const size_t w = (size_t)st->index.width, h = (size_t)st->index.height, fb = nv12 ? w * h * 3 / 2 : w * h * 3;
     std::string kerr;
     for (const VideoInterval& iv : slice_into_intervals(st->index, rows)) {
@@ -757,8 +858,7 @@ Result Engine::decode_rows(InputStream& stref, const std::vector<i64>& rows, i32
     cudaStreamSynchronize(cs);
     if (r.success() && !kerr.empty()) RESULT_ERROR(&r, "%s", kerr.c_str());
   }
-  cudaStreamDestroy(cs);
-  return r;
+  return r;  // a call-local context (session, stream) is destroyed here
 }
 
 // ---- stencil halo exchange of sharded jobs (halo.h) ------------------------------------------------
@@ -854,7 +954,9 @@ Result Engine::exchange_halos(Graph& graph, const std::vector<Job*>& jobs) {
     if (p.send) {
       if (on_device) {
         p.staging = new_buffer(dev, p.rows.size() * p.frame_bytes);
-        r = decode_rows(*p.st, p.rows, dev.id, p.nv12, p.staging);
+        std::unique_ptr<DecodeContext>& hd = halo_decoders_[dev.id];
+        if (!hd) hd.reset(new DecodeContext());
+        r = decode_rows(*p.st, p.rows, dev.id, p.nv12, p.staging, hd.get());
         if (!r.success()) break;
         for (size_t i = 0; i < p.rows.size(); ++i) xfers.push_back({p.peer, p.staging + i * p.frame_bytes, p.frame_bytes, true});
       } else {
@@ -1046,6 +1148,11 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
       }
     }
   }
+  if (rs.db) {
+    const char* sw = getenv("SCN_SAVE_WORKERS");
+    const int n = sw ? atoi(sw) : 4;  // reference default save_workers_per_node (scanner/api/database.cpp:68-84)
+    if (n > 0) rs.savers.reset(new SavePool(n));
+  }
   const auto t0 = std::chrono::steady_clock::now();
   {
     Result hr = exchange_halos(graph, jobs);
@@ -1054,6 +1161,10 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
   if (!rs.failed.load()) {
     for (auto& inst : instances) inst->th = std::thread([this, p = inst.get()] { instance_main(p); });
     for (auto& inst : instances) inst->th.join();
+  }
+  if (rs.savers) {
+    rs.savers->wait_idle();  // every item is on disk before the run returns (the caller commits the tables next)
+    rs.savers.reset();
   }
   for (auto& kv : rs.halo_rows) delete_buffer(rs.halo_dev, kv.second);
   rs.halo_rows.clear();

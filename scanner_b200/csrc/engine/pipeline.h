@@ -192,7 +192,12 @@ class Engine {
 
   std::unique_ptr<HaloTransport> halo_;
   Result exchange_halos(Graph& graph, const std::vector<Job*>& jobs);
-  Result decode_rows(InputStream& st, const std::vector<i64>& rows, i32 gpu_id, bool nv12, u8* dst);
+  // `reuse`: a persistent decode session + stream (the halo exchange of every run decodes a few boundary rows;
+  // creating a decoder costs ~0.25 s); nullptr: a session for this call only
+  struct DecodeContext;
+  Result decode_rows(InputStream& st, const std::vector<i64>& rows, i32 gpu_id, bool nv12, u8* dst,
+                     DecodeContext* reuse = nullptr);
+  std::map<i32, std::unique_ptr<DecodeContext>> halo_decoders_;  // per GPU
 
   // state of the run in flight
   struct RunState;

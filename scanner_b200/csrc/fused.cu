@@ -5,6 +5,10 @@
 // taken from RGB values converted in registers, and the resize converts just the 4 taps of each
 // destination pixel.  Results are bit-identical to the three-pass composition.
 #include "nv12_stream.cuh"
+
+#ifndef SCN_NV12_RESIZE_DEFAULT
+#define SCN_NV12_RESIZE_DEFAULT kOverlap
+#endif
 #include "nv12_math.cuh"
 #include "scn_common.cuh"
 
@@ -102,14 +106,24 @@ nv12_resize_kernel(PtrBatch lumas, PtrBatch chromas, size_t pitch, int width, in
     o[2] = (uint8_t)((a.b + b.b + c.b + d.b + 2) >> 2);
     return;
   }
-  // the lean tap chain of the streaming kernel (nv12_stream.cuh): row state once, byte -> float on the XU pipe
-  nvs::ResizeArgs a{luma, chroma, dst.p[blockIdx.y], reinterpret_cast<const nvs::Tap*>(plan + kPlanHeaderBytes), pitch, height,
-                    dw, dh, 0u};
-  const int4 ty = __ldg(reinterpret_cast<const int4*>(a.xt + dw + dy));
-  const nvs::Rgb24 p = nvs::resize_pixel(a, nvs::tap_row(a, ty.x), nvs::tap_row(a, ty.y), ty.z, ty.w, dx);
-  o[0] = p.r;
-  o[1] = p.g;
-  o[2] = p.b;
+  // (the XU-converting tap chain of nv12_stream.cuh was tried here: 46 us instead of 37 us per 64 frames -- this
+  // kernel is latency-bound and the extra conversion latency costs more than the saved instructions)
+  const Tap* __restrict__ xt = reinterpret_cast<const Tap*>(plan + kPlanHeaderBytes);
+  const Tap* __restrict__ yt = xt + dw;
+  const int4 tx = __ldg(reinterpret_cast<const int4*>(xt + dx));
+  const int4 ty = __ldg(reinterpret_cast<const int4*>(yt + dy));
+  const Rgb8 p00 = nv12_pixel(luma, chroma, pitch, height, tx.x, ty.x);
+  const Rgb8 p01 = nv12_pixel(luma, chroma, pitch, height, tx.y, ty.x);
+  const Rgb8 p10 = nv12_pixel(luma, chroma, pitch, height, tx.x, ty.y);
+  const Rgb8 p11 = nv12_pixel(luma, chroma, pitch, height, tx.y, ty.y);
+  const int a0 = tx.z, a1 = tx.w, b0 = ty.z, b1 = ty.w;
+  auto blend = [&](uint32_t v00, uint32_t v01, uint32_t v10, uint32_t v11) {
+    const int h0 = (int)v00 * a0 + (int)v01 * a1, h1 = (int)v10 * a0 + (int)v11 * a1;
+    return (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+  };
+  o[0] = blend(p00.r, p01.r, p10.r, p11.r);
+  o[1] = blend(p00.g, p01.g, p10.g, p11.g);
+  o[2] = blend(p00.b, p01.b, p10.b, p11.b);
 }
 
 // Histogram and Resize of the configs[1] DAG are independent readers of the same surfaces: the
@@ -184,25 +198,40 @@ extern "C" int scn_nv12_hist_resize(const uint8_t* const* host_luma_ptrs,
     const int cnt = (n - i0 < SCN_MAX_PTRS) ? (n - i0) : SCN_MAX_PTRS;
     stream_ok = nvs::eligible(host_luma_ptrs + i0, host_chroma_ptrs + i0, cnt, pitch, width, height);
   }
-  // SCN_NV12_RESIZE=split (measurement switch): histogram by the streaming kernel, Resize by its own kernel
-  // behind it, instead of the Resize rows produced inside the streaming pass
-  static const bool split_resize = [] {
+  // How Histogram + Resize of the same surfaces run (SCN_NV12_RESIZE, measured in profiles/r02_nv12_stream.md):
+  //   fused    the Resize rows are produced inside the streaming pass (one HBM read of the surface);
+  //   split    streaming histogram kernel, then nv12_resize_kernel behind it on the same stream;
+  //   overlap  nv12_resize_kernel on a side stream next to the streaming kernel.
+  enum { kFused, kSplit, kOverlap };
+  static const int resize_mode = [] {
     const char* e = getenv("SCN_NV12_RESIZE");
-    return e && e[0] == 's';
+    if (e && e[0] == 'f') return (int)kFused;
+    if (e && e[0] == 'o') return (int)kOverlap;
+    if (e && e[0] == 's') return (int)kSplit;
+    return (int)SCN_NV12_RESIZE_DEFAULT;
   }();
   // (the exact-2x Resize, an INTER_AREA average, is not produced inside the streaming pass)
-  if (stream_ok && !(do_resize && (split_resize || area2x)))
+  if (stream_ok && !(do_resize && (resize_mode != kFused || area2x)))
     return nvs::launch(host_luma_ptrs, host_chroma_ptrs, n, pitch, width, height, hist_out, do_resize ? host_dst_ptrs : nullptr,
                        (do_resize && !area2x) ? (const uint8_t*)plan + kPlanHeaderBytes : nullptr, dst_w, dst_h, area2x ? 1 : 0, st);
+  SideStream* side = nullptr;
+  cudaStream_t rst = st;
+  if (stream_ok && do_resize && resize_mode == kOverlap && (side = side_stream()) != nullptr) {
+    // fork before the histogram kernel is enqueued so both kernels can be resident together
+    if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+      cudaGetLastError();
+      side = nullptr;
+    } else {
+      rst = side->stream;
+    }
+  }
   if (stream_ok) {
     const int rc0 = nvs::launch(host_luma_ptrs, host_chroma_ptrs, n, pitch, width, height, hist_out, nullptr, nullptr, 0, 0, 0, st);
     if (rc0) return rc0;
   }
   const bool hist_done = stream_ok;
-  // fork: the resize kernels of this call go to the side stream (see SideStream)
-  SideStream* side = (do_hist && do_resize && !hist_done) ? side_stream() : nullptr;
-  cudaStream_t rst = st;
-  if (side) {
+  // generic path: the resize kernels of this call go to the side stream (see SideStream)
+  if (!hist_done && do_hist && do_resize && (side = side_stream()) != nullptr) {
     if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
       cudaGetLastError();
       side = nullptr;

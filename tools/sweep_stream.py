@@ -11,15 +11,14 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = {
-    "w8": "-DNVS_WARPS=8", "w12": "-DNVS_WARPS=12", "w16": "-DNVS_WARPS=16",
-    "w12_xu": "-DNVS_WARPS=12 -DNVS_CHROMA_XU=1", "w16_xu": "-DNVS_WARPS=16 -DNVS_CHROMA_XU=1",
-    "w8_xu": "-DNVS_WARPS=8 -DNVS_CHROMA_XU=1",
-}
+BUILDS = {"w8": "-DNVS_WARPS=8", "w12": "-DNVS_WARPS=12", "w16": "-DNVS_WARPS=16"}
+# (build, SCN_NV12_RESIZE): how Histogram + Resize of the same surfaces run (fused.cu)
+RUNS = [("w12", "fused"), ("w12", "split"), ("w12", "overlap"), ("w8", "fused"), ("w8", "split"), ("w8", "overlap"),
+        ("w16", "split")]
 
 
 def build():
-    for tag, extra in VARIANTS.items():
+    for tag, extra in BUILDS.items():
         out = os.path.join(ROOT, "build", "variants", tag)
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "scanner_b200", "csrc"), "-j8", f"OBJ={out}/obj", f"OUT={out}",
                                f"EXTRA={extra}"], stdout=subprocess.DEVNULL)
@@ -64,9 +63,10 @@ print(json.dumps(out))
 def run():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     res = {}
-    for tag in VARIANTS:
-        so = os.path.join(ROOT, "build", "variants", tag, "libscn_kernels.so")
-        env = dict(os.environ, SCN_KERNELS_LIB=so)
+    for build_tag, mode in RUNS:
+        tag = f"{build_tag}_{mode}"
+        so = os.path.join(ROOT, "build", "variants", build_tag, "libscn_kernels.so")
+        env = dict(os.environ, SCN_KERNELS_LIB=so, SCN_NV12_RESIZE=mode)
         r = subprocess.run([sys.executable, "-c", CHILD], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
         try:
