@@ -58,7 +58,20 @@ class Sampler:
                 "pstate": med(3), "power_w": med(4), "dec_util": med(5), "samples": len(rows)}
 
 
+def cpu_stat():
+    """cgroup v2 CPU accounting of this container: usage and CFS-throttling counters"""
+    out = {}
+    try:
+        for line in open("/sys/fs/cgroup/cpu.stat"):
+            k, v = line.split()
+            out[k] = int(v)
+    except Exception:
+        pass
+    return out
+
+
 def main():
+    import resource
     E.load_stdlib()
     sampler = Sampler()
     trials = int(sys.argv[1]) if len(sys.argv) > 1 else 6
@@ -80,15 +93,21 @@ def main():
             jobs.append(j)
         for run in range(4):
             sampler.take()
+            c0, r0 = cpu_stat(), resource.getrusage(resource.RUSAGE_SELF)
             t0 = time.time()
             eng.run(g, jobs, 30, 60)
             dt = time.time() - t0
+            c1, r1 = cpu_stat(), resource.getrusage(resource.RUSAGE_SELF)
             clocks = sampler.take()
+            host = {"process_cpu_cores": round(((r1.ru_utime - r0.ru_utime) + (r1.ru_stime - r0.ru_stime)) / dt, 2),
+                    "cgroup_cpu_cores": round((c1.get("usage_usec", 0) - c0.get("usage_usec", 0)) / 1e6 / dt, 2),
+                    "cgroup_nr_throttled": c1.get("nr_throttled", 0) - c0.get("nr_throttled", 0),
+                    "cgroup_throttled_ms": round((c1.get("throttled_usec", 0) - c0.get("throttled_usec", 0)) / 1e3, 1)}
             c = eng.stats()["counters"]
             rates = [round(c[f"inst{i}_frames_decoded"] * 1e6 / max(c[f"inst{i}_decode_busy_us"], 1)) for i in range(c["instances"])]
             print(json.dumps({"trial": t, "run": run, "fps": round(56 * 120 / dt), "session_pictures_per_s": rates,
                               "tasks": [c[f"inst{i}_tasks"] for i in range(c["instances"])],
-                              "nvml": clocks,
+                              "nvml": clocks, "host": host,
                               "host_us": {k: c[k] for k in ("nvdec_parse_us", "nvdec_map_us", "nvdec_decode_call_us", "nvdec_release_wait_us")}}),
                   flush=True)
         eng.close()
