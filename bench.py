@@ -385,27 +385,25 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     resize_args = protolite.encode(std["ResizeArgs"], {"width": DW, "height": DH})
 
     def one_step(tag):
-        jobs, tables = [], []
-        for i in mine:
+        # the output tables of the step's jobs are reserved and committed with ONE catalogue lock each
+        # (scn_db_new_tables / scn_db_commit_job_tables): ranks sharing the directory do not queue per table
+        ids = db.new_tables([(f"hist_{tag}_{i:05d}", "histogram", False, "Histogram", i) for i in mine] +
+                            [(f"small_{tag}_{i:05d}", "frame", True, "", i) for i in mine])
+        jobs = []
+        for k, i in enumerate(mine):
             j = E.Job()
             j.bind_source(src, sids[i])
             j.set_stream_args(op_r, resize_args)
-            th = db.new_table(f"hist_{tag}_{i:05d}", "histogram", False, "Histogram", i)
-            tr = db.new_table(f"small_{tag}_{i:05d}", "frame", True, "", i)
-            j.set_sink_table(sink_h, th, keep_rows=False)
-            j.set_sink_table(sink_r, tr, keep_rows=False)
+            j.set_sink_table(sink_h, ids[k], keep_rows=False)
+            j.set_sink_table(sink_r, ids[len(mine) + k], keep_rows=False)
             jobs.append(j)
-            tables.append((th, tr))
         eng.run(graph, jobs, 30, 60, out_dir=root)
-        for j, (th, tr) in zip(jobs, tables):
-            db.commit_job_table(th, j)
-            db.commit_job_table(tr, j)
+        db.commit_job_tables([(ids[k], jobs[k]) for k in range(len(mine))] +
+                             [(ids[len(mine) + k], jobs[k]) for k in range(len(mine))])
         return jobs
 
     def drop(tag):
-        for i in mine:
-            db.delete_table(f"hist_{tag}_{i:05d}")
-            db.delete_table(f"small_{tag}_{i:05d}")
+        db.delete_tables([f"hist_{tag}_{i:05d}" for i in mine] + [f"small_{tag}_{i:05d}" for i in mine])
 
     for k in range(2):
         one_step(f"w{k}")  # warm-up: decoder creation, memory pools

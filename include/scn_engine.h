@@ -280,6 +280,13 @@ SCN_ENGINE_API int scn_db_save_job(scn_db* db, scn_job* j, const char* table, co
 SCN_ENGINE_API int scn_db_new_table(scn_db* db, const char* table, const char* column_name, int is_video,
                                     const char* type_name, int job_id); /* -> table id */
 SCN_ENGINE_API int scn_job_set_sink_table(scn_job* j, int sink, int table_id, int keep_rows);
+/* The same for many tables with ONE catalogue lock / rewrite per call (a job list with hundreds of output streams;
+ * several ranks sharing the directory): n one-column tables -> out_ids[n]; commit of n (table, job) pairs; delete. */
+SCN_ENGINE_API int scn_db_new_tables(scn_db* db, int n, const char* const* tables, const char* const* column_names,
+                                     const int* is_video, const char* const* type_names, const int* job_ids,
+                                     int* out_ids);
+SCN_ENGINE_API int scn_db_commit_job_tables(scn_db* db, int n, const int* table_ids, scn_job* const* jobs);
+SCN_ENGINE_API int scn_db_delete_tables(scn_db* db, int n, const char* const* tables);
 /* A table of byte columns written from host rows in one call (reference Client.new_table ->
  * master.cpp NewTable: one item holding every row): element (row r, column c) is the
  * sizes[r * n_cols + c] bytes at data[r * n_cols + c] (size 0: null).  -> table id */

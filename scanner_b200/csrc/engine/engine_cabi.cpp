@@ -591,6 +591,45 @@ int scn_db_new_table_from_rows(scn_db* db, const char* table, int n_cols, const 
   return id;
 }
 
+int scn_db_new_tables(scn_db* db, int n, const char* const* tables, const char* const* column_names, const int* is_video,
+                      const char* const* type_names, const int* job_ids, int* out_ids) {
+  if (!db || n < 0 || (n > 0 && (!tables || !column_names || !is_video || !out_ids))) return fail("bad arguments");
+  std::vector<Database::NewTable> specs((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    if (!tables[i] || !column_names[i]) return fail("bad arguments");
+    ColumnSpec cs;
+    cs.name = column_names[i];
+    cs.type = is_video[i] ? proto::Video : proto::Bytes;
+    cs.type_name = type_names && type_names[i] ? type_names[i] : "";
+    specs[(size_t)i] = Database::NewTable{tables[i], {cs}, job_ids ? job_ids[i] : -1};
+  }
+  std::vector<i32> ids;
+  Result r = db->impl->new_tables(specs, ids);
+  if (!r.success()) return fail(r.msg());
+  for (int i = 0; i < n; ++i) out_ids[i] = ids[(size_t)i];
+  return 0;
+}
+
+int scn_db_commit_job_tables(scn_db* db, int n, const int* table_ids, scn_job* const* jobs) {
+  if (!db || n < 0 || (n > 0 && (!table_ids || !jobs))) return fail("bad arguments");
+  std::vector<std::pair<i32, std::vector<i64>>> v;
+  for (int i = 0; i < n; ++i) {
+    if (!jobs[i] || jobs[i]->j.task_starts.size() < 1) return fail("bad arguments");
+    v.emplace_back(table_ids[i], std::vector<i64>(jobs[i]->j.task_starts.begin() + 1, jobs[i]->j.task_starts.end()));
+  }
+  return from_result(db->impl->commit_tables(v));
+}
+
+int scn_db_delete_tables(scn_db* db, int n, const char* const* tables) {
+  if (!db || n < 0 || (n > 0 && !tables)) return fail("bad arguments");
+  std::vector<std::string> names;
+  for (int i = 0; i < n; ++i) {
+    if (!tables[i]) return fail("bad arguments");
+    names.push_back(tables[i]);
+  }
+  return from_result(db->impl->delete_tables(names));
+}
+
 int scn_db_commit_job_table(scn_db* db, int table_id, scn_job* j) {
   if (!db || !j || j->j.task_starts.size() < 1) return fail("bad arguments");
   std::vector<i64> end_rows(j->j.task_starts.begin() + 1, j->j.task_starts.end());

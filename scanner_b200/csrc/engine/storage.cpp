@@ -171,69 +171,92 @@ std::string Database::item_base(i32 table_id, i32 column_id, i32 item_id) const 
   return table_dir(table_id) + "/" + std::to_string(column_id) + "_" + std::to_string(item_id);
 }
 
-Result Database::delete_table(const std::string& name) {
+Result Database::delete_table(const std::string& name) { return delete_tables({name}); }
+
+Result Database::delete_tables(const std::vector<std::string>& names) {
   Result r = ok();
-  i32 id = -1;
+  std::vector<i32> ids;
   {
     std::lock_guard<std::mutex> g(mu_);
     MetaLock file_lock(root_);
     refresh_meta();
     auto* ts = meta_.mutable_tables();
-    for (size_t i = 0; i < ts->size(); ++i)
-      if ((*ts)[i].name() == name) {
-        id = (*ts)[i].id();
-        ts->erase(ts->begin() + (long)i);
+    for (const std::string& name : names) {
+      i32 id = -1;
+      for (size_t i = 0; i < ts->size(); ++i)
+        if ((*ts)[i].name() == name) {
+          id = (*ts)[i].id();
+          ts->erase(ts->begin() + (long)i);
+          break;
+        }
+      if (id < 0) {
+        RESULT_ERROR(&r, "table %s does not exist", name.c_str());
         break;
       }
-    if (id < 0) {
-      RESULT_ERROR(&r, "table %s does not exist", name.c_str());
-      return r;
+      ids.push_back(id);
     }
-    r = save_meta();
+    Result sr = save_meta();  // tables found before a missing one are gone either way
+    if (r.success()) r = sr;
   }
-  remove_tree(table_dir(id));
+  for (i32 id : ids) remove_tree(table_dir(id));
   return r;
 }
 
 Result Database::new_table(const std::string& name, const std::vector<ColumnSpec>& columns, i32 job_id,
                            i32& table_id) {
+  std::vector<i32> ids;
+  Result r = new_tables({NewTable{name, columns, job_id}}, ids);
+  if (r.success()) table_id = ids[0];
+  return r;
+}
+
+Result Database::new_tables(const std::vector<NewTable>& specs, std::vector<i32>& table_ids) {
   Result r = ok();
+  table_ids.clear();
   std::lock_guard<std::mutex> g(mu_);
   MetaLock file_lock(root_);
   refresh_meta();
-  for (const auto& t : meta_.tables())
-    if (t.name() == name) {
+  for (size_t k = 0; k < specs.size(); ++k) {
+    const std::string& name = specs[k].name;
+    bool taken = false;
+    for (const auto& t : meta_.tables()) taken = taken || t.name() == name;
+    if (taken) {
+      refresh_meta();  // drop the entries added so far: nothing of this call is kept
+      for (i32 id : table_ids) pending_.erase(id);
+      table_ids.clear();
       RESULT_ERROR(&r, "table %s already exists", name.c_str());
       return r;
     }
-  table_id = meta_.next_table_id();
-  meta_.set_next_table_id(table_id + 1);
-  tables::DbTable* t = meta_.add_tables();
-  t->set_id(table_id);
-  t->set_name(name);
-  t->set_committed(false);
-  tables::TableDescriptor td;
-  td.set_id(table_id);
-  td.set_name(name);
-  td.set_job_id(job_id);
-  td.set_timestamp(now_seconds());
-  {
-    tables::ColumnDescriptor* c = td.add_columns();  // column 0 is always the index column
-    c->set_id(0);
-    c->set_name("index");
-    c->set_type((int)proto::Bytes);
-  }
-  for (size_t i = 0; i < columns.size(); ++i) {
-    tables::ColumnDescriptor* c = td.add_columns();
-    c->set_id((i32)i + 1);
-    c->set_name(columns[i].name);
-    c->set_type((int)columns[i].type);
-    c->set_type_name(columns[i].type_name);
-  }
-  pending_[table_id] = td;
-  if (!mkdirs(table_dir(table_id))) {
-    RESULT_ERROR(&r, "cannot create %s: %s", table_dir(table_id).c_str(), strerror(errno));
-    return r;
+    const i32 table_id = meta_.next_table_id();
+    meta_.set_next_table_id(table_id + 1);
+    tables::DbTable* t = meta_.add_tables();
+    t->set_id(table_id);
+    t->set_name(name);
+    t->set_committed(false);
+    tables::TableDescriptor td;
+    td.set_id(table_id);
+    td.set_name(name);
+    td.set_job_id(specs[k].job_id);
+    td.set_timestamp(now_seconds());
+    {
+      tables::ColumnDescriptor* c = td.add_columns();  // column 0 is always the index column
+      c->set_id(0);
+      c->set_name("index");
+      c->set_type((int)proto::Bytes);
+    }
+    for (size_t i = 0; i < specs[k].columns.size(); ++i) {
+      tables::ColumnDescriptor* c = td.add_columns();
+      c->set_id((i32)i + 1);
+      c->set_name(specs[k].columns[i].name);
+      c->set_type((int)specs[k].columns[i].type);
+      c->set_type_name(specs[k].columns[i].type_name);
+    }
+    pending_[table_id] = td;
+    table_ids.push_back(table_id);
+    if (!mkdirs(table_dir(table_id))) {
+      RESULT_ERROR(&r, "cannot create %s: %s", table_dir(table_id).c_str(), strerror(errno));
+      return r;
+    }
   }
   return save_meta();
 }
@@ -317,29 +340,35 @@ Result Database::write_item(i32 table_id, i32 column_id, i32 item_id, const Item
 }
 
 Result Database::commit_table(i32 table_id, const std::vector<i64>& end_rows) {
+  return commit_tables({{table_id, end_rows}});
+}
+
+Result Database::commit_tables(const std::vector<std::pair<i32, std::vector<i64>>>& tables) {
   Result r = ok();
   std::lock_guard<std::mutex> g(mu_);
-  auto it = pending_.find(table_id);
-  if (it == pending_.end()) {
-    RESULT_ERROR(&r, "table id %d is not being written", table_id);
-    return r;
+  for (const auto& te : tables) {
+    auto it = pending_.find(te.first);
+    if (it == pending_.end()) {
+      RESULT_ERROR(&r, "table id %d is not being written", te.first);
+      return r;
+    }
+    tables::TableDescriptor& td = it->second;
+    td.clear_end_rows();
+    for (i64 e : te.second) td.add_end_rows(e);
+    const std::string s = td.SerializeAsString();
+    if (!write_file_atomic(table_dir(te.first) + "/descriptor.bin", s.data(), s.size())) {
+      RESULT_ERROR(&r, "cannot write the descriptor of table %d: %s", te.first, strerror(errno));
+      return r;
+    }
   }
-  tables::TableDescriptor& td = it->second;
-  td.clear_end_rows();
-  for (i64 e : end_rows) td.add_end_rows(e);
-  const std::string s = td.SerializeAsString();
-  if (!write_file_atomic(table_dir(table_id) + "/descriptor.bin", s.data(), s.size())) {
-    RESULT_ERROR(&r, "cannot write the descriptor of table %d: %s", table_id, strerror(errno));
-    return r;
-  }
-  {
-    MetaLock file_lock(root_);
-    refresh_meta();
+  MetaLock file_lock(root_);
+  refresh_meta();
+  for (const auto& te : tables) {
     for (auto& t : *meta_.mutable_tables())
-      if (t.id() == table_id) t.set_committed(true);
-    pending_.erase(it);
-    return save_meta();
+      if (t.id() == te.first) t.set_committed(true);
+    pending_.erase(te.first);
   }
+  return save_meta();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -50,6 +50,9 @@ class Database {
   bool has_table(const std::string& name) const;
   i32 table_id(const std::string& name) const;  // -1 if absent
   Result delete_table(const std::string& name);
+  // Several tables under ONE catalogue lock and ONE rewrite of db_metadata.bin (a job with hundreds of output
+  // streams would otherwise take the lock once per table, and ranks sharing the directory queue behind it)
+  Result delete_tables(const std::vector<std::string>& names);
 
   // ---- ingest: `video_path` is an .mp4/.mov (demuxed here) or a raw H.264 Annex-B file
   // inplace (reference ingest.cpp:175-215 `inplace`): the bitstream is not copied into the database;
@@ -73,11 +76,18 @@ class Database {
   // ---- write side (a job's output table)
   // Reserves an id + directory; the table becomes visible with commit_table.
   Result new_table(const std::string& name, const std::vector<ColumnSpec>& columns, i32 job_id, i32& table_id);
+  struct NewTable {
+    std::string name;
+    std::vector<ColumnSpec> columns;
+    i32 job_id = -1;
+  };
+  Result new_tables(const std::vector<NewTable>& specs, std::vector<i32>& table_ids);
   std::string table_dir(i32 table_id) const;
   // Writes one item (= one task) of one column.  Index column (id 0) is written by write_index_item.
   Result write_item(i32 table_id, i32 column_id, i32 item_id, const ItemColumn& col, bool is_video);
   Result write_index_item(i32 table_id, i32 item_id, i64 row0, i64 row1);
   Result commit_table(i32 table_id, const std::vector<i64>& end_rows);
+  Result commit_tables(const std::vector<std::pair<i32, std::vector<i64>>>& tables);
 
  private:
   Database() = default;

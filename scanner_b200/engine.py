@@ -81,6 +81,9 @@ SIGNATURES = {
     "scn_db_save_job": (_I, [_VP, _VP, _CP, _IP, _c.POINTER(_CP), _c.POINTER(_CP), _I, _I]),
     "scn_db_new_table": (_I, [_VP, _CP, _CP, _I, _CP, _I]),
     "scn_job_set_sink_table": (_I, [_VP, _I, _I, _I]),
+    "scn_db_new_tables": (_I, [_VP, _I, _c.POINTER(_CP), _c.POINTER(_CP), _IP, _c.POINTER(_CP), _IP, _IP]),
+    "scn_db_commit_job_tables": (_I, [_VP, _I, _IP, _c.POINTER(_VP)]),
+    "scn_db_delete_tables": (_I, [_VP, _I, _c.POINTER(_CP)]),
     "scn_db_commit_job_table": (_I, [_VP, _I, _VP]),
     "scn_db_read_rows": (_VP, [_VP, _CP, _CP, _c.POINTER(_I64), _I64]),
     "scn_rows_count": (_I64, [_VP]),
@@ -291,6 +294,30 @@ class Database:
         """Reserve a one-column table a job will save into while it runs -> table id."""
         return check(lib().scn_db_new_table(self._h, table.encode(), column.encode(), 1 if is_video else 0,
                                             (type_name or "").encode(), job_id), f"new_table({table})")
+
+    def new_tables(self, specs):
+        """specs: [(table, column, is_video, type_name, job_id)] -> table ids, under one catalogue lock."""
+        n = len(specs)
+        names = (ctypes.c_char_p * n)(*[s[0].encode() for s in specs])
+        cols = (ctypes.c_char_p * n)(*[s[1].encode() for s in specs])
+        vid = (ctypes.c_int * n)(*[1 if s[2] else 0 for s in specs])
+        tys = (ctypes.c_char_p * n)(*[(s[3] or "").encode() for s in specs])
+        jids = (ctypes.c_int * n)(*[int(s[4]) for s in specs])
+        out = (ctypes.c_int * n)()
+        check(lib().scn_db_new_tables(self._h, n, names, cols, vid, tys, jids, out), "new_tables")
+        return list(out)
+
+    def commit_job_tables(self, pairs):
+        """pairs: [(table id, job)], under one catalogue lock."""
+        n = len(pairs)
+        ids = (ctypes.c_int * n)(*[p[0] for p in pairs])
+        jobs = (ctypes.c_void_p * n)(*[p[1]._h for p in pairs])
+        check(lib().scn_db_commit_job_tables(self._h, n, ids, jobs), "commit_job_tables")
+
+    def delete_tables(self, tables):
+        n = len(tables)
+        names = (ctypes.c_char_p * n)(*[t.encode() for t in tables])
+        check(lib().scn_db_delete_tables(self._h, n, names), "delete_tables")
 
     def commit_job_table(self, table_id, job):
         check(lib().scn_db_commit_job_table(self._h, table_id, job._h), "commit_job_table")

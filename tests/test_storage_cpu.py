@@ -532,6 +532,46 @@ def test_processes_sharing_one_database_do_not_lose_tables(tmp_path):
     db.close()
 
 
+def test_many_tables_reserved_committed_and_deleted_under_one_catalogue_update(tmp_path):
+    """scn_db_new_tables / scn_db_commit_job_tables / scn_db_delete_tables: the per-table calls, batched so a job
+    list with many output streams rewrites db_metadata.bin once (reference: the master writes the descriptors of
+    all of a bulk job's tables in one go, master.cpp new-job path)."""
+    n, h, w = 7, 16, 24
+    frames = np.stack([synth.rand_frame(500 + i, h, w) for i in range(n)])
+    db = E.Database(str(tmp_path / "db"))
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    g = E.Graph()
+    src = g.add_source(True)
+    hs = g.add_op("TestHistogramOracle", [(src, "frame")])
+    s_h = g.add_sink((hs, "histogram"))
+    ids = db.new_tables([(f"h{k}", "histogram", False, "Histogram", k) for k in range(3)])
+    assert len(set(ids)) == 3 and db.tables() == []
+    with pytest.raises(E.EngineError):
+        db.new_tables([("fresh", "c", False, "", 0), ("h1", "c", False, "", 0)])   # all or nothing
+    meta = parse_ref("DatabaseDescriptor", os.path.join(db.path, "db_metadata.bin"))
+    assert sorted(t.name for t in meta.tables) == ["h0", "h1", "h2"]
+    jobs = []
+    for k in range(3):
+        j = E.Job()
+        j.bind_source(src, eng.add_raw_frames(frames[k:k + 4]))
+        j.set_sink_table(s_h, ids[k], keep_rows=False)
+        jobs.append(j)
+    eng.run(g, jobs, 3, 3, db.path)
+    db.commit_job_tables(list(zip(ids, jobs)))
+    assert sorted(db.tables()) == ["h0", "h1", "h2"]
+    for k in range(3):
+        rows = db.read_rows(f"h{k}", "histogram")
+        assert [r for r in rows] == [oracle.hist16(frames[k + i]).tobytes() for i in range(4)]
+        assert db.table_info(f"h{k}")["job_id"] == k
+    with pytest.raises(E.EngineError):
+        db.delete_tables(["h0", "missing", "h2"])
+    assert db.tables() == ["h1", "h2"]            # tables named before the missing one are gone, as with single calls
+    db.delete_tables(["h1", "h2"])
+    assert db.tables() == [] and not os.path.exists(os.path.join(db.path, "tables", str(ids[1])))
+    eng.close()
+    db.close()
+
+
 # ---- re-layout of an .mp4 in Python: the shapes other muxers produce (several chunks, 64-bit chunk
 # offsets, moov in front of mdat = "faststart"), to exercise the demuxer's table walking
 def _boxes(buf, start, end):
