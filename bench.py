@@ -25,9 +25,10 @@ NVDEC layout, pitch 2048): surfaces -> RGB -> {Histogram 3x16 int32, Resize 224x
           the reference runs one pipeline instance per core) on a bounded sample of the same
           clips on this box's host cores (rank 0, N=1 only).  The clips of the reference arm come from
           oracle/h264_writer.py (pure numpy): that arm loads no product library.
-Limitation stated with every line: configs[0] (Histogram on a 640x480 H.264 clip on a CPU-only instance)
-has no counterpart -- there is no software H.264 decoder in this tree (FFmpeg is not available offline);
-CPU instances run raw-frame columns only (tests/test_engine_cpu.py::test_config0_cpu_plumbing_histogram_640x480).
+configs[0] (Histogram on one 640x480 H.264 clip, CPU pipeline_instances=1, no GPU) is run beside it on rank 0 at N=1
+as `config0_cpu`: the engine's CPU instance decodes with FFmpeg (libavcodec + libswscale through dlopen,
+scanner_b200/csrc/engine/swdec.h -- what the reference's SoftwareVideoDecoder is) and the stdlib Histogram runs on
+the CPU; a second or two, sampled rows checked against cv2 + the oracle.  Not part of `value` / `e2e`.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -48,8 +49,51 @@ SURF_ROWS = H * 3 // 2
 B_ALG_FUSED = W * H * 3 // 2 + DW * DH * 3 + 192      # 3,261,120 B / frame
 B_ALG_HIST_NV12 = W * H * 3 // 2 + 192                  # the histogram kernel alone
 METRIC = "frames/sec (1080p H.264 decode+resize+histogram)"
-CONFIG0_NOTE = ("configs[0] (H.264 on a CPU-only instance) is not implemented: no software H.264 decoder "
-                "(FFmpeg unavailable offline); CPU instances take raw-frame columns")
+
+
+def config0_cpu(frames=240):
+    """BASELINE configs[0] as stated, on this box's host: one 640x480 H.264 clip, one CPU pipeline instance."""
+    import cv2
+    import numpy as np
+    import oracle
+    from scanner_b200 import engine as E, synth_h264
+    caps = E.swdec_caps()
+    if not caps["available"]:
+        return {"unavailable": caps.get("error", "")}
+    data, _ = synth_h264.write(640, 480, frames, gop=30, seed=9)
+    E.load_stdlib()
+    eng = E.Engine(gpus=[], cpu_instances=1)
+    sid = eng.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    sink = g.add_sink((g.add_op("Histogram", [(src, "frame")], device=0), "histogram"))
+    j = E.Job()
+    j.bind_source(src, sid)
+    eng.run(g, [j], 30, 60)                      # warm: libraries loaded, codec opened
+    t0 = time.perf_counter()
+    eng.run(g, [j], 30, 60)
+    dt = time.perf_counter() - t0
+    hist = j.output_array(sink, 192, np.int32).reshape(frames, 3, 16)
+    tmp = tempfile.mkdtemp(prefix="scn_c0_")
+    try:
+        path = os.path.join(tmp, "c.h264")
+        open(path, "wb").write(data)
+        cap = cv2.VideoCapture(path)
+        checked = 0
+        for i in range(frames):
+            ok, f = cap.read()
+            assert ok
+            if i % 40 == 0:
+                assert (hist[i] == oracle.hist16(np.ascontiguousarray(f[..., ::-1]))).all(), i
+                checked += 1
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    eng.close()
+    return {"workload": "configs[0]: Histogram on one 640x480 H.264 clip, CPU pipeline_instances=1 (no GPU)",
+            "value": frames / dt, "unit": "frames/s", "frames": frames, "cores": 1,
+            "decoder": f"libavcodec {caps['avcodec']} / libswscale {caps['swscale']} via dlopen ({os.path.basename(caps['where'])})",
+            "rows_checked_against_cv2_and_oracle": checked}
+
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the committed ncu --set full
 # capture of the bench's own launch shape (64 surfaces 1920x1080, pitch 2048, histogram + resize):
@@ -243,8 +287,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
                              "ipcm_stream": {"value": fps_ipcm, "unit": "frames/s"}},
             "e2e": {"value": fps, "unit": "frames/s", "stream": "cavlc", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "e2e_ipcm_stream": {"value": fps_ipcm, "unit": "frames/s", "stream": "pcm"},
-            "not_implemented": CONFIG0_NOTE}
+            "e2e_ipcm_stream": {"value": fps_ipcm, "unit": "frames/s", "stream": "pcm"}}
     emit(line)
     return 0
 
@@ -568,10 +611,10 @@ def run_config1(args, R):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": workload_config(args, B), "clocks": clocks, "e2e": e2e, "e2e_ipcm_stream": e2e_ipcm,
                 "gpu_launches": int(launches), "roofline": roof,
-                "whole_step_roofline_frac": value / world * B_ALG_FUSED / 1e9 / peak,
-                "not_implemented": CONFIG0_NOTE}
+                "whole_step_roofline_frac": value / world * B_ALG_FUSED / 1e9 / peak}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
+            line["config0_cpu"] = config0_cpu()
         emit(line)
     return 0
 

@@ -238,6 +238,10 @@ SCN_ENGINE_API int64_t scn_h264_synth(const uint8_t* yuv, int width, int height,
                                       int non_key_mode, uint8_t* out, size_t cap);
 /* NVDEC probe: info[0..5] = available, h264_supported, engines, max_w, max_h, min_w. */
 SCN_ENGINE_API int scn_nvdec_caps(int gpu_id, int info[6]);
+/* Software decoder probe (CPU pipeline instances; reference SoftwareVideoDecoder = FFmpeg, software_video_decoder.cpp):
+ * info[0..3] = available, libavcodec major, libavutil major, libswscale major.  The libraries are resolved with
+ * dlopen from $SCN_FFMPEG_DIR or the system search path; when unavailable scn_last_error() says why. */
+SCN_ENGINE_API int scn_swdec_caps(int info[4]);
 
 /* ---------------------------------------------------------------------------------------------
  * Tables on disk: a Scanner database directory in the reference's layout (db_metadata.bin,

@@ -155,6 +155,18 @@ SCN_API int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const uint8
                                int n, int width, int height, float* const* host_flow_ptrs, int num_levels,
                                double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* The same for a caller that walks a clip pair by pair and keeps the workspace between calls (the OpticalFlow op,
+ * stencil [0, 1]: one pair per call).  Within a call, a pair whose `prev` pointer equals the previous pair's `next`
+ * reuses that frame's pyramid of polynomial expansions (gray conversion, the full-resolution Gaussians, resizes and
+ * expansions are per frame, about 40 % of a pair's work).  `chain` (host int owned by the caller with the workspace,
+ * 0 initially and after anything else used the workspace) carries this over calls: with reuse_prev != 0 and
+ * *chain != 0 the caller asserts that pair 0's `prev` frame has the content of the last call's last `next` frame (the
+ * same table row), and it is not expanded again.  Results are identical to scn_farneback_u8c3's. */
+SCN_API int scn_farneback_u8c3_chain(const uint8_t* const* host_prev_ptrs, const uint8_t* const* host_next_ptrs,
+                                     int n, int width, int height, float* const* host_flow_ptrs, int num_levels,
+                                     double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
+                                     void* workspace, size_t workspace_bytes, int reuse_prev, int* chain,
+                                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * FrameDigest: a 16-byte fingerprint of each of n equally sized buffers (`bytes` a multiple of 4):

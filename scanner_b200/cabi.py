@@ -35,6 +35,9 @@ SIGNATURES = {
     "scn_farneback_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "scn_farneback_u8c3": (_c.c_int, [_PP, _PP, _c.c_int, _c.c_int, _c.c_int, _PP, _c.c_int, _c.c_double, _c.c_int,
                                       _c.c_int, _c.c_int, _c.c_double, _VP, _c.c_size_t, _VP]),
+    "scn_farneback_u8c3_chain": (_c.c_int, [_PP, _PP, _c.c_int, _c.c_int, _c.c_int, _PP, _c.c_int, _c.c_double,
+                                            _c.c_int, _c.c_int, _c.c_int, _c.c_double, _VP, _c.c_size_t, _c.c_int,
+                                            _c.POINTER(_c.c_int), _VP]),
     "scn_nv12_hist_resize": (_c.c_int, [_PP, _PP, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _VP, _PP,
                                         _c.c_int, _c.c_int, _VP, _VP]),
     "scn_frame_digest": (_c.c_int, [_PP, _c.c_int, _c.c_size_t, _VP, _VP]),

@@ -4,6 +4,7 @@
 #include <sstream>
 
 #include "nvdec.h"
+#include "swdec.h"
 #include "pipeline.h"
 #include "mp4.h"
 #include "scn_engine.h"
@@ -416,6 +417,17 @@ int scn_nvdec_caps(int gpu_id, int info[6]) {
   info[4] = c.max_height;
   info[5] = c.min_width;
   if (!c.available) t_error = c.error;
+  return 0;
+}
+
+int scn_swdec_caps(int info[4]) {
+  if (!info) return fail("null info");
+  const SwdecCaps& c = swdec_caps();
+  info[0] = c.available;
+  info[1] = c.avcodec_major;
+  info[2] = c.avutil_major;
+  info[3] = c.swscale_major;
+  t_error = c.available ? c.where : c.error;
   return 0;
 }
 

@@ -17,6 +17,7 @@
 
 #include "engine_internal.h"
 #include "nvdec.h"
+#include "swdec.h"
 #include "storage.h"
 #include "scn_kernels.h"
 
@@ -180,7 +181,8 @@ struct Engine::Instance {
 struct Engine::Slot {
   i32 gpu_id = -1;
   cudaStream_t stream = nullptr;
-  std::map<i32, std::unique_ptr<NvdecSession>> sessions;  // per video source op index
+  std::map<i32, std::unique_ptr<NvdecSession>> sessions;     // per video source op index
+  std::map<i32, std::unique_ptr<SwdecSession>> sw_sessions;  // the same for a CPU instance (swdec.h)
 };
 
 Engine::Engine(std::vector<i32> gpu_ids, i32 instances_per_gpu, i32 cpu_instances)
@@ -352,6 +354,7 @@ void Engine::instance_main(Instance* inst) {
   cudaStream_t stream = slot.stream;
   Profiler::thread_worker() = inst->index;
   const DeviceHandle gpu_dev(DeviceType::GPU, gpu);
+  const DeviceHandle dec_dev = gpu >= 0 ? gpu_dev : CPU_DEVICE;  // where decoded pictures live
   {
     EvaluateWorker ew(*rs.graph, rs.an, gpu, inst->node_id, &rs.profiler, &rs.resource_gate);
     Result r = ew.init();
@@ -365,6 +368,10 @@ void Engine::instance_main(Instance* inst) {
       decoded0 += kv.second->frames_decoded();
       used0 += kv.second->frames_used();
       busy0 += kv.second->busy_ns();
+    }
+    for (auto& kv : slot.sw_sessions) {
+      decoded0 += kv.second->frames_decoded();
+      used0 += kv.second->frames_used();
     }
     const auto inst_t0 = std::chrono::steady_clock::now();
 
@@ -407,7 +414,7 @@ void Engine::instance_main(Instance* inst) {
           c.stream = bit == job.source_streams.end() ? nullptr : this->stream(bit->second);
         }
         c.wps = rs.wps;
-        c.gpu_dev = gpu_dev;
+        c.gpu_dev = dec_dev;
         c.rows = streams[k].valid_output_rows;
         if (!c.stream) {
           RESULT_ERROR(&r, "job %d does not bind source op %zu to a stream", t.job, k);
@@ -428,23 +435,39 @@ void Engine::instance_main(Instance* inst) {
         }
         if (c.stream->kind == InputStream::H264) {
           if (gpu < 0) {
-            RESULT_ERROR(&r, "H.264 sources need a GPU pipeline instance (NVDEC); there is no software decoder");
-            break;
-          }
-          auto& s = sessions[(i32)k];
-          if (!s) {
-            s.reset(new NvdecSession(gpu, stream));
-            Result ir = s->init();
-            if (!ir.success()) {
-              r = ir;
-              break;
+            // CPU instance: libavcodec + libswscale -> RGB24 in host memory (swdec.h; reference
+            // SoftwareVideoDecoder).  Fails here, with the reason, when no FFmpeg can be loaded.
+            auto& s = slot.sw_sessions[(i32)k];
+            if (!s) {
+              static const int threads = [] {
+                const char* e = getenv("SCN_SWDEC_THREADS");
+                const int v = e ? atoi(e) : 1;
+                return v < 1 ? 1 : (v > 64 ? 64 : v);
+              }();
+              s.reset(new SwdecSession(threads));
+              Result ir = s->init();
+              if (!ir.success()) {
+                slot.sw_sessions.erase((i32)k);
+                r = ir;
+                break;
+              }
+            }
+          } else {
+            auto& s = sessions[(i32)k];
+            if (!s) {
+              s.reset(new NvdecSession(gpu, stream));
+              Result ir = s->init();
+              if (!ir.success()) {
+                r = ir;
+                break;
+              }
             }
           }
           c.intervals = slice_into_intervals(c.stream->index, c.rows, c.halo.empty() ? nullptr : &c.halo);
           // decoder-native delivery when every consumer kernel takes NV12 (frame.h FrameLayout);
           // SCN_DECODE_RGB=1 forces the reference's RGB24 elements
           const char* force_rgb = getenv("SCN_DECODE_RGB");
-          c.nv12 = !(force_rgb && force_rgb[0] == '1') &&
+          c.nv12 = gpu >= 0 && !(force_rgb && force_rgb[0] == '1') &&
                    rs.graph->consumers_accept_layout((i32)k, FrameLayout::NV12);
           const size_t px = (size_t)c.stream->index.width * c.stream->index.height;
           c.frame_bytes = c.nv12 ? px + px / 2 : px * 3;
@@ -470,13 +493,15 @@ void Engine::instance_main(Instance* inst) {
           if (st.kind == InputStream::H264) {
             // ---- decode stage (reference PreEvaluateWorker::yield + DecoderAutomata::get_frames)
             const timepoint_t d0 = now();
-            cb.device = gpu_dev;
-            NvdecSession& sess = *sessions[c.op];
+            cb.device = dec_dev;
+            NvdecSession* hw = gpu >= 0 ? sessions[c.op].get() : nullptr;
+            SwdecSession* sw = gpu >= 0 ? nullptr : slot.sw_sessions[c.op].get();
+            auto sess_delivered = [&] { return hw ? hw->delivered() : sw->delivered(); };
             const FrameInfo finfo = c.nv12 ? FrameInfo::nv12(st.index.width, st.index.height)
                                            : FrameInfo(st.index.height, st.index.width, 3, FrameType::U8);
             size_t delivered_global = c.cur_interval < c.intervals.size()
                                           ? (size_t)c.intervals[c.cur_interval].out_base +
-                                                (c.interval_open ? sess.delivered() : 0)
+                                                (c.interval_open ? sess_delivered() : 0)
                                           : c.rows.size();
             while (delivered_global < i1 && r.success()) {
               VideoInterval& iv = c.intervals[c.cur_interval];
@@ -486,7 +511,12 @@ void Engine::instance_main(Instance* inst) {
                 std::vector<u64> szs(st.index.sample_sizes.begin() + iv.kf_start,
                                      st.index.sample_sizes.begin() + iv.kf_end);
                 const size_t w = (size_t)st.index.width, h = (size_t)st.index.height;
-                r = sess.begin_interval(
+                if (sw)
+                  r = sw->begin_interval(st.encoded.data(), offs, szs, st.index.metadata_packets, st.index.may_reorder,
+                                         iv.wanted, iv.out_base, (int)w, (int)h,
+                                         [cur = &c](i64 out_index) { return cur->slot(out_index); });
+                else
+                r = hw->begin_interval(
                     st.encoded.data(), offs, szs, st.index.metadata_packets, st.index.may_reorder, iv.wanted, iv.out_base,
                     [cur = &c, rsp = &rs, stream, w, h](i64 out_index, const Nv12Surface& s) {
                       const u8* lp = s.luma;
@@ -511,25 +541,25 @@ void Engine::instance_main(Instance* inst) {
                 c.interval_open = true;
               }
               const size_t want_in_iv = std::min(iv.wanted.size(), i1 - (size_t)iv.out_base);
-              r = sess.advance(want_in_iv);
+              r = hw ? hw->advance(want_in_iv) : sw->advance(want_in_iv);
               if (!r.success()) break;
-              if (sess.delivered() >= iv.wanted.size()) {
-                r = sess.end_interval();
+              if (sess_delivered() >= iv.wanted.size()) {
+                r = hw ? hw->end_interval() : sw->end_interval();
                 c.interval_open = false;
                 ++c.cur_interval;
                 delivered_global = c.cur_interval < c.intervals.size() ? (size_t)c.intervals[c.cur_interval].out_base
                                                                        : c.rows.size();
               } else {
-                delivered_global = (size_t)iv.out_base + sess.delivered();
+                delivered_global = (size_t)iv.out_base + sess_delivered();
               }
             }
             if (!r.success()) break;
             for (size_t i = i0; i < i1; ++i) {
               if (!c.halo.empty() && c.halo[i]) {  // received from the rank that owns the row
-                add_buffer_ref(gpu_dev, c.halo[i]);
+                add_buffer_ref(dec_dev, c.halo[i]);
                 cb.elements.push_back(Element(new Frame(finfo, c.halo[i])));
                 // the packet's block counts one reference per row: give back this row's unused slot
-                if (c.blocks.count((i64)i / c.wps)) delete_buffer(gpu_dev, c.slot((i64)i));
+                if (c.blocks.count((i64)i / c.wps)) delete_buffer(dec_dev, c.slot((i64)i));
               } else {
                 cb.elements.push_back(Element(new Frame(finfo, c.slot((i64)i))));
               }
@@ -724,6 +754,11 @@ void Engine::instance_main(Instance* inst) {
       rs.frames_used += kv.second->frames_used();
       decoded1 += kv.second->frames_decoded();
       busy1 += kv.second->busy_ns();
+    }
+    for (auto& kv : slot.sw_sessions) {
+      rs.frames_decoded += kv.second->frames_decoded();
+      rs.frames_used += kv.second->frames_used();
+      decoded1 += kv.second->frames_decoded();
     }
     rs.frames_decoded -= decoded0;
     rs.frames_used -= used0;

@@ -8,8 +8,8 @@
 //   M     = UpdateMatrices(R0, R1 warped by the current flow)        (5 floats per pixel)
 //   flow  = solve 2x2 from the winSize x winSize box average of M,   numIters times
 // Floating point: sums are taken in a different order than OpenCV's SIMD code, so parity is within
-// a tolerance (tests/test_flow_gpu.py), not bit-exact.  The box sums and the 2x2 solve run in
-// double like OpenCV's (the determinant cancels catastrophically in float).
+// a tolerance (tests/test_flow_gpu.py), not bit-exact.  The 2x2 solve runs in double like OpenCV's (the
+// determinant cancels catastrophically in float); the window sums in float (box_solve_f32_kernel) or double.
 // All kernels are plain per-pixel / separable memory-bound passes (no tensor cores).
 #include <math.h>
 #include <stdlib.h>
@@ -431,6 +431,98 @@ box_solve_fused_kernel(const float* __restrict__ M, int w, int h, double scale, 
   }
 }
 
+// The same stage with FLOAT window sums (the default): the 225 addends of a window are float32 values; summed in
+// float32 in a fixed tree (12 shared core rows/columns, then the 3 edge terms of each of 4 overlapping windows -- no
+// subtraction, so no cancellation beyond the data's own) the relative error of a sum is ~1e-6 of sum|m|, and only the
+// 2x2 solve -- where g11 g22 - g12^2 cancels -- is done in double, from those sums.  Against the double sums this
+// moves the flow by <= 2e-4 px on the test pairs (tests/test_flow_gpu.py keeps the 2e-3 / 1e-4 px bounds against
+// cv2), removes the f32->f64 conversions (XU pipe, 4.5 per sum) and halves the shared-memory traffic.
+// SCN_FLOW_BOX=f64 selects the double kernel above.
+// Tile 88 x 32 outputs: 5 * (88 + 14) = 510 column-channels ~ 2 x 256 threads.  A thread takes a column-channel
+// and loads its 32 + 14 input rows ONCE into registers (coalesced: consecutive threads, consecutive floats), then
+// forms the 32 vertical window sums from them -- the first version re-read 18 rows for every 4 outputs through an
+// L1 squeezed by the shared-memory carve-out and was L2-bound (ncu: 490 MB of L2 traffic per 1080p launch for a
+// 41 MB input, 7.5 TB/s; profiles/r02_flow.md).
+constexpr int B32W = 88, B32H = 32;
+template <int MW>
+__global__ void __launch_bounds__(FT)
+box_solve_f32_kernel(const float* __restrict__ M, int w, int h, double scale, float* __restrict__ flow) {
+  extern __shared__ float bsm[];
+  constexpr int iw = B32W + 2 * MW, rowf = iw * 5, vstride = rowf | 1, taps = 2 * MW + 1, in_rows = B32H + 2 * MW;
+  static_assert(taps >= 7, "the 4-window tree needs at least 3 edge terms on each side");
+  float* V = bsm;  // B32H x vstride
+  const int x0 = blockIdx.x * B32W, y0 = blockIdx.y * B32H;
+  const int stride = w * 5;
+  for (int q = threadIdx.x; q < rowf; q += FT) {
+    const int i = q / 5, c = q - i * 5;
+    const int idx0 = clampi(x0 - MW + i, 0, w - 1) * 5 + c;
+    const int ytop = y0 - MW;
+    float f[in_rows];
+    if (ytop >= 0 && ytop + in_rows <= h) {
+      const float* col = M + idx0 + ytop * stride;
+#pragma unroll
+      for (int k = 0; k < in_rows; ++k) f[k] = col[k * stride];
+    } else {
+#pragma unroll
+      for (int k = 0; k < in_rows; ++k) f[k] = M[idx0 + clampi(ytop + k, 0, h - 1) * stride];
+    }
+    // rows 4g .. 4g+3: windows f[4g + o .. 4g + o + taps - 1], o = 0..3; f[4g + 3 .. 4g + taps - 1] is common
+#pragma unroll
+    for (int g = 0; g < B32H / 4; ++g) {
+      const float* e = f + 4 * g;
+      float core = e[3];
+#pragma unroll
+      for (int k = 4; k < taps; ++k) core += e[k];
+      float* vo = V + (size_t)(g * 4) * vstride + q;
+      vo[0] = core + ((e[0] + e[1]) + e[2]);
+      vo[vstride] = core + ((e[1] + e[2]) + e[taps]);
+      vo[2 * vstride] = core + ((e[2] + e[taps]) + e[taps + 1]);
+      vo[3 * vstride] = core + ((e[taps] + e[taps + 1]) + e[taps + 2]);
+    }
+  }
+  __syncthreads();
+  // horizontal + solve: item = (row, group of 4 columns); a warp's lanes are 32 rows (odd row stride: no bank conflicts)
+  for (int e = threadIdx.x; e < B32H * (B32W / 4); e += FT) {
+    const int ty = e & (B32H - 1), gx = e / B32H;
+    const int y = y0 + ty;
+    if (y >= h || x0 + gx * 4 >= w) continue;
+    const float* p = V + (size_t)ty * vstride + (gx * 4) * 5;
+    float hs[4][5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      float core = p[3 * 5 + c];
+#pragma unroll
+      for (int k = 4; k < taps; ++k) core += p[k * 5 + c];
+      const float a0 = p[c], a1 = p[5 + c], a2 = p[10 + c];
+      const float b0 = p[taps * 5 + c], b1 = p[(taps + 1) * 5 + c], b2 = p[(taps + 2) * 5 + c];
+      hs[0][c] = core + ((a0 + a1) + a2);
+      hs[1][c] = core + ((a1 + a2) + b0);
+      hs[2][c] = core + ((a2 + b0) + b1);
+      hs[3][c] = core + ((b0 + b1) + b2);
+    }
+    float2 out[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const double g11 = hs[o][0] * scale, g12 = hs[o][1] * scale, g22 = hs[o][2] * scale, h1 = hs[o][3] * scale,
+                   h2 = hs[o][4] * scale;
+      const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
+      out[o] = make_float2((float)((g11 * h2 - g12 * h1) * idet), (float)((g22 * h1 - g12 * h2) * idet));
+    }
+    float2* dst = reinterpret_cast<float2*>(flow) + (size_t)y * w + x0 + gx * 4;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if (x0 + gx * 4 + o < w) dst[o] = out[o];
+  }
+}
+inline size_t box32_smem(int m) { return (size_t)B32H * (((B32W + 2 * m) * 5) | 1) * 4; }
+inline bool box_in_f64() {
+  static const bool v = [] {
+    const char* e = getenv("SCN_FLOW_BOX");
+    return e && strcmp(e, "f64") == 0;
+  }();
+  return v;
+}
+
 constexpr size_t kFusedSmemCap = 160 * 1024;
 inline size_t gauss_smem(int r) { return ((size_t)(GTH + 2 * r) * (GTW + 2 * r) + (size_t)(GTH + 2 * r) * GTW) * 4; }
 inline size_t poly_smem(int n) { return ((size_t)(PTH + 2 * n) * (PTW + 2 * n) + (size_t)PTH * (PTW + 2 * n) * 3) * 4; }
@@ -448,6 +540,8 @@ inline bool use_fused() {
            big((const void*)gauss_fused_kernel<3>) && big((const void*)gauss_fused_kernel<8>) &&
            big((const void*)poly_fused_kernel<0>) && big((const void*)poly_fused_kernel<5>) &&
            cudaFuncSetAttribute(box_solve_fused_kernel<kBoxMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kFusedSmemCap) == cudaSuccess &&
+           cudaFuncSetAttribute(box_solve_f32_kernel<kBoxMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kFusedSmemCap) == cudaSuccess;
   }();
   return v;
@@ -555,6 +649,7 @@ int plan_levels(int width, int height, int num_levels, double pyr_scale, Level* 
 }
 
 // workspace layout (floats unless noted), all sized for the full-resolution level
+constexpr int kPyramidRoom = 2;
 struct Workspace {
   float *gray[2], *tmp, *blur, *I, *poly3, *R[2], *M, *flow_a, *flow_b;
   double* V;
@@ -576,8 +671,8 @@ size_t carve(void* base, int w, int h, Workspace* ws) {
   o.blur = (float*)take(px * 4);
   o.I = (float*)take(px * 4);
   o.poly3 = (float*)take(px * 12);
-  o.R[0] = (float*)take(px * 20);
-  o.R[1] = (float*)take(px * 20);
+  o.R[0] = (float*)take(px * 20 * kPyramidRoom);  // all levels of a frame's expansion when they fit (pyr_scale <= 0.7)
+  o.R[1] = (float*)take(px * 20 * kPyramidRoom);
   o.M = (float*)take(px * 20);
   o.flow_a = (float*)take(px * 8);
   o.flow_b = (float*)take(px * 8);
@@ -597,7 +692,18 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
                                   int width, int height, float* const* host_flow_ptrs, int num_levels,
                                   double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
                                   void* workspace, size_t workspace_bytes, void* stream) {
+  return scn_farneback_u8c3_chain(host_prev_ptrs, host_next_ptrs, n, width, height, host_flow_ptrs, num_levels,
+                                  pyr_scale, win_size, num_iters, poly_n, poly_sigma, workspace, workspace_bytes, 0,
+                                  nullptr, stream);
+}
+
+extern "C" int scn_farneback_u8c3_chain(const uint8_t* const* host_prev_ptrs, const uint8_t* const* host_next_ptrs,
+                                        int n, int width, int height, float* const* host_flow_ptrs, int num_levels,
+                                        double pyr_scale, int win_size, int num_iters, int poly_n, double poly_sigma,
+                                        void* workspace, size_t workspace_bytes, int reuse_prev, int* chain,
+                                        void* stream) {
   using namespace scn;
+  if (chain && (*chain < 0 || *chain > 2)) return SCN_E_BADARG;
   if (n < 0 || width <= 0 || height <= 0 || num_levels < 0 || num_levels > 15 || pyr_scale <= 0 || pyr_scale >= 1 ||
       win_size < 1 || num_iters < 1 || poly_n < 1 || poly_n > kMaxPolyN || poly_sigma <= 0)
     return SCN_E_BADARG;
@@ -617,15 +723,96 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
   const int T = 128;
   auto grid2 = [&](int w, int h) { return dim3((unsigned)((w + T - 1) / T), (unsigned)h); };
 
-  for (int pair = 0; pair < n; ++pair) {
-    const int npx = width * height;
-    {
-      LaunchScope ls("flow_gray_kernel", st);
-      gray_kernel<<<(npx + 255) / 256, 256, 0, st>>>(host_prev_ptrs[pair], npx, ws.gray[0]);
+  // Polynomial expansion of one frame at one level: GaussianBlur of the full-resolution gray image with the level's
+  // sigma, resize to the level, expansion -> 5 coefficients per pixel at dstR.
+  auto expand = [&](const float* gray, int k, float* dstR) {
+    const int w = lv[k].w, h = lv[k].h;
+    GaussK gk;
+    make_gauss(lv[k].smooth, lv[k].sigma, gk);
+    if (use_fused() && gauss_smem(gk.radius) <= kFusedSmemCap) {
+      LaunchScope ls("flow_gauss_fused_kernel", st);
+      const dim3 gg((unsigned)((width + GTW - 1) / GTW), (unsigned)((height + GTH - 1) / GTH));
+      const size_t sm = gauss_smem(gk.radius);
+      // the radii of the reference's pyramid (pyrScale 0.5: ksize 3, 3, 7, 17) are instantiated
+      switch (gk.radius) {
+        case 1: gauss_fused_kernel<1><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
+        case 3: gauss_fused_kernel<3><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
+        case 8: gauss_fused_kernel<8><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
+        default: gauss_fused_kernel<0><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
+      }
+    } else {
+      {
+        LaunchScope ls("flow_gauss_h_kernel", st);
+        gauss_h_kernel<<<grid2(width, height), T, 0, st>>>(gray, width, height, gk, ws.tmp);
+      }
+      {
+        LaunchScope ls("flow_gauss_v_kernel", st);
+        gauss_v_kernel<<<grid2(width, height), T, 0, st>>>(ws.tmp, width, height, gk, ws.blur);
+      }
     }
-    {
-      LaunchScope ls("flow_gray_kernel", st);
-      gray_kernel<<<(npx + 255) / 256, 256, 0, st>>>(host_next_ptrs[pair], npx, ws.gray[1]);
+    const float* I = ws.blur;
+    if (w != width || h != height) {
+      LaunchScope ls("flow_resize_kernel", st);
+      resize_f32_kernel<1><<<grid2(w, h), T, 0, st>>>(ws.blur, width, height, ws.I, w, h, (double)width / w,
+                                                      (double)height / h, 1.f);
+      I = ws.I;
+    }
+    if (use_fused() && poly_smem(pk.n) <= kFusedSmemCap) {
+      LaunchScope ls("flow_poly_fused_kernel", st);
+      const dim3 pg((unsigned)((w + PTW - 1) / PTW), (unsigned)((h + PTH - 1) / PTH));
+      if (pk.n == 5) poly_fused_kernel<5><<<pg, FT, poly_smem(pk.n), st>>>(I, w, h, pk, dstR);
+      else poly_fused_kernel<0><<<pg, FT, poly_smem(pk.n), st>>>(I, w, h, pk, dstR);
+    } else {
+      {
+        LaunchScope ls("flow_poly_v_kernel", st);
+        poly_v_kernel<<<grid2(w, h), T, 0, st>>>(I, w, h, pk, ws.poly3);
+      }
+      {
+        LaunchScope ls("flow_poly_h_kernel", st);
+        poly_h_kernel<<<grid2(w, h), T, 0, st>>>(ws.poly3, w, h, pk, dstR);
+      }
+    }
+  };
+  // When every level of a frame's expansion fits its R buffer (pyr_scale <= ~0.7: the reference's 0.5 does), the
+  // whole pyramid of a frame is built once and kept: in a run of consecutive pairs (next[p] == prev[p + 1], what the
+  // OpticalFlow op's stencil [0, 1] produces) the second frame of a pair is the first of the next, and its gray
+  // conversion, 4 full-resolution Gaussians, resizes and expansions are not repeated (1 frame per pair instead of 2).
+  size_t level_off[16], pyr_px = 0;
+  for (int k = 0; k <= levels; ++k) {
+    level_off[k] = pyr_px * 5;
+    pyr_px += ((size_t)lv[k].w * lv[k].h + 63) & ~(size_t)63;
+  }
+  const bool whole_pyramid = pyr_px <= (size_t)kPyramidRoom * width * height && !getenv("SCN_FLOW_NO_PYRAMID_CACHE");
+  float* Rbuf[2] = {ws.R[0], ws.R[1]};
+  // a caller that keeps the workspace between calls (the OpticalFlow op: one pair per call) says so through `chain`
+  const bool chained = whole_pyramid && reuse_prev && chain && *chain != 0;
+  if (chained) {  // *chain: 1 = the last call's `next` expansion is in ws.R[0], 2 = in ws.R[1]; it is pair 0's `prev`
+    Rbuf[0] = ws.R[*chain - 1];
+    Rbuf[1] = ws.R[2 - *chain];
+  }
+  const int npx = width * height;
+  auto to_gray = [&](const uint8_t* src, float* dst) {
+    LaunchScope ls("flow_gray_kernel", st);
+    gray_kernel<<<(npx + 255) / 256, 256, 0, st>>>(src, npx, dst);
+  };
+  auto build_pyramid = [&](const uint8_t* src, float* R) {
+    to_gray(src, ws.gray[0]);
+    for (int k = levels; k >= 0; --k) expand(ws.gray[0], k, R + level_off[k]);
+  };
+
+  for (int pair = 0; pair < n; ++pair) {
+    if (whole_pyramid) {
+      if (pair > 0 && host_prev_ptrs[pair] == host_next_ptrs[pair - 1]) {
+        float* t = Rbuf[0];
+        Rbuf[0] = Rbuf[1];
+        Rbuf[1] = t;
+      } else if (pair > 0 || !chained) {
+        build_pyramid(host_prev_ptrs[pair], Rbuf[0]);
+      }
+      build_pyramid(host_next_ptrs[pair], Rbuf[1]);
+    } else {
+      to_gray(host_prev_ptrs[pair], ws.gray[0]);
+      to_gray(host_next_ptrs[pair], ws.gray[1]);
     }
     float* prev_flow = nullptr;
     int pw = 0, ph = 0;
@@ -641,60 +828,25 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
         resize_f32_kernel<2><<<grid2(w, h), T, 0, st>>>(prev_flow, pw, ph, flow, w, h, (double)pw / w,
                                                         (double)ph / h, (float)(1. / pyr_scale));
       }
-      GaussK gk;
-      make_gauss(lv[k].smooth, lv[k].sigma, gk);
-      for (int i = 0; i < 2; ++i) {
-        if (use_fused() && gauss_smem(gk.radius) <= kFusedSmemCap) {
-          LaunchScope ls("flow_gauss_fused_kernel", st);
-          const dim3 gg((unsigned)((width + GTW - 1) / GTW), (unsigned)((height + GTH - 1) / GTH));
-          const size_t sm = gauss_smem(gk.radius);
-          // the radii of the reference's pyramid (pyrScale 0.5: ksize 3, 3, 7, 17) are instantiated
-          switch (gk.radius) {
-            case 1: gauss_fused_kernel<1><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
-            case 3: gauss_fused_kernel<3><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
-            case 8: gauss_fused_kernel<8><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
-            default: gauss_fused_kernel<0><<<gg, FT, sm, st>>>(ws.gray[i], width, height, gk, ws.blur); break;
-          }
-        } else {
-          {
-            LaunchScope ls("flow_gauss_h_kernel", st);
-            gauss_h_kernel<<<grid2(width, height), T, 0, st>>>(ws.gray[i], width, height, gk, ws.tmp);
-          }
-          {
-            LaunchScope ls("flow_gauss_v_kernel", st);
-            gauss_v_kernel<<<grid2(width, height), T, 0, st>>>(ws.tmp, width, height, gk, ws.blur);
-          }
-        }
-        const float* I = ws.blur;
-        if (w != width || h != height) {
-          LaunchScope ls("flow_resize_kernel", st);
-          resize_f32_kernel<1><<<grid2(w, h), T, 0, st>>>(ws.blur, width, height, ws.I, w, h, (double)width / w,
-                                                          (double)height / h, 1.f);
-          I = ws.I;
-        }
-        if (use_fused() && poly_smem(pk.n) <= kFusedSmemCap) {
-          LaunchScope ls("flow_poly_fused_kernel", st);
-          const dim3 pg((unsigned)((w + PTW - 1) / PTW), (unsigned)((h + PTH - 1) / PTH));
-          if (pk.n == 5) poly_fused_kernel<5><<<pg, FT, poly_smem(pk.n), st>>>(I, w, h, pk, ws.R[i]);
-          else poly_fused_kernel<0><<<pg, FT, poly_smem(pk.n), st>>>(I, w, h, pk, ws.R[i]);
-        } else {
-          {
-            LaunchScope ls("flow_poly_v_kernel", st);
-            poly_v_kernel<<<grid2(w, h), T, 0, st>>>(I, w, h, pk, ws.poly3);
-          }
-          {
-            LaunchScope ls("flow_poly_h_kernel", st);
-            poly_h_kernel<<<grid2(w, h), T, 0, st>>>(ws.poly3, w, h, pk, ws.R[i]);
-          }
-        }
+      const float *R0 = Rbuf[0], *R1 = Rbuf[1];
+      if (whole_pyramid) {
+        R0 += level_off[k];
+        R1 += level_off[k];
+      } else {
+        expand(ws.gray[0], k, Rbuf[0]);
+        expand(ws.gray[1], k, Rbuf[1]);
       }
       {
         LaunchScope ls("flow_update_matrices_kernel", st);
-        update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(ws.R[0], ws.R[1], flow, w, h, ws.M);
+        update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(R0, R1, flow, w, h, ws.M);
       }
       const int m = win_size / 2;
       for (int it = 0; it < num_iters; ++it) {
-        if (use_fused() && m == kBoxMW && (size_t)w * h * 5 < ((size_t)1 << 31)) {
+        if (use_fused() && !box_in_f64() && m == kBoxMW && (size_t)w * h * 5 < ((size_t)1 << 31)) {
+          LaunchScope ls("flow_box_solve_f32_kernel", st);
+          box_solve_f32_kernel<kBoxMW><<<dim3((unsigned)((w + B32W - 1) / B32W), (unsigned)((h + B32H - 1) / B32H)), FT,
+                                         box32_smem(m), st>>>(ws.M, w, h, 1.0 / ((double)win_size * win_size), flow);
+        } else if (use_fused() && m == kBoxMW && (size_t)w * h * 5 < ((size_t)1 << 31)) {
           LaunchScope ls("flow_box_solve_fused_kernel", st);
           box_solve_fused_kernel<kBoxMW><<<dim3((unsigned)((w + BTW - 1) / BTW), (unsigned)((h + BTH - 1) / BTH)), FT,
                                            box_smem(m), st>>>(ws.M, w, h, 1.0 / ((double)win_size * win_size), flow);
@@ -710,7 +862,7 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
         }
         if (it < num_iters - 1) {
           LaunchScope ls("flow_update_matrices_kernel", st);
-          update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(ws.R[0], ws.R[1], flow, w, h, ws.M);
+          update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(R0, R1, flow, w, h, ws.M);
         }
       }
       prev_flow = flow;
@@ -718,7 +870,11 @@ extern "C" int scn_farneback_u8c3(const uint8_t* const* host_prev_ptrs, const ui
       ph = h;
     }
     int rc = launch_status();
-    if (rc) return rc;
+    if (rc) {
+      if (chain) *chain = 0;
+      return rc;
+    }
   }
+  if (chain) *chain = whole_pyramid ? (Rbuf[1] == ws.R[0] ? 1 : 2) : 0;
   return 0;
 }

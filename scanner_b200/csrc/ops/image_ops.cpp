@@ -344,5 +344,56 @@ REGISTER_KERNEL(ImageDecoder, ImageDecoderKernelGPU)
     .num_devices(1)
     .input_device("img", DeviceType::CPU);
 
+// ---------------------------------------------------------------------------------------------
+// Histogram on a CPU pipeline instance (BASELINE configs[0]: "Histogram op on one 640x480 H.264 clip, CPU
+// pipeline_instances=1 (plumbing, no GPU)").  The reference registers its Histogram kernel for DeviceType::CPU
+// (tests/test_ops.cpp:13-59: cv::calcHist, 16 bins over [0, 256) per channel, int32 counts); this is that kernel
+// without OpenCV: bin = value >> 4.  It is chosen only by a graph that places the op on the CPU -- a GPU
+// placement runs HistogramKernelGPU (stdlib_ops.cu) and fails without CUDA; nothing falls back to this.
+class HistogramKernelCPU : public BatchedKernel {
+ public:
+  HistogramKernelCPU(const KernelConfig& config) : BatchedKernel(config), device_(config.devices[0]) {}
+
+  void execute(const BatchedElements& input_columns, BatchedElements& output_columns) override {
+    const Elements& frames = input_columns[0];
+    const i32 n = (i32)num_rows(frames);
+    if (n == 0) return;
+    constexpr size_t kHistBytes = 3 * 16 * sizeof(i32);
+    u8* block = new_block_buffer_size(device_, kHistBytes, n);
+    for (i32 i = 0; i < n; ++i) {
+      const Frame* f = frames[i].as_const_frame();
+      if (f->layout != FrameLayout::HWC || f->channels() != 3 || (proto::FrameType)f->type != proto::U8)
+        LOG(FATAL) << "Histogram expects HxWx3 uint8 frames, got " << f->height() << "x" << f->width() << "x"
+                   << f->channels();
+      i32* out = reinterpret_cast<i32*>(block + (size_t)i * kHistBytes);
+      // four sub-histograms per channel break the store-to-load chain on runs of equal values
+      i32 part[4][3][16];
+      memset(part, 0, sizeof(part));
+      const u8* p = f->data;
+      const size_t px = (size_t)f->width() * f->height();
+      size_t k = 0;
+      for (; k + 4 <= px; k += 4, p += 12)
+        for (int u = 0; u < 4; ++u) {
+          ++part[u][0][p[3 * u] >> 4];
+          ++part[u][1][p[3 * u + 1] >> 4];
+          ++part[u][2][p[3 * u + 2] >> 4];
+        }
+      for (; k < px; ++k, p += 3) {
+        ++part[0][0][p[0] >> 4];
+        ++part[0][1][p[1] >> 4];
+        ++part[0][2][p[2] >> 4];
+      }
+      for (int c = 0; c < 3; ++c)
+        for (int b = 0; b < 16; ++b) out[c * 16 + b] = part[0][c][b] + part[1][c][b] + part[2][c][b] + part[3][c][b];
+      insert_element(output_columns[0], reinterpret_cast<u8*>(out), kHistBytes);
+    }
+  }
+
+ private:
+  DeviceHandle device_;
+};
+
+REGISTER_KERNEL(Histogram, HistogramKernelCPU).device(DeviceType::CPU).batch(8).num_devices(1);
+
 }  // namespace
 }  // namespace scanner

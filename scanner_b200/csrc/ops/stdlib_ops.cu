@@ -237,9 +237,15 @@ class OpticalFlowKernelGPU : public StenciledKernel, public VideoKernel {
       b = nullptr;
     }
     rgb_of_[0] = rgb_of_[1] = -1;
+    chain_ = 0;
+    last_next_row_ = -1;
   }
 
-  void reset() override { rgb_of_[0] = rgb_of_[1] = -1; }  // row ids identify a frame within one task only
+  void reset() override {  // row ids identify a frame within one task only
+    rgb_of_[0] = rgb_of_[1] = -1;
+    chain_ = 0;
+    last_next_row_ = -1;
+  }
 
   void execute(const StenciledElements& input_columns, Elements& output_columns) override {
     const Elements& window = input_columns[0];
@@ -259,8 +265,12 @@ class OpticalFlowKernelGPU : public StenciledKernel, public VideoKernel {
     const u8* prev = is_nv12(f0) ? rgb_of(f0, window[0].index, w, h) : f0->data;
     const u8* next = is_nv12(f1) ? rgb_of(f1, window[1].index, w, h) : f1->data;
     float* flow = reinterpret_cast<float*>(out->data);
-    SCN_CHECK(scn_farneback_u8c3(&prev, &next, 1, w, h, &flow, 3, 0.5, 15, 3, 5, 1.2, workspace_, workspace_bytes_,
-                                 device_stream(device_)));
+    // rows are walked in order: the `next` frame of the last window is this window's `prev` (same input row), and
+    // its pyramid of polynomial expansions is still in the workspace
+    const int reuse = window[0].index >= 0 && window[0].index == last_next_row_;
+    SCN_CHECK(scn_farneback_u8c3_chain(&prev, &next, 1, w, h, &flow, 3, 0.5, 15, 3, 5, 1.2, workspace_,
+                                       workspace_bytes_, reuse, &chain_, device_stream(device_)));
+    last_next_row_ = window[1].index;
     insert_frame(output_columns[0], out);
   }
 
@@ -289,6 +299,8 @@ class OpticalFlowKernelGPU : public StenciledKernel, public VideoKernel {
   u8* rgb_[2] = {nullptr, nullptr};          // RGB24 copies of the window's NV12 elements
   i64 rgb_of_[2] = {-1, -1};                 // input row (Element::index) each holds
   int last_used_ = 1;
+  int chain_ = 0;                            // scn_farneback_u8c3_chain state of workspace_
+  i64 last_next_row_ = -1;                   // input row whose expansion the workspace holds
 };
 
 REGISTER_OP(OpticalFlow).frame_input("frame").frame_output("flow").stencil({0, 1});

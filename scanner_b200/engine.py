@@ -58,6 +58,7 @@ SIGNATURES = {
     "scn_engine_stats_json": (_I, [_VP, _CP, _SZ]),
     "scn_h264_synth": (_I64, [_VP, _I, _I, _I64, _I, _I, _VP, _SZ]),
     "scn_nvdec_caps": (_I, [_I, _IP]),
+    "scn_swdec_caps": (_I, [_IP]),
     "scn_graph_add_slice": (_I, [_VP, _I, _CP]),
     "scn_graph_add_unslice": (_I, [_VP, _I, _CP]),
     "scn_job_set_partitioner": (_I, [_VP, _I, _CP, _VP, _SZ]),
@@ -107,6 +108,10 @@ def lib():
         if not os.path.exists(ENGINE_PATH):
             raise EngineError(f"{ENGINE_PATH} not found: run __graft_entry__.build()")
         cabi.lib()  # the engine links libscn_kernels.so
+        if "SCN_FFMPEG_DIR" not in os.environ:  # where CPU instances find libavcodec (swdec.h); unused by GPU instances
+            d = _default_ffmpeg_dir()
+            if d:
+                os.environ["SCN_FFMPEG_DIR"] = d
         l = ctypes.CDLL(ENGINE_PATH, mode=ctypes.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
@@ -150,6 +155,31 @@ def list_ops():
                       unbounded=bool(int(ub)), warmup=int(w), protobuf_name=names[0] if names else "",
                       stream_protobuf_name=names[1] if len(names) > 1 else "")
     return out
+
+
+def _default_ffmpeg_dir():
+    """The FFmpeg build this image ships: inside the opencv-python-headless wheel (no system libavcodec here).
+    Only a path is computed -- cv2 is not imported."""
+    import importlib.util
+    spec = importlib.util.find_spec("cv2")
+    if not spec or not spec.origin:
+        return None
+    site = os.path.dirname(os.path.dirname(spec.origin))
+    for name in ("opencv_python_headless.libs", "opencv_python.libs", "opencv_contrib_python_headless.libs"):
+        d = os.path.join(site, name)
+        if os.path.isdir(d) and any(f.startswith("libavcodec") for f in os.listdir(d)):
+            return d
+    return None
+
+
+def swdec_caps():
+    """Software (CPU instance) H.264 decoder: FFmpeg libraries found and their majors.  SCN_FFMPEG_DIR selects the
+    directory; when it is unset and the image's OpenCV wheel bundles FFmpeg, that copy is used."""
+    info = (ctypes.c_int * 4)()
+    lib().scn_swdec_caps(info)
+    d = dict(zip(["available", "avcodec", "avutil", "swscale"], list(info)))
+    d["where" if d["available"] else "error"] = last_error()
+    return d
 
 
 def nvdec_caps(gpu=0):

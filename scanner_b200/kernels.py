@@ -154,6 +154,31 @@ def nv12_hist_resize(surfaces, width, height, dst_w, dst_h, plan=None, want_resi
     return hist, res
 
 
+def optical_flow_sequence(frames, workspace=None, pairs_per_call=None):
+    """Flow of every consecutive pair of a clip: (N,H,W,3) uint8 -> (N-1,H,W,2) float32.  Every frame is expanded
+    once (scn_farneback_u8c3_chain); pairs_per_call splits the clip over several calls on one workspace, the way
+    the OpticalFlow op walks it."""
+    _need_cuda(frames)
+    frames = frames.contiguous()
+    n, h, w, _ = frames.shape
+    out = torch.empty((max(n - 1, 0), h, w, 2), dtype=torch.float32, device=frames.device)
+    need = cabi.lib().scn_farneback_workspace_bytes(w, h)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=frames.device)
+    fb = h * w * 3
+    chain = ctypes.c_int(0)
+    step = pairs_per_call or max(n - 1, 1)
+    for p0 in range(0, n - 1, step):
+        m = min(step, n - 1 - p0)
+        pp, k1 = cabi.ptr_array([frames.data_ptr() + (p0 + i) * fb for i in range(m)])
+        np_, k2 = cabi.ptr_array([frames.data_ptr() + (p0 + i + 1) * fb for i in range(m)])
+        op, k3 = cabi.ptr_array([out.data_ptr() + (p0 + i) * h * w * 8 for i in range(m)])
+        rc = cabi.lib().scn_farneback_u8c3_chain(pp, np_, m, w, h, op, 3, 0.5, 15, 3, 5, 1.2, workspace.data_ptr(),
+                                                 workspace.numel(), 1, ctypes.byref(chain), _stream())
+        cabi.check(rc, "scn_farneback_u8c3_chain")
+    return out
+
+
 def optical_flow(prev_frames, next_frames, num_levels=3, pyr_scale=0.5, win_size=15, num_iters=3, poly_n=5,
                  poly_sigma=1.2, workspace=None):
     """Farneback flow of n frame pairs: (N,H,W,3) uint8 x2 -> (N,H,W,2) float32 (reference OpticalFlow op)."""

@@ -339,18 +339,98 @@ def test_frame_stencil_0_1_row_counts(eng):
         assert got == want
 
 
-def test_h264_needs_gpu_instance_no_software_fallback(eng):
-    yuv = np.random.default_rng(0).integers(16, 235, (4, 48 * 64 * 3 // 2), dtype=np.uint8)
-    data = E.h264_synth(yuv, 64, 48, gop=2)
-    sid = eng.add_h264(data)
-    assert eng.stream_rows(sid) == 4 and eng.stream_info(sid)["keyframes"] == 2
+def _cv2_rgb_frames(path):
+    import cv2
+    cap = cv2.VideoCapture(path)
+    out = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            return out
+        out.append(f[..., ::-1].copy())
+
+
+def test_config0_as_stated_h264_clip_histogram_on_a_cpu_instance(tmp_path):
+    """BASELINE configs[0] as written: Histogram on one 640x480 H.264 clip, CPU pipeline_instances=1, no GPU.
+    The CPU instance decodes with libavcodec + libswscale (swdec.h -- what the reference's SoftwareVideoDecoder
+    is), so the frames must equal what FFmpeg gives through an independent caller (cv2.VideoCapture, BGR
+    swapped); the op is the stdlib Histogram placed on the CPU.  The stream has Intra16x16/CAVLC key pictures
+    and motion-compensated P pictures (scanner_b200/synth_h264.py)."""
+    from scanner_b200 import synth_h264
+    caps = E.swdec_caps()
+    assert caps["available"], caps
+    n = 24
+    data, _ = synth_h264.write(640, 480, n, gop=8, seed=5)
+    path = str(tmp_path / "clip.h264")
+    open(path, "wb").write(data)
+    want = _cv2_rgb_frames(path)
+    assert len(want) == n
+    E.load_stdlib()
+    e1 = E.Engine(gpus=[], cpu_instances=1)
+    sid = e1.add_h264(data)
     g = E.Graph()
     src = g.add_source(True)
-    g.add_sink((g.add_op("TestHistogramOracle", [(src, "frame")]), "histogram"))
+    hs = g.add_op("Histogram", [(src, "frame")], device=0)
+    s_h, s_f = g.add_sink((hs, "histogram")), g.add_sink((src, "frame"))
     j = E.Job()
     j.bind_source(src, sid)
-    with pytest.raises(E.EngineError, match="NVDEC"):
-        eng.run(g, [j], 2, 2)
+    e1.run(g, [j], 5, 10, str(tmp_path))
+    hist = j.output_array(s_h, 192, np.int32).reshape(n, 3, 16)
+    for i in range(n):
+        got = j.output_row(s_f, i)
+        assert got.shape == (480, 640, 3) and (got == want[i]).all(), i
+        assert (hist[i] == oracle.hist16(want[i])).all(), i
+    st = e1.stats()["counters"]
+    # tasks of 10 rows over GOPs of 8: tasks 1 and 2 start inside a GOP and decode from its key picture (2 + 4 extra)
+    assert st["frames_used"] == n and st["frames_decoded"] == n + 6
+    e1.close()
+
+
+@pytest.mark.parametrize("mode,gop", [("pcm", 4), ("skip", 5), ("bidir", 6)])
+def test_cpu_instance_decodes_sampled_rows_of_every_stream_kind(tmp_path, mode, gop):
+    """Gather over keyframe intervals on the software path: only the intervals that hold wanted rows are fed, B
+    pictures come out in display order (reference DecoderAutomata + SoftwareVideoDecoder semantics)."""
+    n, h, w = 23, 48, 64
+    rng = np.random.default_rng(21)
+    k = n if mode == "pcm" else (n + gop - 1) // gop if mode == "skip" else n
+    yuv = rng.integers(0, 256, (k, h * w * 3 // 2), dtype=np.uint8)
+    data = E.h264_synth(yuv, w, h, gop=gop, non_key=mode, frames=n)
+    path = str(tmp_path / "s.h264")
+    open(path, "wb").write(data)
+    want = _cv2_rgb_frames(path)
+    assert len(want) == n
+    e1 = E.Engine(gpus=[], cpu_instances=2)
+    sid = e1.add_h264(data)
+    g = E.Graph()
+    src = g.add_source(True)
+    samp = g.add_sample((src, "frame"))
+    sink = g.add_sink((samp, "frame"))
+    rows = [0, 3, 4, 11, 17, 22]
+    j = E.Job()
+    j.bind_source(src, sid)
+    j.set_sampler(samp, "Gather", protolite.encode(protolite.SAMPLER_ARGS["GatherSamplerArgs"], {"rows": rows}))
+    e1.run(g, [j], 2, 4)
+    for i, r in enumerate(rows):
+        assert (j.output_row(sink, i) == want[r]).all(), (mode, r)
+    assert e1.stats()["counters"]["frames_decoded"] < n or mode == "bidir" or gop >= n
+    e1.close()
+
+
+def test_cpu_instance_says_why_when_no_ffmpeg_can_be_loaded(tmp_path):
+    """No silent path: without libavcodec an H.264 source on a CPU instance is an error naming the cause."""
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, '.');"
+        "from scanner_b200 import engine as E;"
+        "yuv = np.zeros((2, 48 * 64 * 3 // 2), np.uint8);"
+        "e = E.Engine(gpus=[], cpu_instances=1); sid = e.add_h264(E.h264_synth(yuv, 64, 48, gop=2));"
+        "g = E.Graph(); src = g.add_source(True); g.add_sink((src, 'frame'));"
+        "j = E.Job(); j.bind_source(src, sid);"
+        "\ntry:\n    e.run(g, [j], 2, 2)\n    print('RAN')\nexcept E.EngineError as x:\n    print('ERR', x)")
+    empty = tmp_path / "nothing"
+    empty.mkdir()
+    out = subprocess.run([os.sys.executable, "-c", code], env=dict(os.environ, SCN_FFMPEG_DIR=str(empty)),
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), capture_output=True, text=True)
+    assert "ERR" in out.stdout and "software H.264 decoder unavailable" in out.stdout, out.stdout + out.stderr
 
 
 def test_trace_file_has_one_event_per_interval_and_instance_ids(eng, tmp_path):

@@ -42,6 +42,27 @@ def test_flow_vs_cv2_golden(golden_dir):
             assert d.mean() <= 1e-3 and np.quantile(d, 0.999) <= 5e-2, (k, d.max(), d.mean())
 
 
+def test_flow_1080p_vs_cv2_and_the_oracle():
+    """configs[3]'s size.  cv2 (the library the reference's op calls, optical_flow_kernel_cpu.cpp:27-47 /
+    tests/test_ops.cpp:68-94) is run HERE on the same pair, so this is a direct comparison, not a stored golden;
+    the oracle is run beside it so its own distance to cv2 at this size is on record too.
+    Tolerance (float32 sums in another order): max |d| <= 2e-3 px, mean |d| <= 1e-4 px, both against cv2."""
+    import cv2
+    a, b = synth.flow_pair(941, 1080, 1920, "shift")
+    got = kernels.optical_flow(dev(a[None]), dev(b[None]))[0].cpu().numpy()
+    g0, g1 = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY), cv2.cvtColor(b, cv2.COLOR_BGR2GRAY)
+    ref = cv2.FarnebackOpticalFlow_create(3, 0.5, False, 15, 3, 5, 1.2, 0).calc(g0, g1, None)
+    d = np.abs(got - ref)
+    assert d.max() <= 2e-3 and d.mean() <= 1e-4, (d.max(), d.mean())
+    want = oracle.optical_flow(a, b)
+    assert np.abs(want - ref).max() <= 1e-3                 # the oracle's own pin at this size
+    assert np.abs(got - want).max() <= 2e-3
+    # all three agree on a field that follows the synthetic motion (1.5, -0.75) (3 levels x 3 iterations
+    # under-estimate it: cv2 itself gives a median of (1.13, -0.56))
+    med = np.median(got[200:-200, 200:-200].reshape(-1, 2), axis=0)
+    assert 1.0 < med[0] < 1.6 and -0.8 < med[1] < -0.5, med
+
+
 def test_flow_batch_and_identity():
     frames = np.stack([synth.flow_pair(700, 96, 128, "shift")[i] for i in (0, 1, 0)])
     out = kernels.optical_flow(dev(frames[:2]), dev(frames[1:])).cpu().numpy()
@@ -78,6 +99,46 @@ def test_optical_flow_op_stencil_through_the_engine():
     eng.close()
 
 
+def test_sequence_reuses_every_frames_expansion_and_changes_nothing():
+    """scn_farneback_u8c3_chain: walking a clip pair by pair (one call, several calls, one pair per call like the
+    op) gives the bits of independent pairs; sizes include one whose pyramid stops early (40 x 70: 1 level)."""
+    for (n, h, w) in [(6, 96, 128), (4, 40, 70), (3, 270, 480)]:
+        a, b = synth.flow_pair(810 + h, h, w, "shift")
+        rng = np.random.default_rng(h)
+        frames = np.stack([a, b] + [np.roll(a, (i, 2 * i), (0, 1)) + rng.integers(0, 2, a.shape, dtype=np.uint8)
+                                    for i in range(1, n - 1)])
+        d = dev(frames)
+        want = kernels.optical_flow(d[:-1], d[1:])
+        for step in (None, 2, 1):
+            got = kernels.optical_flow_sequence(d, pairs_per_call=step)
+            assert torch.equal(got, want), (n, h, w, step)
+
+
+def test_float_window_sums_stay_close_to_the_double_ones():
+    """box_solve_f32_kernel (default) against SCN_FLOW_BOX=f64 on the same pairs: the 2x2 solve stays in double,
+    the 15 x 15 sums are float32 trees.  Stated: max |d| <= 5e-4 px on smooth motion."""
+    import subprocess
+    import sys
+    import tempfile
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, '.');"
+        "from scanner_b200 import kernels; from oracle import synth;"
+        "outs = [];"
+        "\nfor (h, w) in [(270, 480), (1080, 1920)]:"
+        "\n    a, b = synth.flow_pair(77 + h, h, w, 'shift')"
+        "\n    outs.append(kernels.optical_flow(torch.from_numpy(a[None]).cuda(), torch.from_numpy(b[None]).cuda()).cpu().numpy())"
+        "\nnp.savez(sys.argv[1], *outs)")
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ("f32", "f64"):
+            subprocess.check_call([sys.executable, "-c", code, os.path.join(d, mode + ".npz")],
+                                  env=dict(os.environ, SCN_FLOW_BOX=mode),
+                                  cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        f, g = np.load(os.path.join(d, "f32.npz")), np.load(os.path.join(d, "f64.npz"))
+        for k in f.files:
+            dd = np.abs(f[k] - g[k])
+            assert 0 < dd.max() <= 5e-4 and dd.mean() <= 2e-5, (k, dd.max(), dd.mean())
+
+
 def test_fused_tiled_kernels_equal_the_two_pass_kernels_bit_for_bit():
     """The shared-memory tiled Gaussian / polynomial-expansion / box+solve kernels keep the summation
     order of the per-row two-pass kernels (SCN_FLOW_UNFUSED=1): same bits, including at image borders
@@ -97,7 +158,7 @@ def test_fused_tiled_kernels_equal_the_two_pass_kernels_bit_for_bit():
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         for mode, name in (("0", "fused.npz"), ("1", "unfused.npz")):
-            env = dict(os.environ, SCN_FLOW_UNFUSED=mode)
+            env = dict(os.environ, SCN_FLOW_UNFUSED=mode, SCN_FLOW_BOX="f64")   # the double box kernel keeps the order
             subprocess.check_call([sys.executable, "-c", code, os.path.join(d, name)], env=env,
                                   cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         f, u = np.load(os.path.join(d, "fused.npz")), np.load(os.path.join(d, "unfused.npz"))

@@ -118,6 +118,17 @@ def test_flow_matches_cv2_golden(golden_dir):
             assert 0.5 < inner[0] < 2.0 and -1.2 < inner[1] < -0.2, inner
 
 
+def test_flow_1080p_matches_cv2_run_here():
+    """configs[3]'s frame size, against cv2 itself (no stored golden: 16 MB of floats): max |d| <= 1e-4 px
+    (measured 3.8e-5)."""
+    import cv2
+    a, b = synth.flow_pair(941, 1080, 1920, "shift")
+    g0, g1 = cv2.cvtColor(a, cv2.COLOR_BGR2GRAY), cv2.cvtColor(b, cv2.COLOR_BGR2GRAY)
+    assert (oracle.bgr2gray(a) == g0).all()
+    ref = cv2.FarnebackOpticalFlow_create(3, 0.5, False, 15, 3, 5, 1.2, 0).calc(g0, g1, None)
+    assert np.abs(oracle.optical_flow(a, b) - ref).max() <= 1e-4
+
+
 def test_nv12_matches_the_reference_kernels_own_output(golden_dir):
     """tests/golden/nv12_ref.npz holds what the reference's OWN kernel (scanner/util/image.cu compiled
     unmodified, oracle/_ref) produced on a B200 (oracle/make_golden_ref.py): seeded surfaces, and the

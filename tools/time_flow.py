@@ -24,6 +24,15 @@ for _ in range(5):
 e1.record()
 torch.cuda.synchronize()
 print("ms per pair (no profiling):", e0.elapsed_time(e1) / 5 / n)
+seq = torch.cat([a, a[:1]])
+for _ in range(2):
+    kernels.optical_flow_sequence(seq)
+e0.record()
+for _ in range(5):
+    kernels.optical_flow_sequence(seq)
+e1.record()
+torch.cuda.synchronize()
+print("ms per pair, consecutive pairs of one clip (each frame expanded once):", e0.elapsed_time(e1) / 5 / n)
 L.scn_prof_enable(1)
 for _ in range(3):
     kernels.optical_flow(a, b)
