@@ -182,6 +182,28 @@ def _load_ints(stream):
     return [struct.unpack("<q", r)[0] for r in stream.load()]
 
 
+def test_reference_tutorial_00_on_the_cpu_with_a_real_video(tmp_path):
+    """examples/tutorials/00_basic.py of the reference with device=CPU: ingest an .mp4, Histogram every frame, load
+    the rows.  No GPU anywhere: the CPU instance decodes with FFmpeg (swdec.h) and runs the CPU Histogram kernel."""
+    import cv2
+    from scanner_b200 import synth_h264
+    from scanner_b200.client import Client, DeviceType, NamedStream, NamedVideoStream, PerfParams
+    data, _ = synth_h264.write(320, 240, 20, gop=5, seed=1)
+    mp4 = str(tmp_path / "a.mp4")
+    open(mp4, "wb").write(E.mp4_mux(data, 30, 1))
+    cl = Client(db_path=str(tmp_path / "db"))
+    frames = cl.io.Input([NamedVideoStream(cl, "clip", path=mp4)])
+    hist = cl.ops.Histogram(frame=frames, device=DeviceType.CPU)
+    out = NamedStream(cl, "hists")
+    cl.run(cl.io.Output(hist, [out]), PerfParams.manual(5, 10))
+    rows = list(out.load())
+    cap = cv2.VideoCapture(mp4)
+    assert len(rows) == 20
+    for r in rows:
+        ok, f = cap.read()
+        assert ok and (np.asarray(r).reshape(3, 16) == oracle.hist16(np.ascontiguousarray(f[..., ::-1]))).all()
+
+
 def test_slice_unslice_keeps_every_row(sc):
     """reference tests/py_test.py:350-358 test_slice: Slice(all(50)) -> Unslice gives the input back."""
     src = _ints(sc, "slice_in", 130)
