@@ -10,9 +10,13 @@
 //                 shifts), summed as packed u16x2 lanes; the vertical pass is a 3-row sliding sum
 //                 held in registers; /9 is an exact multiply-shift; four results are stored as one
 //                 32-bit word.  No shared memory: neighbouring threads' loads overlap in L1.
-//   box_stream_kernel    any kernel_size 2..31 on 16-byte aligned rows: bulk-async (cp.async.bulk + mbarrier) row
+//   box_packed_kernel<K> kernel_size 2..16 on 16-byte aligned rows (every BASELINE frame size): u16x2 lanes, running
+//                 vertical sums, 128-bit loads two rows ahead; 3.9 TB/s at K = 3 (60 % of the copy peak), > 3 TB/s to K = 9.
+//   box_stream_kernel    kernel_size 17..31 on 16-byte aligned rows: bulk-async (cp.async.bulk + mbarrier) row
 //                 ring, sliding horizontal sums, running vertical sums: O(1) work per sample.
 //   box_generic_kernel   the rest (unaligned or tiny frames, kernel_size 1): shared-memory tile, direct sums.
+#include <string.h>
+
 #include "scn_common.cuh"
 
 namespace scn {
@@ -61,26 +65,45 @@ box3_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int words_per_
     const int px = (wx * 4 + b) / 3;
     if (px >= 1 && px <= width - 2) xmask |= 0xFFu << (8 * b);
   }
-  const bool has_m = wx > 0, has_p = wx + 1 < words_per_row;
-
-  auto load_h = [&](int y) -> H3 {
-    H3 h{0u, 0u};
-    if (y >= 0 && y < height) {
-      const uint32_t* row = s + (size_t)y * words_per_row + wx;
-      const uint32_t w0 = __ldg(row);
-      const uint32_t wm = has_m ? __ldg(row - 1) : 0u;
-      const uint32_t wp = has_p ? __ldg(row + 1) : 0u;
-      h = hsum3(wm, w0, wp);
-    }
-    return h;
+  // Loads never branch: a word left of the row / right of it / a row above or below the frame only ever feeds
+  // outputs that are border samples (masked to 0 below), so the index is clamped instead of the value zeroed.
+  const int wm_off = wx > 0 ? -1 : 0, wp_off = wx + 1 < words_per_row ? 1 : 0;
+  struct Raw {
+    uint32_t m, c, p;
   };
-
-  H3 a = load_h(y0 - 1), b = load_h(y0);
-  for (int y = y0; y < y1; ++y) {
-    const H3 c = load_h(y + 1);
+  auto load_raw = [&](int y) -> Raw {
+    const uint32_t* row = s + (size_t)min(max(y, 0), height - 1) * words_per_row + wx;
+    return Raw{__ldg(row + wm_off), __ldg(row), __ldg(row + wp_off)};
+  };
+  auto emit = [&](int y, const H3& a, const H3& b, const H3& c) {
     uint32_t out = 0;
     if (y >= 1 && y <= height - 2) out = div9_pack(a.even + b.even + c.even, a.odd + b.odd + c.odd) & xmask;
     d[(size_t)y * words_per_row + wx] = out;
+  };
+
+  // The kernel is latency-bound when a thread has one row (3 words) in flight: 64 warps x 128 B = 8 KB per SM
+  // against the ~35 KB that 6.5 TB/s x ~0.8 us need (r01: 43 % of the copy peak).  Four rows are requested before
+  // the first is consumed.
+  Raw ra = load_raw(y0 - 1), rb = load_raw(y0);
+  H3 a = hsum3(ra.m, ra.c, ra.p), b = hsum3(rb.m, rb.c, rb.p);
+  int y = y0;
+  for (; y + 4 <= y1; y += 4) {
+    const Raw r0 = load_raw(y + 1), r1 = load_raw(y + 2), r2 = load_raw(y + 3), r3 = load_raw(y + 4);
+    const H3 c0 = hsum3(r0.m, r0.c, r0.p);
+    emit(y, a, b, c0);
+    const H3 c1 = hsum3(r1.m, r1.c, r1.p);
+    emit(y + 1, b, c0, c1);
+    const H3 c2 = hsum3(r2.m, r2.c, r2.p);
+    emit(y + 2, c0, c1, c2);
+    const H3 c3 = hsum3(r3.m, r3.c, r3.p);
+    emit(y + 3, c1, c2, c3);
+    a = c2;
+    b = c3;
+  }
+  for (; y < y1; ++y) {
+    const Raw r = load_raw(y + 1);
+    const H3 c = hsum3(r.m, r.c, r.p);
+    emit(y, a, b, c);
     a = b;
     b = c;
   }
@@ -302,6 +325,148 @@ box_stream_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int fl, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// box_packed_kernel<K>: kernel_size 2..16 on 16-byte aligned rows, all arithmetic on packed u16x2 lanes.
+//   * a thread owns one 16-byte column (a "quad": 4 words) and walks down a strip of rows; a warp owns 32
+//     neighbouring quads of which the R on each side are halo (R = 1 for K <= 11, else 2);
+//   * vertical first: running column sums  acc += row(r) - row(r - K)  with the bytes of a word split into its even
+//     (0, 2) and odd (1, 3) bytes as u16 lanes -- one IADD3 adds the entering and subtracts the leaving row for two
+//     byte columns (lanes cannot borrow: the true lane values stay in [0, 255 K]).  Both rows come by 128-bit loads
+//     (the leaving row from L2), requested one iteration ahead;
+//   * the warp publishes its 32 x 8 lane-words to its own shared-memory row (double-buffered, __syncwarp only) and
+//     every thread reads its neighbours' (2R + 1) quads back with 128-bit loads;
+//   * horizontal: the window of the byte pair (b, b + 2) is K terms 3 bytes apart; a term is, depending on its byte
+//     offset mod 4, an even-lane word, an odd-lane word, or one of those shifted by one lane into the next word
+//     (funnel shift, computed once per word and shared by all outputs): (K - 1) / 2 IADD3 per pair, every index a
+//     compile-time constant.  Lane sums stay below 255 K^2 <= 65280;
+//   * out = sum / K^2 by the exact multiply-shift, border samples masked to 0, one 128-bit store per thread.
+// ~6-12 instructions per byte (K = 3..15) where box_stream_kernel spends 15 and more on byte loads.
+constexpr int BP_WARPS = 4;
+template <int K>
+struct PackedGeom {
+  static constexpr int fl = (K + 1) / 2 - 1, fr = K / 2;
+  static constexpr int R = (3 * fr + 15) / 16;       // halo quads on each side of a thread's quad
+  static constexpr int NW = 4 * (2 * R + 1);         // lane-words a thread reads back
+  static constexpr int OUT_QUADS = 32 - 2 * R;       // output quads per warp
+};
+
+template <int K>
+__global__ void __launch_bounds__(BP_WARPS * 32)
+box_packed_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int rows_per_strip, uint32_t div_magic) {
+  using G = PackedGeom<K>;
+  constexpr int fl = G::fl, fr = G::fr, R = G::R, NW = G::NW;
+  __shared__ __align__(16) uint4 vbuf[BP_WARPS][2][2][32];  // [warp][parity][even / odd lanes][quad]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quads = width * 3 / 16;
+  const int q_out = (blockIdx.x * BP_WARPS + warp) * G::OUT_QUADS + lane - R;  // the quad this lane would output
+  if ((blockIdx.x * BP_WARPS + warp) * G::OUT_QUADS >= quads) return;           // whole warp beyond the row
+  const int q_ld = min(max(q_out, 0), quads - 1);   // clamped: a duplicate only ever feeds border samples
+  const bool writes = lane >= R && lane < 32 - R && q_out < quads;
+  const uint4* __restrict__ s = reinterpret_cast<const uint4*>(src.p[blockIdx.z]) + q_ld;
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst.p[blockIdx.z]) + q_ld;
+  const int y0 = blockIdx.y * rows_per_strip, y1 = min(height, y0 + rows_per_strip);
+  // byte masks of the x-interior samples of this quad
+  uint32_t xmask[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    xmask[w] = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int px = (q_ld * 16 + w * 4 + b) / 3;
+      if (px >= fl && px < width - fr) xmask[w] |= 0xFFu << (8 * b);
+    }
+  }
+  uint32_t accE[4] = {0, 0, 0, 0}, accO[4] = {0, 0, 0, 0};
+  const int r_first = y0 - fl, r_last = y1 + fr;  // input rows [r_first, r_last)
+  // Rows outside the frame count as zero (they only reach border outputs), so the row pointer simply advances by one
+  // row per step and the loads are predicated on the (warp-uniform) row number; the leaving row is K rows behind.
+  // running pointers: pn = the row the next load_rows() call reads, po = K rows behind it, pd = the next output row
+  const uint4* pn = s + (ptrdiff_t)r_first * quads;
+  const uint4* po = pn - (ptrdiff_t)K * quads;
+  uint4* pd = d + (ptrdiff_t)y0 * quads;
+  int r_ld = r_first;
+  auto load_rows = [&](uint4& nw, uint4& od) {  // rows r_ld and r_ld - K (the latter once the window is full)
+    const int ro = r_ld - K;
+    nw = r_ld < r_last && r_ld >= 0 && r_ld < height ? __ldg(pn) : make_uint4(0, 0, 0, 0);
+    od = r_ld < r_last && ro >= r_first && ro >= 0 && ro < height ? __ldg(po) : make_uint4(0, 0, 0, 0);
+    pn += quads;
+    po += quads;
+    ++r_ld;
+  };
+  uint4* const my_e = &vbuf[warp][0][0][lane];  // + 64 uint4 for the odd lanes, + 128 for the other parity
+  const uint4* const nb = my_e - R;
+
+  auto process = [&](int r, const uint4& nw, const uint4& od) {
+    const uint32_t n4[4] = {nw.x, nw.y, nw.z, nw.w}, o4[4] = {od.x, od.y, od.z, od.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      accE[w] = accE[w] + (n4[w] & 0x00FF00FFu) - (o4[w] & 0x00FF00FFu);
+      accO[w] = accO[w] + prmt(n4[w], 0u, 0x4341u) - prmt(o4[w], 0u, 0x4341u);
+    }
+    const int y = r - fr;
+    if (y < y0) return;  // warp-uniform
+    const int par = (y & 1) * 64;
+    my_e[par] = make_uint4(accE[0], accE[1], accE[2], accE[3]);
+    my_e[par + 32] = make_uint4(accO[0], accO[1], accO[2], accO[3]);
+    __syncwarp();
+    if (writes) {
+      uint4 out = make_uint4(0, 0, 0, 0);
+      if (y >= fl && y < height - fr) {
+        // lane-words of quads lane - R .. lane + R: index 4 * R + i = word i of the own quad
+        uint32_t VE[NW], VO[NW];
+#pragma unroll
+        for (int k = 0; k < 2 * R + 1; ++k) {
+          const uint4 e = nb[par + k], o = nb[par + 32 + k];
+          VE[4 * k] = e.x, VE[4 * k + 1] = e.y, VE[4 * k + 2] = e.z, VE[4 * k + 3] = e.w;
+          VO[4 * k] = o.x, VO[4 * k + 1] = o.y, VO[4 * k + 2] = o.z, VO[4 * k + 3] = o.w;
+        }
+        // streams shifted by one lane: (hi of word i, lo of word i + 1)
+        uint32_t SE[NW - 1], SO[NW - 1];
+#pragma unroll
+        for (int i = 0; i < NW - 1; ++i) {
+          SE[i] = __funnelshift_r(VE[i], VE[i + 1], 16);
+          SO[i] = __funnelshift_r(VO[i], VO[i + 1], 16);
+        }
+        uint32_t ow[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          uint32_t he = 0, ho = 0;  // pairs (byte 0, byte 2) and (byte 1, byte 3) of word w
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            // first byte of the pair's term j, relative to the own quad's byte 0, offset so that it is >= 0
+            const int te = 16 * R + 4 * w + 3 * (j - fl), to = te + 1;
+            const int we = te >> 2, wo = to >> 2;
+            he += (te & 3) == 0 ? VE[we] : (te & 3) == 1 ? VO[we] : (te & 3) == 2 ? SE[we] : SO[we];
+            ho += (to & 3) == 0 ? VE[wo] : (to & 3) == 1 ? VO[wo] : (to & 3) == 2 ? SE[wo] : SO[wo];
+          }
+          const uint32_t e0 = __umulhi(he & 0xFFFFu, div_magic), e1 = __umulhi(he >> 16, div_magic);
+          const uint32_t o0 = __umulhi(ho & 0xFFFFu, div_magic), o1 = __umulhi(ho >> 16, div_magic);
+          // quotients are < 256: byte 1 of each is zero and serves as the zero source of the packing
+          ow[w] = prmt(prmt(e0, o0, 0x1140u), prmt(e1, o1, 0x1140u), 0x5410u) & xmask[w];
+        }
+        out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      *pd = out;
+    }
+    pd += quads;
+  };
+
+  // two rows per iteration, each row's loads requested one step ahead (no register rotation)
+  // three rows per iteration, every row's two loads requested two rows ahead of their use (three register sets, no
+  // rotation): with one row ahead the kernel sat at ~53 % of the copy peak for every K <= 9 -- latency, not issue
+  uint4 nA, oA, nB, oB, nC, oC;
+  load_rows(nA, oA);
+  load_rows(nB, oB);
+  for (int r = r_first; r < r_last; r += 3) {
+    load_rows(nC, oC);
+    process(r, nA, oA);
+    load_rows(nA, oA);
+    if (r + 1 < r_last) process(r + 1, nB, oB);
+    load_rows(nB, oB);
+    if (r + 2 < r_last) process(r + 2, nC, oC);
+  }
+}
+
 int launch_blur(const uint8_t* const* sp, int n, int width, int height, int ksize,
                 uint8_t* const* dp, cudaStream_t st) {
   if (n < 0 || width <= 0 || height <= 0 || ksize < 1 || ksize > KMAX) return SCN_E_BADARG;
@@ -337,7 +502,32 @@ int launch_blur(const uint8_t* const* sp, int n, int width, int height, int ksiz
       const char* e = getenv("SCN_BLUR3");
       return e && e[0] == 's';  // SCN_BLUR3=stream: kernel_size 3 through the streaming kernel too (measurement switch)
     }();
-    if (aligned16 && k >= 2 && (ksize != 3 || stream3)) {
+    // SCN_BLUR_PATH=stream keeps kernel sizes 2..16 on the byte-wise streaming kernel; =box3 keeps kernel_size 3 on
+    // box3_kernel even when the rows are 16-byte aligned (measurement switches)
+    static const int path = [] {
+      const char* e = getenv("SCN_BLUR_PATH");
+      return !e ? 0 : strcmp(e, "stream") == 0 ? 1 : strcmp(e, "box3") == 0 ? 2 : 0;
+    }();
+    if (aligned16 && k >= 2 && k <= 16 && path != 1 && (ksize != 3 || path != 2)) {
+      const unsigned d2 = (unsigned)(k * k);
+      const uint32_t magic = (uint32_t)((1ull << 32) / d2) + 1u;
+      const int quads = width * 3 / 16;
+      const int out_quads = 32 - 2 * ((3 * fr + 15) / 16);
+      const unsigned gx = (unsigned)((quads + out_quads * BP_WARPS - 1) / (out_quads * BP_WARPS));
+      // rows per strip: a strip re-reads k - 1 rows of its neighbour; shorter strips when the grid would not fill the GPU
+      int rows = 128;
+      while (rows > 32 && (size_t)gx * ((height + rows - 1) / rows) * cnt < 2 * 148) rows >>= 1;
+      dim3 grid(gx, (unsigned)((height + rows - 1) / rows), (unsigned)cnt);
+      LaunchScope ls("box_packed_kernel", st);
+      switch (k) {
+#define SCN_BP_CASE(KK) \
+  case KK: box_packed_kernel<KK><<<grid, BP_WARPS * 32, 0, st>>>(s, d, width, height, rows, magic); break;
+        SCN_BP_CASE(2) SCN_BP_CASE(3) SCN_BP_CASE(4) SCN_BP_CASE(5) SCN_BP_CASE(6) SCN_BP_CASE(7) SCN_BP_CASE(8)
+        SCN_BP_CASE(9) SCN_BP_CASE(10) SCN_BP_CASE(11) SCN_BP_CASE(12) SCN_BP_CASE(13) SCN_BP_CASE(14)
+        SCN_BP_CASE(15) SCN_BP_CASE(16)
+#undef SCN_BP_CASE
+      }
+    } else if (aligned16 && k >= 2 && (ksize != 3 || stream3)) {
       const size_t smem_s = (size_t)kRowSlots * (48 + kStripBytes + 128) + (size_t)k * kStripBytes * 2;
       static bool attr2 = false;
       if (!attr2) {

@@ -299,6 +299,23 @@ def test_blur_streaming_kernel_vs_oracle(h, w, k, n):
         assert (got[i] == want).all(), (i, np.argwhere(got[i] != want)[:4])
 
 
+@pytest.mark.parametrize("k", list(range(2, 17)))
+def test_blur_packed_kernel_every_size_vs_oracle(k):
+    """box_packed_kernel<K> (u16x2 lanes): every kernel size it serves, a row narrower than one warp's span and one
+    that needs several warps with a ragged tail, strips that end inside the frame, and all-255 frames (the lane sums
+    reach 255 k^2 -- 65280 at k = 16 -- and must not carry into the neighbouring lane)."""
+    for (h, w, n) in [(67, 144, 2), (140, 2064, 1), (k + 1, 16, 1)]:
+        frames = np.stack([synth.rand_frame(90 + k + i, h, w) for i in range(n)])
+        frames[-1, : h // 2] = 255
+        got = kernels.blur(dev(frames), k).cpu().numpy()
+        for i in range(n):
+            want = oracle.blur(frames[i], k)
+            assert (got[i] == want).all(), (k, h, w, i, np.argwhere(got[i] != want)[:4])
+    sat = np.full((1, 40, 64, 3), 255, np.uint8)
+    got = kernels.blur(dev(sat), k).cpu().numpy()[0]
+    assert (got == oracle.blur(sat[0], k)).all()
+
+
 def test_blur_division_by_multiply_shift_is_exact():
     """box_stream_kernel divides a window sum by k*k with umulhi(v, floor(2^32 / k^2) + 1)."""
     for k in range(2, 32):
