@@ -128,21 +128,32 @@ __global__ void poly_h_kernel(const float* __restrict__ src3, int w, int h, Poly
     b6 = __fmaf_rn(p[1] - m[1], pk.xg[k], b6);
     b5 = __fmaf_rn(p[2] + m[2], pk.g[k], b5);
   }
-  float* d = dst5 + ((size_t)y * w + x) * 5;
-  d[1] = b2 * pk.ig11;
+  float* d = dst5 + (size_t)y * w + x;  // coefficient planes (see "layout" above update_matrices_kernel)
+  const size_t ps = (size_t)w * h;
+  d[1 * ps] = b2 * pk.ig11;
   d[0] = b3 * pk.ig11;
-  d[3] = __fmaf_rn(b4, pk.ig33, __fmul_rn(b1, pk.ig03));
-  d[2] = __fmaf_rn(b5, pk.ig33, __fmul_rn(b1, pk.ig03));
-  d[4] = b6 * pk.ig55;
+  d[3 * ps] = __fmaf_rn(b4, pk.ig33, __fmul_rn(b1, pk.ig03));
+  d[2 * ps] = __fmaf_rn(b5, pk.ig33, __fmul_rn(b1, pk.ig03));
+  d[4 * ps] = b6 * pk.ig55;
 }
 
+constexpr int UMW = 32, UMH = 8;
+// Layout: the 5 expansion coefficients (R0, R1) and the 5 matrix elements (M) of a level are PLANES of w x h floats,
+// coefficient c of pixel (x, y) at [c * w * h + y * w + x].  With the 5 values of a pixel adjacent (20 bytes: no
+// 128-bit access possible) every one of the 30 loads / stores of a pixel here touched 5-6 cache lines per warp and the
+// kernel ran against the L1 wavefront rate (32 us at 1080p for 115 MB, profiles/r02_flow.md); planes make each a
+// contiguous 128-byte row segment.
 __global__ void update_matrices_kernel(const float* __restrict__ R0, const float* __restrict__ R1,
                                        const float* __restrict__ flow, int w, int h, float* __restrict__ M) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w) return;
+  // a CTA is a UMW x UMH pixel tile (a warp = 32 pixels of a row): the bilinear taps of row y + 1 are mostly the
+  // lower taps of row y, and with eight rows in one CTA they meet in L1 instead of L2
+  const int x = blockIdx.x * UMW + (threadIdx.x & (UMW - 1)), y = blockIdx.y * UMH + threadIdx.x / UMW;
+  if (x >= w || y >= h) return;
   const float border[5] = {0.14f, 0.14f, 0.4472f, 0.4472f, 0.4472f};
   const int BORDER = 5;
-  const float* r0 = R0 + ((size_t)y * w + x) * 5;
+  const size_t ps = (size_t)w * h;
+  const float* r0p = R0 + (size_t)y * w + x;
+  const float r0[5] = {r0p[0], r0p[ps], r0p[2 * ps], r0p[3 * ps], r0p[4 * ps]};
   const float dx = flow[((size_t)y * w + x) * 2], dy = flow[((size_t)y * w + x) * 2 + 1];
   float fx = (float)x + dx, fy = (float)y + dy;
   const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
@@ -151,13 +162,13 @@ __global__ void update_matrices_kernel(const float* __restrict__ R0, const float
   float r2, r3, r4, r5, r6;
   if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
     const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    const float* p = R1 + ((size_t)y1 * w + x1) * 5;
-    const float* q = p + (size_t)w * 5;
-    r2 = a00 * p[0] + a01 * p[5] + a10 * q[0] + a11 * q[5];
-    r3 = a00 * p[1] + a01 * p[6] + a10 * q[1] + a11 * q[6];
-    r4 = a00 * p[2] + a01 * p[7] + a10 * q[2] + a11 * q[7];
-    r5 = a00 * p[3] + a01 * p[8] + a10 * q[3] + a11 * q[8];
-    r6 = a00 * p[4] + a01 * p[9] + a10 * q[4] + a11 * q[9];
+    const float* p = R1 + (size_t)y1 * w + x1;
+    const float* q = p + w;
+    r2 = a00 * p[0] + a01 * p[1] + a10 * q[0] + a11 * q[1];
+    r3 = a00 * p[ps] + a01 * p[ps + 1] + a10 * q[ps] + a11 * q[ps + 1];
+    r4 = a00 * p[2 * ps] + a01 * p[2 * ps + 1] + a10 * q[2 * ps] + a11 * q[2 * ps + 1];
+    r5 = a00 * p[3 * ps] + a01 * p[3 * ps + 1] + a10 * q[3 * ps] + a11 * q[3 * ps + 1];
+    r6 = a00 * p[4 * ps] + a01 * p[4 * ps + 1] + a10 * q[4 * ps] + a11 * q[4 * ps + 1];
     r4 = (r0[2] + r4) * 0.5f;
     r5 = (r0[3] + r5) * 0.5f;
     r6 = (r0[4] + r6) * 0.25f;
@@ -180,21 +191,23 @@ __global__ void update_matrices_kernel(const float* __restrict__ R0, const float
     r5 *= scale;
     r6 *= scale;
   }
-  float* m = M + ((size_t)y * w + x) * 5;
+  float* m = M + (size_t)y * w + x;
   m[0] = r4 * r4 + r6 * r6;
-  m[1] = (r4 + r5) * r6;
-  m[2] = r5 * r5 + r6 * r6;
-  m[3] = r4 * r2 + r6 * r3;
-  m[4] = r6 * r2 + r5 * r3;
+  m[ps] = (r4 + r5) * r6;
+  m[2 * ps] = r5 * r5 + r6 * r6;
+  m[3 * ps] = r4 * r2 + r6 * r3;
+  m[4 * ps] = r6 * r2 + r5 * r3;
 }
 
 // box filter, vertical pass in double (rows clamped); one thread per (x, channel)
 __global__ void box_v_kernel(const float* __restrict__ M, int w, int h, int m, double* __restrict__ V) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (i >= w * 5) return;
+  const int c = i / w, x = i - c * w;
+  const size_t ps = (size_t)w * h;
   double s = 0.0;
-  for (int k = -m; k <= m; ++k) s += (double)M[(size_t)clampi(y + k, 0, h - 1) * w * 5 + i];
-  V[(size_t)y * w * 5 + i] = s;
+  for (int k = -m; k <= m; ++k) s += (double)M[c * ps + (size_t)clampi(y + k, 0, h - 1) * w + x];
+  V[c * ps + (size_t)y * w + x] = s;
 }
 
 // horizontal pass (columns clamped) + the 2x2 solve of FarnebackUpdateFlow_Blur
@@ -202,12 +215,13 @@ __global__ void box_h_solve_kernel(const double* __restrict__ V, int w, int h, i
                                    float* __restrict__ flow) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= w) return;
-  const double* row = V + (size_t)y * w * 5;
+  const double* row = V + (size_t)y * w;
+  const size_t ps = (size_t)w * h;
   double hs[5] = {0, 0, 0, 0, 0};
   for (int k = -m; k <= m; ++k) {
-    const double* p = row + (size_t)clampi(x + k, 0, w - 1) * 5;
+    const double* p = row + clampi(x + k, 0, w - 1);
 #pragma unroll
-    for (int c = 0; c < 5; ++c) hs[c] += p[c];
+    for (int c = 0; c < 5; ++c) hs[c] += p[c * ps];
   }
   const double g11 = hs[0] * scale, g12 = hs[1] * scale, g22 = hs[2] * scale, h1 = hs[3] * scale, h2 = hs[4] * scale;
   const double idet = 1. / (g11 * g22 - g12 * g12 + 1e-3);
@@ -339,12 +353,13 @@ poly_fused_kernel(const float* __restrict__ src, int w, int h, PolyK pk, float* 
       b6 = __fmaf_rn(p[1] - m[1], pk.xg[k], b6);
       b5 = __fmaf_rn(p[2] + m[2], pk.g[k], b5);
     }
-    float* d = dst5 + ((size_t)y * w + x) * 5;
-    d[1] = b2 * pk.ig11;
+    float* d = dst5 + (size_t)y * w + x;
+    const size_t ps = (size_t)w * h;
+    d[1 * ps] = b2 * pk.ig11;
     d[0] = b3 * pk.ig11;
-    d[3] = __fmaf_rn(b4, pk.ig33, __fmul_rn(b1, pk.ig03));
-    d[2] = __fmaf_rn(b5, pk.ig33, __fmul_rn(b1, pk.ig03));
-    d[4] = b6 * pk.ig55;
+    d[3 * ps] = __fmaf_rn(b4, pk.ig33, __fmul_rn(b1, pk.ig03));
+    d[2 * ps] = __fmaf_rn(b5, pk.ig33, __fmul_rn(b1, pk.ig03));
+    d[4 * ps] = b6 * pk.ig55;
   }
 }
 
@@ -366,13 +381,14 @@ box_solve_fused_kernel(const float* __restrict__ M, int w, int h, double scale, 
   // global memory (neighbouring groups and CTAs re-read them from L1/L2), all loads issued before
   // the first conversion
   for (int e = threadIdx.x; e < (BTH / 4) * rowf; e += FT) {
-    const int g4 = e / rowf, q = e - g4 * rowf;
-    const int i = q / 5, c = q - i * 5;
+    const int g4 = e / rowf, qq = e - g4 * rowf;
+    const int c = qq / iw, i = qq - c * iw;  // consecutive threads: consecutive columns of one plane
+    const int q = i * 5 + c;                 // shared-memory slot (pixel-major, as the horizontal pass reads it)
     // 32-bit element indices (the launcher checks w * h * 5 < 2^31); rows away from the top and
     // bottom edge need no clamp, which was most of this kernel's instructions (r01 ncu: 45 %
     // IMAD / SHF / VIADDMNMX / SEL index arithmetic)
-    const int stride = w * 5;
-    const int idx0 = clampi(x0 - MW + i, 0, w - 1) * 5 + c;
+    const int stride = w;
+    const int idx0 = c * (w * h) + clampi(x0 - MW + i, 0, w - 1);
     const int ytop = y0 + g4 * 4 - MW;
     float f[taps + 3];
     if (ytop >= 0 && ytop + taps + 2 < h) {
@@ -445,17 +461,26 @@ box_solve_fused_kernel(const float* __restrict__ M, int w, int h, double scale, 
 // 41 MB input, 7.5 TB/s; profiles/r02_flow.md).
 constexpr int B32W = 88, B32H = 32;
 template <int MW>
-__global__ void __launch_bounds__(FT)
+struct Box32Geom {
+  static constexpr int iw = B32W + 2 * MW;          // columns of a tile with its halo
+  static constexpr int cp = (iw + 3) & ~3;          // pitch of one channel's row segment: 16-byte aligned
+  static constexpr int vstride = 5 * cp + 4;        // floats per tile row; (vstride / 4) odd: a quarter-warp's
+                                                    // eight 128-bit reads (8 rows) cover all 32 banks
+  static_assert(((5 * cp + 4) / 4) % 2 == 1, "row stride must be 4 x odd floats");
+};
+template <int MW>
+__global__ void __launch_bounds__(FT)  // 128 registers, 2 CTAs / SM: capping at 80 (3 CTAs) serialises the 46 loads: slower
 box_solve_f32_kernel(const float* __restrict__ M, int w, int h, double scale, float* __restrict__ flow) {
-  extern __shared__ float bsm[];
-  constexpr int iw = B32W + 2 * MW, rowf = iw * 5, vstride = rowf | 1, taps = 2 * MW + 1, in_rows = B32H + 2 * MW;
+  extern __shared__ __align__(16) float bsm[];
+  using G = Box32Geom<MW>;
+  constexpr int iw = G::iw, cp = G::cp, vstride = G::vstride, taps = 2 * MW + 1, in_rows = B32H + 2 * MW;
   static_assert(taps >= 7, "the 4-window tree needs at least 3 edge terms on each side");
-  float* V = bsm;  // B32H x vstride
+  float* V = bsm;  // B32H x vstride: row r, channel c, column i at [r * vstride + c * cp + i]
   const int x0 = blockIdx.x * B32W, y0 = blockIdx.y * B32H;
-  const int stride = w * 5;
-  for (int q = threadIdx.x; q < rowf; q += FT) {
-    const int i = q / 5, c = q - i * 5;
-    const int idx0 = clampi(x0 - MW + i, 0, w - 1) * 5 + c;
+  const int stride = w, ps = w * h;
+  for (int q = threadIdx.x; q < 5 * iw; q += FT) {
+    const int c = q / iw, i = q - c * iw;  // consecutive threads: consecutive columns of one plane
+    const int idx0 = c * ps + clampi(x0 - MW + i, 0, w - 1);
     const int ytop = y0 - MW;
     float f[in_rows];
     if (ytop >= 0 && ytop + in_rows <= h) {
@@ -467,38 +492,46 @@ box_solve_f32_kernel(const float* __restrict__ M, int w, int h, double scale, fl
       for (int k = 0; k < in_rows; ++k) f[k] = M[idx0 + clampi(ytop + k, 0, h - 1) * stride];
     }
     // rows 4g .. 4g+3: windows f[4g + o .. 4g + o + taps - 1], o = 0..3; f[4g + 3 .. 4g + taps - 1] is common
+    float* vo = V + c * cp + i;
 #pragma unroll
     for (int g = 0; g < B32H / 4; ++g) {
       const float* e = f + 4 * g;
       float core = e[3];
 #pragma unroll
       for (int k = 4; k < taps; ++k) core += e[k];
-      float* vo = V + (size_t)(g * 4) * vstride + q;
-      vo[0] = core + ((e[0] + e[1]) + e[2]);
-      vo[vstride] = core + ((e[1] + e[2]) + e[taps]);
-      vo[2 * vstride] = core + ((e[2] + e[taps]) + e[taps + 1]);
-      vo[3 * vstride] = core + ((e[taps] + e[taps + 1]) + e[taps + 2]);
+      vo[(4 * g) * vstride] = core + ((e[0] + e[1]) + e[2]);
+      vo[(4 * g + 1) * vstride] = core + ((e[1] + e[2]) + e[taps]);
+      vo[(4 * g + 2) * vstride] = core + ((e[2] + e[taps]) + e[taps + 1]);
+      vo[(4 * g + 3) * vstride] = core + ((e[taps] + e[taps + 1]) + e[taps + 2]);
     }
   }
   __syncthreads();
-  // horizontal + solve: item = (row, group of 4 columns); a warp's lanes are 32 rows (odd row stride: no bank conflicts)
+  // horizontal + solve: item = (row, group of 4 columns); a warp's lanes are 32 rows.  The taps + 3 = 18 values of a
+  // channel are contiguous: four 128-bit reads and one 64-bit read instead of 18 scalar ones.
+  static_assert(taps + 3 == 18, "the vector reads below are laid out for winSize 15");
   for (int e = threadIdx.x; e < B32H * (B32W / 4); e += FT) {
     const int ty = e & (B32H - 1), gx = e / B32H;
     const int y = y0 + ty;
     if (y >= h || x0 + gx * 4 >= w) continue;
-    const float* p = V + (size_t)ty * vstride + (gx * 4) * 5;
+    const float* p = V + (size_t)ty * vstride + gx * 4;
     float hs[4][5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-      float core = p[3 * 5 + c];
+      float v[20];
 #pragma unroll
-      for (int k = 4; k < taps; ++k) core += p[k * 5 + c];
-      const float a0 = p[c], a1 = p[5 + c], a2 = p[10 + c];
-      const float b0 = p[taps * 5 + c], b1 = p[(taps + 1) * 5 + c], b2 = p[(taps + 2) * 5 + c];
-      hs[0][c] = core + ((a0 + a1) + a2);
-      hs[1][c] = core + ((a1 + a2) + b0);
-      hs[2][c] = core + ((a2 + b0) + b1);
-      hs[3][c] = core + ((b0 + b1) + b2);
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const float4 t = *reinterpret_cast<const float4*>(p + c * cp + 4 * k4);
+        v[4 * k4] = t.x, v[4 * k4 + 1] = t.y, v[4 * k4 + 2] = t.z, v[4 * k4 + 3] = t.w;
+      }
+      const float2 t2 = *reinterpret_cast<const float2*>(p + c * cp + 16);
+      v[16] = t2.x, v[17] = t2.y;
+      float core = v[3];
+#pragma unroll
+      for (int k = 4; k < taps; ++k) core += v[k];
+      hs[0][c] = core + ((v[0] + v[1]) + v[2]);
+      hs[1][c] = core + ((v[1] + v[2]) + v[taps]);
+      hs[2][c] = core + ((v[2] + v[taps]) + v[taps + 1]);
+      hs[3][c] = core + ((v[taps] + v[taps + 1]) + v[taps + 2]);
     }
     float2 out[4];
 #pragma unroll
@@ -514,7 +547,7 @@ box_solve_f32_kernel(const float* __restrict__ M, int w, int h, double scale, fl
       if (x0 + gx * 4 + o < w) dst[o] = out[o];
   }
 }
-inline size_t box32_smem(int m) { return (size_t)B32H * (((B32W + 2 * m) * 5) | 1) * 4; }
+inline size_t box32_smem(int) { return (size_t)B32H * Box32Geom<7>::vstride * 4; }  // kBoxMW
 inline bool box_in_f64() {
   static const bool v = [] {
     const char* e = getenv("SCN_FLOW_BOX");
@@ -537,7 +570,7 @@ inline bool use_fused() {
       return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemCap) == cudaSuccess;
     };
     return big((const void*)gauss_fused_kernel<0>) && big((const void*)gauss_fused_kernel<1>) &&
-           big((const void*)gauss_fused_kernel<3>) && big((const void*)gauss_fused_kernel<8>) &&
+           big((const void*)gauss_fused_kernel<4>) && big((const void*)gauss_fused_kernel<9>) &&
            big((const void*)poly_fused_kernel<0>) && big((const void*)poly_fused_kernel<5>) &&
            cudaFuncSetAttribute(box_solve_fused_kernel<kBoxMW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kFusedSmemCap) == cudaSuccess &&
@@ -733,11 +766,12 @@ extern "C" int scn_farneback_u8c3_chain(const uint8_t* const* host_prev_ptrs, co
       LaunchScope ls("flow_gauss_fused_kernel", st);
       const dim3 gg((unsigned)((width + GTW - 1) / GTW), (unsigned)((height + GTH - 1) / GTH));
       const size_t sm = gauss_smem(gk.radius);
-      // the radii of the reference's pyramid (pyrScale 0.5: ksize 3, 3, 7, 17) are instantiated
+      // the radii of the reference's pyramid are instantiated: pyrScale 0.5 gives sigma 0, 0.5, 1.5, 3.5 and
+      // ksize = max(3, lrint(5 sigma) | 1) = 3, 3, 9, 19 (lrint rounds 7.5 and 17.5 to even)
       switch (gk.radius) {
         case 1: gauss_fused_kernel<1><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
-        case 3: gauss_fused_kernel<3><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
-        case 8: gauss_fused_kernel<8><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
+        case 4: gauss_fused_kernel<4><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
+        case 9: gauss_fused_kernel<9><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
         default: gauss_fused_kernel<0><<<gg, FT, sm, st>>>(gray, width, height, gk, ws.blur); break;
       }
     } else {
@@ -838,7 +872,7 @@ extern "C" int scn_farneback_u8c3_chain(const uint8_t* const* host_prev_ptrs, co
       }
       {
         LaunchScope ls("flow_update_matrices_kernel", st);
-        update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(R0, R1, flow, w, h, ws.M);
+        update_matrices_kernel<<<dim3((unsigned)((w + UMW - 1) / UMW), (unsigned)((h + UMH - 1) / UMH)), UMW * UMH, 0, st>>>(R0, R1, flow, w, h, ws.M);
       }
       const int m = win_size / 2;
       for (int it = 0; it < num_iters; ++it) {
@@ -862,7 +896,7 @@ extern "C" int scn_farneback_u8c3_chain(const uint8_t* const* host_prev_ptrs, co
         }
         if (it < num_iters - 1) {
           LaunchScope ls("flow_update_matrices_kernel", st);
-          update_matrices_kernel<<<grid2(w, h), T, 0, st>>>(R0, R1, flow, w, h, ws.M);
+          update_matrices_kernel<<<dim3((unsigned)((w + UMW - 1) / UMW), (unsigned)((h + UMH - 1) / UMH)), UMW * UMH, 0, st>>>(R0, R1, flow, w, h, ws.M);
         }
       }
       prev_flow = flow;
