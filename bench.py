@@ -399,6 +399,9 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     clips_per_rank, frames = args.e2e_clips, args.e2e_frames
     steps = steps or args.steps
     total = clips_per_rank * world
+    if getattr(args, "e2e_total_clips", 0):       # strong scaling: ONE table list of fixed size split over the ranks
+        total = args.e2e_total_clips
+        clips_per_rank = (total + world - 1) // world
     root = R.bcast(tempfile.mkdtemp(prefix="scn_bench_db_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
                    if rank == 0 else None)
     db = E.Database(root)
@@ -727,6 +730,8 @@ def main():
     ap.add_argument("--config", type=int, default=1, choices=[1, 3])
     ap.add_argument("--batch", type=int, default=256,
                     help="surfaces per step (kernels take 64 per launch: a step of 256 is 4 launches)")
+    ap.add_argument("--e2e-total-clips", type=int, default=0,
+                    help="e2e leg: total clips over ALL ranks (strong scaling; configs[1] as stated: 1000); overrides --e2e-clips")
     ap.add_argument("--e2e-clips", type=int, default=56, help="clips (tables) per rank in the e2e leg; configs[1] as stated: 1000")
     ap.add_argument("--e2e-frames", type=int, default=120, help="frames per clip in the e2e leg; configs[1] as stated: 300")
     ap.add_argument("--flow-clips", type=int, default=8, help="--config 3: clips; configs[3] as stated: 16")
