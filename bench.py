@@ -426,35 +426,54 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     op_r = graph.add_op("Resize", [(src, "frame")], device=1)
     sink_h = graph.add_sink((op_h, "histogram"))
     sink_r = graph.add_sink((op_r, "frame"))
-    sids = {i: db.add_video_stream(eng, f"clip_{i:05d}") for i in mine}
-    h2d = sum(db.table_info(f"clip_{i:05d}").get("bytes", 0) or 0 for i in mine)
+    # N > 1: the ranks PULL tasks of the one job list from a queue they share (scn_engine_share_task_queue; the
+    # reference's workers pull from the master), so a rank whose NVDEC sessions are in a slow spell takes fewer
+    # tasks instead of holding the step up.  --static-shards gives every rank a fixed share of the tables instead.
+    dynamic = world > 1 and not getattr(args, "static_shards", False)
+    listed = list(range(total)) if dynamic else mine
+    sids = {i: db.add_video_stream(eng, f"clip_{i:05d}") for i in listed}
+    h2d = sum(db.table_info(f"clip_{i:05d}").get("bytes", 0) or 0 for i in listed) // (world if dynamic else 1)
     resize_args = protolite.encode(std["ResizeArgs"], {"width": DW, "height": DH})
+    if dynamic:
+        eng.share_task_queue(os.path.join(root, "task_queue"))
 
     def one_step(tag):
         # the output tables of the step's jobs are reserved and committed with ONE catalogue lock each
         # (scn_db_new_tables / scn_db_commit_job_tables): ranks sharing the directory do not queue per table
-        ids = db.new_tables([(f"hist_{tag}_{i:05d}", "histogram", False, "Histogram", i) for i in mine] +
-                            [(f"small_{tag}_{i:05d}", "frame", True, "", i) for i in mine])
+        specs = ([(f"hist_{tag}_{i:05d}", "histogram", False, "Histogram", i) for i in listed] +
+                 [(f"small_{tag}_{i:05d}", "frame", True, "", i) for i in listed])
+        if dynamic:   # rank 0 reserves the tables of the whole list; every rank writes the items of the tasks it pulls
+            ids = R.bcast(db.new_tables(specs) if rank == 0 else None)
+        else:
+            ids = db.new_tables(specs)
         jobs = []
-        for k, i in enumerate(mine):
+        for k, i in enumerate(listed):
             j = E.Job()
             j.bind_source(src, sids[i])
             j.set_stream_args(op_r, resize_args)
             j.set_sink_table(sink_h, ids[k], keep_rows=False)
-            j.set_sink_table(sink_r, ids[len(mine) + k], keep_rows=False)
+            j.set_sink_table(sink_r, ids[len(listed) + k], keep_rows=False)
             jobs.append(j)
+        if dynamic:
+            if rank == 0:
+                eng.reset_task_queue()
+            R.barrier()
         eng.run(graph, jobs, 30, 60, out_dir=root)
-        db.commit_job_tables([(ids[k], jobs[k]) for k in range(len(mine))] +
-                             [(ids[len(mine) + k], jobs[k]) for k in range(len(mine))])
+        if dynamic:
+            R.barrier()          # every rank's items are on disk
+        if not dynamic or rank == 0:
+            db.commit_job_tables([(ids[k], jobs[k]) for k in range(len(listed))] +
+                                 [(ids[len(listed) + k], jobs[k]) for k in range(len(listed))])
         return jobs
 
     def drop(tag):
-        db.delete_tables([f"hist_{tag}_{i:05d}" for i in mine] + [f"small_{tag}_{i:05d}" for i in mine])
+        if not dynamic or rank == 0:
+            db.delete_tables([f"hist_{tag}_{i:05d}" for i in listed] + [f"small_{tag}_{i:05d}" for i in listed])
 
     for k in range(2):
         one_step(f"w{k}")  # warm-up: decoder creation, memory pools
         drop(f"w{k}")
-    step_s, rates, video = [], [], []
+    step_s, rates, video, done_frames = [], [], [], []
     for k in range(steps):
         R.barrier()
         sampler.reset()
@@ -465,12 +484,14 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
         sampler.sample_now()
         step_s.append(dt)
         rates.append(session_rates(eng.stats()["counters"]))
+        done_frames.append(int(eng.stats()["counters"].get("frames_used", 0)))
         video.append(sampler.video_result())
         if k + 1 < steps:
             drop(f"s{k}")  # untimed: the next step writes fresh tables
     stats = eng.stats()["counters"]
     # parity on what the save stage stored (last step): rows of one of this rank's clips against the oracle
     last = f"s{steps - 1}"
+    R.barrier()               # (dynamic: rank 0 has committed the last step's tables)
     i0 = mine[0]
     yuv = clip_yuv(uniq_seed(i0), frames) if stream_kind == "pcm" else make_clip_cavlc(uniq_seed(i0), frames)[1]
     check_rows = sorted({0, 1, min(frames - 1, 31), frames - 1})
@@ -489,7 +510,8 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     assert n_rows == frames, (n_rows, frames)
     eng.close()
     R.barrier()
-    per_rank = R.gather({"rank": rank, "step_s": step_s, "frames_per_step": len(mine) * frames, "session_pictures_per_s": rates,
+    per_rank = R.gather({"rank": rank, "step_s": step_s, "frames_per_step": sum(done_frames) / max(1, len(done_frames)),
+                         "frames_done_per_step": done_frames, "session_pictures_per_s": rates,
                          "nvml": video, "numa_pinned_cpus": stats.get("numa_pinned_cpus")})
     step_max = R.max(step_s)
     if rank == 0:
@@ -504,8 +526,11 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
                       "writing every task into them, commit}, max over ranks; the steps summed",
             "stored_rows_checked_against_oracle": len(check_rows) * 2,
             "step_fps": [frames_per_step_all / s for s in step_max],
-            "per_rank": [{"rank": p["rank"], "fps": p["frames_per_step"] * steps / sum(p["step_s"]),
-                          "step_fps_min_median_max": _mmm([p["frames_per_step"] / s for s in p["step_s"]]),
+            "task_assignment": "ranks pull tasks from one shared queue (scn_engine_share_task_queue)" if dynamic
+                               else "static: every rank owns a fixed share of the tables",
+            "per_rank": [{"rank": p["rank"], "fps": sum(p["frames_done_per_step"]) / sum(p["step_s"]),
+                          "frames_done_per_step": p["frames_done_per_step"],
+                          "step_fps_min_median_max": _mmm([f / s for f, s in zip(p["frames_done_per_step"], p["step_s"])]),
                           "session_pictures_per_s_last_step": p["session_pictures_per_s"][-1],
                           "session_rate_spread_worst_step": max((max(r) - min(r)) / max(1, max(r)) for r in p["session_pictures_per_s"] if r),
                           "nvml_last_step": p["nvml"][-1], "numa_pinned_cpus": p["numa_pinned_cpus"]} for p in per_rank],
@@ -895,6 +920,8 @@ def main():
                     help="surfaces per step (kernels take 64 per launch: a step of 256 is 4 launches)")
     ap.add_argument("--clips", type=int, default=0, help="--config 2 / 4: total clips (0 = that config's default)")
     ap.add_argument("--frames", type=int, default=0, help="--config 2 / 4: frames per clip (0 = that config's default)")
+    ap.add_argument("--static-shards", action="store_true",
+                    help="e2e leg at N > 1: give every rank a fixed share of the tables instead of the shared task queue")
     ap.add_argument("--e2e-total-clips", type=int, default=0,
                     help="e2e leg: total clips over ALL ranks (strong scaling; configs[1] as stated: 1000); overrides --e2e-clips")
     ap.add_argument("--e2e-clips", type=int, default=56, help="clips (tables) per rank in the e2e leg; configs[1] as stated: 1000")

@@ -141,6 +141,17 @@ SCN_ENGINE_API int scn_engine_set_halo_callback(scn_engine* e, int rank, int wor
                                                 void* user);
 SCN_ENGINE_API int scn_job_set_shard(scn_job* j, int index, int n, const int64_t* bounds, const int* ranks);
 
+/* ---- one task queue for the engines of several processes (one rank per GPU) ------------------
+ * The reference's workers PULL tasks from the master (master.cpp NextWork), so a slow worker simply does fewer.
+ * Here: every rank builds the SAME job list (same clips, same order, same packet sizes) and maps the same small file
+ * (a directory all ranks see, e.g. the database's); scn_engine_run then takes each next task with an atomic
+ * fetch-add on a counter in that file, so every task of the run is executed by exactly one rank.  A rank's jobs
+ * hold outputs only for the tasks it ran; sink tables (scn_job_set_sink_table with ids every rank agrees on) collect
+ * the items of all ranks.  Between runs ONE rank calls scn_engine_reset_task_queue while no rank is inside
+ * scn_engine_run (i.e. between two barriers).  path == NULL returns the engine to its private queue. */
+SCN_ENGINE_API int scn_engine_share_task_queue(scn_engine* e, const char* path);
+SCN_ENGINE_API int scn_engine_reset_task_queue(scn_engine* e);
+
 /* ---- run ----------------------------------------------------------------------------------- */
 /* work_packet_size / io_packet_size: rows per evaluate packet / per task (reference
  * BulkJobParameters, rpc.proto:238-274; io must be a multiple of work).  out_dir: if non-NULL the

@@ -3,6 +3,10 @@
 #include <cstring>
 #include <sstream>
 
+#include <sys/mman.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include "nvdec.h"
 #include "swdec.h"
 #include "pipeline.h"
@@ -15,6 +19,13 @@ using namespace scanner::internal;
 
 struct scn_engine {
   std::unique_ptr<Engine> impl;
+  void* shared_map = nullptr;  // the mapped task-queue file (scn_engine_share_task_queue)
+  ~scn_engine() {
+    if (shared_map) {
+      if (impl) impl->set_shared_task_counter(nullptr);
+      munmap(shared_map, 64);
+    }
+  }
 };
 struct scn_graph {
   Graph g;
@@ -537,6 +548,38 @@ int scn_engine_comm_init(scn_engine* e, int gpu_id, int rank, int world, const u
 int scn_engine_set_halo_callback(scn_engine* e, int rank, int world, scn_halo_exchange_fn fn, void* user) {
   if (!e || !fn || world < 1 || rank < 0 || rank >= world) return fail("bad arguments");
   e->impl->set_halo_transport(make_callback_transport(rank, world, fn, user));
+  return 0;
+}
+
+int scn_engine_share_task_queue(scn_engine* e, const char* path) {
+  if (!e) return fail("null engine");
+  e->impl->set_shared_task_counter(nullptr);
+  if (e->shared_map) {
+    munmap(e->shared_map, 64);
+    e->shared_map = nullptr;
+  }
+  if (!path) return 0;
+  const int fd = open(path, O_RDWR | O_CREAT, 0600);
+  if (fd < 0) return fail(std::string("cannot open ") + path + ": " + strerror(errno));
+  // a fresh file reads as zeros; ranks that arrive later must not shrink what another rank already counts in
+  struct stat sb;
+  if (fstat(fd, &sb) != 0 || (sb.st_size < 64 && ftruncate(fd, 64) != 0)) {
+    close(fd);
+    return fail(std::string("cannot size ") + path + ": " + strerror(errno));
+  }
+  void* m = mmap(nullptr, 64, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return fail(std::string("cannot map ") + path + ": " + strerror(errno));
+  e->shared_map = m;
+  e->impl->set_shared_task_counter(static_cast<volatile unsigned long long*>(m));
+  return 0;
+}
+
+int scn_engine_reset_task_queue(scn_engine* e) {
+  if (!e) return fail("null engine");
+  volatile unsigned long long* c = e->impl->shared_task_counter();
+  if (!c) return fail("the engine has no shared task queue");
+  __atomic_store_n(c, 0ull, __ATOMIC_SEQ_CST);
   return 0;
 }
 

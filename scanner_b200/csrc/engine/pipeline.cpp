@@ -376,7 +376,8 @@ void Engine::instance_main(Instance* inst) {
     const auto inst_t0 = std::chrono::steady_clock::now();
 
     while (!rs.failed.load()) {
-      const size_t ti = rs.next.fetch_add(1);
+      const size_t ti = shared_next_ ? (size_t)__atomic_fetch_add(shared_next_, 1ull, __ATOMIC_RELAXED)
+                                    : rs.next.fetch_add(1);
       if (ti >= rs.tasks.size()) break;
       const RunState::Task& t = rs.tasks[ti];
       Job& job = *rs.jobs[t.job];

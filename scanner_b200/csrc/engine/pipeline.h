@@ -174,6 +174,12 @@ class Engine {
   // Transport for the stencil halo exchange of sharded jobs (NCCL between the ranks' GPUs, or a host
   // callback); the engine owns it.
   void set_halo_transport(std::unique_ptr<HaloTransport> t) { halo_ = std::move(t); }
+  // One task queue for several engines (one per process / GPU) that run the SAME job list: `counter` lives in
+  // memory they all map (scn_engine_share_task_queue); a pipeline instance takes the next task of the run with an
+  // atomic fetch-add on it instead of the engine's own counter, so every task is executed by exactly one engine
+  // and a slow engine simply takes fewer (the reference's workers pull tasks from the master: master.cpp NextWork).
+  void set_shared_task_counter(volatile unsigned long long* counter) { shared_next_ = counter; }
+  volatile unsigned long long* shared_task_counter() const { return shared_next_; }
   const HaloTransport* halo_transport() const { return halo_.get(); }
 
  private:
@@ -191,6 +197,7 @@ class Engine {
   bool trace_ = false;
 
   std::unique_ptr<HaloTransport> halo_;
+  volatile unsigned long long* shared_next_ = nullptr;
   Result exchange_halos(Graph& graph, const std::vector<Job*>& jobs);
   // `reuse`: a persistent decode session + stream (the halo exchange of every run decodes a few boundary rows;
   // creating a decoder costs ~0.25 s); nullptr: a session for this call only

@@ -125,8 +125,13 @@ Result Database::load_meta() {
   std::string bytes;
   const std::string p = root_ + "db_metadata.bin";
   if (!read_file(p, bytes)) {  // fresh database (reference: master creates it on first start)
-    meta_ = tables::DatabaseDescriptor();
-    return save_meta();
+    // several ranks may open the same new directory at once: only one of them writes the empty catalogue, and
+    // none overwrites a catalogue another rank has meanwhile created (and perhaps already added tables to)
+    MetaLock file_lock(root_);
+    if (!read_file(p, bytes)) {
+      meta_ = tables::DatabaseDescriptor();
+      return save_meta();
+    }
   }
   if (!meta_.ParseFromString(bytes)) RESULT_ERROR(&r, "%s is not a DatabaseDescriptor", p.c_str());
   return r;

@@ -57,6 +57,8 @@ SIGNATURES = {
     "scn_job_output_copy": (_I, [_VP, _I, _I64, _I64, _VP, _SZ]),
     "scn_engine_stats_json": (_I, [_VP, _CP, _SZ]),
     "scn_h264_synth": (_I64, [_VP, _I, _I, _I64, _I, _I, _VP, _SZ]),
+    "scn_engine_share_task_queue": (_I, [_VP, _CP]),
+    "scn_engine_reset_task_queue": (_I, [_VP]),
     "scn_nvdec_caps": (_I, [_I, _IP]),
     "scn_swdec_caps": (_I, [_IP]),
     "scn_graph_add_slice": (_I, [_VP, _I, _CP]),
@@ -410,6 +412,14 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def share_task_queue(self, path):
+        """Take tasks from a queue shared with the engines of other processes that run the same job list
+        (scn_engine_share_task_queue); None returns to the private queue."""
+        check(lib().scn_engine_share_task_queue(self._h, path.encode() if path else None), "share_task_queue")
+
+    def reset_task_queue(self):
+        check(lib().scn_engine_reset_task_queue(self._h), "reset_task_queue")
 
     def add_h264(self, data):
         buf = np.frombuffer(data, np.uint8)

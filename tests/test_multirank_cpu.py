@@ -184,3 +184,72 @@ def test_engine_halo_exchange_for_sharded_clips_gloo(tmp_path, world):
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-3000:]
     assert f"ENGINE_HALO_OK {world}" in out.stdout, out.stdout[-3000:]
+
+
+QUEUE_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["SCN_ROOT"])
+import oracle
+from oracle import synth
+from scanner_b200 import engine as E
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+E.load_op_library(os.path.join(os.environ["SCN_ROOT"], "build", "tests", "libtest_plugin_ops.so"))
+root = os.environ["SCN_TEST_DB"]
+db = E.Database(root)
+n_clips, lengths = 6, [9, 14, 5, 11, 8, 13]
+frames = [np.stack([synth.rand_frame(3000 * i + k, 24, 32) for k in range(lengths[i])]) for i in range(n_clips)]
+eng = E.Engine(gpus=[], cpu_instances=2)
+g = E.Graph(); src = g.add_source(True)
+h = g.add_op("TestHistogramOracle", [(src, "frame")]); sink = g.add_sink((h, "histogram"))
+eng.share_task_queue(os.path.join(root, "task_queue"))
+for run in range(2):                                   # the queue is reset between runs
+    box = [db.new_tables([(f"h{run}_{i}", "histogram", False, "Histogram", i) for i in range(n_clips)]) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ids = box[0]
+    jobs = []
+    for i in range(n_clips):                           # EVERY rank lists every clip, in the same order
+        j = E.Job(); j.bind_source(src, eng.add_raw_frames(frames[i]))
+        j.set_sink_table(sink, ids[i], keep_rows=False)
+        jobs.append(j)
+    if rank == 0:
+        eng.reset_task_queue()
+    dist.barrier()
+    eng.run(g, jobs, 2, 4, root)
+    dist.barrier()
+    done = [None] * world
+    dist.all_gather_object(done, sum(v for k, v in eng.stats()["counters"].items() if k.startswith("inst") and k.endswith("_tasks")))
+    if rank == 0:
+        db.commit_job_tables(list(zip(ids, jobs)))
+        total_tasks = sum((n + 3) // 4 for n in lengths)
+        assert sum(done) == total_tasks, (done, total_tasks)          # every task ran exactly once, somewhere
+        for i in range(n_clips):
+            rows = db.read_rows(f"h{run}_{i}", "histogram")
+            assert len(rows) == lengths[i]
+            for k in range(lengths[i]):
+                assert rows[k] == oracle.hist16(frames[i][k]).tobytes(), (run, i, k)
+        print("QUEUE_OK", run, done)
+    dist.barrier()
+eng.close()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_pull_tasks_from_one_shared_queue_gloo(tmp_path, world):
+    """scn_engine_share_task_queue: every rank lists the same jobs; each task of a run is executed by exactly one rank
+    (the reference's workers pull tasks from the master), the items of all ranks land in the same tables."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liborc.so"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp")], stdout=subprocess.DEVNULL)
+    script = tmp_path / "worker.py"
+    script.write_text(QUEUE_WORKER)
+    db = tmp_path / "db"
+    env = dict(os.environ, SCN_ROOT=ROOT, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT, SCN_TEST_DB=str(db))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29640 + world), str(script)]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert out.stdout.count("QUEUE_OK") == 2, out.stdout[-3000:]
