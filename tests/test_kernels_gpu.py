@@ -316,6 +316,17 @@ def test_blur_packed_kernel_every_size_vs_oracle(k):
     assert (got == oracle.blur(sat[0], k)).all()
 
 
+@pytest.mark.parametrize("k", [17, 18, 21, 24, 27, 30, 31])
+def test_blur_stream_kernel_large_sizes_vs_oracle(k):
+    """Kernel sizes above 16 (lane sums no longer fit u16) stay on box_stream_kernel."""
+    frames = np.stack([synth.rand_frame(400 + k + i, 90, 1040) for i in range(2)])
+    frames[1, 20:70] = 255
+    got = kernels.blur(dev(frames), k).cpu().numpy()
+    for i in range(2):
+        want = oracle.blur(frames[i], k)
+        assert (got[i] == want).all(), (k, i, np.argwhere(got[i] != want)[:4])
+
+
 def test_blur_division_by_multiply_shift_is_exact():
     """box_stream_kernel divides a window sum by k*k with umulhi(v, floor(2^32 / k^2) + 1)."""
     for k in range(2, 32):
