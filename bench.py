@@ -437,14 +437,23 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     resize_args = protolite.encode(std["ResizeArgs"], {"width": DW, "height": DH})
     if dynamic:
         eng.share_task_queue(os.path.join(root, "task_queue"))
+    own = [k for k in range(2 * len(listed)) if k % world == rank] if dynamic else list(range(2 * len(listed)))
+    phases = []   # per step: seconds for {reserve tables, scn_engine_run, commit}
 
     def one_step(tag):
         # the output tables of the step's jobs are reserved and committed with ONE catalogue lock each
         # (scn_db_new_tables / scn_db_commit_job_tables): ranks sharing the directory do not queue per table
         specs = ([(f"hist_{tag}_{i:05d}", "histogram", False, "Histogram", i) for i in listed] +
                  [(f"small_{tag}_{i:05d}", "frame", True, "", i) for i in listed])
-        if dynamic:   # rank 0 reserves the tables of the whole list; every rank writes the items of the tasks it pulls
-            ids = R.bcast(db.new_tables(specs) if rank == 0 else None)
+        t_a = time.perf_counter()
+        if dynamic:
+            # every rank reserves (and later commits) the tables of ITS share of the list -- one catalogue lock per
+            # rank -- and all ranks learn all ids; the items of a table are written by whichever ranks pull its tasks
+            part = db.new_tables([specs[k] for k in own])
+            ids = [None] * len(specs)
+            for ks, vs in R.gather((own, part)):
+                for k, v in zip(ks, vs):
+                    ids[k] = v
         else:
             ids = db.new_tables(specs)
         jobs = []
@@ -459,17 +468,20 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
             if rank == 0:
                 eng.reset_task_queue()
             R.barrier()
+        t_b = time.perf_counter()
         eng.run(graph, jobs, 30, 60, out_dir=root)
+        t_c = time.perf_counter()
         if dynamic:
             R.barrier()          # every rank's items are on disk
-        if not dynamic or rank == 0:
-            db.commit_job_tables([(ids[k], jobs[k]) for k in range(len(listed))] +
-                                 [(ids[len(listed) + k], jobs[k]) for k in range(len(listed))])
+            db.commit_job_tables([(ids[k], jobs[k % len(listed)]) for k in own])
+        else:
+            db.commit_job_tables([(ids[k], jobs[k % len(listed)]) for k in range(2 * len(listed))])
+        phases.append([t_b - t_a, t_c - t_b, time.perf_counter() - t_c])
         return jobs
 
     def drop(tag):
-        if not dynamic or rank == 0:
-            db.delete_tables([f"hist_{tag}_{i:05d}" for i in listed] + [f"small_{tag}_{i:05d}" for i in listed])
+        names = [f"hist_{tag}_{i:05d}" for i in listed] + [f"small_{tag}_{i:05d}" for i in listed]
+        db.delete_tables([names[k] for k in own] if dynamic else names)
 
     for k in range(2):
         one_step(f"w{k}")  # warm-up: decoder creation, memory pools
@@ -513,6 +525,7 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
     R.barrier()
     per_rank = R.gather({"rank": rank, "step_s": step_s, "frames_per_step": sum(done_frames) / max(1, len(done_frames)),
                          "frames_done_per_step": done_frames, "session_pictures_per_s": rates,
+                         "phase_ms": [[round(x * 1e3, 2) for x in ph] for ph in phases[-len(step_s):]],
                          "nvml": video, "numa_pinned_cpus": stats.get("numa_pinned_cpus")})
     step_max = R.max(step_s)
     if rank == 0:
@@ -531,6 +544,7 @@ def e2e_config1(args, R, sampler, stream_kind="pcm", steps=None):
                                else "static: every rank owns a fixed share of the tables",
             "per_rank": [{"rank": p["rank"], "fps": sum(p["frames_done_per_step"]) / sum(p["step_s"]),
                           "frames_done_per_step": p["frames_done_per_step"],
+                          "reserve_run_commit_ms_per_step": p["phase_ms"],
                           "step_fps_min_median_max": _mmm([f / s for f, s in zip(p["frames_done_per_step"], p["step_s"])]),
                           "session_pictures_per_s_last_step": p["session_pictures_per_s"][-1],
                           "session_rate_spread_worst_step": max((max(r) - min(r)) / max(1, max(r)) for r in p["session_pictures_per_s"] if r),
