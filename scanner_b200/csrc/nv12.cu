@@ -10,7 +10,7 @@
 namespace scn {
 namespace {
 
-// ---- FMA-pipe colour math (same scheme as nv12_csa.cuh, here down to the 8-bit value) -----------
+// ---- FMA-pipe colour math (same scheme as nv12_stream.cuh, here down to the 8-bit value) -----------
 //   byte -> float : PRMT builds the bits of 2^23 + byte (no I2F: the conversion unit runs at a quarter
 //                   of the FMA rate and made the first version of this kernel XU-bound)
 //   x  = value * 2^-11 computed with fma.sat (lower clamp), min(x, 1023 * 2^-11) (upper clamp)
