@@ -76,6 +76,7 @@ def config0_cpu(frames=720):
     eng.run(g, [j], 10, 100)
     dt = time.perf_counter() - t0
     hist = j.output_array(sink, 192, np.int32).reshape(frames, 3, 16)
+    dec_threads = int(os.environ.get("SCN_SWDEC_THREADS", "1"))
     tmp = tempfile.mkdtemp(prefix="scn_c0_")
     try:
         path = os.path.join(tmp, "c.h264")
@@ -91,7 +92,8 @@ def config0_cpu(frames=720):
         shutil.rmtree(tmp, ignore_errors=True)
     eng.close()
     return {"workload": "configs[0]: Histogram on one 640x480 H.264 clip, CPU pipeline_instances=1 (no GPU)",
-            "value": frames / dt, "unit": "frames/s", "frames": frames, "cores": 1,
+            "value": frames / dt, "unit": "frames/s", "frames": frames, "pipeline_instances": 1,
+            "decoder_threads": dec_threads,
             "decoder": f"libavcodec {caps['avcodec']} / libswscale {caps['swscale']} via dlopen ({os.path.basename(caps['where'])})",
             "rows_checked_against_cv2_and_oracle": checked}
 

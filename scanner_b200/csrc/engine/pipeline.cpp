@@ -440,11 +440,12 @@ void Engine::instance_main(Instance* inst) {
             // SoftwareVideoDecoder).  Fails here, with the reason, when no FFmpeg can be loaded.
             auto& s = slot.sw_sessions[(i32)k];
             if (!s) {
-              static const int threads = [] {
-                const char* e = getenv("SCN_SWDEC_THREADS");
-                const int v = e ? atoi(e) : 1;
-                return v < 1 ? 1 : (v > 64 ? 64 : v);
-              }();
+              // libavcodec threads per session (reference: num_cpus / instances, worker.cpp:1631).  One by default:
+              // on the 640x480 configs[0] clip 8 frame threads gave 1,045 frames/s against 986 with one -- the
+              // instance's own swscale + op work is the serial part; SCN_SWDEC_THREADS raises it
+              int threads = 1;
+              if (const char* e = getenv("SCN_SWDEC_THREADS")) threads = atoi(e);
+              threads = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
               s.reset(new SwdecSession(threads));
               Result ir = s->init();
               if (!ir.success()) {
