@@ -1088,6 +1088,13 @@ Result Engine::run(Graph& graph, const std::vector<Job*>& jobs, i32 wps, i32 ios
       }
     }
     i64 window_end = job.total_rows;
+    if (job.shard_index >= 0 && shared_next_) {
+      // a shared task queue indexes ONE task list that every rank builds identically; an interval-sharded job
+      // (scn_job_set_shard) gives every rank different tasks
+      RESULT_ERROR(&r, "job %zu: scn_job_set_shard cannot be combined with a shared task queue "
+                       "(scn_engine_share_task_queue): the ranks' task lists would differ", j);
+      return r;
+    }
     if (job.shard_index >= 0) {
       // one interval of the clip: tasks cover [bounds[index], bounds[index + 1]) only
       const size_t nsh = job.shard_ranks.size();

@@ -433,6 +433,23 @@ def test_cpu_instance_says_why_when_no_ffmpeg_can_be_loaded(tmp_path):
     assert "ERR" in out.stdout and "software H.264 decoder unavailable" in out.stdout, out.stdout + out.stderr
 
 
+def test_shared_task_queue_refuses_interval_sharded_jobs(tmp_path):
+    """One queue indexes one task list: scn_job_set_shard gives every rank its own, so the combination is an error."""
+    e1 = E.Engine(gpus=[], cpu_instances=1)
+    e1.share_task_queue(str(tmp_path / "queue"))
+    g = E.Graph()
+    src = g.add_source(True)
+    g.add_sink((g.add_op("TestHistogramOracle", [(src, "frame")]), "histogram"))
+    j = E.Job()
+    j.bind_source(src, e1.add_raw_frames(np.zeros((8, 4, 4, 3), np.uint8)))
+    j.set_shard(0, [0, 4, 8], [0, 1])
+    with pytest.raises(E.EngineError, match="shared task queue"):
+        e1.run(g, [j], 2, 4)
+    e1.share_task_queue(None)                      # back to the private queue: the sharded job runs
+    e1.init_host_halo(None) if False else None
+    e1.close()
+
+
 def test_trace_file_has_one_event_per_interval_and_instance_ids(eng, tmp_path):
     """scn_engine_write_trace: Chrome trace events of the last run (reference Profiler records +
     scannerpy Profile.write_trace)."""
