@@ -446,7 +446,6 @@ def test_shared_task_queue_refuses_interval_sharded_jobs(tmp_path):
     with pytest.raises(E.EngineError, match="shared task queue"):
         e1.run(g, [j], 2, 4)
     e1.share_task_queue(None)                      # back to the private queue: the sharded job runs
-    e1.init_host_halo(None) if False else None
     e1.close()
 
 
