@@ -106,8 +106,11 @@ nv12_resize_kernel(PtrBatch lumas, PtrBatch chromas, size_t pitch, int width, in
     o[2] = (uint8_t)((a.b + b.b + c.b + d.b + 2) >> 2);
     return;
   }
-  // (the XU-converting tap chain of nv12_stream.cuh was tried here: 46 us instead of 37 us per 64 frames -- this
-  // kernel is latency-bound and the extra conversion latency costs more than the saved instructions)
+  // ncu (profiles/r02_nv12_resize.md): 300 instructions per destination pixel, issue-active 75 %, ALU pipe 69 % --
+  // instruction-bound.  Two leaner-looking forms were measured and were not faster: the XU-converting tap chain of
+  // nv12_stream.cuh (46 us instead of 37 us per 64 frames) and a row-organised kernel (a CTA per destination row,
+  // uniform row addresses, u16 chroma loads, chroma terms computed once per sample, mulhi blend: 312 static
+  // instructions, the same 37 us).
   const Tap* __restrict__ xt = reinterpret_cast<const Tap*>(plan + kPlanHeaderBytes);
   const Tap* __restrict__ yt = xt + dw;
   const int4 tx = __ldg(reinterpret_cast<const int4*>(xt + dx));
@@ -128,7 +131,7 @@ nv12_resize_kernel(PtrBatch lumas, PtrBatch chromas, size_t pitch, int width, in
 
 // Histogram and Resize of the configs[1] DAG are independent readers of the same surfaces: the
 // histogram kernel is bound by instruction issue (one persistent CTA per SM, most registers), the
-// resize kernel by memory latency (few registers).  When both are requested the resize runs on a
+// resize kernel too, at far fewer registers per thread.  When both are requested the resize runs on a
 // side stream forked from / joined to the caller's stream with events, so its CTAs share the SMs
 // with the histogram CTAs instead of queueing behind them.  One side stream per calling thread
 // and device (pipeline instances call from their own threads).
