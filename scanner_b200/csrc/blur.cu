@@ -10,9 +10,9 @@
 //                 shifts), summed as packed u16x2 lanes; the vertical pass is a 3-row sliding sum
 //                 held in registers; /9 is an exact multiply-shift; four results are stored as one
 //                 32-bit word.  No shared memory: neighbouring threads' loads overlap in L1.
-//   box_packed_kernel<K> kernel_size 2..16 on 16-byte aligned rows (every BASELINE frame size): u16x2 lanes, running
+//   box_packed_kernel<K> kernel_size 2..31 on 16-byte aligned rows (every BASELINE frame size): u16x2 lanes, running
 //                 vertical sums, 128-bit loads two rows ahead; 3.9 TB/s at K = 3 (60 % of the copy peak), > 3 TB/s to K = 9.
-//   box_stream_kernel    kernel_size 17..31 on 16-byte aligned rows: bulk-async (cp.async.bulk + mbarrier) row
+//   box_stream_kernel    SCN_BLUR_PATH=stream only (r02 first kernel): bulk-async (cp.async.bulk + mbarrier) row
 //                 ring, sliding horizontal sums, running vertical sums: O(1) work per sample.
 //   box_generic_kernel   the rest (unaligned or tiny frames, kernel_size 1): shared-memory tile, direct sums.
 #include <string.h>
@@ -326,9 +326,9 @@ box_stream_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int fl, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// box_packed_kernel<K>: kernel_size 2..16 on 16-byte aligned rows, all arithmetic on packed u16x2 lanes.
+// box_packed_kernel<K>: kernel_size 2..31 on 16-byte aligned rows, all arithmetic on packed u16x2 lanes.
 //   * a thread owns one 16-byte column (a "quad": 4 words) and walks down a strip of rows; a warp owns 32
-//     neighbouring quads of which the R on each side are halo (R = 1 for K <= 11, else 2);
+//     neighbouring quads of which the R on each side are halo (R = 1 for K <= 11, 2 up to K = 21, else 3);
 //   * vertical first: running column sums  acc += row(r) - row(r - K)  with the bytes of a word split into its even
 //     (0, 2) and odd (1, 3) bytes as u16 lanes -- one IADD3 adds the entering and subtracts the leaving row for two
 //     byte columns (lanes cannot borrow: the true lane values stay in [0, 255 K]).  Both rows come by 128-bit loads
@@ -338,7 +338,8 @@ box_stream_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int fl, 
 //   * horizontal: the window of the byte pair (b, b + 2) is K terms 3 bytes apart; a term is, depending on its byte
 //     offset mod 4, an even-lane word, an odd-lane word, or one of those shifted by one lane into the next word
 //     (funnel shift, computed once per word and shared by all outputs): (K - 1) / 2 IADD3 per pair, every index a
-//     compile-time constant.  Lane sums stay below 255 K^2 <= 65280;
+//     compile-time constant.  Lane sums stay below 255 K^2 <= 65280 for K <= 16; above, the terms are summed in
+//     groups of 8 (8 x 255 x 31 fits a lane) and the groups unpacked into 32-bit sums;
 //   * out = sum / K^2 by the exact multiply-shift, border samples masked to 0, one 128-bit store per thread.
 // ~6-12 instructions per byte (K = 3..15) where box_stream_kernel spends 15 and more on byte loads.
 constexpr int BP_WARPS = 4;
@@ -348,6 +349,9 @@ struct PackedGeom {
   static constexpr int R = (3 * fr + 15) / 16;       // halo quads on each side of a thread's quad
   static constexpr int NW = 4 * (2 * R + 1);         // lane-words a thread reads back
   static constexpr int OUT_QUADS = 32 - 2 * R;       // output quads per warp
+  static constexpr int kGroup = K <= 16 ? K : 8;     // terms whose packed sum still fits a u16 lane (255 K per term)
+  static_assert(255 * K * kGroup <= 65535, "a group of packed terms must not carry into the next lane");
+  static_assert(3 * fr <= 16 * R && 3 * fl <= 16 * R, "the halo must cover the window");
 };
 
 template <int K>
@@ -430,17 +434,28 @@ box_packed_kernel(PtrBatch src, MutPtrBatch dst, int width, int height, int rows
         uint32_t ow[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          uint32_t he = 0, ho = 0;  // pairs (byte 0, byte 2) and (byte 1, byte 3) of word w
+          // window sums of the byte pairs (0, 2) and (1, 3) of word w, as four 32-bit values.  A u16 lane holds at
+          // most 65535 = 8 terms of 255 * 31: the K terms are summed packed in groups of kGroup and the groups
+          // unpacked (K <= 16: one group, exactly the code there was before kernel sizes above 16 came here)
+          uint32_t e_lo = 0, e_hi = 0, o_lo = 0, o_hi = 0;
 #pragma unroll
-          for (int j = 0; j < K; ++j) {
-            // first byte of the pair's term j, relative to the own quad's byte 0, offset so that it is >= 0
-            const int te = 16 * R + 4 * w + 3 * (j - fl), to = te + 1;
-            const int we = te >> 2, wo = to >> 2;
-            he += (te & 3) == 0 ? VE[we] : (te & 3) == 1 ? VO[we] : (te & 3) == 2 ? SE[we] : SO[we];
-            ho += (to & 3) == 0 ? VE[wo] : (to & 3) == 1 ? VO[wo] : (to & 3) == 2 ? SE[wo] : SO[wo];
+          for (int j0 = 0; j0 < K; j0 += G::kGroup) {
+            uint32_t he = 0, ho = 0;
+#pragma unroll
+            for (int j = j0; j < (j0 + G::kGroup < K ? j0 + G::kGroup : K); ++j) {
+              // first byte of the pair's term j, relative to the own quad's byte 0, offset so that it is >= 0
+              const int te = 16 * R + 4 * w + 3 * (j - fl), to = te + 1;
+              const int we = te >> 2, wo = to >> 2;
+              he += (te & 3) == 0 ? VE[we] : (te & 3) == 1 ? VO[we] : (te & 3) == 2 ? SE[we] : SO[we];
+              ho += (to & 3) == 0 ? VE[wo] : (to & 3) == 1 ? VO[wo] : (to & 3) == 2 ? SE[wo] : SO[wo];
+            }
+            e_lo += he & 0xFFFFu;
+            e_hi += he >> 16;
+            o_lo += ho & 0xFFFFu;
+            o_hi += ho >> 16;
           }
-          const uint32_t e0 = __umulhi(he & 0xFFFFu, div_magic), e1 = __umulhi(he >> 16, div_magic);
-          const uint32_t o0 = __umulhi(ho & 0xFFFFu, div_magic), o1 = __umulhi(ho >> 16, div_magic);
+          const uint32_t e0 = __umulhi(e_lo, div_magic), e1 = __umulhi(e_hi, div_magic);
+          const uint32_t o0 = __umulhi(o_lo, div_magic), o1 = __umulhi(o_hi, div_magic);
           // quotients are < 256: byte 1 of each is zero and serves as the zero source of the packing
           ow[w] = prmt(prmt(e0, o0, 0x1140u), prmt(e1, o1, 0x1140u), 0x5410u) & xmask[w];
         }
@@ -508,7 +523,7 @@ int launch_blur(const uint8_t* const* sp, int n, int width, int height, int ksiz
       const char* e = getenv("SCN_BLUR_PATH");
       return !e ? 0 : strcmp(e, "stream") == 0 ? 1 : strcmp(e, "box3") == 0 ? 2 : 0;
     }();
-    if (aligned16 && k >= 2 && k <= 16 && path != 1 && (ksize != 3 || path != 2)) {
+    if (aligned16 && k >= 2 && k <= 31 && path != 1 && (ksize != 3 || path != 2)) {
       const unsigned d2 = (unsigned)(k * k);
       const uint32_t magic = (uint32_t)((1ull << 32) / d2) + 1u;
       const int quads = width * 3 / 16;
@@ -524,7 +539,9 @@ int launch_blur(const uint8_t* const* sp, int n, int width, int height, int ksiz
   case KK: box_packed_kernel<KK><<<grid, BP_WARPS * 32, 0, st>>>(s, d, width, height, rows, magic); break;
         SCN_BP_CASE(2) SCN_BP_CASE(3) SCN_BP_CASE(4) SCN_BP_CASE(5) SCN_BP_CASE(6) SCN_BP_CASE(7) SCN_BP_CASE(8)
         SCN_BP_CASE(9) SCN_BP_CASE(10) SCN_BP_CASE(11) SCN_BP_CASE(12) SCN_BP_CASE(13) SCN_BP_CASE(14)
-        SCN_BP_CASE(15) SCN_BP_CASE(16)
+        SCN_BP_CASE(15) SCN_BP_CASE(16) SCN_BP_CASE(17) SCN_BP_CASE(18) SCN_BP_CASE(19) SCN_BP_CASE(20) SCN_BP_CASE(21)
+        SCN_BP_CASE(22) SCN_BP_CASE(23) SCN_BP_CASE(24) SCN_BP_CASE(25) SCN_BP_CASE(26) SCN_BP_CASE(27) SCN_BP_CASE(28)
+        SCN_BP_CASE(29) SCN_BP_CASE(30) SCN_BP_CASE(31)
 #undef SCN_BP_CASE
       }
     } else if (aligned16 && k >= 2 && (ksize != 3 || stream3)) {

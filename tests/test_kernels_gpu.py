@@ -299,11 +299,12 @@ def test_blur_streaming_kernel_vs_oracle(h, w, k, n):
         assert (got[i] == want).all(), (i, np.argwhere(got[i] != want)[:4])
 
 
-@pytest.mark.parametrize("k", list(range(2, 17)))
+@pytest.mark.parametrize("k", list(range(2, 32)))
 def test_blur_packed_kernel_every_size_vs_oracle(k):
     """box_packed_kernel<K> (u16x2 lanes): every kernel size it serves, a row narrower than one warp's span and one
     that needs several warps with a ragged tail, strips that end inside the frame, and all-255 frames (the lane sums
-    reach 255 k^2 -- 65280 at k = 16 -- and must not carry into the neighbouring lane)."""
+    reach 255 k^2 -- 65280 at k = 16 -- and must not carry into the neighbouring lane; above 16 the terms are summed
+    in groups of 8 and the groups unpacked)."""
     for (h, w, n) in [(67, 144, 2), (140, 2064, 1), (k + 1, 16, 1)]:
         frames = np.stack([synth.rand_frame(90 + k + i, h, w) for i in range(n)])
         frames[-1, : h // 2] = 255
@@ -325,6 +326,24 @@ def test_blur_stream_kernel_large_sizes_vs_oracle(k):
     for i in range(2):
         want = oracle.blur(frames[i], k)
         assert (got[i] == want).all(), (k, i, np.argwhere(got[i] != want)[:4])
+
+
+def test_blur_stream_kernel_still_exact_when_selected():
+    """box_stream_kernel (bulk-async row ring) is no longer the default for any size; SCN_BLUR_PATH=stream selects it
+    (the variable is read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, '.');"
+        "import oracle; from oracle import synth; from scanner_b200 import kernels, cabi;"
+        "\nfor (h, w, k) in [(90, 1040, 5), (70, 3088, 7), (40, 1040, 31), (129, 1024, 4), (131, 48, 2), (200, 1920, 16)]:"
+        "\n    f = np.stack([synth.rand_frame(7 * k + i, h, w) for i in range(2)])"
+        "\n    got = kernels.blur(torch.from_numpy(f).cuda(), k).cpu().numpy()"
+        "\n    assert all((got[i] == oracle.blur(f[i], k)).all() for i in range(2)), (h, w, k)"
+        "\nprint('STREAM_OK')")
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCN_BLUR_PATH="stream"),
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), capture_output=True, text=True)
+    assert "STREAM_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_blur_division_by_multiply_shift_is_exact():

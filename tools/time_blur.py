@@ -15,7 +15,7 @@ n, h, w = 16, 2160, 3840
 frames = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = {"blur3_path": os.environ.get("SCN_BLUR3", "box3"), "path": os.environ.get("SCN_BLUR_PATH", "default")}
-for k in (3, 5, 7, 9, 15, 16, 31):
+for k in (3, 5, 7, 9, 15, 16, 17, 23, 31):
     kernels.blur(frames, k)
     ts = []
     for _ in range(7):
