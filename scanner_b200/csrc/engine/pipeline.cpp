@@ -842,7 +842,8 @@ Result Engine::decode_rows(InputStream& stref, const std::vector<i64>& rows, i32
     }
   if (rows.empty()) return ok();
   if (!cuda_available() || gpu_id < 0 || !dst) {
-    RESULT_ERROR(&r, "decode needs a GPU (NVDEC); there is no software decoder");
+    RESULT_ERROR(&r, "decoding rows into device memory (scn_engine_decode_to_device, halo rows of a sharded clip) "
+                     "needs a GPU: it goes through NVDEC; CPU pipeline instances decode inside scn_engine_run");
     return r;
   }
   ScopedDevice sd(gpu_id);
