@@ -1,6 +1,10 @@
 // storage.cpp -- see storage.h.
 #include "storage.h"
 
+#include <thread>
+
+#include <atomic>
+
 #include <dirent.h>
 #include <fcntl.h>
 #include <sys/file.h>
@@ -351,6 +355,7 @@ Result Database::commit_table(i32 table_id, const std::vector<i64>& end_rows) {
 Result Database::commit_tables(const std::vector<std::pair<i32, std::vector<i64>>>& tables) {
   Result r = ok();
   std::lock_guard<std::mutex> g(mu_);
+  std::vector<std::pair<i32, std::string>> files;  // (table id, serialised descriptor)
   for (const auto& te : tables) {
     auto it = pending_.find(te.first);
     if (it == pending_.end()) {
@@ -360,11 +365,32 @@ Result Database::commit_tables(const std::vector<std::pair<i32, std::vector<i64>
     tables::TableDescriptor& td = it->second;
     td.clear_end_rows();
     for (i64 e : te.second) td.add_end_rows(e);
-    const std::string s = td.SerializeAsString();
-    if (!write_file_atomic(table_dir(te.first) + "/descriptor.bin", s.data(), s.size())) {
-      RESULT_ERROR(&r, "cannot write the descriptor of table %d: %s", te.first, strerror(errno));
-      return r;
+    files.emplace_back(te.first, td.SerializeAsString());
+  }
+  // One small file per table (create, write, rename): a job list with hundreds of output tables writes them from a
+  // few threads -- at 8 ranks x 112 tables per step this was most of the commit's ~25 ms
+  const size_t workers = files.size() >= 64 ? 4 : 1;
+  std::atomic<size_t> next{0};
+  std::atomic<int> failed_id{-1};
+  std::atomic<int> failed_errno{0};
+  auto write_some = [&] {
+    for (size_t k = next.fetch_add(1); k < files.size(); k = next.fetch_add(1)) {
+      const std::string& bytes = files[k].second;
+      if (!write_file_atomic(table_dir(files[k].first) + "/descriptor.bin", bytes.data(), bytes.size())) {
+        failed_errno = errno;
+        failed_id = files[k].first;
+      }
     }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < workers; ++t) pool.emplace_back(write_some);
+    write_some();
+    for (auto& th : pool) th.join();
+  }
+  if (failed_id.load() >= 0) {
+    RESULT_ERROR(&r, "cannot write the descriptor of table %d: %s", failed_id.load(), strerror(failed_errno.load()));
+    return r;
   }
   MetaLock file_lock(root_);
   refresh_meta();

@@ -572,6 +572,34 @@ def test_many_tables_reserved_committed_and_deleted_under_one_catalogue_update(t
     db.close()
 
 
+def test_committing_a_hundred_tables_writes_every_descriptor(tmp_path):
+    """commit_tables writes the descriptors of a long table list from several threads (>= 64 tables)."""
+    n_tables, n = 100, 5
+    frames = np.stack([synth.rand_frame(700 + i, 8, 12) for i in range(n)])
+    db = E.Database(str(tmp_path / "db"))
+    eng = E.Engine(gpus=[], cpu_instances=2)
+    g = E.Graph()
+    src = g.add_source(True)
+    s_h = g.add_sink((g.add_op("TestHistogramOracle", [(src, "frame")]), "histogram"))
+    ids = db.new_tables([(f"t{k:03d}", "histogram", False, "Histogram", k) for k in range(n_tables)])
+    sid = eng.add_raw_frames(frames)
+    jobs = []
+    for k in range(n_tables):
+        j = E.Job()
+        j.bind_source(src, sid)
+        j.set_sink_table(s_h, ids[k], keep_rows=False)
+        jobs.append(j)
+    eng.run(g, jobs, 5, 5, db.path)
+    db.commit_job_tables(list(zip(ids, jobs)))
+    assert len(db.tables()) == n_tables
+    for k in (0, 37, 63, 64, 99):
+        td = parse_ref("TableDescriptor", str(tmp_path / f"db/tables/{ids[k]}/descriptor.bin"))
+        assert td.name == f"t{k:03d}" and list(td.end_rows) == [n] and td.job_id == k
+        assert db.read_rows(f"t{k:03d}", "histogram")[n - 1] == oracle.hist16(frames[n - 1]).tobytes()
+    eng.close()
+    db.close()
+
+
 # ---- re-layout of an .mp4 in Python: the shapes other muxers produce (several chunks, 64-bit chunk
 # offsets, moov in front of mdat = "faststart"), to exercise the demuxer's table walking
 def _boxes(buf, start, end):
